@@ -1,0 +1,304 @@
+"""CPU oracle for the SS-HSLIE hot path (TEST INFRASTRUCTURE — never shipped, never timed as product).
+
+A plain PyTorch fp32 *functional* restatement of the reference's forward, six-term loss
+and (through torch autograd) its gradients.  Only `tests/`, `__graft_entry__.smoke()` and
+`bench.py`'s `cpu_baseline` / `--impl reference` leg may import this file.
+
+Parity status: PINNED.  `oracle/gen_golden.py` imports the unmodified reference
+(`/root/reference/model.py`, through `oracle/ref_shims.py`) in the build container and
+records outputs, the seven loss values, gradient samples and post-Adam weights into
+`tests/golden/*.npz`; `tests/test_oracle_golden.py` checks this restatement against those
+fixtures.  The reference itself ships no tests or golden vectors.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+Parameters are addressed by the reference's state_dict keys.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+# (state_dict prefix, weight shape) in the reference's registration order, model.py:33-47, 125-141.
+PARAM_SPECS = [
+    ("decomposition_net.conv0.0", (32, 64, 3, 3)),
+    ("decomposition_net.shallow_conv.0", (64, 64, 9, 9)),
+    ("decomposition_net.conv1.0", (64, 64, 3, 3)),
+    ("decomposition_net.conv2.0", (128, 64, 3, 3)),
+    ("decomposition_net.conv3.0", (128, 128, 3, 3)),
+    ("decomposition_net.deconv.0", (128, 64, 3, 3)),  # ConvTranspose2d: (in, out, kH, kW)
+    ("decomposition_net.conv5.0", (64, 128, 3, 3)),
+    ("decomposition_net.conv7.0", (64, 96, 3, 3)),
+    ("decomposition_net.recon", (65, 64, 3, 3)),
+    ("illum_adjust_net.conv0.0", (64, 65, 3, 3)),
+    ("illum_adjust_net.conv1.0", (64, 64, 3, 3)),
+    ("illum_adjust_net.conv2.0", (64, 64, 3, 3)),
+    ("illum_adjust_net.conv3.0", (64, 64, 3, 3)),
+    ("illum_adjust_net.attn.q_linear", (64, 64)),
+    ("illum_adjust_net.attn.k_linear", (64, 64)),
+    ("illum_adjust_net.attn.v_linear", (64, 64)),
+    ("illum_adjust_net.attn.ff_linear1", (64, 64)),
+    ("illum_adjust_net.attn.ff_linear2", (64, 64)),
+    ("illum_adjust_net.deconv1.0", (64, 64, 3, 3)),
+    ("illum_adjust_net.deconv2.0", (64, 64, 3, 3)),
+    ("illum_adjust_net.deconv3.0", (64, 64, 3, 3)),
+    ("illum_adjust_net.feature_fusion.0", (64, 192, 1, 1)),
+    ("illum_adjust_net.final_conv", (1, 64, 3, 3)),
+]
+
+
+def param_specs(channels: int = 64):
+    """Shapes for an arbitrary band count C (model.py:26-47, 122-141 with in_channels=C)."""
+    out = []
+    for name, shp in PARAM_SPECS:
+        shp = list(shp)
+        if name == "decomposition_net.conv0.0":
+            shp[1] = channels
+        elif name == "decomposition_net.shallow_conv.0":
+            shp[1] = channels
+        elif name == "decomposition_net.recon":
+            shp[0] = channels + 1
+        elif name == "illum_adjust_net.conv0.0":
+            shp[1] = channels + 1
+        out.append((name, tuple(shp)))
+    return out
+
+
+def init_params(seed: int = 41, channels: int = 64) -> Params:
+    """Default PyTorch init in the reference's module-construction order.
+
+    model.py:210-211 builds DecompositionNet then IllumAdjustmentNet; each nn.Conv2d /
+    nn.ConvTranspose2d / nn.Linear draws kaiming_uniform(a=sqrt(5)) for the weight and then
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for the bias, consuming the global RNG in that order.
+    Restated here without nn.Module so that seed -> weights is reproducible without the reference.
+    """
+    g = torch.Generator().manual_seed(seed)
+    params: Params = OrderedDict()
+    for name, shp in param_specs(channels):
+        w = torch.empty(shp)
+        # fan_in as torch.nn.init._calculate_fan_in_and_fan_out: size(1) * receptive field
+        rf = 1
+        for s in shp[2:]:
+            rf *= s
+        fan_in = shp[1] * rf
+        gain = math.sqrt(2.0 / (1 + 5.0))  # leaky_relu gain with a = sqrt(5)
+        bound_w = gain * math.sqrt(3.0 / fan_in)
+        w.uniform_(-bound_w, bound_w, generator=g)
+        nb = shp[1] if name == "decomposition_net.deconv.0" else shp[0]
+        b = torch.empty(nb)
+        bound_b = 1.0 / math.sqrt(fan_in)
+        b.uniform_(-bound_b, bound_b, generator=g)
+        params[name + ".weight"] = w
+        params[name + ".bias"] = b
+    return params
+
+
+def synthetic_patches(batch: int, channels: int = 64, size: int = 128, seed: int = 41) -> torch.Tensor:
+    """Synthetic low-light HSI patches: smooth low-frequency scene, dim,
+    slightly noisy, normalised so that the batch max is 1 (what utils.py:45-57 load_hsi produces)."""
+    g = torch.Generator().manual_seed(seed)
+    coarse = torch.rand(batch, channels, 9, 9, generator=g)
+    x = F.interpolate(coarse, size=(size, size), mode="bicubic", align_corners=False)
+    x = 0.12 * x + 0.01 * torch.rand(batch, channels, size, size, generator=g)
+    x = x.clamp_(0, 1)
+    x = x / x.max()
+    return x.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# networks
+# --------------------------------------------------------------------------------------------
+
+def _conv(p: Params, name: str, x, stride=1, relu=False):
+    """model.py:17-23: Conv2d(pad=(k-1)//2) + optional ReLU."""
+    w = p[name + ".weight"]
+    y = F.conv2d(x, w, p[name + ".bias"], stride=stride, padding=(w.shape[-1] - 1) // 2)
+    return F.relu(y) if relu else y
+
+
+def decomposition_net(p: Params, x, prefix="decomposition_net."):
+    """model.py:49-70."""
+    c0 = _conv(p, prefix + "conv0.0", x, relu=True)
+    sh = _conv(p, prefix + "shallow_conv.0", x)
+    c1 = _conv(p, prefix + "conv1.0", sh, relu=True)
+    c2 = _conv(p, prefix + "conv2.0", c1, stride=2, relu=True)
+    c3 = _conv(p, prefix + "conv3.0", c2, relu=True)
+    dc = F.relu(F.conv_transpose2d(c3, p[prefix + "deconv.0.weight"], p[prefix + "deconv.0.bias"],
+                                   stride=2, padding=1, output_padding=1))
+    c5 = _conv(p, prefix + "conv5.0", torch.cat([dc, c1], 1), relu=True)
+    c7 = _conv(p, prefix + "conv7.0", torch.cat([c5, c0], 1))
+    c8 = _conv(p, prefix + "recon", c7)
+    C = c8.shape[1] - 1
+    return torch.sigmoid(c8[:, :C]), torch.sigmoid(c8[:, C:])
+
+
+def transformer_block(p: Params, x, prefix="illum_adjust_net.attn.", heads=4, head_dim=16):
+    """model.py:99-119."""
+    n, c, h, w = x.shape
+    L = h * w
+    t = x.reshape(n, c, L).permute(0, 2, 1)
+    lin = lambda nm, v: F.linear(v, p[prefix + nm + ".weight"], p[prefix + nm + ".bias"])
+    q = lin("q_linear", t).reshape(n, L, heads, head_dim).permute(0, 2, 1, 3)
+    k = lin("k_linear", t).reshape(n, L, heads, head_dim).permute(0, 2, 1, 3)
+    v = lin("v_linear", t).reshape(n, L, heads, head_dim).permute(0, 2, 1, 3)
+    logits = torch.matmul(q, k.transpose(-2, -1)) / (head_dim ** 0.5)
+    o = torch.matmul(torch.softmax(logits, dim=-1), v)
+    o = o.permute(0, 2, 1, 3).reshape(n, L, heads * head_dim)
+    y = t + lin("ff_linear2", F.relu(lin("ff_linear1", o)))
+    return y.permute(0, 2, 1).reshape(n, c, h, w)
+
+
+def illum_adjust_net(p: Params, I, R, prefix="illum_adjust_net."):
+    """model.py:143-175."""
+    a0 = _conv(p, prefix + "conv0.0", torch.cat([R, I], 1))
+    a1 = _conv(p, prefix + "conv1.0", a0, stride=2, relu=True)
+    a2 = _conv(p, prefix + "conv2.0", a1, stride=2, relu=True)
+    a3 = _conv(p, prefix + "conv3.0", a2, stride=2, relu=True)
+    t = transformer_block(p, a3, prefix + "attn.")
+    up = lambda v, ref: F.interpolate(v, size=ref.shape[2:], mode="nearest")
+    d1 = _conv(p, prefix + "deconv1.0", up(t, a2), relu=True) + a2
+    d2 = _conv(p, prefix + "deconv2.0", up(d1, a1), relu=True) + a1
+    d3 = _conv(p, prefix + "deconv3.0", up(d2, a0), relu=True) + a0
+    fg = torch.cat([up(d1, d3), up(d2, d3), d3], 1)
+    ff = _conv(p, prefix + "feature_fusion.0", fg)
+    return _conv(p, prefix + "final_conv", ff)
+
+
+def forward(p: Params, x):
+    """model.py:229-234 -> (R_low, I_low, I_delta, S)."""
+    R, I = decomposition_net(p, x)
+    Id = illum_adjust_net(p, I, R)
+    S = R * Id + R * I
+    return R, I, Id, S
+
+
+# --------------------------------------------------------------------------------------------
+# loss
+# --------------------------------------------------------------------------------------------
+
+def _dx(t):
+    return t[..., :, 1:] - t[..., :, :-1]          # model.py:483-485
+
+
+def _dy(t):
+    return t[..., 1:, :] - t[..., :-1, :]          # model.py:487-489
+
+
+def smooth_loss(I, R, alpha):
+    """model.py:450-454 (I has 1 channel and broadcasts over R's bands)."""
+    return (torch.mean(_dx(I).abs() * torch.exp(-alpha * _dx(R).abs()))
+            + torch.mean(_dy(I).abs() * torch.exp(-alpha * _dy(R).abs())))
+
+
+def fourier_mask(H, W, cutoff=0.1, device=None):
+    """model.py:460-464: radial mask on an UNSHIFTED spectrum grid."""
+    y = torch.linspace(-1, 1, H, device=device)
+    x = torch.linspace(-1, 1, W, device=device)
+    Y, X = torch.meshgrid(y, x, indexing="ij")
+    return (torch.sqrt(X ** 2 + Y ** 2) >= cutoff).float()
+
+
+def fourier_spectrum_loss(a, b, cutoff=0.1):
+    """model.py:456-473, loss_type='l1'."""
+    m = fourier_mask(a.shape[-2], a.shape[-1], cutoff, a.device)
+    fa = torch.abs(torch.fft.fft2(a) * m)
+    fb = torch.abs(torch.fft.fft2(b) * m)
+    return torch.mean(torch.abs(fa - fb))
+
+
+def spectral_smoothness_loss(S):
+    """model.py:475-481, loss_type='l1'."""
+    return torch.mean(torch.abs(S[:, 1:] - S[:, :-1]))
+
+
+def structure_aware_loss(R, I, R_enh, alpha, beta):
+    """model.py:491-542 -> (L_I_smooth_low, L_R_fidelity)."""
+    wx = torch.exp(-alpha * _dx(R).abs().mean(dim=1, keepdim=True))
+    wy = torch.exp(-alpha * _dy(R).abs().mean(dim=1, keepdim=True))
+    loss_I = torch.mean(wx * _dx(I).abs()) + torch.mean(wy * _dy(I).abs())
+    loss_R = (torch.mean(torch.abs(R - R_enh))
+              + beta * (torch.mean(torch.abs(_dx(R) - _dx(R_enh))) + torch.mean(torch.abs(_dy(R) - _dy(R_enh)))))
+    return loss_I, loss_R
+
+
+DEFAULT_COEF = dict(c_loss_reconstruction=10.0, c_loss_r_fidelity=1.0, c_loss_i_smooth_low=1.0,
+                    c_loss_i_smooth_delta=20.0, c_loss_fourier=0.2, c_loss_spectral_cons=1.0,
+                    alpha_i_smooth_low=1.0, alpha_i_smooth_delta=10.0)
+JYU_COEF = dict(DEFAULT_COEF, c_loss_i_smooth_delta=2000.0, c_loss_fourier=20.0)  # config_outdoor_jyu.yml:24-31
+LOSS_KEYS = ["total_loss", "L_reconstruction", "L_R_fidelity", "L_I_smooth_low", "L_I_smooth_delta",
+             "L_fourier", "L_spectral_cons"]
+
+
+def loss_terms(x, R, I, Id, S, R_enh, coef):
+    """model.py:551-564; returns (total, dict of the six unweighted terms) as tensors."""
+    L_rec = torch.mean(torch.abs(R * I - x))
+    L_Ilow, L_Rfid = structure_aware_loss(R, I, R_enh, alpha=coef["alpha_i_smooth_low"], beta=0.5)
+    L_Idelta = smooth_loss(Id, R, alpha=coef["alpha_i_smooth_delta"])
+    L_four = fourier_spectrum_loss(x, S, cutoff=0.1)
+    L_spec = spectral_smoothness_loss(S)
+    total = (coef["c_loss_reconstruction"] * L_rec + coef["c_loss_r_fidelity"] * L_Rfid
+             + coef["c_loss_i_smooth_low"] * L_Ilow + coef["c_loss_i_smooth_delta"] * L_Idelta
+             + coef["c_loss_fourier"] * L_four + coef["c_loss_spectral_cons"] * L_spec)
+    terms = OrderedDict(total_loss=total, L_reconstruction=L_rec, L_R_fidelity=L_Rfid, L_I_smooth_low=L_Ilow,
+                        L_I_smooth_delta=L_Idelta, L_fourier=L_four, L_spectral_cons=L_spec)
+    return total, terms
+
+
+def compute_loss(p: Params, x, coef=None):
+    """model.py:544-575 -> (total_loss tensor, dict of tensors, (R, I, Id, S, R_enh))."""
+    coef = dict(DEFAULT_COEF, **(coef or {}))
+    R, I, Id, S = forward(p, x)
+    R_enh, _ = decomposition_net(p, S)             # model.py:546 (I_enh unused)
+    total, terms = loss_terms(x, R, I, Id, S, R_enh, coef)
+    return total, terms, (R, I, Id, S, R_enh)
+
+
+def loss_and_grads(p: Params, x, coef=None):
+    """Loss dict (python floats) + gradient per parameter, as loss.backward() gives (model.py:314-315)."""
+    leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
+    total, terms, outs = compute_loss(leaves, x, coef)
+    grads = torch.autograd.grad(total, list(leaves.values()), allow_unused=True)
+    gd = OrderedDict()
+    for (k, v), g in zip(leaves.items(), grads):
+        gd[k] = torch.zeros_like(v) if g is None else g.detach()
+    return {k: float(v.detach()) for k, v in terms.items()}, gd, tuple(o.detach() for o in outs)
+
+
+def adam_step(p: Params, grads: Params, state: dict, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """torch.optim.Adam defaults as used at model.py:213,316 (no weight decay, no amsgrad)."""
+    state["step"] = state.get("step", 0) + 1
+    t = state["step"]
+    b1, b2 = betas
+    out = OrderedDict()
+    for k, w in p.items():
+        g = grads[k]
+        m = state.setdefault("m", {}).get(k, torch.zeros_like(w))
+        v = state.setdefault("v", {}).get(k, torch.zeros_like(w))
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g * g
+        state["m"][k], state["v"][k] = m, v
+        denom = (v.sqrt() / math.sqrt(1 - b2 ** t)) + eps
+        out[k] = w - (lr / (1 - b1 ** t)) * m / denom
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# metrics (metrics.py:13-34 call torchmetrics 1.6.2, which is absent here: PARITY UNPINNED)
+# --------------------------------------------------------------------------------------------
+
+def psnr(pred, target, data_range):
+    """torchmetrics.functional.peak_signal_noise_ratio with scalar data_range (metrics.py:13-14)."""
+    mse = torch.mean((pred - target) ** 2)
+    return 10.0 * torch.log10(torch.as_tensor(float(data_range)) ** 2 / mse)
+
+
+def sam(pred_hwc, target_hwc):
+    """torchmetrics spectral_angle_mapper over the band axis (metrics.py:31-34), radians, mean."""
+    dot = (pred_hwc * target_hwc).sum(-1)
+    den = pred_hwc.norm(dim=-1) * target_hwc.norm(dim=-1)
+    return torch.acos(torch.clamp(dot / den, -1, 1)).mean()

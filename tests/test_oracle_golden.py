@@ -1,0 +1,81 @@
+"""The CPU oracle (oracle/sshslie_oracle.py) against fixtures recorded from the UNMODIFIED reference
+(tests/golden/*.npz, made by oracle/gen_golden.py).  This is what pins the oracle (prompt ③)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sshslie_oracle as O
+
+CASES = ["jyu_b2_128", "cv_b1_128", "jyu_b2_32_trained", "cv_b1_64_trained"]
+COEFS = {"jyu": O.JYU_COEF, "cv": O.DEFAULT_COEF}
+
+
+def _samples(t, n):
+    f = t.detach().reshape(-1).double()
+    idx = torch.linspace(0, f.numel() - 1, min(n, f.numel())).long()
+    return f[idx].numpy()
+
+
+def _check(prefix, t, g, n, rtol, atol):
+    f = t.detach().double()
+    np.testing.assert_allclose(float(f.sum()), float(g[prefix + "/sum"]), rtol=rtol, atol=atol * 10)
+    np.testing.assert_allclose(float(f.norm()), float(g[prefix + "/l2"]), rtol=rtol, atol=atol)
+    np.testing.assert_allclose(_samples(t, n), g[prefix + "/samples"], rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference_fixture(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    batch, size, pre = int(g["meta/batch"]), int(g["meta/size"]), int(g["meta/pre_steps"])
+    coef = COEFS[str(g["meta/coef"])]
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = O.init_params(41)
+    state = {}
+    for s in range(pre):                       # the oracle's own Adam must reproduce the reference's weights
+        xs = O.synthetic_patches(batch, 64, size, seed=100 + s)
+        _, grads, _ = O.loss_and_grads(p, xs, coef)
+        p = O.adam_step(p, grads, state, lr=1e-3)
+    for k, v in p.items():
+        _check("w0/" + k, v, g, 64, rtol=2e-4, atol=2e-6)
+    x = O.synthetic_patches(batch, 64, size, seed=41)
+    losses, grads, (R, I, Id, S, Re) = O.loss_and_grads(p, x, coef)
+    for k in O.LOSS_KEYS:
+        np.testing.assert_allclose(losses[k], float(g["loss/" + k]), rtol=2e-5, atol=1e-7, err_msg=k)
+    for nm, t in [("R_low", R), ("I_low", I), ("I_delta", Id), ("S", S), ("R_enh", Re)]:
+        _check("out/" + nm, t, g, 256, rtol=1e-4, atol=1e-5)
+    for k, gr in grads.items():
+        # fp32 summation-order noise only: tolerance relative to the largest sampled gradient entry
+        scale = float(np.abs(g["grad/" + k + "/samples"]).max())
+        _check("grad/" + k, gr, g, 64, rtol=2e-3, atol=2e-3 * scale + 1e-9)
+    p1 = O.adam_step(p, grads, {}, lr=1e-3)
+    # First Adam step moves every weight by lr*g/(|g|+eps): entries whose gradient is pure fp32 noise can
+    # flip sign between two correct implementations, i.e. differ by up to 2*lr.  Hence atol = 2.1e-3 per entry
+    # and no check on the plain sum.
+    for k, v in p1.items():
+        np.testing.assert_allclose(_samples(v, 64), g["w1/" + k + "/samples"], rtol=2e-4, atol=2.1e-3)
+        np.testing.assert_allclose(float(v.double().norm()), float(g["w1/" + k + "/l2"]), rtol=2e-3, atol=1e-4)
+
+
+def test_fourier_mask_quirk():
+    """un-shifted mask zeroes 120 bins around Nyquist at 128x128 and keeps DC."""
+    m = O.fourier_mask(128, 128)
+    assert int((m == 0).sum()) == 120
+    assert m[0, 0] == 1 and m[64, 64] == 0 and m[63, 63] == 0
+
+
+def test_half_spectrum_identity():
+    """The rfft2 restatement of the Fourier loss equals the full-spectrum form."""
+    torch.manual_seed(0)
+    a, b = torch.rand(2, 3, 32, 32), torch.rand(2, 3, 32, 32)
+    full = O.fourier_spectrum_loss(a, b)
+    H = W = 32
+    m = O.fourier_mask(H, W)
+    ky = torch.arange(H)
+    w = m[:, : W // 2 + 1].clone()
+    for kx in range(1, W // 2):
+        w[:, kx] = m[:, kx] + m[(-ky) % H, (-kx) % W]
+    fa, fb = torch.fft.rfft2(a).abs(), torch.fft.rfft2(b).abs()
+    half = (w * (fa - fb).abs()).sum() / a.numel()
+    np.testing.assert_allclose(float(half), float(full), rtol=1e-5)
