@@ -1,0 +1,127 @@
+/*
+ * sshslie_b200 — C-ABI of the B200-native SS-HSLIE hot path.
+ *
+ * The reference (medemirhan/Self-supervised-Image-Enhancement-Network-Training-With-Low-Light-Images-Only)
+ * has no FFI layer: its hot path is reached through `LowLightEnhance.forward` / `.compute_loss` /
+ * `loss.backward()` / `optimizer.step()` (model.py:229-234, 544-575, 313-316).  These entry points are
+ * what a binding for exactly those calls needs; the Python drop-in (`sshslie_b200/model.py`) binds them
+ * with ctypes, and INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer except `sshslie_engine*`, `const char*` and host tables is a DEVICE pointer;
+ *   - the caller owns every buffer; functions only ENQUEUE work on `stream` (a cudaStream_t passed as
+ *     void*), never allocate, free or synchronise, and are CUDA-graph capturable
+ *     (exception: sshslie_engine_bind, which uploads constant tables and synchronises `stream`);
+ *   - return value: 0 = ok, negative = error; `sshslie_last_error()` describes the last failure of the
+ *     calling thread; no C++ exception crosses the boundary;
+ *   - fp32 tensors are NCHW contiguous (the reference's layout); parameters and gradients are ONE flat
+ *     fp32 buffer in the reference's state_dict order (`sshslie_param_table`).
+ */
+#ifndef SSHSLIE_B200_H
+#define SSHSLIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(SSHSLIE_BUILD)
+#define SSHSLIE_API __attribute__((visibility("default")))
+#else
+#define SSHSLIE_API
+#endif
+
+#define SSHSLIE_OK 0
+#define SSHSLIE_ERR_ARG (-1)      /* bad shape / null pointer / unsupported configuration */
+#define SSHSLIE_ERR_CUDA (-2)     /* a CUDA runtime or driver call failed (launch error, wrong arch) */
+#define SSHSLIE_ERR_WORKSPACE (-3)/* workspace too small or engine not bound to this workspace */
+
+#define SSHSLIE_NUM_PARAM_TENSORS 46
+#define SSHSLIE_NUM_LOSSES 7      /* total, rec, R_fid, I_smooth_low, I_smooth_delta, fourier, spectral (model.py:566-574) */
+
+/* engine flags */
+#define SSHSLIE_FLAG_TRAIN 1      /* reserve workspace for compute_loss + backward */
+#define SSHSLIE_FLAG_FORCE_SIMT 2 /* run every conv GEMM on the CUDA-core cross-check kernels (tests only) */
+
+typedef struct sshslie_engine sshslie_engine;
+
+/* loss weights: LowLightEnhance.__init__ (model.py:178-194), values from config/*.yml:24-31 */
+typedef struct sshslie_loss_cfg {
+  float c_loss_reconstruction;
+  float c_loss_r_fidelity;
+  float c_loss_i_smooth_low;
+  float c_loss_i_smooth_delta;
+  float c_loss_fourier;
+  float c_loss_spectral_cons;
+  float alpha_i_smooth_low;
+  float alpha_i_smooth_delta;
+} sshslie_loss_cfg;
+
+SSHSLIE_API int sshslie_version(void);
+SSHSLIE_API const char* sshslie_last_error(void);
+
+/* Flat parameter layout.  Entry i of the reference's state_dict (46 tensors for any band count) starts
+ * at offsets[i] and has sizes[i] floats.  Returns the total float count (1,141,922 for channels=64). */
+SSHSLIE_API int64_t sshslie_param_table(int channels, int64_t* offsets, int64_t* sizes);
+
+/* Engine = host-side launch plan for one (batch, channels, height, width).  height and width must be
+ * multiples of 8 (the reference itself needs them even, model.py:59; the /8 pyramid adds the rest). */
+SSHSLIE_API int sshslie_engine_create(sshslie_engine** out, int batch, int channels, int height, int width, int flags);
+SSHSLIE_API void sshslie_engine_destroy(sshslie_engine* e);
+SSHSLIE_API int64_t sshslie_engine_workspace_bytes(const sshslie_engine* e);
+/* Bind the engine to a caller-owned workspace (>= workspace_bytes, 1024-byte aligned): uploads the launch
+ * plan, the Fourier mask (model.py:460-464) and FFT twiddles, zeroes padding lanes.  Synchronises. */
+SSHSLIE_API int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* LowLightEnhance.forward (model.py:229-234): x (B,C,H,W) -> R (B,C,H,W), I (B,1,H,W), I_delta (B,1,H,W),
+ * S (B,C,H,W).  Output pointers may alias nothing in the workspace. */
+SSHSLIE_API int sshslie_forward(sshslie_engine* e, const float* x, const float* params,
+                    float* R, float* I, float* I_delta, float* S, void* stream);
+
+/* LowLightEnhance.compute_loss + loss.backward() (model.py:544-575, 315): writes the seven loss values
+ * (order of SSHSLIE_NUM_LOSSES) to losses[7], d(total_loss)/d(params) to grads (flat, overwritten),
+ * and the four forward outputs when the pointers are non-null.  phase_mask selects sub-ranges of the
+ * step so that a data-parallel caller can start the gradient all-reduce of finished buckets early:
+ *   bit0: forward + loss + backward through the second DecompositionNet pass and IllumAdjustmentNet
+ *         (illum_adjust_net gradients are final afterwards)
+ *   bit1: backward through the first DecompositionNet pass (decomposition_net gradients final afterwards)
+ */
+SSHSLIE_API int sshslie_loss_and_grad(sshslie_engine* e, const float* x, const float* params,
+                          const sshslie_loss_cfg* cfg, float* grads, float* losses,
+                          float* R, float* I, float* I_delta, float* S, int phase_mask, void* stream);
+
+/* torch.optim.Adam defaults as used by the reference (model.py:213, 316): one fused launch over the flat
+ * buffers.  grad_scale multiplies the gradient first (1/world_size after an all-reduce(sum)). */
+SSHSLIE_API int sshslie_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* ---- single kernels, exported for kernel-level parity tests and profiling ---- */
+
+/* fourier_spectrum_loss (model.py:456-473) forward + d/dS.  x,S,dS: (n_img,H,W) fp32 planes, H and W
+ * powers of two in [8,128]; mask (H,W) fp32; accumulates sum_k mask*| |X|-|S| | into *sum_out (not zeroed);
+ * dS += grad_scale * d(sum)/dS when dS != NULL. */
+SSHSLIE_API int sshslie_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out,
+                         int n_img, int H, int W, float grad_scale, void* stream);
+
+/* The five pixel-space loss terms (model.py:450-454, 475-481, 491-542, 551) and their gradients.
+ * sums[8] (device) receives the raw term sums; gradients are written (not accumulated) already scaled by
+ * c_loss_x / count.  Any gradient pointer may be NULL (forward only). */
+SSHSLIE_API int sshslie_pixel_losses(const float* x, const float* R, const float* I, const float* Idelta, const float* S,
+                         const float* R_enh, const sshslie_loss_cfg* cfg, int B, int C, int H, int W,
+                         float* sums, float* dR, float* dI, float* dIdelta, float* dS, float* dR_enh, void* stream);
+
+/* One conv layer through the implicit-GEMM executors, for kernel parity tests: x (B,Cin,H,W) fp32,
+ * w (Cout,Cin,k,k) [or (Cin,Cout,k,k) when transposed], y (B,Cout,OH,OW) fp32.  Internally converts to the
+ * engine's bf16 NHWC layout, runs the tcgen05 (impl=1) or CUDA-core (impl=0) kernel, converts back.
+ * kind: 0 = forward, 1 = dgrad (x is dY, y is dX), 2 = wgrad (x is the layer input, w receives dW, y is dY).
+ * scratch must hold sshslie_conv2d_scratch_bytes(...) bytes. */
+SSHSLIE_API int64_t sshslie_conv2d_scratch_bytes(int B, int Cin, int Cout, int H, int W, int k, int stride);
+SSHSLIE_API int sshslie_conv2d(int kind, int impl, int transposed, float* x, float* w, const float* bias, float* y,
+                   int B, int Cin, int Cout, int H, int W, int k, int stride, int relu,
+                   void* scratch, int64_t scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSHSLIE_B200_H */

@@ -1,0 +1,440 @@
+// Layout, resampling and head/glue kernels around the conv GEMMs (all HBM-bound, fp32 math).
+//   fp32 tensors: NCHW planes (the reference's layout, consumed by the loss/FFT kernels and returned to the caller)
+//   bf16 tensors: NHWC (the GEMM operand layout), channel stride `ld`
+#include "common.cuh"
+#include "kernels.h"
+
+#define EW_CHECK(name) return ss_check_launch(name)
+
+// A 32-pixel x 32-channel transposing tile.  blockDim = (32, 8).  HW is a multiple of 32 (H, W multiples of 8),
+// so the 32 consecutive pixels of a tile never straddle two images.
+
+// ---------------------------------------------------------------------------------------------
+// x (B,C,H,W) fp32  ->  out (B,H,W,ldo) bf16        [decomposition_net input, model.py:51-52]
+// ---------------------------------------------------------------------------------------------
+__global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int C, int HW, int ldo) {
+  __shared__ float tile[32][33];
+  const int64_t p0 = (int64_t)blockIdx.x * 32;          // linear pixel over B*HW
+  const int b = (int)(p0 / HW);
+  const int hw0 = (int)(p0 - (int64_t)b * HW);
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    tile[i][threadIdx.x] = (c < C) ? x[((int64_t)b * C + c) * HW + hw0 + threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {            // i = pixel, threadIdx.x = channel
+    const int c = c0 + threadIdx.x;
+    if (c < C) out[(p0 + i) * ldo + c] = f2bf(tile[threadIdx.x][i]);
+  }
+}
+int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st) {
+  dim3 grid((unsigned)((int64_t)B * H * W / 32), (C + 31) / 32);
+  nchw32_to_nhwc16_kernel<<<grid, dim3(32, 8), 0, st>>>(x, out, C, H * W, ldo);
+  EW_CHECK("nchw32_to_nhwc16");
+}
+
+__global__ void nhwc16_to_nchw32_kernel(const bf16* __restrict__ in, float* __restrict__ y, int C, int HW, int ldi) {
+  __shared__ float tile[32][33];
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int b = (int)(p0 / HW);
+  const int hw0 = (int)(p0 - (int64_t)b * HW);
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {            // i = pixel, x = channel
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C) ? bf2f(in[(p0 + i) * ldi + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {            // i = channel, x = pixel
+    const int c = c0 + i;
+    if (c < C) y[((int64_t)b * C + c) * HW + hw0 + threadIdx.x] = tile[threadIdx.x][i];
+  }
+}
+int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, int W, int ldi, cudaStream_t st) {
+  dim3 grid((unsigned)((int64_t)B * H * W / 32), (C + 31) / 32);
+  nhwc16_to_nchw32_kernel<<<grid, dim3(32, 8), 0, st>>>(in, y, C, H * W, ldi);
+  EW_CHECK("nhwc16_to_nchw32");
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[b, y, x, :] = r[b, y/2, x/2, :] (+ a[b, y/2, x/2, :])      nearest x2 of (relu-out + skip), 64 channels
+// [F.interpolate(mode='nearest') of deconv_k + conv_k, model.py:156-165]
+// ---------------------------------------------------------------------------------------------
+__global__ void upsample2_add_kernel(const bf16* __restrict__ r, const bf16* __restrict__ a, bf16* __restrict__ out,
+                                     int h, int w, int64_t total /* B*h*w*8 vectors of the SOURCE */) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i & 7);
+  const int64_t pix = i >> 3;
+  const int xs = (int)(pix % w);
+  const int64_t t = pix / w;
+  const int ys = (int)(t % h);
+  const int64_t b = t / h;
+  uint4 v = reinterpret_cast<const uint4*>(r)[i];
+  if (a) {
+    float f[8], g[8];
+    unpack8(v, f);
+    unpack8(reinterpret_cast<const uint4*>(a)[i], g);
+    v.x = pack2(f[0] + g[0], f[1] + g[1]);
+    v.y = pack2(f[2] + g[2], f[3] + g[3]);
+    v.z = pack2(f[4] + g[4], f[5] + g[5]);
+    v.w = pack2(f[6] + g[6], f[7] + g[7]);
+  }
+  const int W2 = 2 * w;
+  uint4* o = reinterpret_cast<uint4*>(out) + ((b * 2 * h + 2 * ys) * W2 + 2 * xs) * 8 + q;
+  o[0] = v;
+  o[8] = v;
+  o[(int64_t)W2 * 8] = v;
+  o[(int64_t)W2 * 8 + 8] = v;
+}
+int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, cudaStream_t st) {
+  const int64_t total = (int64_t)B * h * w * 8;
+  upsample2_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r, a, out, h, w, total);
+  EW_CHECK("upsample2_add");
+}
+
+// ---------------------------------------------------------------------------------------------
+// fg[b,y,x,:] = [ (r1+a2)[y/4,x/4] | (r2+a1)[y/2,x/2] | (r3+a0)[y,x] ]   192 channels  [model.py:168-172]
+// ---------------------------------------------------------------------------------------------
+SS_DEVINL uint4 add8(const uint4& p, const uint4& q) {
+  float f[8], g[8];
+  unpack8(p, f);
+  unpack8(q, g);
+  uint4 v;
+  v.x = pack2(f[0] + g[0], f[1] + g[1]);
+  v.y = pack2(f[2] + g[2], f[3] + g[3]);
+  v.z = pack2(f[4] + g[4], f[5] + g[5]);
+  v.w = pack2(f[6] + g[6], f[7] + g[7]);
+  return v;
+}
+__global__ void fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __restrict__ a2,
+                                   const uint4* __restrict__ r2, const uint4* __restrict__ a1,
+                                   const uint4* __restrict__ r3, const uint4* __restrict__ a0, uint4* __restrict__ fg,
+                                   int H, int W, int64_t total /* B*H*W*24 */) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i % 24);
+  const int64_t pix = i / 24;
+  const int x = (int)(pix % W);
+  const int64_t t = pix / W;
+  const int y = (int)(t % H);
+  const int64_t b = t / H;
+  uint4 v;
+  if (q < 8) {
+    const int64_t s = ((b * (H / 4) + y / 4) * (W / 4) + x / 4) * 8 + q;
+    v = add8(r1[s], a2[s]);
+  } else if (q < 16) {
+    const int64_t s = ((b * (H / 2) + y / 2) * (W / 2) + x / 2) * 8 + (q - 8);
+    v = add8(r2[s], a1[s]);
+  } else {
+    const int64_t s = pix * 8 + (q - 16);
+    v = add8(r3[s], a0[s]);
+  }
+  fg[i] = v;
+}
+int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
+                          const bf16* a0, bf16* fg, int B, int H, int W, cudaStream_t st) {
+  const int64_t total = (int64_t)B * H * W * 24;
+  fuse_concat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      (const uint4*)r1, (const uint4*)a2, (const uint4*)r2, (const uint4*)a1, (const uint4*)r3, (const uint4*)a0,
+      (uint4*)fg, H, W, total);
+  EW_CHECK("fuse_concat");
+}
+
+// ---------------------------------------------------------------------------------------------
+// S = R*I_delta + R*I_low  (model.py:233) -> S32 (B,C,H,W) fp32 and Sb (B,H,W,C) bf16 (2nd decomposition input)
+// ---------------------------------------------------------------------------------------------
+__global__ void make_s_kernel(const float* __restrict__ R, const float* __restrict__ I, const float* __restrict__ Id,
+                              float* __restrict__ S32, bf16* __restrict__ Sb, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int b = (int)(p0 / HW);
+  const int hw0 = (int)(p0 - (int64_t)b * HW);
+  const int c0 = blockIdx.y * 32;
+  const float id = Id[p0 + threadIdx.x], il = I[p0 + threadIdx.x];
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    if (c < C) {
+      const int64_t a = ((int64_t)b * C + c) * HW + hw0 + threadIdx.x;
+      const float r = R[a];
+      const float s = r * id + r * il;
+      S32[a] = s;
+      tile[i][threadIdx.x] = s;
+    }
+  }
+  __syncthreads();
+  if (Sb) {
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int c = c0 + threadIdx.x;
+      if (c < C) Sb[(p0 + i) * C + c] = f2bf(tile[threadIdx.x][i]);
+    }
+  }
+}
+int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
+                     cudaStream_t st) {
+  dim3 grid((unsigned)((int64_t)B * H * W / 32), (C + 31) / 32);
+  make_s_kernel<<<grid, dim3(32, 8), 0, st>>>(R, I, Id, S32, Sb, C, H * W);
+  EW_CHECK("make_s");
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of S = R*(Id + I):  dS = dS32 (loss terms) + dSb (second decomposition pass, bf16 NHWC)
+//   dR32 += dS*(Id+I) ;  t = sum_c dS*R ;  dId32 += t ;  dI32 += t        (block = 32 pixels x all channels)
+// ---------------------------------------------------------------------------------------------
+__global__ void s_bwd_kernel(const float* __restrict__ dS32, const bf16* __restrict__ dSb, const float* __restrict__ R,
+                             const float* __restrict__ I, const float* __restrict__ Id, float* __restrict__ dR32,
+                             float* __restrict__ dI32, float* __restrict__ dId32, int C, int HW) {
+  __shared__ float tile[32][33];
+  __shared__ float part[8][32];
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int b = (int)(p0 / HW);
+  const int hw0 = (int)(p0 - (int64_t)b * HW);
+  const float gain = Id[p0 + threadIdx.x] + I[p0 + threadIdx.x];
+  float t = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {          // i = pixel, x = channel
+      const int c = c0 + threadIdx.x;
+      tile[threadIdx.x][i] = (c < C) ? bf2f(dSb[(p0 + i) * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {          // i = channel, x = pixel
+      const int c = c0 + i;
+      if (c < C) {
+        const int64_t a = ((int64_t)b * C + c) * HW + hw0 + threadIdx.x;
+        const float ds = dS32[a] + tile[i][threadIdx.x];
+        dR32[a] += ds * gain;
+        t = fmaf(ds, R[a], t);
+      }
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
+    dId32[p0 + threadIdx.x] += s;
+    dI32[p0 + threadIdx.x] += s;
+  }
+}
+int ss_launch_s_bwd(const float* dS32, const bf16* dSb, const float* R, const float* I, const float* Id, float* dR32,
+                    float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st) {
+  s_bwd_kernel<<<(unsigned)((int64_t)B * H * W / 32), dim3(32, 8), 0, st>>>(dS32, dSb, R, I, Id, dR32, dI32, dId32, C,
+                                                                           H * W);
+  EW_CHECK("s_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of the sigmoid heads (model.py:68-69):
+//   dc8[pix, c] = (dR32[b,c,pix] + dRI[pix, c]) * R(1-R)      c < C
+//   dc8[pix, C] = (dI32[pix] + dRI[pix, C]) * I(1-I)          (only when dI32 != NULL; else no column C)
+//   columns above are left untouched (zeroed once at bind time)
+// ---------------------------------------------------------------------------------------------
+__global__ void head_bwd_kernel(const float* __restrict__ dR32, const float* __restrict__ R32,
+                                const bf16* __restrict__ dRI, int ld_dri, const float* __restrict__ dI32,
+                                const float* __restrict__ I32, bf16* __restrict__ dc8, int ld_out, int C, int HW) {
+  __shared__ float tg[32][33];   // raw gradient
+  __shared__ float tr[32][33];   // sigmoid'(.) = R(1-R)
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int b = (int)(p0 / HW);
+  const int hw0 = (int)(p0 - (int64_t)b * HW);
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {          // i = channel, x = pixel (coalesced NCHW reads)
+      const int c = c0 + i;
+      float g = 0.f, d = 0.f;
+      if (c < C) {
+        const int64_t a = ((int64_t)b * C + c) * HW + hw0 + threadIdx.x;
+        const float r = R32[a];
+        g = dR32[a];
+        d = r * (1.f - r);
+      }
+      tg[i][threadIdx.x] = g;
+      tr[i][threadIdx.x] = d;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {          // i = pixel, x = channel (coalesced NHWC writes)
+      const int c = c0 + threadIdx.x;
+      if (c < C) {
+        float g = tg[threadIdx.x][i];
+        if (dRI) g += bf2f(dRI[(p0 + i) * ld_dri + c]);
+        dc8[(p0 + i) * ld_out + c] = f2bf(g * tr[threadIdx.x][i]);
+      }
+    }
+  }
+  if (dI32 && threadIdx.y == 0) {
+    const int64_t p = p0 + threadIdx.x;
+    float g = dI32[p];
+    if (dRI) g += bf2f(dRI[p * ld_dri + C]);
+    const float il = I32[p];
+    dc8[p * ld_out + C] = f2bf(g * il * (1.f - il));
+  }
+}
+int ss_launch_head_bwd(const float* dR32, const float* R32, const bf16* dRI, int ld_dri, const float* dI32,
+                       const float* I32, bf16* dc8, int ld_out, int B, int C, int H, int W, cudaStream_t st) {
+  head_bwd_kernel<<<(unsigned)((int64_t)B * H * W / 32), dim3(32, 8), 0, st>>>(dR32, R32, dRI, ld_dri, dI32, I32, dc8,
+                                                                              ld_out, C, H * W);
+  EW_CHECK("head_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of the concat/upsample that feeds feature_fusion (model.py:168-172), given dfg (B,H,W,192):
+//   dr3 = dfg[...,128:192] * (r3 > 0)                          (B,H,W,64)
+//   p2  = 2x2 sum-pool of dfg[..., 64:128]                     (B,H/2,W/2,64)
+//   p1  = 4x4 sum-pool of dfg[...,  0: 64]                     (B,H/4,W/4,64)
+// one thread = one (H/4 x W/4 pixel, 8-channel vector)
+// ---------------------------------------------------------------------------------------------
+__global__ void concat_bwd_kernel(const uint4* __restrict__ dfg, const uint4* __restrict__ r3, uint4* __restrict__ dr3,
+                                  uint4* __restrict__ p2, uint4* __restrict__ p1, int H, int W, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i & 7);
+  const int64_t pix = i >> 3;
+  const int w4 = W / 4, h4 = H / 4;
+  const int x4 = (int)(pix % w4);
+  const int64_t t = pix / w4;
+  const int y4 = (int)(t % h4);
+  const int64_t b = t / h4;
+  float s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = 0.f;
+  for (int yy = 0; yy < 2; ++yy)
+    for (int xx = 0; xx < 2; ++xx) {
+      float s2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s2[j] = 0.f;
+      for (int y1 = 0; y1 < 2; ++y1)
+        for (int x1 = 0; x1 < 2; ++x1) {
+          const int y = y4 * 4 + yy * 2 + y1, x = x4 * 4 + xx * 2 + x1;
+          const int64_t p = (b * H + y) * W + x;
+          float f[8], m[8];
+          unpack8(dfg[p * 24 + q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s1[j] += f[j];
+          unpack8(dfg[p * 24 + 8 + q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s2[j] += f[j];
+          unpack8(dfg[p * 24 + 16 + q], f);
+          unpack8(r3[p * 8 + q], m);
+          uint4 o;
+          o.x = pack2(m[0] > 0.f ? f[0] : 0.f, m[1] > 0.f ? f[1] : 0.f);
+          o.y = pack2(m[2] > 0.f ? f[2] : 0.f, m[3] > 0.f ? f[3] : 0.f);
+          o.z = pack2(m[4] > 0.f ? f[4] : 0.f, m[5] > 0.f ? f[5] : 0.f);
+          o.w = pack2(m[6] > 0.f ? f[6] : 0.f, m[7] > 0.f ? f[7] : 0.f);
+          dr3[p * 8 + q] = o;
+        }
+      uint4 o;
+      o.x = pack2(s2[0], s2[1]); o.y = pack2(s2[2], s2[3]); o.z = pack2(s2[4], s2[5]); o.w = pack2(s2[6], s2[7]);
+      p2[((b * (H / 2) + y4 * 2 + yy) * (W / 2) + x4 * 2 + xx) * 8 + q] = o;
+    }
+  uint4 o;
+  o.x = pack2(s1[0], s1[1]); o.y = pack2(s1[2], s1[3]); o.z = pack2(s1[4], s1[5]); o.w = pack2(s1[6], s1[7]);
+  p1[pix * 8 + q] = o;
+}
+int ss_launch_concat_bwd(const bf16* dfg, const bf16* r3, bf16* dr3, bf16* p2, bf16* p1, int B, int H, int W,
+                         cudaStream_t st) {
+  const int64_t total = (int64_t)B * (H / 4) * (W / 4) * 8;
+  concat_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)dfg, (const uint4*)r3, (uint4*)dr3,
+                                                                    (uint4*)p2, (uint4*)p1, H, W, total);
+  EW_CHECK("concat_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of nearest x2 upsampling of (relu-out + skip):  s = 2x2 sum-pool(du) (+ addp)
+//   out_sum    = s                  (gradient of the skip tensor)               optional
+//   out_masked = s * (maskr > 0)    (gradient of the ReLU output)               optional
+//   out32      = s as fp32          (gradient of the transformer output)        optional
+// du: (B,2h,2w,64) ; everything else (B,h,w,64)
+// ---------------------------------------------------------------------------------------------
+__global__ void pool2_kernel(const uint4* __restrict__ du, const uint4* __restrict__ addp,
+                             const uint4* __restrict__ maskr, uint4* __restrict__ out_sum,
+                             uint4* __restrict__ out_masked, float* __restrict__ out32, int h, int w, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i & 7);
+  const int64_t pix = i >> 3;
+  const int x = (int)(pix % w);
+  const int64_t t = pix / w;
+  const int y = (int)(t % h);
+  const int64_t b = t / h;
+  const int W2 = 2 * w;
+  const uint4* s = du + ((b * 2 * h + 2 * y) * W2 + 2 * x) * 8 + q;
+  float acc[8], f[8];
+  unpack8(s[0], acc);
+  unpack8(s[8], f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  unpack8(s[(int64_t)W2 * 8], f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  unpack8(s[(int64_t)W2 * 8 + 8], f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  if (addp) {
+    unpack8(addp[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+  if (out_sum) {
+    uint4 o;
+    o.x = pack2(acc[0], acc[1]); o.y = pack2(acc[2], acc[3]); o.z = pack2(acc[4], acc[5]); o.w = pack2(acc[6], acc[7]);
+    out_sum[i] = o;
+  }
+  if (out_masked) {
+    float m[8];
+    unpack8(maskr[i], m);
+    uint4 o;
+    o.x = pack2(m[0] > 0.f ? acc[0] : 0.f, m[1] > 0.f ? acc[1] : 0.f);
+    o.y = pack2(m[2] > 0.f ? acc[2] : 0.f, m[3] > 0.f ? acc[3] : 0.f);
+    o.z = pack2(m[4] > 0.f ? acc[4] : 0.f, m[5] > 0.f ? acc[5] : 0.f);
+    o.w = pack2(m[6] > 0.f ? acc[6] : 0.f, m[7] > 0.f ? acc[7] : 0.f);
+    out_masked[i] = o;
+  }
+  if (out32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out32[i * 8 + j] = acc[j];
+  }
+}
+int ss_launch_pool2(const bf16* du, const bf16* addp, const bf16* maskr, bf16* out_sum, bf16* out_masked, float* out32,
+                    int B, int h, int w, cudaStream_t st) {
+  const int64_t total = (int64_t)B * h * w * 8;
+  pool2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)du, (const uint4*)addp,
+                                                               (const uint4*)maskr, (uint4*)out_sum,
+                                                               (uint4*)out_masked, out32, h, w, total);
+  EW_CHECK("pool2");
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw term sums -> the seven loss values of model.py:557-574
+//   sums: 0 rec | 1,2 I_smooth_low x,y | 3 |R-Re| | 4,5 grad fidelity x,y | 6,7 I_smooth_delta x,y | 8 spectral | 9 fourier
+// ---------------------------------------------------------------------------------------------
+__global__ void finalize_losses_kernel(const float* __restrict__ sums, sshslie_loss_cfg cfg, float* __restrict__ losses,
+                                       int B, int C, int H, int W) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double n0 = (double)B * C * H * W;
+  const double nx1 = (double)B * H * (W - 1), ny1 = (double)B * (H - 1) * W;
+  const double nxc = nx1 * C, nyc = ny1 * C;
+  const double nsp = (double)B * (C - 1) * H * W;
+  const double l_rec = sums[0] / n0;
+  const double l_ilow = sums[1] / nx1 + sums[2] / ny1;
+  const double l_rfid = sums[3] / n0 + 0.5 * (sums[4] / nxc + sums[5] / nyc);
+  const double l_idel = sums[6] / nxc + sums[7] / nyc;
+  const double l_spec = sums[8] / nsp;
+  const double l_four = sums[9] / n0;
+  const double total = cfg.c_loss_reconstruction * l_rec + cfg.c_loss_r_fidelity * l_rfid +
+                       cfg.c_loss_i_smooth_low * l_ilow + cfg.c_loss_i_smooth_delta * l_idel +
+                       cfg.c_loss_fourier * l_four + cfg.c_loss_spectral_cons * l_spec;
+  losses[0] = (float)total;
+  losses[1] = (float)l_rec;
+  losses[2] = (float)l_rfid;
+  losses[3] = (float)l_ilow;
+  losses[4] = (float)l_idel;
+  losses[5] = (float)l_four;
+  losses[6] = (float)l_spec;
+}
+int ss_launch_finalize_losses(const float* sums, const sshslie_loss_cfg* cfg, float* losses, int B, int C, int H, int W,
+                              cudaStream_t st) {
+  finalize_losses_kernel<<<1, 32, 0, st>>>(sums, *cfg, losses, B, C, H, W);
+  EW_CHECK("finalize_losses");
+}

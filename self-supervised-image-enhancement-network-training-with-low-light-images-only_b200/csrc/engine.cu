@@ -1,0 +1,1102 @@
+// Host-side launch planner ("engine") and the C-ABI of include/sshslie_b200.h.
+//
+// An engine is built for one (batch, 64 bands, H, W).  Binding it to a caller-owned workspace lays out every
+// activation / gradient tensor with a bump allocator, lowers each conv-like layer of the reference network
+// (model.py:25-70, 121-175) to ConvGeoms (plan.h), builds the TMA descriptors of the tcgen05 path and records the
+// forward and backward launch sequences.  Running a step only enqueues those launches on the caller's stream.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void ss_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int ss_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ss_set_error("%s: %s", what, cudaGetErrorString(e));
+    return SSHSLIE_ERR_CUDA;
+  }
+  return SSHSLIE_OK;
+}
+extern "C" const char* sshslie_last_error(void) { return g_err; }
+extern "C" int sshslie_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------------------
+// parameter table (reference state_dict order)
+// ---------------------------------------------------------------------------------------------
+enum Layer {
+  L_D_CONV0 = 0, L_D_SHALLOW, L_D_CONV1, L_D_CONV2, L_D_CONV3, L_D_DECONV, L_D_CONV5, L_D_CONV7, L_D_RECON,
+  L_I_CONV0, L_I_CONV1, L_I_CONV2, L_I_CONV3, L_Q, L_K, L_V, L_FF1, L_FF2, L_I_DECONV1, L_I_DECONV2, L_I_DECONV3,
+  L_I_FUSION, L_I_FINAL, L_COUNT
+};
+struct LayerShape { int d0, d1, k; bool transposed; };   // weight (d0, d1, k, k); k = 0 -> Linear (d0, d1)
+static void layer_shapes(int C, LayerShape* s) {
+  s[L_D_CONV0] = {32, C, 3, false};     s[L_D_SHALLOW] = {64, C, 9, false};  s[L_D_CONV1] = {64, 64, 3, false};
+  s[L_D_CONV2] = {128, 64, 3, false};   s[L_D_CONV3] = {128, 128, 3, false}; s[L_D_DECONV] = {128, 64, 3, true};
+  s[L_D_CONV5] = {64, 128, 3, false};   s[L_D_CONV7] = {64, 96, 3, false};   s[L_D_RECON] = {C + 1, 64, 3, false};
+  s[L_I_CONV0] = {64, C + 1, 3, false}; s[L_I_CONV1] = {64, 64, 3, false};   s[L_I_CONV2] = {64, 64, 3, false};
+  s[L_I_CONV3] = {64, 64, 3, false};    s[L_Q] = {64, 64, 0, false};         s[L_K] = {64, 64, 0, false};
+  s[L_V] = {64, 64, 0, false};          s[L_FF1] = {64, 64, 0, false};       s[L_FF2] = {64, 64, 0, false};
+  s[L_I_DECONV1] = {64, 64, 3, false};  s[L_I_DECONV2] = {64, 64, 3, false}; s[L_I_DECONV3] = {64, 64, 3, false};
+  s[L_I_FUSION] = {64, 192, 1, false};  s[L_I_FINAL] = {1, 64, 3, false};
+}
+extern "C" int64_t sshslie_param_table(int channels, int64_t* offsets, int64_t* sizes) {
+  LayerShape s[L_COUNT];
+  layer_shapes(channels, s);
+  int64_t off = 0;
+  for (int l = 0; l < L_COUNT; ++l) {
+    const int64_t kk = s[l].k ? (int64_t)s[l].k * s[l].k : 1;
+    const int64_t wsz = (int64_t)s[l].d0 * s[l].d1 * kk;
+    const int64_t bsz = s[l].transposed ? s[l].d1 : s[l].d0;
+    if (offsets) { offsets[2 * l] = off; offsets[2 * l + 1] = off + wsz; }
+    if (sizes) { sizes[2 * l] = wsz; sizes[2 * l + 1] = bsz; }
+    off += wsz + bsz;
+  }
+  return off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// planner helpers
+// ---------------------------------------------------------------------------------------------
+struct Tens {          // bf16 NHWC tensor
+  bf16* p = nullptr;
+  int B = 0, H = 0, W = 0, ld = 0;
+  int64_t pix() const { return (int64_t)B * H * W; }
+};
+struct SrcSpec { Tens t; int c_off; int c_cnt; int wc_off; };
+struct WAddr { int64_t w_off; int sN, sC, sKH, sKW; };
+
+struct GeomOp {        // one lowered GEMM: geometry + (for gathers) epilogue template
+  ConvGeom g;
+  int geom_index = -1;
+  bool use_umma = false;
+};
+
+struct sshslie_engine {
+  int B, C, H, W, flags;
+  bool train, force_simt;
+  int64_t ws_bytes = 0;
+  unsigned char* ws = nullptr;
+  bool bound = false;
+  int64_t poff[2 * L_COUNT], psize[2 * L_COUNT], nparams;
+  LayerShape shapes[L_COUNT];
+
+  // bump allocator (dry run when base == nullptr)
+  unsigned char* base = nullptr;
+  int64_t cursor = 0;
+  std::vector<std::pair<int64_t, int64_t>> zero_ranges;   // regions zeroed at bind (padding lanes)
+  void* alloc(int64_t bytes, bool zero = false) {
+    const int64_t off = cursor;
+    cursor += (bytes + 1023) / 1024 * 1024;
+    if (zero) zero_ranges.push_back({off, bytes});
+    return base ? (void*)(base + off) : (void*)(uintptr_t)(off + 1024);   // non-null placeholder in dry runs
+  }
+  Tens talloc(int b, int h, int w, int ld, bool zero = false) {
+    Tens t;
+    t.B = b; t.H = h; t.W = w; t.ld = ld;
+    t.p = (bf16*)alloc((int64_t)b * h * w * ld * sizeof(bf16), zero);
+    return t;
+  }
+  float* falloc(int64_t n, bool zero = false) { return (float*)alloc(n * sizeof(float), zero); }
+
+  // plan
+  std::vector<ConvGeom> geoms;           // host copy, index = geom id
+  std::vector<char> geom_umma;           // 1 if the tcgen05 kernel takes this geom
+  std::vector<unsigned char> maps_blob;  // UmmaMaps per geom
+  ConvGeom* geoms_dev = nullptr;
+  int* pack_start_dev = nullptr;
+  std::vector<int> pack_start;
+  int pack_blocks = 0;
+  float* mask_dev = nullptr;
+  float* sums_dev = nullptr;
+  int64_t* attn_poff_dummy = nullptr;
+
+  // per-call state read by the recorded launches
+  const float* x = nullptr;
+  const float* params = nullptr;
+  float* grads = nullptr;
+  float* losses = nullptr;
+  sshslie_loss_cfg cfg;
+
+  typedef std::function<int(cudaStream_t)> OpFn;
+  std::vector<OpFn> ops_fwd, ops_loss_bwd2_illum, ops_bwd1;
+
+  // persistent tensors needed by the ABI
+  float *R32 = nullptr, *I32 = nullptr, *Id32 = nullptr, *S32 = nullptr;
+
+  int add_geom(const ConvGeom& g) {
+    geoms.push_back(g);
+    geom_umma.push_back(0);
+    return (int)geoms.size() - 1;
+  }
+};
+
+static ConvGeom geom_init(int B, int OH, int OW, int N, const WAddr& wa) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.OH = OH; g.OW = OW;
+  g.N = N; g.Npad = (N + 15) / 16 * 16;
+  g.w_off = wa.w_off; g.w_sN = wa.sN; g.w_sC = wa.sC;
+  // tcgen05 tile: th x tw output pixels = 128 GEMM rows
+  int tw = 128;
+  while (tw > 8 && (OW % tw) != 0) tw >>= 1;
+  g.tw = tw; g.th = 128 / tw;
+  return g;
+}
+static void geom_add_slabs(ConvGeom& g, int src, int dh, int dw, const SrcSpec& s, int kh, int kw, const WAddr& wa) {
+  const int ns = (s.c_cnt + SS_SLAB - 1) / SS_SLAB;
+  for (int i = 0; i < ns; ++i) {
+    Slab& sl = g.slab[g.nslabs++];
+    sl.src = (int8_t)src; sl.dh = (int8_t)dh; sl.dw = (int8_t)dw; sl.wcn_hi = 0;
+    sl.c0 = (int16_t)(s.c_off + i * SS_SLAB);
+    const int rem = s.c_cnt - i * SS_SLAB;
+    sl.wcn = (int16_t)(rem < SS_SLAB ? rem : SS_SLAB);
+    sl.woff = kh * wa.sKH + kw * wa.sKW + (s.wc_off + i * SS_SLAB) * wa.sC;
+  }
+}
+static SrcView view_full(const Tens& t) {
+  SrcView v;
+  v.base = t.p; v.sB = (int64_t)t.H * t.W * t.ld; v.sH = (int64_t)t.W * t.ld; v.sW = t.ld; v.H = t.H; v.W = t.W;
+  return v;
+}
+static SrcView view_parity(const Tens& t, int ph, int pw) {
+  SrcView v;
+  v.base = t.p + (int64_t)ph * t.W * t.ld + (int64_t)pw * t.ld;
+  v.sB = (int64_t)t.H * t.W * t.ld; v.sH = 2LL * t.W * t.ld; v.sW = 2LL * t.ld;
+  v.H = (t.H - ph + 1) / 2; v.W = (t.W - pw + 1) / 2;
+  return v;
+}
+
+// gather geometry of a stride-1 / stride-2 "conv-like" read:  in_coord = out_coord*stride + sign*(k_idx) + off
+//   conv forward:         sign=+1, off=-pad          (stride 1 or 2)
+//   dgrad of s1 conv:     sign=-1, off=+pad          (stride 1)
+static ConvGeom geom_conv(int B, int OH, int OW, const std::vector<SrcSpec>& srcs, int k, int stride, int pad, int sign,
+                          int N, const WAddr& wa) {
+  ConvGeom g = geom_init(B, OH, OW, N, wa);
+  if (stride == 1) {
+    for (size_t s = 0; s < srcs.size(); ++s) g.src[g.nsrc++] = view_full(srcs[s].t);
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw)
+        for (size_t s = 0; s < srcs.size(); ++s)
+          geom_add_slabs(g, (int)s, sign * kh + (sign > 0 ? -pad : pad), sign * kw + (sign > 0 ? -pad : pad), srcs[s],
+                         kh, kw, wa);
+  } else {
+    // stride 2 forward-type read: in = 2*out + k_idx - pad  ->  parity views of the single source
+    const SrcSpec& s = srcs[0];
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) g.src[g.nsrc++] = view_parity(s.t, ph, pw);
+    for (int kh = 0; kh < k; ++kh)
+      for (int kw = 0; kw < k; ++kw) {
+        const int eh = kh - pad, ew = kw - pad;
+        const int ph = ((eh % 2) + 2) % 2, pw = ((ew % 2) + 2) % 2;
+        geom_add_slabs(g, ph * 2 + pw, (eh - ph) / 2, (ew - pw) / 2, s, kh, kw, wa);
+      }
+  }
+  return g;
+}
+// transposed (stride-2) gather for output parity class (qh,qw): in = out_class_coord + (q + pad - k_idx)/2
+static ConvGeom geom_tconv_class(int B, int OHc, int OWc, const SrcSpec& s, int k, int pad, int qh, int qw, int N,
+                                 const WAddr& wa) {
+  ConvGeom g = geom_init(B, OHc, OWc, N, wa);
+  g.src[g.nsrc++] = view_full(s.t);
+  for (int kh = 0; kh < k; ++kh) {
+    if ((qh + pad - kh) & 1) continue;
+    for (int kw = 0; kw < k; ++kw) {
+      if ((qw + pad - kw) & 1) continue;
+      geom_add_slabs(g, 0, (qh + pad - kh) / 2, (qw + pad - kw) / 2, s, kh, kw, wa);
+    }
+  }
+  return g;
+}
+
+static Epi epi_bf16(const Tens& out, int n_store, int qh = 0, int qw = 0, int scale = 1) {
+  Epi e;
+  memset(&e, 0, sizeof(e));
+  e.mode = EPI_BF16;
+  e.out = out.p + (int64_t)qh * out.W * out.ld + (int64_t)qw * out.ld;
+  e.oB = (int64_t)out.H * out.W * out.ld; e.oH = (int64_t)scale * out.W * out.ld; e.oW = (int64_t)scale * out.ld;
+  e.n_store = n_store;
+  return e;
+}
+static void epi_set_add(Epi& e, const Tens& t, int c_off = 0, int qh = 0, int qw = 0, int scale = 1) {
+  e.add = t.p + c_off + (int64_t)qh * t.W * t.ld + (int64_t)qw * t.ld;
+  e.aB = (int64_t)t.H * t.W * t.ld; e.aH = (int64_t)scale * t.W * t.ld; e.aW = (int64_t)scale * t.ld;
+}
+static void epi_set_mask(Epi& e, const Tens& t, int qh = 0, int qw = 0, int scale = 1) {
+  e.mask = t.p + (int64_t)qh * t.W * t.ld + (int64_t)qw * t.ld;
+  e.mB = (int64_t)t.H * t.W * t.ld; e.mH = (int64_t)scale * t.W * t.ld; e.mW = (int64_t)scale * t.ld;
+}
+
+// ---------------------------------------------------------------------------------------------
+// thin kernels for final_conv (64 -> 1, model.py:141,174): its data- and weight-gradient are not GEMM shaped
+// ---------------------------------------------------------------------------------------------
+// dff[pix, c] = sum_taps dId[pix - tap] * w[c][tap]
+__global__ void __launch_bounds__(256) final_dgrad_kernel(const float* __restrict__ dId, const float* __restrict__ w,
+                                                          bf16* __restrict__ dff, int H, int W, int64_t total) {
+  __shared__ float ws[64 * 9];
+  for (int i = threadIdx.x; i < 576; i += 256) ws[i] = w[i];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i & 7);
+  const int64_t pix = i >> 3;
+  const int x = (int)(pix % W);
+  const int64_t t = pix / W;
+  const int y = (int)(t % H);
+  const int64_t b = t / H;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int oy = y - kh + 1, ox = x - kw + 1;
+      if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
+      const float g = dId[(b * H + oy) * W + ox];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(g, ws[(q * 8 + j) * 9 + kh * 3 + kw], acc[j]);
+    }
+  uint4 o;
+  o.x = pack2(acc[0], acc[1]); o.y = pack2(acc[2], acc[3]); o.z = pack2(acc[4], acc[5]); o.w = pack2(acc[6], acc[7]);
+  reinterpret_cast<uint4*>(dff)[i] = o;
+}
+// dw[c][tap] += sum_pix dId[pix] * ff[pix + tap, c] ; db += sum dId.   block = 576 threads (c = t%64, tap = t/64)
+__global__ void __launch_bounds__(576) final_wgrad_kernel(const float* __restrict__ dId, const bf16* __restrict__ ff,
+                                                          float* __restrict__ dw, float* __restrict__ db, int B, int H,
+                                                          int W, int rows_per_block) {
+  const int c = threadIdx.x & 63, tap = threadIdx.x >> 6;
+  const int kh = tap / 3, kw = tap - kh * 3;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;      // image rows over B*H
+  float acc = 0.f, accb = 0.f;
+  for (int64_t r = r0; r < r0 + rows_per_block && r < (int64_t)B * H; ++r) {
+    const int y = (int)(r % H);
+    const int64_t b = r / H;
+    const int iy = y + kh - 1;
+    for (int x = 0; x < W; ++x) {
+      const float g = dId[r * W + x];
+      accb += g;
+      const int ix = x + kw - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      acc = fmaf(g, bf2f(ff[((b * H + iy) * W + ix) * 64 + c]), acc);
+    }
+  }
+  atomicAdd(dw + c * 9 + tap, acc);
+  if (threadIdx.x == 0) atomicAdd(db, accb);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan construction
+// ---------------------------------------------------------------------------------------------
+struct DecompBufs { Tens c0, sh, c1, c2, c3, dc, c5, c7; };
+
+static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaStream_t st) {
+  if (bias_layer >= 0) epi.bias = e->params + e->poff[2 * bias_layer + 1];
+  const ConvGeom& g = e->geoms[gi];
+  if (e->geom_umma[gi])
+    return ss_launch_conv_gather_umma(e->geoms_dev + gi, g,
+                                      *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
+                                      epi, st);
+  return ss_launch_conv_gather_simt(e->geoms_dev + gi, g, epi, st);
+}
+static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, int qw, int scale, cudaStream_t st) {
+  const ConvGeom& g = e->geoms[gi];
+  const bf16* gp = G.p + (int64_t)qh * G.W * G.ld + (int64_t)qw * G.ld;
+  const int64_t gB = (int64_t)G.H * G.W * G.ld, gH = (int64_t)scale * G.W * G.ld, gW = (int64_t)scale * G.ld;
+  if (e->geom_umma[gi])
+    return ss_launch_conv_wgrad_umma(e->geoms_dev + gi, g,
+                                     *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
+                                     gp, gB, gH, gW, gN, e->grads, st);
+  return ss_launch_conv_wgrad_simt(e->geoms_dev + gi, g, gp, gB, gH, gW, gN, e->grads, st);
+}
+
+static WAddr waddr_conv_fwd(const sshslie_engine* e, int layer, int n_off = 0) {
+  const LayerShape& s = e->shapes[layer];
+  const int kk = s.k * s.k;
+  WAddr w;
+  if (!s.transposed) { w.sN = s.d1 * kk; w.sC = kk; }       // W[co][ci][kh][kw], n = co, inner = ci
+  else { w.sN = kk; w.sC = s.d1 * kk; }                     // Wt[i][o][kh][kw], n = o,  inner = i
+  w.sKH = s.k; w.sKW = 1;
+  w.w_off = e->poff[2 * layer] + (int64_t)n_off * w.sN;
+  return w;
+}
+static WAddr waddr_conv_dgrad(const sshslie_engine* e, int layer, int n_off = 0) {
+  const LayerShape& s = e->shapes[layer];
+  const int kk = s.k * s.k;
+  WAddr w;
+  if (!s.transposed) { w.sN = kk; w.sC = s.d1 * kk; }       // n = ci, inner = co
+  else { w.sN = s.d1 * kk; w.sC = kk; }                     // n = i,  inner = o
+  w.sKH = s.k; w.sKW = 1;
+  w.w_off = e->poff[2 * layer] + (int64_t)n_off * w.sN;
+  return w;
+}
+
+#define PUSH(vec, ...) (vec).push_back([=](cudaStream_t st) -> int { __VA_ARGS__ })
+
+// forward of one DecompositionNet pass (model.py:49-70).  Returns the geom ids for reuse by the backward pass.
+struct DecompGeoms {
+  int conv0, shallow, conv1, conv2, conv3, deconv[4], conv5, conv7, recon;
+};
+static DecompGeoms plan_decomp_fwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>& ops, const Tens& in,
+                                   DecompBufs& d, Epi head_epi) {
+  const int B = e->B, H = e->H, W = e->W;
+  DecompGeoms G;
+  {  // conv0: 64 -> 32, ReLU
+    WAddr wa = waddr_conv_fwd(e, L_D_CONV0);
+    G.conv0 = e->add_geom(geom_conv(B, H, W, {{in, 0, e->C, 0}}, 3, 1, 1, +1, 32, wa));
+    Epi ep = epi_bf16(d.c0, 32); ep.relu = 1;
+    const int gi = G.conv0;
+    PUSH(ops, return run_gather(e, gi, ep, L_D_CONV0, st););
+  }
+  {  // shallow 9x9: 64 -> 64, no activation
+    WAddr wa = waddr_conv_fwd(e, L_D_SHALLOW);
+    G.shallow = e->add_geom(geom_conv(B, H, W, {{in, 0, e->C, 0}}, 9, 1, 4, +1, 64, wa));
+    Epi ep = epi_bf16(d.sh, 64);
+    const int gi = G.shallow;
+    PUSH(ops, return run_gather(e, gi, ep, L_D_SHALLOW, st););
+  }
+  {
+    WAddr wa = waddr_conv_fwd(e, L_D_CONV1);
+    G.conv1 = e->add_geom(geom_conv(B, H, W, {{d.sh, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
+    Epi ep = epi_bf16(d.c1, 64); ep.relu = 1;
+    const int gi = G.conv1;
+    PUSH(ops, return run_gather(e, gi, ep, L_D_CONV1, st););
+  }
+  {  // conv2: stride 2, 64 -> 128
+    WAddr wa = waddr_conv_fwd(e, L_D_CONV2);
+    G.conv2 = e->add_geom(geom_conv(B, H / 2, W / 2, {{d.c1, 0, 64, 0}}, 3, 2, 1, +1, 128, wa));
+    Epi ep = epi_bf16(d.c2, 128); ep.relu = 1;
+    const int gi = G.conv2;
+    PUSH(ops, return run_gather(e, gi, ep, L_D_CONV2, st););
+  }
+  {
+    WAddr wa = waddr_conv_fwd(e, L_D_CONV3);
+    G.conv3 = e->add_geom(geom_conv(B, H / 2, W / 2, {{d.c2, 0, 128, 0}}, 3, 1, 1, +1, 128, wa));
+    Epi ep = epi_bf16(d.c3, 128); ep.relu = 1;
+    const int gi = G.conv3;
+    PUSH(ops, return run_gather(e, gi, ep, L_D_CONV3, st););
+  }
+  for (int q = 0; q < 4; ++q) {  // ConvTranspose 3x3 s2 p1 op1: 128 -> 64, four output parity classes
+    const int qh = q >> 1, qw = q & 1;
+    WAddr wa = waddr_conv_fwd(e, L_D_DECONV);
+    G.deconv[q] = e->add_geom(geom_tconv_class(B, H / 2, W / 2, {d.c3, 0, 128, 0}, 3, 1, qh, qw, 64, wa));
+    Epi ep = epi_bf16(d.dc, 64, qh, qw, 2); ep.relu = 1;
+    const int gi = G.deconv[q];
+    PUSH(ops, return run_gather(e, gi, ep, L_D_DECONV, st););
+  }
+  {  // conv5 on cat[deconv, conv1]
+    WAddr wa = waddr_conv_fwd(e, L_D_CONV5);
+    G.conv5 = e->add_geom(geom_conv(B, H, W, {{d.dc, 0, 64, 0}, {d.c1, 0, 64, 64}}, 3, 1, 1, +1, 64, wa));
+    Epi ep = epi_bf16(d.c5, 64); ep.relu = 1;
+    const int gi = G.conv5;
+    PUSH(ops, return run_gather(e, gi, ep, L_D_CONV5, st););
+  }
+  {  // conv7 on cat[conv5, conv0(32)]
+    WAddr wa = waddr_conv_fwd(e, L_D_CONV7);
+    G.conv7 = e->add_geom(geom_conv(B, H, W, {{d.c5, 0, 64, 0}, {d.c0, 0, 32, 64}}, 3, 1, 1, +1, 64, wa));
+    Epi ep = epi_bf16(d.c7, 64);
+    const int gi = G.conv7;
+    PUSH(ops, return run_gather(e, gi, ep, L_D_CONV7, st););
+  }
+  {  // recon: 64 -> C+1, sigmoid heads
+    WAddr wa = waddr_conv_fwd(e, L_D_RECON);
+    G.recon = e->add_geom(geom_conv(B, H, W, {{d.c7, 0, 64, 0}}, 3, 1, 1, +1, e->C + 1, wa));
+    const int gi = G.recon;
+    PUSH(ops, return run_gather(e, gi, head_epi, L_D_RECON, st););
+  }
+  return G;
+}
+
+// backward of one DecompositionNet pass, given dc8 (gradient wrt the recon pre-activation, `dc8_n` valid columns)
+struct DecompGrads { Tens dc7, dc5, dc0, ddc, dc1p, dc3, dc2, dc1, dsh, din; };
+static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>& ops, const Tens& in,
+                            const DecompBufs& d, const DecompGeoms& G, const Tens& dc8, int dc8_n, DecompGrads& g,
+                            bool need_din) {
+  const int B = e->B, H = e->H, W = e->W;
+  float** grads = &e->grads;
+  const int64_t* poff = e->poff;
+  auto bias_grad = [&](const Tens& t, int n, int layer) {
+    PUSH(ops, return ss_launch_bias_grad(t.p, t.pix(), t.ld, n, *grads + poff[2 * layer + 1], st););
+  };
+  // recon
+  { const int gi = G.recon; PUSH(ops, return run_wgrad(e, gi, dc8, dc8_n, 0, 0, 1, st);); }
+  bias_grad(dc8, dc8_n, L_D_RECON);
+  {
+    WAddr wa = waddr_conv_dgrad(e, L_D_RECON);
+    const int gi = e->add_geom(geom_conv(B, H, W, {{dc8, 0, dc8_n, 0}}, 3, 1, 1, -1, 64, wa));
+    Epi ep = epi_bf16(g.dc7, 64);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  // conv7 (no activation): inputs [c5 | c0]
+  { const int gi = G.conv7; PUSH(ops, return run_wgrad(e, gi, g.dc7, 64, 0, 0, 1, st);); }
+  bias_grad(g.dc7, 64, L_D_CONV7);
+  {
+    WAddr wa = waddr_conv_dgrad(e, L_D_CONV7, 0);
+    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc7, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+    Epi ep = epi_bf16(g.dc5, 64); epi_set_mask(ep, d.c5);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  {
+    WAddr wa = waddr_conv_dgrad(e, L_D_CONV7, 64);
+    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc7, 0, 64, 0}}, 3, 1, 1, -1, 32, wa));
+    Epi ep = epi_bf16(g.dc0, 32); epi_set_mask(ep, d.c0);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  // conv5 (ReLU already folded into dc5): inputs [dc | c1]
+  { const int gi = G.conv5; PUSH(ops, return run_wgrad(e, gi, g.dc5, 64, 0, 0, 1, st);); }
+  bias_grad(g.dc5, 64, L_D_CONV5);
+  {
+    WAddr wa = waddr_conv_dgrad(e, L_D_CONV5, 0);
+    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc5, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+    Epi ep = epi_bf16(g.ddc, 64); epi_set_mask(ep, d.dc);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  {
+    WAddr wa = waddr_conv_dgrad(e, L_D_CONV5, 64);
+    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc5, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+    Epi ep = epi_bf16(g.dc1p, 64);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  // deconv: dgrad = stride-2 conv of ddc (n = 128 input channels); the same geom drives its wgrad with G = c3
+  {
+    WAddr wa = waddr_conv_dgrad(e, L_D_DECONV);
+    const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{g.ddc, 0, 64, 0}}, 3, 2, 1, +1, 128, wa));
+    const Tens c3 = d.c3;
+    PUSH(ops, return run_wgrad(e, gi, c3, 128, 0, 0, 1, st););
+    bias_grad(g.ddc, 64, L_D_DECONV);
+    Epi ep = epi_bf16(g.dc3, 128); epi_set_mask(ep, d.c3);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  // conv3
+  { const int gi = G.conv3; PUSH(ops, return run_wgrad(e, gi, g.dc3, 128, 0, 0, 1, st);); }
+  bias_grad(g.dc3, 128, L_D_CONV3);
+  {
+    WAddr wa = waddr_conv_dgrad(e, L_D_CONV3);
+    const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{g.dc3, 0, 128, 0}}, 3, 1, 1, -1, 128, wa));
+    Epi ep = epi_bf16(g.dc2, 128); epi_set_mask(ep, d.c2);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  // conv2 (stride 2): wgrad on its forward geom; dgrad = transposed gather per input parity class, + dc1p, ReLU mask
+  { const int gi = G.conv2; PUSH(ops, return run_wgrad(e, gi, g.dc2, 128, 0, 0, 1, st);); }
+  bias_grad(g.dc2, 128, L_D_CONV2);
+  for (int q = 0; q < 4; ++q) {
+    const int qh = q >> 1, qw = q & 1;
+    WAddr wa = waddr_conv_dgrad(e, L_D_CONV2);
+    const int gi = e->add_geom(geom_tconv_class(B, H / 2, W / 2, {g.dc2, 0, 128, 0}, 3, 1, qh, qw, 64, wa));
+    Epi ep = epi_bf16(g.dc1, 64, qh, qw, 2);
+    epi_set_add(ep, g.dc1p, 0, qh, qw, 2);
+    epi_set_mask(ep, d.c1, qh, qw, 2);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  // conv1
+  { const int gi = G.conv1; PUSH(ops, return run_wgrad(e, gi, g.dc1, 64, 0, 0, 1, st);); }
+  bias_grad(g.dc1, 64, L_D_CONV1);
+  {
+    WAddr wa = waddr_conv_dgrad(e, L_D_CONV1);
+    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc1, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+    Epi ep = epi_bf16(g.dsh, 64);
+    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  }
+  // shallow 9x9 and conv0 read the pass input
+  { const int gi = G.shallow; PUSH(ops, return run_wgrad(e, gi, g.dsh, 64, 0, 0, 1, st);); }
+  bias_grad(g.dsh, 64, L_D_SHALLOW);
+  { const int gi = G.conv0; PUSH(ops, return run_wgrad(e, gi, g.dc0, 32, 0, 0, 1, st);); }
+  bias_grad(g.dc0, 32, L_D_CONV0);
+  if (need_din) {  // d(input) = dgrad_shallow(dsh) + dgrad_conv0(dc0)
+    {
+      WAddr wa = waddr_conv_dgrad(e, L_D_SHALLOW);
+      const int gi = e->add_geom(geom_conv(B, H, W, {{g.dsh, 0, 64, 0}}, 9, 1, 4, -1, e->C, wa));
+      Epi ep = epi_bf16(g.din, e->C);
+      PUSH(ops, return run_gather(e, gi, ep, -1, st););
+    }
+    {
+      WAddr wa = waddr_conv_dgrad(e, L_D_CONV0);
+      const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc0, 0, 32, 0}}, 3, 1, 1, -1, e->C, wa));
+      Epi ep = epi_bf16(g.din, e->C); epi_set_add(ep, g.din);
+      PUSH(ops, return run_gather(e, gi, ep, -1, st););
+    }
+  }
+  (void)in;
+}
+
+static int build_plan(sshslie_engine* e, unsigned char* base) {
+  e->base = base;
+  e->cursor = 0;
+  e->zero_ranges.clear();
+  e->geoms.clear();
+  e->geom_umma.clear();
+  e->ops_fwd.clear();
+  e->ops_loss_bwd2_illum.clear();
+  e->ops_bwd1.clear();
+  const int B = e->B, C = e->C, H = e->H, W = e->W;
+  const int64_t n = (int64_t)B * H * W;
+  const bool train = e->train;
+
+  // device copies of the plan
+  e->geoms_dev = (ConvGeom*)e->alloc(sizeof(ConvGeom) * 128);
+  e->pack_start_dev = (int*)e->alloc(sizeof(int) * 130);
+  e->mask_dev = e->falloc((int64_t)H * W);
+  e->sums_dev = e->falloc(16);
+
+  // ---- tensors -----------------------------------------------------------------------------
+  Tens X = e->talloc(B, H, W, 64);
+  e->R32 = e->falloc(n * C); e->I32 = e->falloc(n); e->Id32 = e->falloc(n); e->S32 = e->falloc(n * C);
+  Tens RI = e->talloc(B, H, W, 128, true);
+  auto decomp_bufs = [&]() {
+    DecompBufs d;
+    d.c0 = e->talloc(B, H, W, 64, true);
+    d.sh = e->talloc(B, H, W, 64); d.c1 = e->talloc(B, H, W, 64);
+    d.c2 = e->talloc(B, H / 2, W / 2, 128); d.c3 = e->talloc(B, H / 2, W / 2, 128);
+    d.dc = e->talloc(B, H, W, 64); d.c5 = e->talloc(B, H, W, 64); d.c7 = e->talloc(B, H, W, 64);
+    return d;
+  };
+  DecompBufs d1 = decomp_bufs();
+  Tens a0 = e->talloc(B, H, W, 64), a1 = e->talloc(B, H / 2, W / 2, 64), a2 = e->talloc(B, H / 4, W / 4, 64),
+       a3 = e->talloc(B, H / 8, W / 8, 64), tt = e->talloc(B, H / 8, W / 8, 64);
+  Tens u1 = e->talloc(B, H / 4, W / 4, 64), r1 = e->talloc(B, H / 4, W / 4, 64), u2 = e->talloc(B, H / 2, W / 2, 64),
+       r2 = e->talloc(B, H / 2, W / 2, 64), u3 = e->talloc(B, H, W, 64), r3 = e->talloc(B, H, W, 64);
+  Tens fg = e->talloc(B, H, W, 192), ff = e->talloc(B, H, W, 64);
+  const int L = (H / 8) * (W / 8);
+  const int64_t T64 = (int64_t)B * L * 64;
+  AttnBuffers ab;
+  memset(&ab, 0, sizeof(ab));
+  ab.x = e->falloc(T64); ab.q = e->falloc(T64); ab.k = e->falloc(T64); ab.v = e->falloc(T64); ab.o = e->falloc(T64);
+  ab.lse = e->falloc((int64_t)B * 4 * L); ab.h = e->falloc(T64); ab.t32 = e->falloc(T64);
+  if (train) {
+    ab.dq = e->falloc(T64); ab.dk = e->falloc(T64); ab.dv = e->falloc(T64); ab.d_o = e->falloc(T64);
+    ab.dh = e->falloc(T64); ab.dx = e->falloc(T64); ab.Dv = e->falloc((int64_t)B * 4 * L);
+  }
+
+  // ---- forward (model.py:229-234) ----------------------------------------------------------
+  auto& F = e->ops_fwd;
+  PUSH(F, return ss_launch_nchw32_to_nhwc16(e->x, X.p, B, C, H, W, 64, st););
+  {
+    const int total = e->pack_blocks;   // filled after planning; read at run time through e
+    (void)total;
+    PUSH(F, return ss_launch_pack_weights(e->geoms_dev, e->pack_start_dev, (int)e->geoms.size(), e->pack_blocks,
+                                          e->params, st););
+  }
+  Epi head1;
+  memset(&head1, 0, sizeof(head1));
+  head1.mode = EPI_HEAD; head1.R32 = e->R32; head1.I32 = e->I32; head1.RI = RI.p; head1.ri_c = 128;
+  head1.C = C; head1.H = H; head1.W = W;
+  DecompGeoms G1 = plan_decomp_fwd(e, F, X, d1, head1);
+
+  // IllumAdjustmentNet (model.py:143-175)
+  int g_i0, g_i1, g_i2, g_i3, g_d1, g_d2, g_d3, g_fus, g_fin;
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_CONV0);
+    g_i0 = e->add_geom(geom_conv(B, H, W, {{RI, 0, C + 1, 0}}, 3, 1, 1, +1, 64, wa));
+    Epi ep = epi_bf16(a0, 64);
+    PUSH(F, return run_gather(e, g_i0, ep, L_I_CONV0, st););
+  }
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_CONV1);
+    g_i1 = e->add_geom(geom_conv(B, H / 2, W / 2, {{a0, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
+    Epi ep = epi_bf16(a1, 64); ep.relu = 1;
+    PUSH(F, return run_gather(e, g_i1, ep, L_I_CONV1, st););
+  }
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_CONV2);
+    g_i2 = e->add_geom(geom_conv(B, H / 4, W / 4, {{a1, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
+    Epi ep = epi_bf16(a2, 64); ep.relu = 1;
+    PUSH(F, return run_gather(e, g_i2, ep, L_I_CONV2, st););
+  }
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_CONV3);
+    g_i3 = e->add_geom(geom_conv(B, H / 8, W / 8, {{a2, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
+    Epi ep = epi_bf16(a3, 64); ep.relu = 1;
+    PUSH(F, return run_gather(e, g_i3, ep, L_I_CONV3, st););
+  }
+  const int64_t* apoff = e->poff + 2 * L_Q;
+  PUSH(F, return ss_attention_forward(a3.p, tt.p, e->params, apoff, ab, B, L, st););
+  PUSH(F, return ss_launch_upsample2_add(tt.p, nullptr, u1.p, B, H / 8, W / 8, st););
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_DECONV1);
+    g_d1 = e->add_geom(geom_conv(B, H / 4, W / 4, {{u1, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
+    Epi ep = epi_bf16(r1, 64); ep.relu = 1;
+    PUSH(F, return run_gather(e, g_d1, ep, L_I_DECONV1, st););
+  }
+  PUSH(F, return ss_launch_upsample2_add(r1.p, a2.p, u2.p, B, H / 4, W / 4, st););
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_DECONV2);
+    g_d2 = e->add_geom(geom_conv(B, H / 2, W / 2, {{u2, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
+    Epi ep = epi_bf16(r2, 64); ep.relu = 1;
+    PUSH(F, return run_gather(e, g_d2, ep, L_I_DECONV2, st););
+  }
+  PUSH(F, return ss_launch_upsample2_add(r2.p, a1.p, u3.p, B, H / 2, W / 2, st););
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_DECONV3);
+    g_d3 = e->add_geom(geom_conv(B, H, W, {{u3, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
+    Epi ep = epi_bf16(r3, 64); ep.relu = 1;
+    PUSH(F, return run_gather(e, g_d3, ep, L_I_DECONV3, st););
+  }
+  PUSH(F, return ss_launch_fuse_concat(r1.p, a2.p, r2.p, a1.p, r3.p, a0.p, fg.p, B, H, W, st););
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_FUSION);
+    g_fus = e->add_geom(geom_conv(B, H, W, {{fg, 0, 192, 0}}, 1, 1, 0, +1, 64, wa));
+    Epi ep = epi_bf16(ff, 64);
+    PUSH(F, return run_gather(e, g_fus, ep, L_I_FUSION, st););
+  }
+  {
+    WAddr wa = waddr_conv_fwd(e, L_I_FINAL);
+    g_fin = e->add_geom(geom_conv(B, H, W, {{ff, 0, 64, 0}}, 3, 1, 1, +1, 1, wa));
+    Epi ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.mode = EPI_PLANE32; ep.plane32 = e->Id32; ep.H = H; ep.W = W;
+    PUSH(F, return run_gather(e, g_fin, ep, L_I_FINAL, st););
+  }
+  Tens Sb;
+  if (train) Sb = e->talloc(B, H, W, 64);
+  {
+    bf16* sbp = train ? Sb.p : nullptr;
+    PUSH(F, return ss_launch_make_s(e->R32, e->I32, e->Id32, e->S32, sbp, B, C, H, W, st););
+  }
+
+  if (train) {
+    // ---- second decomposition pass on S, losses, backward ------------------------------------
+    auto& Lq = e->ops_loss_bwd2_illum;
+    float* Re32 = e->falloc(n * C);
+    float *dR32 = e->falloc(n * C), *dI32 = e->falloc(n), *dId32 = e->falloc(n), *dS32 = e->falloc(n * C),
+          *dRe32 = e->falloc(n * C);
+    DecompBufs d2 = decomp_bufs();
+    Epi head2;
+    memset(&head2, 0, sizeof(head2));
+    head2.mode = EPI_HEAD; head2.R32 = Re32; head2.C = C; head2.H = H; head2.W = W;
+    DecompGeoms G2 = plan_decomp_fwd(e, Lq, Sb, d2, head2);          // model.py:546
+
+    const int64_t np = e->nparams;
+    PUSH(Lq, return cudaMemsetAsync(e->grads, 0, np * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
+    PUSH(Lq, return cudaMemsetAsync(e->sums_dev, 0, 16 * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
+    PUSH(Lq, return ss_pixel_losses(e->x, e->R32, e->I32, e->Id32, Re32, e->cfg, B, C, H, W, e->sums_dev, dR32, dI32,
+                                    dId32, dS32, dRe32, st););
+    PUSH(Lq, return sshslie_fourier_loss(e->x, e->S32, e->mask_dev, dS32, e->sums_dev + 9, B * C, H, W,
+                                         (float)(e->cfg.c_loss_fourier / ((double)B * C * H * W)), st););
+    PUSH(Lq, return ss_launch_finalize_losses(e->sums_dev, &e->cfg, e->losses, B, C, H, W, st););
+
+    // backward, pass 2 (R_enh branch).  I_enh is unused (model.py:546) -> only C gradient columns.
+    DecompGrads gr;
+    gr.dc7 = e->talloc(B, H, W, 64); gr.dc5 = e->talloc(B, H, W, 64); gr.dc0 = e->talloc(B, H, W, 64, true);
+    gr.ddc = e->talloc(B, H, W, 64); gr.dc1p = e->talloc(B, H, W, 64); gr.dc3 = e->talloc(B, H / 2, W / 2, 128);
+    gr.dc2 = e->talloc(B, H / 2, W / 2, 128); gr.dc1 = e->talloc(B, H, W, 64); gr.dsh = e->talloc(B, H, W, 64);
+    gr.din = e->talloc(B, H, W, 64);
+    Tens dc8 = e->talloc(B, H, W, 128, true);
+    PUSH(Lq, return ss_launch_head_bwd(dRe32, Re32, nullptr, 0, nullptr, nullptr, dc8.p, 128, B, C, H, W, st););
+    plan_decomp_bwd(e, Lq, Sb, d2, G2, dc8, C, gr, true);
+    // S = R*(Id+I)
+    PUSH(Lq, return ss_launch_s_bwd(dS32, gr.din.p, e->R32, e->I32, e->Id32, dR32, dI32, dId32, B, C, H, W, st););
+
+    // IllumAdjustmentNet backward
+    Tens dff = e->talloc(B, H, W, 64), dfg = e->talloc(B, H, W, 192), dr3 = e->talloc(B, H, W, 64),
+         p2 = e->talloc(B, H / 2, W / 2, 64), p1 = e->talloc(B, H / 4, W / 4, 64), du3 = e->talloc(B, H, W, 64),
+         dr2 = e->talloc(B, H / 2, W / 2, 64), da1p = e->talloc(B, H / 2, W / 2, 64),
+         du2 = e->talloc(B, H / 2, W / 2, 64), dr1 = e->talloc(B, H / 4, W / 4, 64),
+         da2p = e->talloc(B, H / 4, W / 4, 64), du1 = e->talloc(B, H / 4, W / 4, 64),
+         da3 = e->talloc(B, H / 8, W / 8, 64), da2 = e->talloc(B, H / 4, W / 4, 64),
+         da1 = e->talloc(B, H / 2, W / 2, 64), da0 = e->talloc(B, H, W, 64), dRI = e->talloc(B, H, W, 128, true);
+    float* dt32 = e->falloc(T64);
+    {
+      const int64_t total = n * 8;
+      const int rows_pb = 2;
+      PUSH(Lq, final_wgrad_kernel<<<(unsigned)(((int64_t)B * H + rows_pb - 1) / rows_pb), 576, 0, st>>>(
+                   dId32, ff.p, e->grads + e->poff[2 * L_I_FINAL], e->grads + e->poff[2 * L_I_FINAL + 1], B, H, W,
+                   rows_pb);
+               return ss_check_launch("final_wgrad"););
+      PUSH(Lq, final_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                   dId32, e->params + e->poff[2 * L_I_FINAL], dff.p, H, W, total);
+               return ss_check_launch("final_dgrad"););
+    }
+    PUSH(Lq, return run_wgrad(e, g_fus, dff, 64, 0, 0, 1, st););
+    PUSH(Lq, return ss_launch_bias_grad(dff.p, dff.pix(), 64, 64, e->grads + e->poff[2 * L_I_FUSION + 1], st););
+    {
+      WAddr wa = waddr_conv_dgrad(e, L_I_FUSION);
+      const int gi = e->add_geom(geom_conv(B, H, W, {{dff, 0, 64, 0}}, 1, 1, 0, -1, 192, wa));
+      Epi ep = epi_bf16(dfg, 192);
+      PUSH(Lq, return run_gather(e, gi, ep, -1, st););
+    }
+    PUSH(Lq, return ss_launch_concat_bwd(dfg.p, r3.p, dr3.p, p2.p, p1.p, B, H, W, st););
+    // deconv3
+    PUSH(Lq, return run_wgrad(e, g_d3, dr3, 64, 0, 0, 1, st););
+    PUSH(Lq, return ss_launch_bias_grad(dr3.p, dr3.pix(), 64, 64, e->grads + e->poff[2 * L_I_DECONV3 + 1], st););
+    {
+      WAddr wa = waddr_conv_dgrad(e, L_I_DECONV3);
+      const int gi = e->add_geom(geom_conv(B, H, W, {{dr3, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+      Epi ep = epi_bf16(du3, 64);
+      PUSH(Lq, return run_gather(e, gi, ep, -1, st););
+    }
+    PUSH(Lq, return ss_launch_pool2(du3.p, p2.p, r2.p, da1p.p, dr2.p, nullptr, B, H / 2, W / 2, st););
+    // deconv2
+    PUSH(Lq, return run_wgrad(e, g_d2, dr2, 64, 0, 0, 1, st););
+    PUSH(Lq, return ss_launch_bias_grad(dr2.p, dr2.pix(), 64, 64, e->grads + e->poff[2 * L_I_DECONV2 + 1], st););
+    {
+      WAddr wa = waddr_conv_dgrad(e, L_I_DECONV2);
+      const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{dr2, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+      Epi ep = epi_bf16(du2, 64);
+      PUSH(Lq, return run_gather(e, gi, ep, -1, st););
+    }
+    PUSH(Lq, return ss_launch_pool2(du2.p, p1.p, r1.p, da2p.p, dr1.p, nullptr, B, H / 4, W / 4, st););
+    // deconv1
+    PUSH(Lq, return run_wgrad(e, g_d1, dr1, 64, 0, 0, 1, st););
+    PUSH(Lq, return ss_launch_bias_grad(dr1.p, dr1.pix(), 64, 64, e->grads + e->poff[2 * L_I_DECONV1 + 1], st););
+    {
+      WAddr wa = waddr_conv_dgrad(e, L_I_DECONV1);
+      const int gi = e->add_geom(geom_conv(B, H / 4, W / 4, {{dr1, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+      Epi ep = epi_bf16(du1, 64);
+      PUSH(Lq, return run_gather(e, gi, ep, -1, st););
+    }
+    PUSH(Lq, return ss_launch_pool2(du1.p, nullptr, nullptr, nullptr, nullptr, dt32, B, H / 8, W / 8, st););
+    PUSH(Lq, return ss_attention_backward(dt32, a3.p, da3.p, e->params, e->grads, apoff, ab, B, L, st););
+    // conv3 / conv2 / conv1 (stride 2): wgrad on the forward geom, dgrad per input parity class (+ skip gradient)
+    struct S2 { int layer, gfwd; Tens dy, x_in, dx, addp; bool mask; };
+    const S2 s2[3] = {{L_I_CONV3, g_i3, da3, a2, da2, da2p, true},
+                      {L_I_CONV2, g_i2, da2, a1, da1, da1p, true},
+                      {L_I_CONV1, g_i1, da1, a0, da0, Tens(), false}};
+    for (int i = 0; i < 3; ++i) {
+      const S2 s = s2[i];
+      PUSH(Lq, return run_wgrad(e, s.gfwd, s.dy, 64, 0, 0, 1, st););
+      PUSH(Lq, return ss_launch_bias_grad(s.dy.p, s.dy.pix(), 64, 64, e->grads + e->poff[2 * s.layer + 1], st););
+      for (int q = 0; q < 4; ++q) {
+        const int qh = q >> 1, qw = q & 1;
+        WAddr wa = waddr_conv_dgrad(e, s.layer);
+        const int gi = e->add_geom(geom_tconv_class(B, s.dy.H, s.dy.W, {s.dy, 0, 64, 0}, 3, 1, qh, qw, 64, wa));
+        Epi ep = epi_bf16(s.dx, 64, qh, qw, 2);
+        if (s.mask) {
+          epi_set_add(ep, s.addp, 0, qh, qw, 2);
+          epi_set_mask(ep, s.x_in, qh, qw, 2);
+        } else {
+          epi_set_add(ep, dfg, 128, qh, qw, 2);     // d(a0) also receives dfg[...,128:192] (deconv3 + conv0 skip)
+        }
+        PUSH(Lq, return run_gather(e, gi, ep, -1, st););
+      }
+    }
+    // conv0 of the illumination net reads cat[R, I]
+    PUSH(Lq, return run_wgrad(e, g_i0, da0, 64, 0, 0, 1, st););
+    PUSH(Lq, return ss_launch_bias_grad(da0.p, da0.pix(), 64, 64, e->grads + e->poff[2 * L_I_CONV0 + 1], st););
+    {
+      WAddr wa = waddr_conv_dgrad(e, L_I_CONV0);
+      const int gi = e->add_geom(geom_conv(B, H, W, {{da0, 0, 64, 0}}, 3, 1, 1, -1, C + 1, wa));
+      Epi ep = epi_bf16(dRI, (C + 1 + 15) / 16 * 16);
+      PUSH(Lq, return run_gather(e, gi, ep, -1, st););
+    }
+
+    // ---- backward, pass 1 -------------------------------------------------------------------
+    auto& B1 = e->ops_bwd1;
+    PUSH(B1, return ss_launch_head_bwd(dR32, e->R32, dRI.p, 128, dI32, e->I32, dc8.p, 128, B, C, H, W, st););
+    plan_decomp_bwd(e, B1, X, d1, G1, dc8, C + 1, gr, false);
+  }
+
+  if ((int)e->geoms.size() > 128) {
+    ss_set_error("internal: %d geoms exceed the plan table", (int)e->geoms.size());
+    return SSHSLIE_ERR_ARG;
+  }
+  // packed weights + pack job table
+  e->pack_start.assign(e->geoms.size() + 1, 0);
+  for (size_t i = 0; i < e->geoms.size(); ++i) {
+    ConvGeom& g = e->geoms[i];
+    const int64_t elems = (int64_t)g.Npad * g.nslabs * SS_SLAB;
+    g.wp = (bf16*)e->alloc(elems * sizeof(bf16));
+    e->pack_start[i + 1] = e->pack_start[i] + (int)((elems + 255) / 256);
+  }
+  e->pack_blocks = e->pack_start.back();
+  e->ws_bytes = e->cursor;
+  return SSHSLIE_OK;
+}
+
+// Fourier mask on the un-shifted grid (model.py:460-464): torch.linspace(-1,1,n) semantics in fp32
+static void make_mask(std::vector<float>& m, int H, int W) {
+  auto lin = [](int i, int n) -> float {
+    const float step = 2.0f / (float)(n - 1);
+    return (i < n / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(n - 1 - i));
+  };
+  m.resize((size_t)H * W);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const float Y = lin(y, H), X = lin(x, W);
+      m[(size_t)y * W + x] = (sqrtf(X * X + Y * Y) >= 0.1f) ? 1.f : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channels, int height, int width, int flags) {
+  if (!out || batch < 1 || channels != 64 || height < 16 || width < 16 || (height % 8) || (width % 8)) {
+    ss_set_error("sshslie_engine_create: need batch>=1, channels==64, H,W multiples of 8 and >=16 (got B=%d C=%d %dx%d)",
+                 batch, channels, height, width);
+    return SSHSLIE_ERR_ARG;
+  }
+  if ((flags & SSHSLIE_FLAG_TRAIN)) {
+    bool pow2 = (height & (height - 1)) == 0 && (width & (width - 1)) == 0;
+    if (!pow2 || height > 128 || width > 128) {
+      ss_set_error("sshslie_engine_create: training needs power-of-two H,W <= 128 for the shared-memory FFT loss "
+                   "(config patch_size is 128); got %dx%d", height, width);
+      return SSHSLIE_ERR_ARG;
+    }
+  }
+  sshslie_engine* e = new sshslie_engine();
+  e->B = batch; e->C = channels; e->H = height; e->W = width; e->flags = flags;
+  e->train = (flags & SSHSLIE_FLAG_TRAIN) != 0;
+  e->force_simt = (flags & SSHSLIE_FLAG_FORCE_SIMT) != 0;
+  layer_shapes(channels, e->shapes);
+  e->nparams = sshslie_param_table(channels, e->poff, e->psize);
+  memset(&e->cfg, 0, sizeof(e->cfg));
+  const int rc = build_plan(e, nullptr);   // dry run: sizes only
+  if (rc != SSHSLIE_OK) { delete e; return rc; }
+  *out = e;
+  return SSHSLIE_OK;
+}
+extern "C" void sshslie_engine_destroy(sshslie_engine* e) { delete e; }
+extern "C" int64_t sshslie_engine_workspace_bytes(const sshslie_engine* e) { return e ? e->ws_bytes : 0; }
+
+extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!e || !workspace) { ss_set_error("sshslie_engine_bind: null argument"); return SSHSLIE_ERR_ARG; }
+  if (workspace_bytes < e->ws_bytes || ((uintptr_t)workspace & 1023)) {
+    ss_set_error("sshslie_engine_bind: workspace must be >= %lld bytes and 1024-byte aligned", (long long)e->ws_bytes);
+    return SSHSLIE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  e->bound = false;
+  int rc = build_plan(e, (unsigned char*)workspace);
+  if (rc != SSHSLIE_OK) return rc;
+  e->ws = (unsigned char*)workspace;
+  // tcgen05 eligibility + TMA descriptors
+  const size_t msz = ss_umma_maps_size();
+  e->maps_blob.assign(e->geoms.size() * msz, 0);
+  for (size_t i = 0; i < e->geoms.size(); ++i) {
+    e->geom_umma[i] = 0;
+    if (!e->force_simt && ss_umma_supported(e->geoms[i])) {
+      rc = ss_umma_build_maps(e->geoms[i], reinterpret_cast<UmmaMaps*>(e->maps_blob.data() + i * msz));
+      if (rc != SSHSLIE_OK) return rc;
+      e->geom_umma[i] = 1;
+    }
+  }
+  for (auto& zr : e->zero_ranges)
+    if (cudaMemsetAsync(e->ws + zr.first, 0, (size_t)zr.second, st) != cudaSuccess) {
+      ss_set_error("bind: memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return SSHSLIE_ERR_CUDA;
+    }
+  std::vector<float> mask;
+  make_mask(mask, e->H, e->W);
+  cudaError_t ce = cudaMemcpyAsync(e->geoms_dev, e->geoms.data(), e->geoms.size() * sizeof(ConvGeom),
+                                   cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess)
+    ce = cudaMemcpyAsync(e->pack_start_dev, e->pack_start.data(), e->pack_start.size() * sizeof(int),
+                         cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess)
+    ce = cudaMemcpyAsync(e->mask_dev, mask.data(), mask.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) {
+    ss_set_error("bind: upload failed: %s", cudaGetErrorString(ce));
+    return SSHSLIE_ERR_CUDA;
+  }
+  e->bound = true;
+  return SSHSLIE_OK;
+}
+
+static int run_ops(std::vector<sshslie_engine::OpFn>& ops, cudaStream_t st) {
+  for (auto& f : ops) {
+    const int rc = f(st);
+    if (rc != SSHSLIE_OK) return rc;
+  }
+  return SSHSLIE_OK;
+}
+static int copy_out(float* dst, const float* src, int64_t n, cudaStream_t st) {
+  if (!dst) return SSHSLIE_OK;
+  if (cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    ss_set_error("output copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SSHSLIE_ERR_CUDA;
+  }
+  return SSHSLIE_OK;
+}
+static int copy_outputs(sshslie_engine* e, float* R, float* I, float* Id, float* S, cudaStream_t st) {
+  const int64_t n = (int64_t)e->B * e->H * e->W;
+  int rc = copy_out(R, e->R32, n * e->C, st);
+  if (!rc) rc = copy_out(I, e->I32, n, st);
+  if (!rc) rc = copy_out(Id, e->Id32, n, st);
+  if (!rc) rc = copy_out(S, e->S32, n * e->C, st);
+  return rc;
+}
+
+extern "C" int sshslie_forward(sshslie_engine* e, const float* x, const float* params, float* R, float* I,
+                               float* I_delta, float* S, void* stream) {
+  if (!e || !x || !params) { ss_set_error("sshslie_forward: null argument"); return SSHSLIE_ERR_ARG; }
+  if (!e->bound) { ss_set_error("sshslie_forward: engine not bound to a workspace"); return SSHSLIE_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  e->x = x; e->params = params;
+  int rc = run_ops(e->ops_fwd, st);
+  if (!rc) rc = copy_outputs(e, R, I, I_delta, S, st);
+  return rc;
+}
+
+extern "C" int sshslie_loss_and_grad(sshslie_engine* e, const float* x, const float* params,
+                                     const sshslie_loss_cfg* cfg, float* grads, float* losses, float* R, float* I,
+                                     float* I_delta, float* S, int phase_mask, void* stream) {
+  if (!e || !x || !params || !cfg || !grads || !losses) {
+    ss_set_error("sshslie_loss_and_grad: null argument");
+    return SSHSLIE_ERR_ARG;
+  }
+  if (!e->train) { ss_set_error("sshslie_loss_and_grad: engine created without SSHSLIE_FLAG_TRAIN"); return SSHSLIE_ERR_ARG; }
+  if (!e->bound) { ss_set_error("sshslie_loss_and_grad: engine not bound to a workspace"); return SSHSLIE_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  e->x = x; e->params = params; e->grads = grads; e->losses = losses; e->cfg = *cfg;
+  int rc = SSHSLIE_OK;
+  if (phase_mask & 1) {
+    rc = run_ops(e->ops_fwd, st);
+    if (!rc) rc = run_ops(e->ops_loss_bwd2_illum, st);
+    if (!rc) rc = copy_outputs(e, R, I, I_delta, S, st);
+  }
+  if (!rc && (phase_mask & 2)) rc = run_ops(e->ops_bwd1, st);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-layer entry point for kernel-level parity tests (tests/test_gpu_conv.py)
+// ---------------------------------------------------------------------------------------------
+static int pad64(int c) { return (c + 63) / 64 * 64; }
+
+extern "C" int64_t sshslie_conv2d_scratch_bytes(int B, int Cin, int Cout, int H, int W, int k, int stride) {
+  (void)k;
+  const int64_t big = (int64_t)B * H * W * (stride == 2 ? 4 : 1);   // the larger of the two spatial sizes
+  int64_t bytes = 0;
+  bytes += big * pad64(Cin) * 2 + 1024;
+  bytes += big * pad64(Cout) * 2 + 1024;
+  bytes += (int64_t)sizeof(ConvGeom) * 8 + 4096;
+  bytes += 4 * ((int64_t)(pad64(Cin) + pad64(Cout)) * k * k * pad64(Cin > Cout ? Cin : Cout) * 2 + 1024);
+  return bytes + (1 << 16);
+}
+
+extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, float* w, const float* bias, float* y,
+                              int B, int Cin, int Cout, int H, int W, int k, int stride, int relu, void* scratch,
+                              int64_t scratch_bytes, void* stream) {
+  if (!x || !w || !y || !scratch || kind < 0 || kind > 2 || (stride != 1 && stride != 2) || (k != 1 && k != 3 && k != 9) ||
+      (transposed && (stride != 2 || k != 3)) || (H % 8) || (W % 8) || ((uintptr_t)scratch & 1023)) {
+    ss_set_error("sshslie_conv2d: unsupported arguments");
+    return SSHSLIE_ERR_ARG;
+  }
+  if (scratch_bytes < sshslie_conv2d_scratch_bytes(B, Cin, Cout, H, W, k, stride)) {
+    ss_set_error("sshslie_conv2d: scratch too small");
+    return SSHSLIE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  sshslie_engine E;
+  sshslie_engine* e = &E;
+  e->B = B; e->C = 64; e->H = H; e->W = W; e->flags = 0; e->train = false; e->force_simt = (impl == 0);
+  e->base = (unsigned char*)scratch; e->cursor = 0;
+  memset(e->poff, 0, sizeof(e->poff));
+  e->shapes[0] = {transposed ? Cin : Cout, transposed ? Cout : Cin, k, transposed != 0};
+  e->params = w; e->grads = w;
+  const int pad = (k - 1) / 2;
+  // spatial sizes: "small" side is the strided-conv output / transposed-conv input
+  const int Hin = H, Win = W;
+  const int Hout = transposed ? 2 * H : (stride == 2 ? H / 2 : H), Wout = transposed ? 2 * W : (stride == 2 ? W / 2 : W);
+  Tens tin = e->talloc(B, Hin, Win, pad64(Cin)), tout = e->talloc(B, Hout, Wout, pad64(Cout));
+  e->geoms_dev = (ConvGeom*)e->alloc(sizeof(ConvGeom) * 8);
+  e->pack_start_dev = (int*)e->alloc(sizeof(int) * 16);
+  cudaMemsetAsync(tin.p, 0, (size_t)tin.pix() * tin.ld * 2, st);
+  cudaMemsetAsync(tout.p, 0, (size_t)tout.pix() * tout.ld * 2, st);
+
+  struct Job { int gi; Epi ep; };
+  std::vector<Job> jobs;
+  const Tens* gt = nullptr;   // wgrad: the "G" tensor
+  int gN = 0;
+  if (kind == 0) {
+    int rc = ss_launch_nchw32_to_nhwc16(x, tin.p, B, Cin, Hin, Win, tin.ld, st);
+    if (rc) return rc;
+    WAddr wa = waddr_conv_fwd(e, 0);
+    if (!transposed) {
+      const int gi = e->add_geom(geom_conv(B, Hout, Wout, {{tin, 0, Cin, 0}}, k, stride, pad, +1, Cout, wa));
+      Epi ep = epi_bf16(tout, (Cout + 15) / 16 * 16); ep.relu = relu; ep.bias = bias;
+      jobs.push_back({gi, ep});
+    } else {
+      for (int q = 0; q < 4; ++q) {
+        const int gi = e->add_geom(geom_tconv_class(B, Hin, Win, {tin, 0, Cin, 0}, 3, 1, q >> 1, q & 1, Cout, wa));
+        Epi ep = epi_bf16(tout, (Cout + 15) / 16 * 16, q >> 1, q & 1, 2); ep.relu = relu; ep.bias = bias;
+        jobs.push_back({gi, ep});
+      }
+    }
+  } else if (kind == 1) {
+    // x holds dY (B,Cout,Hout,Wout); y receives dX (B,Cin,Hin,Win)
+    int rc = ss_launch_nchw32_to_nhwc16(x, tout.p, B, Cout, Hout, Wout, tout.ld, st);
+    if (rc) return rc;
+    WAddr wa = waddr_conv_dgrad(e, 0);
+    if (!transposed && stride == 1) {
+      const int gi = e->add_geom(geom_conv(B, Hin, Win, {{tout, 0, Cout, 0}}, k, 1, pad, -1, Cin, wa));
+      jobs.push_back({gi, epi_bf16(tin, (Cin + 15) / 16 * 16)});
+    } else if (!transposed) {
+      for (int q = 0; q < 4; ++q) {
+        const int gi = e->add_geom(geom_tconv_class(B, Hout, Wout, {tout, 0, Cout, 0}, 3, 1, q >> 1, q & 1, Cin, wa));
+        jobs.push_back({gi, epi_bf16(tin, (Cin + 15) / 16 * 16, q >> 1, q & 1, 2)});
+      }
+    } else {
+      const int gi = e->add_geom(geom_conv(B, Hin, Win, {{tout, 0, Cout, 0}}, 3, 2, 1, +1, Cin, wa));
+      jobs.push_back({gi, epi_bf16(tin, (Cin + 15) / 16 * 16)});
+    }
+  } else {
+    // wgrad: x = layer input (B,Cin,Hin,Win), y = dY (B,Cout,Hout,Wout), w <- dW
+    int rc = ss_launch_nchw32_to_nhwc16(x, tin.p, B, Cin, Hin, Win, tin.ld, st);
+    if (!rc) rc = ss_launch_nchw32_to_nhwc16(y, tout.p, B, Cout, Hout, Wout, tout.ld, st);
+    if (rc) return rc;
+    const int64_t wn = (int64_t)Cin * Cout * k * k;
+    cudaMemsetAsync(w, 0, (size_t)wn * sizeof(float), st);
+    if (!transposed) {
+      WAddr wa = waddr_conv_fwd(e, 0);
+      e->add_geom(geom_conv(B, Hout, Wout, {{tin, 0, Cin, 0}}, k, stride, pad, +1, Cout, wa));
+      gt = &tout; gN = Cout;
+    } else {
+      WAddr wa = waddr_conv_dgrad(e, 0);
+      e->add_geom(geom_conv(B, Hin, Win, {{tout, 0, Cout, 0}}, 3, 2, 1, +1, Cin, wa));
+      gt = &tin; gN = Cin;
+    }
+  }
+  // packed weights, plan upload, descriptors
+  e->pack_start.assign(e->geoms.size() + 1, 0);
+  for (size_t i = 0; i < e->geoms.size(); ++i) {
+    ConvGeom& g = e->geoms[i];
+    const int64_t elems = (int64_t)g.Npad * g.nslabs * SS_SLAB;
+    g.wp = (bf16*)e->alloc(elems * sizeof(bf16));
+    e->pack_start[i + 1] = e->pack_start[i] + (int)((elems + 255) / 256);
+  }
+  if (e->cursor > scratch_bytes) { ss_set_error("sshslie_conv2d: scratch overflow"); return SSHSLIE_ERR_WORKSPACE; }
+  const size_t msz = ss_umma_maps_size();
+  e->maps_blob.assign(e->geoms.size() * msz, 0);
+  for (size_t i = 0; i < e->geoms.size(); ++i) {
+    if (impl == 1) {
+      if (!ss_umma_supported(e->geoms[i])) { ss_set_error("sshslie_conv2d: shape not taken by the tcgen05 kernel"); return SSHSLIE_ERR_ARG; }
+      int rc = ss_umma_build_maps(e->geoms[i], reinterpret_cast<UmmaMaps*>(e->maps_blob.data() + i * msz));
+      if (rc) return rc;
+      e->geom_umma[i] = 1;
+    }
+  }
+  cudaMemcpyAsync(e->geoms_dev, e->geoms.data(), e->geoms.size() * sizeof(ConvGeom), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(e->pack_start_dev, e->pack_start.data(), e->pack_start.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+  int rc = SSHSLIE_OK;
+  if (kind != 2) {
+    rc = ss_launch_pack_weights(e->geoms_dev, e->pack_start_dev, (int)e->geoms.size(), e->pack_start.back(), w, st);
+    for (size_t j = 0; j < jobs.size() && !rc; ++j) rc = run_gather(e, jobs[j].gi, jobs[j].ep, -1, st);
+    if (!rc) {
+      if (kind == 0) rc = ss_launch_nhwc16_to_nchw32(tout.p, y, B, Cout, Hout, Wout, tout.ld, st);
+      else rc = ss_launch_nhwc16_to_nchw32(tin.p, y, B, Cin, Hin, Win, tin.ld, st);
+    }
+  } else {
+    rc = run_wgrad(e, 0, *gt, gN, 0, 0, 1, st);
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) {   // the plan lives on this stack frame: finish before returning
+    ss_set_error("sshslie_conv2d: %s", cudaGetErrorString(cudaGetLastError()));
+    return SSHSLIE_ERR_CUDA;
+  }
+  return rc;
+}

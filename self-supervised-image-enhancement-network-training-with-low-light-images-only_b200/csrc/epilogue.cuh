@@ -1,0 +1,63 @@
+// Shared GEMM epilogue: 16 consecutive output columns of one GEMM row (= one output pixel).
+// Used identically by the tcgen05 kernel (conv_umma.cu) and the CUDA-core cross-check kernel (conv_simt.cu).
+#pragma once
+#include "common.cuh"
+
+SS_DEVINL void epi_apply16(const Epi& e, int b, int oh, int ow, int n0, int N, float* v /*[16]*/) {
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += (n0 + i < N) ? __ldg(e.bias + n0 + i) : 0.f;
+  }
+  if (e.add) {
+    const bf16* p = e.add + b * e.aB + oh * e.aH + ow * e.aW + n0;
+    float a[16];
+    unpack8(*reinterpret_cast<const uint4*>(p), a);
+    unpack8(*reinterpret_cast<const uint4*>(p + 8), a + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += a[i];
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (e.mask) {
+    const bf16* p = e.mask + b * e.mB + oh * e.mH + ow * e.mW + n0;
+    float m[16];
+    unpack8(*reinterpret_cast<const uint4*>(p), m);
+    unpack8(*reinterpret_cast<const uint4*>(p + 8), m + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (m[i] > 0.f) ? v[i] : 0.f;
+  }
+  if (e.mode == EPI_BF16) {
+    if (n0 >= e.n_store) return;
+    bf16* p = e.out + b * e.oB + oh * e.oH + ow * e.oW + n0;
+    uint4 lo, hi;
+    lo.x = pack2(v[0], v[1]);  lo.y = pack2(v[2], v[3]);  lo.z = pack2(v[4], v[5]);   lo.w = pack2(v[6], v[7]);
+    hi.x = pack2(v[8], v[9]);  hi.y = pack2(v[10], v[11]); hi.z = pack2(v[12], v[13]); hi.w = pack2(v[14], v[15]);
+    *reinterpret_cast<uint4*>(p) = lo;
+    *reinterpret_cast<uint4*>(p + 8) = hi;
+  } else if (e.mode == EPI_HEAD) {
+    const int64_t pix = ((int64_t)b * e.H + oh) * e.W + ow;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int n = n0 + i;
+      const float s = sigmoidf_(v[i]);
+      if (n < e.C) {
+        e.R32[(((int64_t)b * e.C + n) * e.H + oh) * e.W + ow] = s;
+      } else if (n == e.C && e.I32) {
+        e.I32[pix] = s;
+      }
+      v[i] = (n <= e.C) ? s : 0.f;
+    }
+    if (e.RI) {
+      bf16* p = e.RI + pix * e.ri_c + n0;
+      uint4 lo, hi;
+      lo.x = pack2(v[0], v[1]);  lo.y = pack2(v[2], v[3]);  lo.z = pack2(v[4], v[5]);   lo.w = pack2(v[6], v[7]);
+      hi.x = pack2(v[8], v[9]);  hi.y = pack2(v[10], v[11]); hi.z = pack2(v[12], v[13]); hi.w = pack2(v[14], v[15]);
+      *reinterpret_cast<uint4*>(p) = lo;
+      *reinterpret_cast<uint4*>(p + 8) = hi;
+    }
+  } else {  // EPI_PLANE32
+    if (n0 == 0) e.plane32[((int64_t)b * e.H + oh) * e.W + ow] = v[0];
+  }
+}

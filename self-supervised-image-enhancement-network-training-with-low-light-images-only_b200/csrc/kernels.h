@@ -1,0 +1,57 @@
+// Host-callable launchers of every kernel (internal header; the public ABI is include/sshslie_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include "plan.h"
+#include "../../include/sshslie_b200.h"
+
+// conv_simt.cu
+int ss_launch_conv_gather_simt(const ConvGeom* g_dev, const ConvGeom& g_host, const Epi& epi, cudaStream_t st);
+int ss_launch_conv_wgrad_simt(const ConvGeom* g_dev, const ConvGeom& g_host, const bf16* G, int64_t gB, int64_t gH,
+                              int64_t gW, int gN, float* grads, cudaStream_t st);
+int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, cudaStream_t st);
+int ss_launch_pack_weights(const ConvGeom* geoms_dev, const int* block_start_dev, int njobs, int total_blocks,
+                           const float* params, cudaStream_t st);
+
+// conv_umma.cu (tcgen05 / TMEM / TMA)
+struct UmmaMaps;   // host-built CUtensorMaps of one geom (opaque here)
+int ss_umma_supported(const ConvGeom& g);
+int ss_umma_build_maps(const ConvGeom& g, UmmaMaps* maps);     // needs final device pointers
+int ss_launch_conv_gather_umma(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const Epi& epi,
+                               cudaStream_t st);
+int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const bf16* G,
+                              int64_t gB, int64_t gH, int64_t gW, int gN, float* grads, cudaStream_t st);
+size_t ss_umma_maps_size();
+
+// elementwise.cu
+int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st);
+int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, int W, int ldi, cudaStream_t st);
+int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, cudaStream_t st);
+int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
+                          const bf16* a0, bf16* fg, int B, int H, int W, cudaStream_t st);
+int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
+                     cudaStream_t st);
+int ss_launch_s_bwd(const float* dS32, const bf16* dSb, const float* R, const float* I, const float* Id, float* dR32,
+                    float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st);
+int ss_launch_head_bwd(const float* dR32, const float* R32, const bf16* dRI, int ld_dri, const float* dI32,
+                       const float* I32, bf16* dc8, int ld_out, int B, int C, int H, int W, cudaStream_t st);
+int ss_launch_concat_bwd(const bf16* dfg, const bf16* r3, bf16* dr3, bf16* p2, bf16* p1, int B, int H, int W,
+                         cudaStream_t st);
+int ss_launch_pool2(const bf16* du, const bf16* addp, const bf16* maskr, bf16* out_sum, bf16* out_masked, float* out32,
+                    int B, int h, int w, cudaStream_t st);
+int ss_launch_finalize_losses(const float* sums, const sshslie_loss_cfg* cfg_dev, float* losses, int B, int C, int H,
+                              int W, cudaStream_t st);
+
+// attention.cu   (tokens: T = B*L rows of 64 fp32)
+struct AttnBuffers {
+  float *x, *q, *k, *v, *o, *lse, *h, *t32;                  // forward (x = a3 as fp32)
+  float *dq, *dk, *dv, *d_o, *dh, *dx, *Dv;                  // backward scratch
+};
+int ss_attention_forward(const bf16* a3, bf16* t_out, const float* params, const int64_t* poff, AttnBuffers bufs,
+                         int B, int L, cudaStream_t st);
+int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const float* params, float* grads,
+                          const int64_t* poff, AttnBuffers bufs, int B, int L, cudaStream_t st);
+
+// loss.cu / fft_loss.cu / adam.cu : see include/sshslie_b200.h (exported directly)
+int ss_pixel_losses(const float* x, const float* R, const float* I, const float* Id, const float* Re,
+                    const sshslie_loss_cfg& cfg, int B, int C, int H, int W, float* sums, float* dR, float* dI,
+                    float* dId, float* dS, float* dRe, cudaStream_t st);

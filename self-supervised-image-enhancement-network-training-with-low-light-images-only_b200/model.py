@@ -1,0 +1,570 @@
+"""Drop-in replacement for the reference's `model.py` hot path (the nn.Module surface of SURVEY.md §8b).
+
+Same constructor signature, attribute names, state_dict keys, `forward` / `compute_loss` return contract,
+`train_model` / `evaluate_model` / `test_model` / `save_checkpoint` / `load_checkpoint` entry points as
+/root/reference/model.py:177-607.  All arithmetic of forward, loss, backward and Adam runs in the CUDA library
+behind include/sshslie_b200.h; this file is host glue only and has no PyTorch compute fallback.
+
+Differences a caller can observe: parameters live in ONE flat fp32 buffer (each nn.Parameter
+is a view, so `state_dict()` is unchanged); `compute_loss` runs forward AND backward in the same call (the
+returned loss still supports `loss.backward()`, which just hands the finished gradients to autograd);
+`self.optimizer` is a fused single-launch Adam with torch.optim.Adam's state_dict layout.
+"""
+import ctypes
+import os
+import time
+from glob import glob
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lib as L
+
+LOSS_KEYS = ["total_loss", "L_reconstruction", "L_R_fidelity", "L_I_smooth_low", "L_I_smooth_delta",
+             "L_fourier", "L_spectral_cons"]
+
+
+def conv(in_channels, out_channels, kernel_size, stride=1, padding=None, activation=True):
+    """Parameter container with the reference's module structure (model.py:17-23) -> keys '<name>.0.weight'."""
+    if padding is None:
+        padding = (kernel_size - 1) // 2
+    layers = [nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding)]
+    if activation:
+        layers.append(nn.ReLU(inplace=True))
+    return nn.Sequential(*layers)
+
+
+class DecompositionNet(nn.Module):
+    """Parameters of model.py:25-47.  Calling it runs the CUDA forward of the owning LowLightEnhance."""
+
+    def __init__(self, in_channels, channel=64, kernel_size=3):
+        super().__init__()
+        self.in_channels, self.channel, self.kernel_size = in_channels, channel, kernel_size
+        self.conv0 = conv(in_channels, channel // 2, kernel_size, activation=True)
+        self.shallow_conv = conv(in_channels, channel, kernel_size * 3, activation=False)
+        self.conv1 = conv(channel, channel, kernel_size, activation=True)
+        self.conv2 = conv(channel, channel * 2, kernel_size, stride=2, activation=True)
+        self.conv3 = conv(channel * 2, channel * 2, kernel_size, activation=True)
+        self.deconv = nn.Sequential(
+            nn.ConvTranspose2d(channel * 2, channel, kernel_size, stride=2, padding=(kernel_size - 1) // 2,
+                               output_padding=1),
+            nn.ReLU(inplace=True))
+        self.conv5 = conv(channel + channel, channel, kernel_size, activation=True)
+        self.conv7 = conv(channel + channel // 2, channel, kernel_size, activation=False)
+        self.recon = nn.Conv2d(channel, in_channels + 1, kernel_size, stride=1, padding=(kernel_size - 1) // 2)
+        self._owner = None
+
+    def forward(self, x):
+        if self._owner is None:
+            raise L.SshslieError("DecompositionNet must be owned by a LowLightEnhance to run")
+        R, I, _, _ = self._owner[0].forward(x)
+        return R, I
+
+
+class TransformerBlock(nn.Module):
+    """Parameters of model.py:87-97."""
+
+    def __init__(self, channels, num_heads=4, head_dim=16, ff_dim=64):
+        super().__init__()
+        self.num_heads, self.head_dim, self.total_dim = num_heads, head_dim, num_heads * head_dim
+        self.q_linear = nn.Linear(channels, self.total_dim)
+        self.k_linear = nn.Linear(channels, self.total_dim)
+        self.v_linear = nn.Linear(channels, self.total_dim)
+        self.ff_linear1 = nn.Linear(self.total_dim, ff_dim)
+        self.ff_linear2 = nn.Linear(ff_dim, channels)
+
+
+class IllumAdjustmentNet(nn.Module):
+    """Parameters of model.py:121-141 (use_transformer=True, the only configuration any caller builds)."""
+
+    def __init__(self, in_channels, channel=64, kernel_size=3):
+        super().__init__()
+        self.conv0 = conv(in_channels + 1, channel, kernel_size, activation=False)
+        self.conv1 = conv(channel, channel, kernel_size, stride=2, activation=True)
+        self.conv2 = conv(channel, channel, kernel_size, stride=2, activation=True)
+        self.conv3 = conv(channel, channel, kernel_size, stride=2, activation=True)
+        self.attn = TransformerBlock(channel)
+        self.deconv1 = conv(channel, channel, kernel_size, activation=True)
+        self.deconv2 = conv(channel, channel, kernel_size, activation=True)
+        self.deconv3 = conv(channel, channel, kernel_size, activation=True)
+        self.feature_fusion = conv(channel * 3, channel, 1, activation=False)
+        self.final_conv = nn.Conv2d(channel, 1, 3, stride=1, padding=1)
+
+    def forward(self, I, R):
+        raise L.SshslieError("IllumAdjustmentNet alone is not an entry point of the CUDA path; "
+                             "call LowLightEnhance.forward (model.py:229-234)")
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam (defaults) over the owner's flat buffers: one kernel launch per step (model.py:213,316).
+
+    `state_dict()` has torch.optim.Adam's layout: per-parameter 'step', 'exp_avg', 'exp_avg_sq' (views of the
+    flat moment buffers), so reference checkpoints load and ours load in the reference.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, owner=None):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+        self._owner = [owner]
+        self._step = 0
+        self.grad_scale = 1.0
+
+    def _ensure_state(self):
+        own = self._owner[0]
+        own._ensure_flat()
+        if own._flat_m is None or own._flat_m.device != own._flat.device:
+            own._flat_m = torch.zeros_like(own._flat)
+            own._flat_v = torch.zeros_like(own._flat)
+        for p, (off, n) in zip(own._plist, own._pranges):
+            st = self.state[p]
+            if "exp_avg" not in st or st["exp_avg"].data_ptr() != own._flat_m.data_ptr() + 4 * off:
+                if "exp_avg" in st:   # loaded from a checkpoint: copy into the flat buffers
+                    own._flat_m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    own._flat_v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    self._step = max(self._step, int(st.get("step", 0)))
+                st["exp_avg"] = own._flat_m[off:off + n].view(p.shape)
+                st["exp_avg_sq"] = own._flat_v[off:off + n].view(p.shape)
+            st["step"] = torch.tensor(float(self._step))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        own = self._owner[0]
+        self._ensure_state()
+        self._step += 1
+        group = self.param_groups[0]
+        # contiguous ranges of parameters that received a gradient (frozen decomposition_net -> only the tail)
+        ranges = []
+        for p, (off, n) in zip(own._plist, own._pranges):
+            if p.grad is None:
+                continue
+            if p.grad.data_ptr() != own._flat_grad.data_ptr() + 4 * off:
+                own._flat_grad[off:off + n].copy_(p.grad.reshape(-1))
+            if ranges and ranges[-1][1] == off:
+                ranges[-1][1] = off + n
+            else:
+                ranges.append([off, off + n])
+        lib = L.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(own._flat.device).cuda_stream)
+        b1, b2 = group["betas"]
+        for lo, hi in ranges:
+            L.check(lib.sshslie_adam_step(
+                ctypes.c_void_p(own._flat.data_ptr() + 4 * lo), ctypes.c_void_p(own._flat_grad.data_ptr() + 4 * lo),
+                ctypes.c_void_p(own._flat_m.data_ptr() + 4 * lo), ctypes.c_void_p(own._flat_v.data_ptr() + 4 * lo),
+                hi - lo, float(group["lr"]), float(b1), float(b2), float(group["eps"]), self._step,
+                float(self.grad_scale), stream), "sshslie_adam_step")
+        for p in own._plist:
+            self.state[p]["step"] = torch.tensor(float(self._step))
+        return None
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._step = 0
+        for st in self.state.values():
+            if "step" in st:
+                self._step = max(self._step, int(st["step"]))
+        self._ensure_state()
+
+
+class _LossFn(torch.autograd.Function):
+    """Forward runs compute_loss AND backward on the GPU; backward returns the finished gradient views."""
+
+    @staticmethod
+    def forward(ctx, owner_box, *params):
+        own = owner_box[0]
+        ctx.owner_box = owner_box
+        ctx.need = [p.requires_grad for p in params]
+        return own._losses_dev[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        own = ctx.owner_box[0]
+        grads = []
+        unit = None
+        for need, (off, n), p in zip(ctx.need, own._pranges, own._plist):
+            if not need:
+                grads.append(None)
+                continue
+            g = own._flat_grad[off:off + n].view(p.shape)
+            grads.append(g)
+        if gout is not None:
+            unit = float(gout) if gout.numel() == 1 and not gout.is_cuda else None
+            if unit is None:
+                unit = float(gout.item())
+            if unit != 1.0:
+                grads = [None if g is None else g * unit for g in grads]
+        return (None, *grads)
+
+
+class LazyLosses(dict):
+    """dict[str, float] whose values are read back from the device (one sync) on first access."""
+
+    def __init__(self, dev_tensor):
+        super().__init__()
+        self._dev = dev_tensor
+        self._ready = False
+
+    def _sync(self):
+        if not self._ready:
+            vals = self._dev.detach().cpu().tolist()
+            for k, v in zip(LOSS_KEYS, vals):
+                dict.__setitem__(self, k, v)
+            self._ready = True
+
+    def __getitem__(self, k):
+        self._sync()
+        return dict.__getitem__(self, k)
+
+    def keys(self):
+        self._sync()
+        return dict.keys(self)
+
+    def items(self):
+        self._sync()
+        return dict.items(self)
+
+    def values(self):
+        self._sync()
+        return dict.values(self)
+
+    def __iter__(self):
+        self._sync()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        return len(LOSS_KEYS)
+
+    def __repr__(self):
+        self._sync()
+        return dict.__repr__(self)
+
+
+class _Engine:
+    """One bound sshslie_engine + its workspace and static I/O buffers for a (B, H, W, train) shape."""
+
+    def __init__(self, device, B, C, H, W, train, force_simt=False):
+        lib = L.load()
+        self.B, self.C, self.H, self.W, self.train = B, C, H, W, train
+        self.handle = ctypes.c_void_p()
+        flags = (L.FLAG_TRAIN if train else 0) | (L.FLAG_FORCE_SIMT if force_simt else 0)
+        L.check(lib.sshslie_engine_create(ctypes.byref(self.handle), B, C, H, W, flags), "sshslie_engine_create")
+        nbytes = lib.sshslie_engine_workspace_bytes(self.handle)
+        self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        L.check(lib.sshslie_engine_bind(self.handle, ctypes.c_void_p(base), nbytes, stream), "sshslie_engine_bind")
+        self.x = torch.empty(B, C, H, W, device=device)
+        self.R = torch.empty(B, C, H, W, device=device)
+        self.I = torch.empty(B, 1, H, W, device=device)
+        self.Id = torch.empty(B, 1, H, W, device=device)
+        self.S = torch.empty(B, C, H, W, device=device)
+        self.graph = None
+        self.calls = 0
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.load().sshslie_engine_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class LowLightEnhance(nn.Module):
+    def __init__(self, input_channels=64, lr=1e-3, lr_update_factor=1, lr_update_period=None, time_stamp=None,
+                 c_loss_reconstruction=10, c_loss_r_fidelity=1, c_loss_i_smooth_low=1, c_loss_i_smooth_delta=20,
+                 c_loss_fourier=0.2, c_loss_spectral_cons=1, alpha_i_smooth_low=1, alpha_i_smooth_delta=10,
+                 device=torch.device("cpu"), global_min=None, global_max=None,
+                 save_reflectance=False, save_illumination=False, save_i_delta=False):
+        super().__init__()
+        if input_channels != 64:
+            raise L.SshslieError("the CUDA path is built for 64 spectral bands (every reference config)")
+        self.input_channels = input_channels
+        self.device = device
+        self.time_stamp = time_stamp
+        self.c_loss_reconstruction = c_loss_reconstruction
+        self.c_loss_r_fidelity = c_loss_r_fidelity
+        self.c_loss_i_smooth_low = c_loss_i_smooth_low
+        self.c_loss_i_smooth_delta = c_loss_i_smooth_delta
+        self.c_loss_fourier = c_loss_fourier
+        self.c_loss_spectral_cons = c_loss_spectral_cons
+        self.alpha_i_smooth_low = alpha_i_smooth_low
+        self.alpha_i_smooth_delta = alpha_i_smooth_delta
+        self.lr = lr
+        self.lr_update_factor = lr_update_factor
+        self.lr_update_period = lr_update_period
+        self.adaptive_lr = abs(self.lr_update_factor - 1) > 1e-6          # model.py:207-208
+        self.global_min, self.global_max = global_min, global_max
+        self.save_reflectance = save_reflectance
+        self.save_illumination = save_illumination
+        self.save_i_delta = save_i_delta
+        self.eval_metrics = {}
+
+        self.decomposition_net = DecompositionNet(in_channels=input_channels)
+        self.illum_adjust_net = IllumAdjustmentNet(in_channels=input_channels)
+        self.decomposition_net._owner = [self]
+
+        self._plist = list(self.parameters())
+        total, offs, sizes = L.param_table(input_channels)
+        assert len(self._plist) == L.NUM_PARAM_TENSORS and [p.numel() for p in self._plist] == sizes
+        self._pranges = list(zip(offs, sizes))
+        self._nparams = total
+        self._flat = self._flat_grad = self._flat_m = self._flat_v = None
+        self._engines = {}
+        self._losses_dev = None
+        self.use_cuda_graph = True
+        self.force_simt = False
+        self.dp_group = None                 # set by enable_data_parallel()
+        self._box = [self]
+
+        self.optimizer = FusedAdam(self.parameters(), lr=self.lr, owner=self)
+        self.freeze_decom_epochs = 0
+        if self.adaptive_lr:
+            self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=self.lr_update_period,
+                                                             gamma=self.lr_update_factor)
+        self.all_epoch_losses = {k: [] for k in LOSS_KEYS}
+
+    # ------------------------------------------------------------------ flat parameter storage
+    def _ensure_flat(self):
+        p0 = self._plist[0]
+        ok = (self._flat is not None and self._flat.device == p0.device
+              and p0.data_ptr() == self._flat.data_ptr()
+              and self._plist[-1].data_ptr() == self._flat.data_ptr() + 4 * self._pranges[-1][0])
+        if ok:
+            return
+        if not p0.is_cuda:
+            raise L.SshslieError("LowLightEnhance parameters must be on a CUDA device (call .to('cuda')); "
+                                 "there is no CPU implementation of the hot path")
+        with torch.no_grad():
+            flat = torch.empty(self._nparams, dtype=torch.float32, device=p0.device)
+            for p, (off, n) in zip(self._plist, self._pranges):
+                flat[off:off + n].copy_(p.detach().reshape(-1).float())
+                p.data = flat[off:off + n].view(p.shape)
+        self._flat = flat
+        self._flat_grad = torch.zeros_like(flat)
+        self._losses_dev = torch.zeros(8, dtype=torch.float32, device=p0.device)
+        self._engines = {}
+
+    def _cfg(self):
+        return L.LossCfg(float(self.c_loss_reconstruction), float(self.c_loss_r_fidelity),
+                         float(self.c_loss_i_smooth_low), float(self.c_loss_i_smooth_delta),
+                         float(self.c_loss_fourier), float(self.c_loss_spectral_cons),
+                         float(self.alpha_i_smooth_low), float(self.alpha_i_smooth_delta))
+
+    def _engine(self, x, train):
+        B, C, H, W = x.shape
+        key = (B, C, H, W, train, self.force_simt)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _Engine(self._flat.device, B, C, H, W, train, self.force_simt)
+            self._engines[key] = eng
+        return eng
+
+    def _stage_input(self, eng, x):
+        if x.dtype != torch.float32:
+            x = x.float()
+        eng.x.copy_(x, non_blocking=True)      # H2D (or D2D) into the engine's static input buffer
+
+    # ------------------------------------------------------------------ hot path
+    def forward(self, input_low):
+        """model.py:229-234 -> (R_low, I_low, I_delta, S), fp32 (N,C,H,W)/(N,1,H,W) on the module's device."""
+        self._ensure_flat()
+        eng = self._engine(input_low, train=False)
+        self._stage_input(eng, input_low)
+        lib = L.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)
+        L.check(lib.sshslie_forward(eng.handle, L.ptr(eng.x), L.ptr(self._flat), L.ptr(eng.R), L.ptr(eng.I),
+                                    L.ptr(eng.Id), L.ptr(eng.S), stream), "sshslie_forward")
+        return eng.R, eng.I, eng.Id, eng.S
+
+    def _launch_loss_and_grad(self, eng, phase_mask=3):
+        lib = L.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)
+        cfg = self._cfg()
+        L.check(lib.sshslie_loss_and_grad(eng.handle, L.ptr(eng.x), L.ptr(self._flat), ctypes.byref(cfg),
+                                          L.ptr(self._flat_grad), L.ptr(self._losses_dev), L.ptr(eng.R),
+                                          L.ptr(eng.I), L.ptr(eng.Id), L.ptr(eng.S), phase_mask, stream),
+                "sshslie_loss_and_grad")
+
+    def compute_loss(self, input_low):
+        """model.py:544-575 -> (total_loss 0-dim tensor supporting .backward(), dict of 7 floats)."""
+        self._ensure_flat()
+        eng = self._engine(input_low, train=True)
+        self._stage_input(eng, input_low)
+        dp = self.dp_group is not None
+        if dp:
+            self._dp_step(eng)
+        elif self.use_cuda_graph:
+            eng.calls += 1
+            if eng.graph is None and eng.calls >= 3:       # two eager warm-up steps, then capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_loss_and_grad(eng)
+                eng.graph = g
+            if eng.graph is not None:
+                eng.graph.replay()
+            else:
+                self._launch_loss_and_grad(eng)
+        else:
+            self._launch_loss_and_grad(eng)
+        self.last_outputs = (eng.R, eng.I, eng.Id, eng.S)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._plist):
+            total = _LossFn.apply(self._box, *self._plist)
+        else:
+            total = self._losses_dev[0].clone()
+        return total, LazyLosses(self._losses_dev[:7].clone())
+
+    # ------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, group=None):
+        """Average gradients over `group` (NCCL) inside compute_loss; the illum_adjust_net bucket is reduced
+        while the first-pass decomposition backward still runs (phase split of sshslie_loss_and_grad)."""
+        import torch.distributed as dist
+        self.dp_group = group if group is not None else dist.group.WORLD
+        self._dp_world = dist.get_world_size(self.dp_group)
+        self._dp_stream = torch.cuda.Stream(device=self._plist[0].device)
+        # identical weights on every rank
+        self._ensure_flat()
+        dist.broadcast(self._flat, src=dist.get_global_rank(self.dp_group, 0), group=self.dp_group)
+
+    def _dp_step(self, eng):
+        import torch.distributed as dist
+        n_dec = self._pranges[18][0]                 # first illum_adjust_net parameter (decomposition has 9x2 tensors)
+        cur = torch.cuda.current_stream(self._flat.device)
+        self._launch_loss_and_grad(eng, phase_mask=1)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        with torch.cuda.stream(self._dp_stream):
+            self._dp_stream.wait_event(ev)
+            dist.all_reduce(self._flat_grad[n_dec:], group=self.dp_group)     # bucket 1: illum_adjust_net
+        self._launch_loss_and_grad(eng, phase_mask=2)
+        dist.all_reduce(self._flat_grad[:n_dec], group=self.dp_group)          # bucket 2: decomposition_net
+        cur.wait_stream(self._dp_stream)
+        self._flat_grad.mul_(1.0 / self._dp_world)
+        dist.all_reduce(self._losses_dev, group=self.dp_group)
+        self._losses_dev.mul_(1.0 / self._dp_world)
+
+    # ------------------------------------------------------------------ loops (host glue, model.py:236-443)
+    def train_model(self, train_data_path, eval_data_path, batch_size, patch_size, num_epochs, start_lr, ckpt_dir,
+                    eval_result_dir, eval_every_epoch, label_dir, plot_every_epoch=10):
+        from .utils import load_hsi, data_augmentation
+        ckpt_dir = os.path.join(ckpt_dir, 'Decomposition_' + str(self.time_stamp))
+        os.makedirs(ckpt_dir, exist_ok=True)
+        os.makedirs(eval_result_dir, exist_ok=True)
+        train_files = sorted(glob(os.path.join(train_data_path, "*.mat")))
+        train_low_data = [load_hsi(f, matContentHeader='data', normalization='global_normalization',
+                                   max_val=self.global_max, min_val=self.global_min) for f in train_files]
+        eval_files = sorted(glob(os.path.join(eval_data_path, "*.mat")))
+        eval_low_data = [load_hsi(f, matContentHeader='data', normalization='global_normalization',
+                                  max_val=self.global_max, min_val=self.global_min) for f in eval_files]
+        num_batches = len(train_low_data) // batch_size
+        dev = self._plist[0].device
+        pinned = torch.empty(batch_size, self.input_channels, patch_size, patch_size).pin_memory()
+        for epoch in range(num_epochs):
+            if getattr(self, 'freeze_decom_epochs', 0) > 0:
+                if epoch < self.freeze_decom_epochs:
+                    for p in self.decomposition_net.parameters():
+                        p.requires_grad = False
+                    print(f"Epoch {epoch+1}: DecompositionNet frozen")
+                elif epoch == self.freeze_decom_epochs:
+                    for p in self.decomposition_net.parameters():
+                        p.requires_grad = True
+                    self.optimizer = FusedAdam(self.parameters(), lr=self.optimizer.param_groups[0]['lr'], owner=self)
+                    self._flat_m = None
+                    if self.adaptive_lr:
+                        self.scheduler = torch.optim.lr_scheduler.StepLR(
+                            self.optimizer, step_size=self.lr_update_period, gamma=self.lr_update_factor)
+                    print(f"Epoch {epoch+1}: DecompositionNet unfrozen")
+            cur = {k: 0 for k in LOSS_KEYS}
+            count = 0
+            for batch_id in range(num_batches):
+                batch = np.zeros((batch_size, patch_size, patch_size, self.input_channels), dtype=np.float32)
+                for i in range(batch_size):
+                    idx = (batch_id * batch_size + i) % len(train_low_data)
+                    h, w, _ = train_low_data[idx].shape
+                    x = np.random.randint(0, h - patch_size)
+                    y = np.random.randint(0, w - patch_size)
+                    mode = np.random.randint(0, 8)
+                    batch[i] = data_augmentation(train_low_data[idx][x:x + patch_size, y:y + patch_size, :], mode)
+                pinned.copy_(torch.from_numpy(batch).permute(0, 3, 1, 2))
+                self.optimizer.zero_grad()
+                loss, batch_losses = self.compute_loss(pinned if dev.type == 'cuda' else pinned.to(dev))
+                loss.backward()
+                self.optimizer.step()
+                for k in LOSS_KEYS:
+                    cur[k] += batch_losses[k]
+                count += 1
+                print(f"Epoch [{epoch+1}/{num_epochs}] Batch [{batch_id+1}/{num_batches}] "
+                      f"Loss: {batch_losses['total_loss']:.6f}")
+            for k in LOSS_KEYS:
+                self.all_epoch_losses[k].append(cur[k] / count if count > 0 else 0)
+            avg = cur['total_loss'] / count if count > 0 else 0
+            if (epoch + 1) % eval_every_epoch == 0:
+                self.evaluate_model(eval_low_data, eval_files, eval_result_dir, epoch + 1, label_dir)
+                self.save_checkpoint(os.path.join(ckpt_dir, f"model_epoch_{epoch+1}.pth"), epoch + 1)
+                self.save_checkpoint(os.path.join(ckpt_dir, "model_epoch_latest.pth"), epoch + 1)
+            if self.adaptive_lr:
+                self.scheduler.step()
+            print(f"Epoch [{epoch+1}/{num_epochs}] Average Loss: {avg:.6f}")
+
+    def _save_outputs(self, out_dir, filename, R, I, Id, S, save_r, save_i, save_d):
+        from .utils import save_hsi
+        S_np = S.squeeze(0).permute(1, 2, 0).cpu().numpy()
+        if self.global_min is not None and self.global_max is not None:
+            S_np = S_np * (self.global_max - self.global_min) + self.global_min        # model.py:423-424
+        save_hsi(os.path.join(out_dir, filename), S_np)
+        art = os.path.join(out_dir, 'artifacts')
+        os.makedirs(art, exist_ok=True)
+        stem = filename.split('.')[0]
+        if save_r:
+            save_hsi(os.path.join(art, stem + '_R_low.mat'), R.squeeze(0).permute(1, 2, 0).cpu().numpy())
+        if save_i:
+            save_hsi(os.path.join(art, stem + '_I_low.mat'), I.squeeze(0).permute(1, 2, 0).cpu().numpy())
+        if save_d:
+            save_hsi(os.path.join(art, stem + '_I_delta.mat'), Id.squeeze(0).permute(1, 2, 0).cpu().numpy())
+
+    def evaluate_model(self, eval_low_data, eval_files, eval_result_dir, epoch, label_dir):
+        if len(eval_low_data) <= 0:
+            print(f"--- No files found for evaluation. Skipping evaluation for epoch {epoch} ---")
+            return
+        epoch_dir = os.path.join(eval_result_dir, f'epoch_{epoch}')
+        os.makedirs(epoch_dir, exist_ok=True)
+        with torch.no_grad():
+            for idx, low_im in enumerate(eval_low_data):
+                x = torch.from_numpy(low_im).unsqueeze(0).permute(0, 3, 1, 2)
+                R, I, Id, S = self.forward(x)
+                self._save_outputs(epoch_dir, os.path.basename(eval_files[idx]), R, I, Id, S,
+                                   self.save_reflectance, self.save_illumination, self.save_i_delta)
+
+    def test_model(self, model_dir, test_low_data, test_low_data_names, save_dir, save_reflectance=False,
+                   save_illumination=False, save_i_delta=False):
+        self.load_checkpoint(os.path.join(model_dir, 'model_epoch_latest.pth'))
+        total = 0.0
+        with torch.no_grad():
+            for idx in range(len(test_low_data)):
+                filename = os.path.basename(test_low_data_names[idx])
+                x = torch.from_numpy(test_low_data[idx]).unsqueeze(0).permute(0, 3, 1, 2)
+                torch.cuda.synchronize()
+                t0 = time.time()
+                R, I, Id, S = self.forward(x)
+                torch.cuda.synchronize()                      # the reference's timer lacks this
+                rt = time.time() - t0
+                total += rt
+                self._save_outputs(save_dir, filename, R, I, Id, S, save_reflectance, save_illumination,
+                                   save_i_delta)
+                print(f"Processed {filename} in {rt:.4f} seconds.")
+        n = len(test_low_data)
+        print(f"Average run time: {total / n if n else 0:.4f} seconds.")
+
+    def save_checkpoint(self, path, epoch):
+        self.optimizer._ensure_state()
+        torch.save({'epoch': epoch, 'model_state_dict': self.state_dict(),
+                    'optimizer_state_dict': self.optimizer.state_dict()}, path)
+        print(f"Checkpoint saved at {path}")
+
+    def load_checkpoint(self, path):
+        ckpt = torch.load(path, map_location=self._plist[0].device)
+        self.load_state_dict(ckpt['model_state_dict'])
+        self.optimizer.load_state_dict(ckpt['optimizer_state_dict'])
+        print(f"Loaded checkpoint from {path}")

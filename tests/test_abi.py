@@ -1,0 +1,77 @@
+"""CPU-side checks of the C-ABI boundary (no GPU): the library loads, exports every symbol the header declares,
+the flat parameter table matches the reference's state_dict, host-only entry points behave, errors are loud."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import sshslie_b200 as S
+from oracle import sshslie_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sshslie_b200.h")).read()
+    declared = sorted(set(re.findall(r"SSHSLIE_API\s+[\w\s\*]+?\b(sshslie_\w+)\s*\(", header)))
+    assert declared == sorted(S.lib.EXPORTS)
+    lib = S.lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sshslie_version() >= 100
+
+
+def test_param_table_is_reference_state_dict_order():
+    total, offs, sizes = S.lib.param_table(64)
+    p = O.init_params(41)
+    assert total == 1141922 == sum(v.numel() for v in p.values())
+    assert sizes == [v.numel() for v in p.values()]
+    assert offs == [sum(sizes[:i]) for i in range(len(sizes))]
+
+
+def test_module_surface_matches_reference():
+    torch.manual_seed(41)
+    m = S.LowLightEnhance(input_channels=64, lr=1e-3, lr_update_factor=0.1, lr_update_period=250)
+    sd = m.state_dict()
+    ref = O.init_params(41)
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert torch.equal(sd[k], ref[k]), k                      # same seed -> same init as the reference
+    assert hasattr(m, "scheduler") and m.adaptive_lr
+    for attr in ("decomposition_net", "illum_adjust_net", "optimizer", "freeze_decom_epochs", "eval_metrics",
+                 "all_epoch_losses", "train_model", "test_model", "evaluate_model", "save_checkpoint",
+                 "load_checkpoint", "compute_loss", "forward"):
+        assert hasattr(m, attr), attr
+    osd = m.optimizer.state_dict()
+    assert set(osd.keys()) == {"state", "param_groups"} and osd["param_groups"][0]["lr"] == 1e-3
+
+
+def test_engine_plan_is_host_only():
+    lib = S.lib.load()
+    h = ctypes.c_void_p()
+    assert lib.sshslie_engine_create(ctypes.byref(h), 2, 64, 128, 128, S.lib.FLAG_TRAIN) == 0
+    train_bytes = lib.sshslie_engine_workspace_bytes(h)
+    lib.sshslie_engine_destroy(h)
+    assert lib.sshslie_engine_create(ctypes.byref(h), 1, 64, 512, 512, 0) == 0
+    infer_bytes = lib.sshslie_engine_workspace_bytes(h)
+    lib.sshslie_engine_destroy(h)
+    assert 50e6 < train_bytes < 2e9 and 100e6 < infer_bytes < 8e9
+
+
+@pytest.mark.parametrize("args", [(2, 32, 128, 128, 0), (2, 64, 130, 128, 0), (0, 64, 128, 128, 0),
+                                  (1, 64, 256, 256, S.lib.FLAG_TRAIN)])
+def test_engine_rejects_unsupported_shapes(args):
+    lib = S.lib.load()
+    h = ctypes.c_void_p()
+    assert lib.sshslie_engine_create(ctypes.byref(h), *args) == -1
+    assert b"sshslie_engine_create" in lib.sshslie_last_error()
+
+
+def test_cpu_tensors_fail_loudly():
+    m = S.LowLightEnhance()
+    with pytest.raises(S.lib.SshslieError):
+        m.compute_loss(torch.rand(1, 64, 32, 32))
+    with pytest.raises(S.lib.SshslieError):
+        m.illum_adjust_net(torch.rand(1, 1, 8, 8), torch.rand(1, 64, 8, 8))

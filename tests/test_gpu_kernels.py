@@ -1,0 +1,195 @@
+"""Kernel-level parity (-m gpu): each CUDA kernel, called through the C-ABI, against a plain PyTorch fp32
+reference of the same op / the CPU oracle.  Tolerances are stated per test."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CONV_CASES = [
+    # (name, Cin, Cout, k, stride, transposed, H, W, B)
+    ("c3_64_64", 64, 64, 3, 1, False, 32, 32, 2),
+    ("c3_64_32", 64, 32, 3, 1, False, 32, 32, 1),
+    ("c9_64_64", 64, 64, 9, 1, False, 32, 32, 1),
+    ("c3s2_64_128", 64, 128, 3, 2, False, 32, 32, 2),
+    ("c3_128_128", 128, 128, 3, 1, False, 16, 16, 2),
+    ("tc3_128_64", 128, 64, 3, 2, True, 16, 16, 2),
+    ("c3_96_64", 96, 64, 3, 1, False, 32, 32, 1),
+    ("c3_64_65", 64, 65, 3, 1, False, 32, 32, 1),
+    ("c3_65_64", 65, 64, 3, 1, False, 32, 32, 1),
+    ("c1_192_64", 192, 64, 1, 1, False, 32, 32, 1),
+    ("c3_64_1", 64, 1, 3, 1, False, 32, 32, 1),
+    ("c3_64_64_full", 64, 64, 3, 1, False, 128, 128, 1),
+]
+
+
+def _ref_conv(x, w, b, k, stride, transposed, relu):
+    if transposed:
+        y = F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1)
+    else:
+        y = F.conv2d(x, w, b, stride=stride, padding=(k - 1) // 2)
+    return F.relu(y) if relu else y
+
+
+def _mk(case, seed=0):
+    from gpu_util import bf16_round
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = bf16_round(torch.randn(B, Cin, H, W, generator=g)).cuda()
+    wshape = (Cin, Cout, k, k) if tr else (Cout, Cin, k, k)
+    w = bf16_round(torch.randn(wshape, generator=g) * (1.0 / (Cin * k * k) ** 0.5)).cuda()
+    b = torch.randn(Cout, generator=g).cuda() * 0.1
+    return x, w, b
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_forward(case, impl):
+    """bf16 operands (pre-rounded, so exact), fp32 accumulate, bf16 output: |err| <= 2^-8 relative + 1e-3."""
+    from gpu_util import conv2d
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    x, w, b = _mk(case)
+    ref = _ref_conv(x, w, b, k, stride, tr, relu=True)
+    y = torch.empty_like(ref)
+    conv2d(0, impl, tr, x, w, b, y, B, Cin, Cout, H, W, k, stride, relu=True)
+    torch.testing.assert_close(y, ref, rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES[:8], ids=[c[0] for c in CONV_CASES[:8]])
+def test_conv_dgrad(case, impl):
+    from gpu_util import conv2d, bf16_round
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    x, w, b = _mk(case)
+    x.requires_grad_(True)
+    yref = _ref_conv(x, w, None, k, stride, tr, relu=False)
+    dy = bf16_round(torch.randn(yref.shape, generator=torch.Generator().manual_seed(3))).cuda()
+    (dx_ref,) = torch.autograd.grad(yref, x, dy)
+    dx = torch.empty_like(dx_ref)
+    conv2d(1, impl, tr, dy, w, None, dx, B, Cin, Cout, H, W, k, stride, relu=False)
+    torch.testing.assert_close(dx, dx_ref, rtol=2 ** -7, atol=2e-3 * float(dx_ref.abs().max()))
+
+
+@pytest.mark.parametrize("case", CONV_CASES[:8], ids=[c[0] for c in CONV_CASES[:8]])
+def test_conv_wgrad(case):
+    """fp32 output, bf16 operands: only summation order differs -> rtol 1e-3 of the largest entry."""
+    from gpu_util import conv2d, bf16_round
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    x, w, b = _mk(case)
+    w.requires_grad_(True)
+    yref = _ref_conv(x, w, None, k, stride, tr, relu=False)
+    dy = bf16_round(torch.randn(yref.shape, generator=torch.Generator().manual_seed(5))).cuda()
+    (dw_ref,) = torch.autograd.grad(yref, w, dy)
+    dw = torch.zeros_like(dw_ref)
+    conv2d(2, 0, tr, x.detach(), dw, None, dy, B, Cin, Cout, H, W, k, stride, relu=False)
+    torch.testing.assert_close(dw, dw_ref, rtol=1e-3, atol=1e-3 * float(dw_ref.abs().max()))
+
+
+def _loss_inputs(B, C, H, W, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, C, H, W, generator=g) * 0.3
+    R = torch.rand(B, C, H, W, generator=g)
+    Re = (R + 0.05 * torch.randn(B, C, H, W, generator=g)).clamp(0, 1)
+    I = torch.rand(B, 1, H, W, generator=g)
+    Id = torch.randn(B, 1, H, W, generator=g) * 0.3
+    return x, R, I, Id, Re
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 16, 24), (2, 64, 32, 32), (2, 64, 128, 128)])
+def test_pixel_losses(shape):
+    """fp32 kernel vs oracle autograd on identical inputs: sums rel 2e-5; gradients 1e-5 of their max + exact zeros."""
+    from gpu_util import cfg_struct, stream
+    from oracle import sshslie_oracle as O
+    import sshslie_b200 as S
+    B, C, H, W = shape
+    coef = O.JYU_COEF
+    x, R, I, Id, Re = _loss_inputs(B, C, H, W)
+    leaves = [t.clone().requires_grad_(True) for t in (R, I, Id, Re)]
+    Rl, Il, Idl, Rel = leaves
+    Sl = Rl * Idl + Rl * Il
+    Sl.retain_grad()
+    L_rec = torch.mean(torch.abs(Rl * Il - x))
+    L_Ilow, L_Rfid = O.structure_aware_loss(Rl, Il, Rel, coef["alpha_i_smooth_low"], 0.5)
+    L_Idel = O.smooth_loss(Idl, Rl, coef["alpha_i_smooth_delta"])
+    L_spec = O.spectral_smoothness_loss(Sl)
+    # gradients of the five terms w.r.t. R, I, Id, Re with S treated as an independent leaf (as the kernel does)
+    S_leaf = Sl.detach().clone().requires_grad_(True)
+    total = (coef["c_loss_reconstruction"] * L_rec + coef["c_loss_r_fidelity"] * L_Rfid
+             + coef["c_loss_i_smooth_low"] * L_Ilow + coef["c_loss_i_smooth_delta"] * L_Idel)
+    gR, gI, gId, gRe = torch.autograd.grad(total, leaves, allow_unused=True)
+    (gS,) = torch.autograd.grad(coef["c_loss_spectral_cons"] * O.spectral_smoothness_loss(S_leaf), S_leaf)
+    lib = S.lib.load()
+    dev = [t.cuda().contiguous() for t in (x, R, I, Id, Re)]
+    sums = torch.zeros(16, device="cuda")
+    outs = [torch.empty_like(dev[1]), torch.empty_like(dev[2]), torch.empty_like(dev[3]), torch.empty_like(dev[1]),
+            torch.empty_like(dev[4])]
+    cfg = cfg_struct(coef)
+    S.lib.check(lib.sshslie_pixel_losses(S.lib.ptr(dev[0]), S.lib.ptr(dev[1]), S.lib.ptr(dev[2]), S.lib.ptr(dev[3]),
+                                         None, S.lib.ptr(dev[4]), ctypes.byref(cfg), B, C, H, W, S.lib.ptr(sums),
+                                         S.lib.ptr(outs[0]), S.lib.ptr(outs[1]), S.lib.ptr(outs[2]),
+                                         S.lib.ptr(outs[3]), S.lib.ptr(outs[4]), stream()), "pixel_losses")
+    torch.cuda.synchronize()
+    s = sums.cpu().double()
+    n0 = B * C * H * W
+    nx1, ny1 = B * H * (W - 1), B * (H - 1) * W
+    np.testing.assert_allclose(float(s[0] / n0), float(L_rec), rtol=2e-5)
+    np.testing.assert_allclose(float(s[1] / nx1 + s[2] / ny1), float(L_Ilow), rtol=2e-5)
+    np.testing.assert_allclose(float(s[3] / n0 + 0.5 * (s[4] / (nx1 * C) + s[5] / (ny1 * C))), float(L_Rfid), rtol=2e-5)
+    np.testing.assert_allclose(float(s[6] / (nx1 * C) + s[7] / (ny1 * C)), float(L_Idel), rtol=2e-5)
+    np.testing.assert_allclose(float(s[8] / (B * (C - 1) * H * W)), float(L_spec), rtol=2e-5)
+    for name, got, ref in [("dR", outs[0], gR), ("dI", outs[1], gI), ("dId", outs[2], gId), ("dS", outs[3], gS),
+                           ("dRe", outs[4], gRe)]:
+        ref = ref.cuda()
+        tol = 2e-5 * float(ref.abs().max())
+        bad = (got - ref).abs() > tol
+        # sign() flips where a difference is within fp32 noise of 0 are legitimate: allow a 1e-4 fraction
+        assert bad.float().mean().item() < 1e-4, (name, bad.float().mean().item(), tol)
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 32), (4, 64, 128), (6, 128, 128)])
+def test_fourier_loss(shape):
+    """Shared-memory FFT loss + gradient vs torch.fft autograd: value rel 2e-5, gradient 2e-4 of its max."""
+    from gpu_util import stream
+    from oracle import sshslie_oracle as O
+    import sshslie_b200 as S
+    n, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(1, n, H, W, generator=g) * 0.3
+    s = (torch.rand(1, n, H, W, generator=g) * 0.5).requires_grad_(True)
+    loss = O.fourier_spectrum_loss(x, s)
+    (gs,) = torch.autograd.grad(loss, s)
+    mask = O.fourier_mask(H, W).cuda().contiguous()
+    xd, sd = x.cuda().contiguous(), s.detach().cuda().contiguous()
+    dS = torch.zeros_like(sd)
+    acc = torch.zeros(1, device="cuda")
+    lib = S.lib.load()
+    S.lib.check(lib.sshslie_fourier_loss(S.lib.ptr(xd), S.lib.ptr(sd), S.lib.ptr(mask), S.lib.ptr(dS), S.lib.ptr(acc),
+                                         n, H, W, 1.0 / (n * H * W), stream()), "fourier_loss")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(float(acc) / (n * H * W), float(loss), rtol=2e-5)
+    torch.testing.assert_close(dS.cpu(), gs, rtol=1e-3, atol=2e-4 * float(gs.abs().max()))
+
+
+def test_adam_step():
+    """Fused Adam vs the oracle's restatement of torch.optim.Adam, 3 steps: 1e-6 absolute."""
+    from gpu_util import stream
+    from oracle import sshslie_oracle as O
+    import sshslie_b200 as S
+    g = torch.Generator().manual_seed(2)
+    p = {"w": torch.randn(1000, generator=g)}
+    pd = p["w"].clone().cuda()
+    m = torch.zeros_like(pd)
+    v = torch.zeros_like(pd)
+    state = {}
+    lib = S.lib.load()
+    for step in range(1, 4):
+        gr = torch.randn(1000, generator=g) * (10.0 ** (-step))
+        p = O.adam_step(p, {"w": gr}, state, lr=1e-3)
+        grd = gr.cuda()
+        S.lib.check(lib.sshslie_adam_step(S.lib.ptr(pd), S.lib.ptr(grd), S.lib.ptr(m), S.lib.ptr(v), 1000, 1e-3, 0.9,
+                                          0.999, 1e-8, step, 1.0, stream()), "adam")
+        torch.cuda.synchronize()
+        torch.testing.assert_close(pd.cpu(), p["w"], rtol=1e-5, atol=1e-6)

@@ -1,0 +1,175 @@
+"""End-to-end parity of the drop-in module (-m gpu): LowLightEnhance.forward / compute_loss / backward / Adam on a
+B200 against the CPU oracle on the same seeded inputs, and against the fixtures recorded from the unmodified
+reference.  Tolerances (bf16 tensor-core operands, fp32 accumulate, fp32 heads and loss kernels):
+  outputs R/I/S  <= 5e-3 abs,  I_delta <= 4e-3 abs
+  loss terms     <= 2e-2 relative
+  gradients      cosine >= 0.995 over the full 1.14M-vector and per-tensor cosine >= 0.97
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+COEFS = None
+
+
+def _coefs():
+    from oracle import sshslie_oracle as O
+    return {"jyu": O.JYU_COEF, "cv": O.DEFAULT_COEF}
+
+
+def _model(coef, seed=41, force_simt=False, graph=False):
+    import sshslie_b200 as S
+    torch.manual_seed(seed)
+    m = S.LowLightEnhance(input_channels=64, lr=1e-3, **coef).to("cuda")
+    m.force_simt = force_simt
+    m.use_cuda_graph = graph
+    return m
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("shape", [(2, 32), (1, 64), (2, 128)])
+def test_forward_matches_oracle(shape, impl):
+    from oracle import sshslie_oracle as O
+    B, size = shape
+    m = _model(O.JYU_COEF, force_simt=(impl == "simt"))
+    x = O.synthetic_patches(B, 64, size, seed=41)
+    with torch.no_grad():
+        R, I, Id, S = m.forward(x.cuda())
+    torch.cuda.synchronize()
+    p = O.init_params(41)
+    Rr, Ir, Idr, Sr = O.forward(p, x)
+    assert (R.cpu() - Rr).abs().max() <= 5e-3
+    assert (I.cpu() - Ir).abs().max() <= 5e-3
+    assert (Id.cpu() - Idr).abs().max() <= 4e-3
+    assert (S.cpu() - Sr).abs().max() <= 5e-3
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("case", [(2, 32, "jyu"), (1, 64, "cv"), (2, 128, "jyu")])
+def test_loss_and_grads_match_oracle(case, impl):
+    from oracle import sshslie_oracle as O
+    B, size, cname = case
+    coef = _coefs()[cname]
+    m = _model(coef, force_simt=(impl == "simt"))
+    x = O.synthetic_patches(B, 64, size, seed=41)
+    m.optimizer.zero_grad()
+    loss, losses = m.compute_loss(x.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    p = O.init_params(41)
+    ref_losses, ref_grads, _ = O.loss_and_grads(p, x, coef)
+    for k in O.LOSS_KEYS:
+        np.testing.assert_allclose(losses[k], ref_losses[k], rtol=2e-2, atol=1e-5, err_msg=k)
+    np.testing.assert_allclose(float(loss), ref_losses["total_loss"], rtol=2e-2)
+    flat_g, flat_r = [], []
+    for (k, prm) in m.named_parameters():
+        g = prm.grad.detach().cpu()
+        r = ref_grads[k]
+        flat_g.append(g.flatten())
+        flat_r.append(r.flatten())
+        if r.abs().max() > 0:
+            assert _cos(g, r) >= 0.97, (k, _cos(g, r))
+            np.testing.assert_allclose(float(g.norm()), float(r.norm()), rtol=0.1, err_msg=k)
+        else:
+            assert g.abs().max() == 0, k
+    assert _cos(torch.cat(flat_g), torch.cat(flat_r)) >= 0.995
+
+
+def test_reference_fixture_full_size(golden_dir):
+    """Same check against the fixture recorded from the UNMODIFIED reference (config_outdoor_jyu.yml, B=2, 128^2)."""
+    from oracle import sshslie_oracle as O
+    g = np.load(os.path.join(golden_dir, "jyu_b2_128.npz"))
+    m = _model(O.JYU_COEF)
+    x = O.synthetic_patches(2, 64, 128, seed=41)
+    m.optimizer.zero_grad()
+    loss, losses = m.compute_loss(x.cuda())
+    loss.backward()
+    for k in O.LOSS_KEYS:
+        np.testing.assert_allclose(losses[k], float(g["loss/" + k]), rtol=2e-2, atol=1e-5, err_msg=k)
+    for k, prm in m.named_parameters():
+        ref = g["grad/" + k + "/samples"]
+        f = prm.grad.detach().reshape(-1).double().cpu()
+        idx = torch.linspace(0, f.numel() - 1, min(64, f.numel())).long()
+        got = f[idx].numpy()
+        if np.abs(ref).max() > 0:
+            c = float(got @ ref / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-300))
+            assert c >= 0.97, (k, c)
+    R, I, Id, S_ = m.last_outputs
+    for nm, t, tol in [("R_low", R, 5e-3), ("I_low", I, 5e-3), ("I_delta", Id, 4e-3), ("S", S_, 5e-3)]:
+        f = t.detach().reshape(-1).double().cpu()
+        idx = torch.linspace(0, f.numel() - 1, 256).long()
+        assert np.abs(f[idx].numpy() - g["out/" + nm + "/samples"]).max() <= tol, nm
+
+
+def test_train_steps_track_oracle():
+    """3 optimizer steps (zero_grad / compute_loss / backward / step, model.py:313-316), CUDA graph on:
+    the loss trajectory follows the oracle's within 3 % and every weight stays within 3 * lr * steps."""
+    from oracle import sshslie_oracle as O
+    coef = O.DEFAULT_COEF
+    m = _model(coef, graph=True)
+    p = O.init_params(41)
+    state = {}
+    for step in range(4):
+        x = O.synthetic_patches(1, 64, 64, seed=200 + step)
+        m.optimizer.zero_grad()
+        loss, losses = m.compute_loss(x.cuda())
+        loss.backward()
+        m.optimizer.step()
+        ref_losses, grads, _ = O.loss_and_grads(p, x, coef)
+        p = O.adam_step(p, grads, state, lr=1e-3)
+        np.testing.assert_allclose(losses["total_loss"], ref_losses["total_loss"], rtol=3e-2, err_msg=f"step {step}")
+    sd = m.state_dict()
+    for k in p:
+        assert (sd[k].cpu() - p[k]).abs().max() <= 3 * 1e-3 * 4 + 1e-6, k
+
+
+def test_state_dict_roundtrip_and_checkpoint(tmp_path):
+    import sshslie_b200 as S
+    from oracle import sshslie_oracle as O
+    m = _model(O.DEFAULT_COEF)
+    x = O.synthetic_patches(1, 64, 32, seed=7).cuda()
+    m.optimizer.zero_grad()
+    loss, _ = m.compute_loss(x)
+    loss.backward()
+    m.optimizer.step()
+    path = str(tmp_path / "ck.pth")
+    m.save_checkpoint(path, 1)
+    ck = torch.load(path)
+    assert set(ck.keys()) == {"epoch", "model_state_dict", "optimizer_state_dict"}
+    assert list(ck["model_state_dict"].keys()) == list(O.init_params(41).keys())
+    m2 = _model(O.DEFAULT_COEF, seed=1)
+    m2.load_checkpoint(path)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    with torch.no_grad():
+        o1 = m.forward(x)
+        o1 = [t.clone() for t in o1]
+        o2 = m2.forward(x)
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b)
+
+
+def test_linearity_of_batch():
+    """Size-independent property: every loss term is a mean over equal shards, so the gradient of a 2-patch batch is
+    the mean of the two single-patch gradients (the basis of the data-parallel all-reduce)."""
+    from oracle import sshslie_oracle as O
+    coef = O.DEFAULT_COEF
+    x = O.synthetic_patches(2, 64, 128, seed=5).cuda()
+    m = _model(coef)
+    grads = []
+    for xs in (x, x[0:1], x[1:2]):
+        m.optimizer.zero_grad()
+        loss, _ = m.compute_loss(xs.contiguous())
+        loss.backward()
+        grads.append(torch.cat([p.grad.detach().flatten().clone() for p in m.parameters()]))
+    mean12 = 0.5 * (grads[1] + grads[2])
+    assert _cos(grads[0], mean12) >= 0.9995
