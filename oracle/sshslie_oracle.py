@@ -121,17 +121,23 @@ def _conv(p: Params, name: str, x, stride=1, relu=False):
     return F.relu(y) if relu else y
 
 
-def decomposition_net(p: Params, x, prefix="decomposition_net."):
-    """model.py:49-70."""
-    c0 = _conv(p, prefix + "conv0.0", x, relu=True)
-    sh = _conv(p, prefix + "shallow_conv.0", x)
-    c1 = _conv(p, prefix + "conv1.0", sh, relu=True)
-    c2 = _conv(p, prefix + "conv2.0", c1, stride=2, relu=True)
-    c3 = _conv(p, prefix + "conv3.0", c2, relu=True)
-    dc = F.relu(F.conv_transpose2d(c3, p[prefix + "deconv.0.weight"], p[prefix + "deconv.0.bias"],
-                                   stride=2, padding=1, output_padding=1))
-    c5 = _conv(p, prefix + "conv5.0", torch.cat([dc, c1], 1), relu=True)
-    c7 = _conv(p, prefix + "conv7.0", torch.cat([c5, c0], 1))
+def _ident(t, name=None):
+    return t
+
+
+def decomposition_net(p: Params, x, prefix="decomposition_net.", q=_ident):
+    """model.py:49-70.  `q(tensor, name)` marks the tensors the CUDA path STORES (identity here; see
+    `bf16_storage` for the emulation of its bf16 storage points)."""
+    x = q(x, "in")
+    c0 = q(_conv(p, prefix + "conv0.0", x, relu=True), "c0")
+    sh = q(_conv(p, prefix + "shallow_conv.0", x), "sh")
+    c1 = q(_conv(p, prefix + "conv1.0", sh, relu=True), "c1")
+    c2 = q(_conv(p, prefix + "conv2.0", c1, stride=2, relu=True), "c2")
+    c3 = q(_conv(p, prefix + "conv3.0", c2, relu=True), "c3")
+    dc = q(F.relu(F.conv_transpose2d(c3, p[prefix + "deconv.0.weight"], p[prefix + "deconv.0.bias"],
+                                     stride=2, padding=1, output_padding=1)), "dc")
+    c5 = q(_conv(p, prefix + "conv5.0", torch.cat([dc, c1], 1), relu=True), "c5")
+    c7 = q(_conv(p, prefix + "conv7.0", torch.cat([c5, c0], 1)), "c7")
     c8 = _conv(p, prefix + "recon", c7)
     C = c8.shape[1] - 1
     return torch.sigmoid(c8[:, :C]), torch.sigmoid(c8[:, C:])
@@ -153,28 +159,56 @@ def transformer_block(p: Params, x, prefix="illum_adjust_net.attn.", heads=4, he
     return y.permute(0, 2, 1).reshape(n, c, h, w)
 
 
-def illum_adjust_net(p: Params, I, R, prefix="illum_adjust_net."):
+def illum_adjust_net(p: Params, I, R, prefix="illum_adjust_net.", q=_ident):
     """model.py:143-175."""
-    a0 = _conv(p, prefix + "conv0.0", torch.cat([R, I], 1))
-    a1 = _conv(p, prefix + "conv1.0", a0, stride=2, relu=True)
-    a2 = _conv(p, prefix + "conv2.0", a1, stride=2, relu=True)
-    a3 = _conv(p, prefix + "conv3.0", a2, stride=2, relu=True)
-    t = transformer_block(p, a3, prefix + "attn.")
+    a0 = q(_conv(p, prefix + "conv0.0", q(torch.cat([R, I], 1), "RI")), "a0")
+    a1 = q(_conv(p, prefix + "conv1.0", a0, stride=2, relu=True), "a1")
+    a2 = q(_conv(p, prefix + "conv2.0", a1, stride=2, relu=True), "a2")
+    a3 = q(_conv(p, prefix + "conv3.0", a2, stride=2, relu=True), "a3")
+    t = q(transformer_block(p, a3, prefix + "attn."), "t")
     up = lambda v, ref: F.interpolate(v, size=ref.shape[2:], mode="nearest")
-    d1 = _conv(p, prefix + "deconv1.0", up(t, a2), relu=True) + a2
-    d2 = _conv(p, prefix + "deconv2.0", up(d1, a1), relu=True) + a1
-    d3 = _conv(p, prefix + "deconv3.0", up(d2, a0), relu=True) + a0
+    r1 = q(_conv(p, prefix + "deconv1.0", up(t, a2), relu=True), "r1")
+    d1 = q(r1 + a2, "d1")
+    r2 = q(_conv(p, prefix + "deconv2.0", up(d1, a1), relu=True), "r2")
+    d2 = q(r2 + a1, "d2")
+    r3 = q(_conv(p, prefix + "deconv3.0", up(d2, a0), relu=True), "r3")
+    d3 = q(r3 + a0, "d3")
     fg = torch.cat([up(d1, d3), up(d2, d3), d3], 1)
-    ff = _conv(p, prefix + "feature_fusion.0", fg)
+    ff = q(_conv(p, prefix + "feature_fusion.0", fg), "ff")
     return _conv(p, prefix + "final_conv", ff)
 
 
-def forward(p: Params, x):
+def forward(p: Params, x, q=_ident):
     """model.py:229-234 -> (R_low, I_low, I_delta, S)."""
-    R, I = decomposition_net(p, x)
-    Id = illum_adjust_net(p, I, R)
+    R, I = decomposition_net(p, x, q=q)
+    Id = illum_adjust_net(p, I, R, q=q)
     S = R * Id + R * I
     return R, I, Id, S
+
+
+class _RoundBf16(torch.autograd.Function):
+    """bf16 storage of an activation (forward) and of its gradient (backward)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+def bf16_storage(t, name=None):
+    """Quantiser emulating the CUDA path's storage precision: every conv operand tensor is kept in bf16
+    (heads R/I/I_delta/S, the loss and the attention internals stay fp32).  Used by tests to separate
+    'bf16 storage noise' from implementation error; arithmetic itself stays fp32 here."""
+    return _RoundBf16.apply(t)
+
+
+def bf16_weights(p: Params) -> Params:
+    """Conv weights as the tensor cores see them (bf16); biases and Linear layers stay fp32."""
+    return OrderedDict((k, _RoundBf16.apply(v) if (k.endswith("weight") and v.dim() == 4) else v)
+                       for k, v in p.items())
 
 
 # --------------------------------------------------------------------------------------------
@@ -249,19 +283,21 @@ def loss_terms(x, R, I, Id, S, R_enh, coef):
     return total, terms
 
 
-def compute_loss(p: Params, x, coef=None):
+def compute_loss(p: Params, x, coef=None, q=_ident):
     """model.py:544-575 -> (total_loss tensor, dict of tensors, (R, I, Id, S, R_enh))."""
     coef = dict(DEFAULT_COEF, **(coef or {}))
-    R, I, Id, S = forward(p, x)
-    R_enh, _ = decomposition_net(p, S)             # model.py:546 (I_enh unused)
+    if q is not _ident:
+        p = bf16_weights(p)
+    R, I, Id, S = forward(p, x, q=q)
+    R_enh, _ = decomposition_net(p, S, q=q)        # model.py:546 (I_enh unused)
     total, terms = loss_terms(x, R, I, Id, S, R_enh, coef)
     return total, terms, (R, I, Id, S, R_enh)
 
 
-def loss_and_grads(p: Params, x, coef=None):
+def loss_and_grads(p: Params, x, coef=None, q=_ident):
     """Loss dict (python floats) + gradient per parameter, as loss.backward() gives (model.py:314-315)."""
     leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
-    total, terms, outs = compute_loss(leaves, x, coef)
+    total, terms, outs = compute_loss(leaves, x, coef, q=q)
     grads = torch.autograd.grad(total, list(leaves.values()), allow_unused=True)
     gd = OrderedDict()
     for (k, v), g in zip(leaves.items(), grads):

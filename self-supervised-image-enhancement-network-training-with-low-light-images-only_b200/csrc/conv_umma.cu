@@ -335,6 +335,8 @@ int ss_launch_conv_gather_umma(const ConvGeom* g_dev, const ConvGeom& g, const U
   return ss_check_launch("conv_gather_umma");
 }
 
+int ss_umma_wgrad_supported(const ConvGeom&) { return 0; }
+
 int ss_launch_conv_wgrad_umma(const ConvGeom*, const ConvGeom&, const UmmaMaps&, const bf16*, int64_t, int64_t,
                               int64_t, int, float*, cudaStream_t) {
   ss_set_error("conv_wgrad_umma: not built in this revision");

@@ -317,7 +317,7 @@ static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, i
   const ConvGeom& g = e->geoms[gi];
   const bf16* gp = G.p + (int64_t)qh * G.W * G.ld + (int64_t)qw * G.ld;
   const int64_t gB = (int64_t)G.H * G.W * G.ld, gH = (int64_t)scale * G.W * G.ld, gW = (int64_t)scale * G.ld;
-  if (e->geom_umma[gi])
+  if (e->geom_umma[gi] && ss_umma_wgrad_supported(g))
     return ss_launch_conv_wgrad_umma(e->geoms_dev + gi, g,
                                      *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
                                      gp, gB, gH, gW, gN, e->grads, st);
