@@ -96,6 +96,15 @@ SSHSLIE_API int sshslie_loss_and_grad(sshslie_engine* e, const float* x, const f
 SSHSLIE_API int sshslie_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* Profiling aid (synchronises, allocates events): runs ONE step eagerly with a cudaEvent pair around every recorded
+ * launch group and returns the number of rows (>0) or a negative status; rows are then read with
+ * sshslie_profile_row: name ("phase/kind:layer[impl]"), device milliseconds, algorithmic FLOPs and bytes. */
+SSHSLIE_API int sshslie_profile_step(sshslie_engine* e, const float* x, const float* params,
+                         const sshslie_loss_cfg* cfg, float* grads, float* losses, void* stream);
+/* number of kernels this library has enqueued since load (for launch accounting) */
+SSHSLIE_API long long sshslie_launch_count(void);
+SSHSLIE_API int sshslie_profile_row(int i, char* name, int name_cap, float* ms, double* flops, double* bytes);
+
 /* ---- single kernels, exported for kernel-level parity tests and profiling ---- */
 
 /* fourier_spectrum_loss (model.py:456-473) forward + d/dS.  x,S,dS: (n_img,H,W) fp32 planes, H and W

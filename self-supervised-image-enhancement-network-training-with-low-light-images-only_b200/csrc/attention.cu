@@ -314,6 +314,7 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* P, const int6
   linear_fwd_kernel<false><<<gl, 256, 0, st>>>(bf.h, P + poff[8], P + poff[9], bf.t32, bf.x, nullptr, T, 0);
   const int64_t n = (int64_t)T * AT_D;
   add_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bf.t32, t_out, n);
+  ss_count_launches(6);
   return ss_check_launch("attention_forward");
 }
 
@@ -340,5 +341,6 @@ int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const floa
   linear_bwd_data_kernel<<<gl, 256, 0, st>>>(bf.dk, P + poff[2], nullptr, bf.dx, T, 1);
   linear_bwd_data_kernel<<<gl, 256, 0, st>>>(bf.dv, P + poff[4], nullptr, bf.dx, T, 1);
   mask_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bf.dx, a3, da3, n);
+  ss_count_launches(13);
   return ss_check_launch("attention_backward");
 }

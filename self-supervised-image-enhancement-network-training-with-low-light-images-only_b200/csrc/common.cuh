@@ -9,7 +9,8 @@
 #define SS_DEVINL __device__ __forceinline__
 
 void ss_set_error(const char* fmt, ...);
-int ss_check_launch(const char* what);   // cudaGetLastError() -> SSHSLIE_ERR_CUDA + message
+int ss_check_launch(const char* what);
+void ss_count_launches(int n);         // extra launches behind one ss_check_launch   // cudaGetLastError() -> SSHSLIE_ERR_CUDA + message
 
 SS_DEVINL float bf2f(bf16 v) { return __bfloat162float(v); }
 SS_DEVINL bf16 f2bf(float v) { return __float2bfloat16_rn(v); }

@@ -24,7 +24,25 @@ void ss_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+// profiling notes: every launcher ends in ss_check_launch(name); the profiled entry point collects them per op
+static thread_local bool g_prof_on = false;
+static thread_local std::string g_prof_names;
+static thread_local double g_prof_flops = 0, g_prof_bytes = 0;
+static void prof_note(const std::string& label, double flops, double bytes) {
+  if (!g_prof_on) return;
+  g_prof_names = label;
+  g_prof_flops += flops;
+  g_prof_bytes += bytes;
+}
+static long long g_launch_count = 0;   // kernels of this library enqueued so far (bench.py's gpu_launches)
+void ss_count_launches(int n) { g_launch_count += n; }
+extern "C" SSHSLIE_API long long sshslie_launch_count(void) { return g_launch_count; }
 int ss_check_launch(const char* what) {
+  g_launch_count += 1;
+  if (g_prof_on && g_prof_names.find(':') == std::string::npos) {
+    if (!g_prof_names.empty()) g_prof_names += "+";
+    g_prof_names += what;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     ss_set_error("%s: %s", what, cudaGetErrorString(e));
@@ -43,6 +61,10 @@ enum Layer {
   L_I_CONV0, L_I_CONV1, L_I_CONV2, L_I_CONV3, L_Q, L_K, L_V, L_FF1, L_FF2, L_I_DECONV1, L_I_DECONV2, L_I_DECONV3,
   L_I_FUSION, L_I_FINAL, L_COUNT
 };
+static const char* kLayerNames[] = {
+  "d.conv0", "d.shallow9x9", "d.conv1", "d.conv2s2", "d.conv3", "d.deconv", "d.conv5", "d.conv7", "d.recon",
+  "i.conv0", "i.conv1s2", "i.conv2s2", "i.conv3s2", "attn.q", "attn.k", "attn.v", "attn.ff1", "attn.ff2",
+  "i.deconv1", "i.deconv2", "i.deconv3", "i.fusion1x1", "i.final"};
 struct LayerShape { int d0, d1, k; bool transposed; };   // weight (d0, d1, k, k); k = 0 -> Linear (d0, d1)
 static void layer_shapes(int C, LayerShape* s) {
   s[L_D_CONV0] = {32, C, 3, false};     s[L_D_SHALLOW] = {64, C, 9, false};  s[L_D_CONV1] = {64, 64, 3, false};
@@ -116,6 +138,9 @@ struct sshslie_engine {
   // plan
   std::vector<ConvGeom> geoms;           // host copy, index = geom id
   std::vector<char> geom_umma;           // 1 if the tcgen05 kernel takes this geom
+  std::vector<int> geom_layer;           // which layer's weights the geom reads (for profiles)
+  std::vector<int> geom_role;            // 0 = forward-type addressing, 1 = dgrad-type addressing
+  mutable int last_layer = -1, last_role = 0;
   std::vector<unsigned char> maps_blob;  // UmmaMaps per geom
   ConvGeom* geoms_dev = nullptr;
   int* pack_start_dev = nullptr;
@@ -141,6 +166,8 @@ struct sshslie_engine {
   int add_geom(const ConvGeom& g) {
     geoms.push_back(g);
     geom_umma.push_back(0);
+    geom_layer.push_back(last_layer);
+    geom_role.push_back(last_role);
     return (int)geoms.size() - 1;
   }
 };
@@ -304,9 +331,21 @@ __global__ void __launch_bounds__(576) final_wgrad_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------------
 struct DecompBufs { Tens c0, sh, c1, c2, c3, dc, c5, c7; };
 
+static double geom_flops(const ConvGeom& g) {
+  double k = 0;
+  for (int i = 0; i < g.nslabs; ++i) k += g.slab[i].wcn;
+  return 2.0 * g.B * g.OH * g.OW * (double)g.N * k;
+}
+static std::string geom_label(const sshslie_engine* e, int gi, const char* kind) {
+  const int l = gi < (int)e->geom_layer.size() ? e->geom_layer[gi] : -1;
+  std::string s = std::string(kind) + ":" + (l >= 0 && l < L_COUNT ? kLayerNames[l] : "layer");
+  s += e->geom_umma[gi] ? "[tcgen05]" : "[simt]";
+  return s;
+}
 static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaStream_t st) {
   if (bias_layer >= 0) epi.bias = e->params + e->poff[2 * bias_layer + 1];
   const ConvGeom& g = e->geoms[gi];
+  prof_note(geom_label(e, gi, e->geom_role[gi] ? "dgrad" : "fwd"), geom_flops(g), 0);
   if (e->geom_umma[gi])
     return ss_launch_conv_gather_umma(e->geoms_dev + gi, g,
                                       *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
@@ -317,6 +356,11 @@ static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, i
   const ConvGeom& g = e->geoms[gi];
   const bf16* gp = G.p + (int64_t)qh * G.W * G.ld + (int64_t)qw * G.ld;
   const int64_t gB = (int64_t)G.H * G.W * G.ld, gH = (int64_t)scale * G.W * G.ld, gW = (int64_t)scale * G.ld;
+  {
+    std::string lbl = geom_label(e, gi, "wgrad");
+    if (!(e->geom_umma[gi] && ss_umma_wgrad_supported(g))) lbl.replace(lbl.find('['), std::string::npos, "[simt]");
+    prof_note(lbl, geom_flops(g) * (double)gN / (double)g.N, 0);
+  }
   if (e->geom_umma[gi] && ss_umma_wgrad_supported(g))
     return ss_launch_conv_wgrad_umma(e->geoms_dev + gi, g,
                                      *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
@@ -325,6 +369,7 @@ static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, i
 }
 
 static WAddr waddr_conv_fwd(const sshslie_engine* e, int layer, int n_off = 0) {
+  e->last_layer = layer; e->last_role = 0;
   const LayerShape& s = e->shapes[layer];
   const int kk = s.k * s.k;
   WAddr w;
@@ -335,6 +380,7 @@ static WAddr waddr_conv_fwd(const sshslie_engine* e, int layer, int n_off = 0) {
   return w;
 }
 static WAddr waddr_conv_dgrad(const sshslie_engine* e, int layer, int n_off = 0) {
+  e->last_layer = layer; e->last_role = 1;
   const LayerShape& s = e->shapes[layer];
   const int kk = s.k * s.k;
   WAddr w;
@@ -539,6 +585,8 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   e->zero_ranges.clear();
   e->geoms.clear();
   e->geom_umma.clear();
+  e->geom_layer.clear();
+  e->geom_role.clear();
   e->ops_fwd.clear();
   e->ops_loss_bwd2_illum.clear();
   e->ops_bwd1.clear();
@@ -1099,4 +1147,61 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
     return SSHSLIE_ERR_CUDA;
   }
   return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// profiling entry point: one eager step with a cudaEvent pair around every recorded op (synchronises)
+// ---------------------------------------------------------------------------------------------
+struct ProfRow { std::string name; float ms; double flops, bytes; };
+static thread_local std::vector<ProfRow> g_prof_rows;
+
+static int run_ops_profiled(std::vector<sshslie_engine::OpFn>& ops, cudaStream_t st, const char* phase) {
+  for (auto& f : ops) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    g_prof_names.clear();
+    g_prof_flops = g_prof_bytes = 0;
+    cudaEventRecord(a, st);
+    const int rc = f(st);
+    cudaEventRecord(b, st);
+    if (rc != SSHSLIE_OK) return rc;
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    g_prof_rows.push_back({std::string(phase) + "/" + (g_prof_names.empty() ? "memop" : g_prof_names), ms, g_prof_flops,
+                           g_prof_bytes});
+  }
+  return SSHSLIE_OK;
+}
+
+extern "C" SSHSLIE_API int sshslie_profile_step(sshslie_engine* e, const float* x, const float* params,
+                                                const sshslie_loss_cfg* cfg, float* grads, float* losses,
+                                                void* stream) {
+  if (!e || !x || !params || !e->bound) { ss_set_error("sshslie_profile_step: bad argument"); return SSHSLIE_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  e->x = x; e->params = params;
+  g_prof_rows.clear();
+  g_prof_on = true;
+  int rc = run_ops_profiled(e->ops_fwd, st, "fwd");
+  if (!rc && e->train && cfg && grads && losses) {
+    e->grads = grads; e->losses = losses; e->cfg = *cfg;
+    rc = run_ops_profiled(e->ops_loss_bwd2_illum, st, "pass2+loss+illum_bwd");
+    if (!rc) rc = run_ops_profiled(e->ops_bwd1, st, "pass1_bwd");
+  }
+  g_prof_on = false;
+  return rc ? rc : (int)g_prof_rows.size();
+}
+extern "C" SSHSLIE_API int sshslie_profile_row(int i, char* name, int name_cap, float* ms, double* flops,
+                                               double* bytes) {
+  if (i < 0 || i >= (int)g_prof_rows.size()) return SSHSLIE_ERR_ARG;
+  const ProfRow& r = g_prof_rows[i];
+  if (name && name_cap > 0) { strncpy(name, r.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (ms) *ms = r.ms;
+  if (flops) *flops = r.flops;
+  if (bytes) *bytes = r.bytes;
+  return SSHSLIE_OK;
 }

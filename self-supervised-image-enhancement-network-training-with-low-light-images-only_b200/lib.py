@@ -19,7 +19,8 @@ EXPORTS = [
     "sshslie_version", "sshslie_last_error", "sshslie_param_table", "sshslie_engine_create",
     "sshslie_engine_destroy", "sshslie_engine_workspace_bytes", "sshslie_engine_bind", "sshslie_forward",
     "sshslie_loss_and_grad", "sshslie_adam_step", "sshslie_fourier_loss", "sshslie_pixel_losses",
-    "sshslie_conv2d_scratch_bytes", "sshslie_conv2d",
+    "sshslie_conv2d_scratch_bytes", "sshslie_conv2d", "sshslie_profile_step", "sshslie_profile_row",
+    "sshslie_launch_count",
 ]
 
 
@@ -65,6 +66,10 @@ def load():
     lib.sshslie_conv2d_scratch_bytes.restype = i64
     lib.sshslie_conv2d_scratch_bytes.argtypes = [i32] * 7
     lib.sshslie_conv2d.argtypes = [i32, i32, i32, vp, vp, vp, vp] + [i32] * 8 + [vp, i64, vp]
+    lib.sshslie_launch_count.restype = ctypes.c_longlong
+    lib.sshslie_profile_step.argtypes = [vp, vp, vp, ctypes.POINTER(LossCfg), vp, vp, vp]
+    lib.sshslie_profile_row.argtypes = [i32, ctypes.c_char_p, i32, ctypes.POINTER(f32),
+                                        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 

@@ -416,6 +416,26 @@ class LowLightEnhance(nn.Module):
             total = self._losses_dev[0].clone()
         return total, LazyLosses(self._losses_dev[:7].clone())
 
+    def profile_step(self, input_low):
+        """One eager training step with device timing per launch group: list of (name, ms, flops, bytes)."""
+        self._ensure_flat()
+        eng = self._engine(input_low, train=True)
+        self._stage_input(eng, input_low)
+        lib = L.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)
+        cfg = self._cfg()
+        n = lib.sshslie_profile_step(eng.handle, L.ptr(eng.x), L.ptr(self._flat), ctypes.byref(cfg),
+                                     L.ptr(self._flat_grad), L.ptr(self._losses_dev), stream)
+        if n < 0:
+            L.check(n, "sshslie_profile_step")
+        rows = []
+        buf = ctypes.create_string_buffer(256)
+        ms, fl, by = ctypes.c_float(), ctypes.c_double(), ctypes.c_double()
+        for i in range(n):
+            lib.sshslie_profile_row(i, buf, 256, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by))
+            rows.append((buf.value.decode(), ms.value, fl.value, by.value))
+        return rows
+
     # ------------------------------------------------------------------ data parallel (SURVEY.md §8e)
     def enable_data_parallel(self, group=None):
         """Average gradients over `group` (NCCL) inside compute_loss; the illum_adjust_net bucket is reduced
@@ -432,17 +452,28 @@ class LowLightEnhance(nn.Module):
         import torch.distributed as dist
         n_dec = self._pranges[18][0]                 # first illum_adjust_net parameter (decomposition has 9x2 tensors)
         cur = torch.cuda.current_stream(self._flat.device)
-        self._launch_loss_and_grad(eng, phase_mask=1)
+        eng.calls += 1
+        if self.use_cuda_graph and eng.graph is None and eng.calls >= 3:
+            torch.cuda.synchronize()
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._launch_loss_and_grad(eng, phase_mask=1)
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                self._launch_loss_and_grad(eng, phase_mask=2)
+            eng.graph = (ga, gb)
+        run = (lambda ph: eng.graph[ph - 1].replay()) if eng.graph is not None else \
+              (lambda ph: self._launch_loss_and_grad(eng, phase_mask=ph))
+        run(1)                                       # fwd + loss + pass-2 bwd + illum bwd
         ev = torch.cuda.Event()
         ev.record(cur)
         with torch.cuda.stream(self._dp_stream):
             self._dp_stream.wait_event(ev)
-            dist.all_reduce(self._flat_grad[n_dec:], group=self.dp_group)     # bucket 1: illum_adjust_net
-        self._launch_loss_and_grad(eng, phase_mask=2)
-        dist.all_reduce(self._flat_grad[:n_dec], group=self.dp_group)          # bucket 2: decomposition_net
+            dist.all_reduce(self._flat_grad[n_dec:], group=self.dp_group)     # bucket 1: illum_adjust_net, overlaps
+            dist.all_reduce(self._losses_dev, group=self.dp_group)            # with the pass-1 backward below
+        run(2)                                       # pass-1 decomposition backward
+        dist.all_reduce(self._flat_grad[:n_dec], group=self.dp_group)         # bucket 2: decomposition_net
         cur.wait_stream(self._dp_stream)
-        self._flat_grad.mul_(1.0 / self._dp_world)
-        dist.all_reduce(self._losses_dev, group=self.dp_group)
+        self._flat_grad.mul_(1.0 / self._dp_world)                            # p.grad = mean over ranks
         self._losses_dev.mul_(1.0 / self._dp_world)
 
     # ------------------------------------------------------------------ loops (host glue, model.py:236-443)
