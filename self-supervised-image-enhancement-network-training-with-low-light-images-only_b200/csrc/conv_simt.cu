@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__
 }
 
 int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, cudaStream_t st) {
-  const int ppb = 512;
+  const int ppb = 64;
   bias_grad_kernel<<<(unsigned)((npix + ppb - 1) / ppb), 256, 0, st>>>(G, npix, ld, N, db, ppb);
   return ss_check_launch("bias_grad");
 }

@@ -335,10 +335,286 @@ int ss_launch_conv_gather_umma(const ConvGeom* g_dev, const ConvGeom& g, const U
   return ss_check_launch("conv_gather_umma");
 }
 
-int ss_umma_wgrad_supported(const ConvGeom&) { return 0; }
+// ---------------------------------------------------------------------------------------------
+// weight-gradient GEMM on tcgen05:   dW[n][slab s, channel j] += sum_pixels G[pixel, n] * A_s[pixel, j]
+//
+// The reduction (K) axis is the pixel axis, which is the ROW axis of both NHWC operands, so both are fed
+// MN-major: the same 128-pixel x 64-channel SWIZZLE_128B tiles the gather kernel uses, read "transposed" by the
+// tensor core (instruction-descriptor major bits 15/16 = 1).  To fill M = 128 the A operand is a PAIR of slab
+// tiles (two 64-channel atoms, LBO = one tile), the B operand is the G tile (N = 64 or 128 gradient channels):
+//     D_pair[(slab 2p | 2p+1, j)][n] += A_pair^T . G            8 x (K=16) MMAs per 128-pixel tile
+// One CTA owns a group of up to 512/N slab pairs (all TMEM columns) and a contiguous range of pixel tiles, keeps
+// the accumulators in TMEM for its whole range, and finally adds them into the flat fp32 gradient buffer with
+// red.global.add.f32 at the weight tensor's own (n, c, kh, kw) strides.
+// ---------------------------------------------------------------------------------------------
+#define WG_STAGES 4
+#define WG_STAGE_BYTES (2 * UM_A_BYTES)
+#define WG_G_BYTES (2 * UM_A_BYTES)
+#define WG_ONES_BYTES UM_A_BYTES          // an all-ones 128 x 64 bf16 tile: ones^T . G = column sums = bias gradient
 
-int ss_launch_conv_wgrad_umma(const ConvGeom*, const ConvGeom&, const UmmaMaps&, const bf16*, int64_t, int64_t,
-                              int64_t, int, float*, cudaStream_t) {
-  ss_set_error("conv_wgrad_umma: not built in this revision");
-  return SSHSLIE_ERR_ARG;
+struct WgradArgs {
+  int slabs_per_group;     // even
+  int tiles_per_cta;
+  int n_tiles;             // B * tiles_h * tiles_w
+  int N;                   // UMMA N: 64 or 128 (G channels loaded)
+  int gN;                  // valid G channels
+  int tmem_cols;
+  long long bias_off;      // >= 0: also produce db[n] = sum_pixels G[pixel, n] (group 0), added at grads + bias_off
+  int groups, splits;      // grid = (splits, groups)
+  int blocks_per_cta;      // accumulator blocks a CTA writes: slabs_per_group/2 pairs + 1 bias block
+};
+
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_wgrad_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps maps,
+                       const __grid_constant__ CUtensorMap gmap, WgradArgs wa, float* __restrict__ partial) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ ConvGeom g;
+  __shared__ __align__(8) uint64_t a_full[WG_STAGES];
+  __shared__ __align__(8) uint64_t a_empty[WG_STAGES];
+  __shared__ __align__(8) uint64_t g_full[2];
+  __shared__ __align__(8) uint64_t g_empty[2];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int* src = reinterpret_cast<const int*>(gp);
+    int* dst = reinterpret_cast<int*>(&g);
+    for (int i = threadIdx.x; i < (int)(sizeof(ConvGeom) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t g_base = dyn_base + WG_STAGES * WG_STAGE_BYTES;
+  const uint32_t ones_base = g_base + 2 * WG_G_BYTES;
+  {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_dyn + (dyn_base - smem_u32(smem_dyn)) +
+                                                 WG_STAGES * WG_STAGE_BYTES + 2 * WG_G_BYTES);
+    for (int i = threadIdx.x; i < WG_ONES_BYTES / 4; i += blockDim.x) ones[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
+  }
+  __syncthreads();
+
+  const int group = blockIdx.y;
+  const bool do_bias = (wa.bias_off >= 0) && (group == 0);
+  const int s_begin = group * wa.slabs_per_group;
+  const int s_end = min(g.nslabs, s_begin + wa.slabs_per_group);
+  const int npairs = (s_end - s_begin + 1) / 2;
+  const int t_begin = blockIdx.x * wa.tiles_per_cta;
+  const int t_end = min(wa.n_tiles, t_begin + wa.tiles_per_cta);
+  const int ntiles = t_end - t_begin;           // >= 1 by construction of the grid
+  const int g_atoms = wa.N / 64;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&maps.src[s]);
+    tma_prefetch_desc(&gmap);
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 1);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&g_full[s]), 1);
+      mbar_init(smem_u32(&g_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&accum_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)wa.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int tiles_w = (g.OW + g.tw - 1) / g.tw, tiles_h = (g.OH + g.th - 1) / g.th;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int ti = 0; ti < ntiles; ++ti) {
+        int t = t_begin + ti;
+        const int twi = t % tiles_w; t /= tiles_w;
+        const int thi = t % tiles_h;
+        const int b = t / tiles_h;
+        const int oh0 = thi * g.th, ow0 = twi * g.tw;
+        {  // G tile of this pixel tile
+          const int gs = ti & 1;
+          mbar_wait(smem_u32(&g_empty[gs]), (((uint32_t)(ti >> 1)) & 1u) ^ 1u);
+          const uint32_t fb = smem_u32(&g_full[gs]);
+          mbar_expect_tx(fb, (uint32_t)g_atoms * UM_A_BYTES);
+          for (int a = 0; a < g_atoms; ++a)
+            tma_load_4d(g_base + gs * WG_G_BYTES + a * UM_A_BYTES, &gmap, fb, a * 64, ow0, oh0, b);
+        }
+        for (int p = 0; p < npairs; ++p, ++it) {
+          const int st = it % WG_STAGES;
+          mbar_wait(smem_u32(&a_empty[st]), (((uint32_t)(it / WG_STAGES)) & 1u) ^ 1u);
+          const uint32_t fb = smem_u32(&a_full[st]);
+          const int s0 = s_begin + 2 * p;
+          const int cnt = (s0 + 1 < s_end) ? 2 : 1;
+          mbar_expect_tx(fb, (uint32_t)cnt * UM_A_BYTES);
+          for (int q = 0; q < cnt; ++q) {
+            const Slab sl = g.slab[s0 + q];
+            tma_load_4d(dyn_base + st * WG_STAGE_BYTES + q * UM_A_BYTES, &maps.src[sl.src], fb, sl.c0, ow0 + sl.dw,
+                        oh0 + sl.dh, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(128, wa.N, 1, 1);
+      int it = 0;
+      for (int ti = 0; ti < ntiles; ++ti) {
+        const int gs = ti & 1;
+        mbar_wait(smem_u32(&g_full[gs]), ((uint32_t)(ti >> 1)) & 1u);
+        for (int p = 0; p < npairs; ++p, ++it) {
+          const int st = it % WG_STAGES;
+          mbar_wait(smem_u32(&a_full[st]), ((uint32_t)(it / WG_STAGES)) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = dyn_base + st * WG_STAGE_BYTES;
+          const uint32_t b_addr = g_base + gs * WG_G_BYTES;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = make_sdesc(a_addr + k * 2048, UM_A_BYTES, 1024);   // 2 slab atoms, LBO = one tile
+            const uint64_t bd = make_sdesc(b_addr + k * 2048, UM_A_BYTES, 1024);   // 1 or 2 G atoms
+            umma_bf16(tmem_base + (uint32_t)(p * wa.N), ad, bd, idesc, (ti > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&a_empty[st]));
+        }
+        if (do_bias) {
+          const uint32_t b_addr = g_base + gs * WG_G_BYTES;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = make_sdesc(ones_base + k * 2048, 0, 1024);          // both M atoms = the ones tile
+            const uint64_t bd = make_sdesc(b_addr + k * 2048, UM_A_BYTES, 1024);
+            umma_bf16(tmem_base + (uint32_t)(npairs * wa.N), ad, bd, idesc, (ti > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&g_empty[gs]));
+      }
+      umma_commit(smem_u32(&accum_bar));
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    // partial[split][group][block][n][row]: lanes = consecutive rows -> 128-byte coalesced stores, no atomics
+    float* out = partial + ((size_t)(blockIdx.x * wa.groups + group) * wa.blocks_per_cta) * (size_t)wa.N * 128;
+    const int nblocks = npairs + (do_bias ? 1 : 0);
+    for (int p = 0; p < nblocks; ++p) {
+      for (int n0 = 0; n0 < wa.N; n0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p * wa.N + n0), v);
+        float* o = out + ((size_t)p * wa.N + n0) * 128 + row;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[(size_t)i * 128] = v[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)wa.tmem_cols);
+}
+
+int ss_umma_wgrad_supported(const ConvGeom& g) { return ss_umma_supported(g) && g.N <= 128; }
+
+int ss_umma_build_gmap(const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld_extent, const ConvGeom& g,
+                       void* out_map) {
+  SrcView v;
+  v.base = G; v.sB = gB; v.sH = gH; v.sW = gW; v.H = g.OH; v.W = g.OW;
+  return encode_src(v, ld_extent, g.tw, g.th, g.B, reinterpret_cast<CUtensorMap*>(out_map));
+}
+
+// second stage: dW[n][slab, j] += sum over pixel splits of the partial accumulators (deterministic, no atomics)
+// grid = (blocks_per_cta, groups, N/8); block = 128 threads = the 128 accumulator rows
+__global__ void __launch_bounds__(128) conv_wgrad_reduce_kernel(const ConvGeom* __restrict__ gp,
+                                                                const float* __restrict__ partial, WgradArgs wa,
+                                                                float* __restrict__ grads) {
+  const int blk = blockIdx.x, group = blockIdx.y, n0 = blockIdx.z * 8;
+  const int row = threadIdx.x;
+  const int s_begin = group * wa.slabs_per_group;
+  const int s_end = min(gp->nslabs, s_begin + wa.slabs_per_group);
+  const int npairs = (s_end - s_begin + 1) / 2;
+  const bool is_bias = (blk == npairs) && (group == 0) && (wa.bias_off >= 0);
+  if (blk > npairs || (blk == npairs && !is_bias)) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const size_t cta_stride = (size_t)wa.groups * wa.blocks_per_cta * wa.N * 128;
+  const float* p = partial + ((size_t)group * wa.blocks_per_cta + blk) * (size_t)wa.N * 128 + (size_t)n0 * 128 + row;
+  for (int sp = 0; sp < wa.splits; ++sp, p += cta_stride) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += p[(size_t)i * 128];
+  }
+  if (is_bias) {
+    if (row == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (n0 + i < wa.gN) grads[wa.bias_off + n0 + i] += acc[i];
+    }
+    return;
+  }
+  const int s = s_begin + 2 * blk + (row >> 6);
+  const int j = row & 63;
+  if (s >= s_end) return;
+  const Slab sl = gp->slab[s];
+  if (j >= sl.wcn) return;
+  float* dst = grads + gp->w_off + sl.woff + (int64_t)j * gp->w_sC;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + i;
+    if (n < gp->N && n < wa.gN) dst[(int64_t)n * gp->w_sN] += acc[i];
+  }
+}
+
+static void wgrad_plan(const ConvGeom& g, int gN, long long bias_off, WgradArgs* out) {
+  WgradArgs wa;
+  wa.gN = gN;
+  wa.bias_off = bias_off;
+  wa.N = (gN > 64) ? 128 : 64;
+  const int max_slabs = 2 * (512 / wa.N - 1);          // one accumulator block is reserved for the bias row
+  const int ngroups = (g.nslabs + max_slabs - 1) / max_slabs;
+  int per = (g.nslabs + ngroups - 1) / ngroups;
+  per += per & 1;
+  wa.slabs_per_group = per;
+  wa.groups = (g.nslabs + per - 1) / per;
+  wa.n_tiles = g.B * ((g.OH + g.th - 1) / g.th) * ((g.OW + g.tw - 1) / g.tw);
+  // split the pixel axis until every CTA still owns ~4 pixel tiles or all SMs are covered
+  int splits = (wa.n_tiles + 3) / 4;
+  if (splits > 148 / wa.groups) splits = 148 / wa.groups;
+  if (splits < 1) splits = 1;
+  wa.tiles_per_cta = (wa.n_tiles + splits - 1) / splits;
+  wa.splits = (wa.n_tiles + wa.tiles_per_cta - 1) / wa.tiles_per_cta;
+  wa.blocks_per_cta = per / 2 + 1;
+  int cols = 32;
+  while (cols < wa.blocks_per_cta * wa.N) cols <<= 1;
+  wa.tmem_cols = cols;
+  *out = wa;
+}
+
+size_t ss_umma_wgrad_partial_floats(const ConvGeom& g, int gN) {
+  WgradArgs wa;
+  wgrad_plan(g, gN, 0, &wa);
+  return (size_t)wa.splits * wa.groups * wa.blocks_per_cta * wa.N * 128;
+}
+
+int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const UmmaMaps& maps, const void* gmap,
+                              int gN, long long bias_off, float* partial, float* grads, cudaStream_t st) {
+  WgradArgs wa;
+  wgrad_plan(g, gN, bias_off, &wa);
+  const size_t smem = (size_t)WG_STAGES * WG_STAGE_BYTES + 2 * WG_G_BYTES + WG_ONES_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
+        cudaSuccess) {
+      ss_set_error("conv_wgrad_umma: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      return SSHSLIE_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(wa.splits, wa.groups);
+  conv_wgrad_umma_kernel<<<grid, UM_THREADS, smem, st>>>(g_dev, maps, *reinterpret_cast<const CUtensorMap*>(gmap), wa,
+                                                         partial);
+  int rc = ss_check_launch("conv_wgrad_umma");
+  if (rc) return rc;
+  dim3 rgrid(wa.blocks_per_cta, wa.groups, wa.N / 8);
+  conv_wgrad_reduce_kernel<<<rgrid, 128, 0, st>>>(g_dev, partial, wa, grads);
+  return ss_check_launch("conv_wgrad_reduce");
 }

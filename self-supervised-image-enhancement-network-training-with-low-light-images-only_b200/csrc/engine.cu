@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <algorithm>
 #include <functional>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -108,8 +110,11 @@ struct GeomOp {        // one lowered GEMM: geometry + (for gathers) epilogue te
   bool use_umma = false;
 };
 
+struct alignas(64) GMapBox { unsigned char bytes[128]; };
+
 struct sshslie_engine {
   int B, C, H, W, flags;
+  std::map<std::pair<int, const void*>, GMapBox> gmaps;   // wgrad G-tensor TMA descriptors
   bool train, force_simt;
   int64_t ws_bytes = 0;
   unsigned char* ws = nullptr;
@@ -148,7 +153,29 @@ struct sshslie_engine {
   int pack_blocks = 0;
   float* mask_dev = nullptr;
   float* sums_dev = nullptr;
+  float* wg_partial = nullptr;           // split-K partial accumulators of the tcgen05 wgrad (largest op)
+  size_t wg_partial_floats = 0;
   int64_t* attn_poff_dummy = nullptr;
+
+  // side stream for weight gradients (created at bind; host objects only)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_dirty = false, use_side = true;
+  cudaStream_t fork(cudaStream_t main_st) {
+    if (!use_side || !side) return main_st;
+    cudaEventRecord(ev_fork, main_st);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+    side_dirty = true;
+    return side;
+  }
+  int join(cudaStream_t main_st) {
+    if (side_dirty) {
+      cudaEventRecord(ev_join, side);
+      cudaStreamWaitEvent(main_st, ev_join, 0);
+      side_dirty = false;
+    }
+    return SSHSLIE_OK;
+  }
 
   // per-call state read by the recorded launches
   const float* x = nullptr;
@@ -352,7 +379,8 @@ static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaSt
                                       epi, st);
   return ss_launch_conv_gather_simt(e->geoms_dev + gi, g, epi, st);
 }
-static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, int qw, int scale, cudaStream_t st) {
+static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, int qw, int scale, cudaStream_t st,
+                     int bias_layer = -1) {
   const ConvGeom& g = e->geoms[gi];
   const bf16* gp = G.p + (int64_t)qh * G.W * G.ld + (int64_t)qw * G.ld;
   const int64_t gB = (int64_t)G.H * G.W * G.ld, gH = (int64_t)scale * G.W * G.ld, gW = (int64_t)scale * G.ld;
@@ -361,10 +389,26 @@ static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, i
     if (!(e->geom_umma[gi] && ss_umma_wgrad_supported(g))) lbl.replace(lbl.find('['), std::string::npos, "[simt]");
     prof_note(lbl, geom_flops(g) * (double)gN / (double)g.N, 0);
   }
-  if (e->geom_umma[gi] && ss_umma_wgrad_supported(g))
+  if (e->geom_umma[gi] && ss_umma_wgrad_supported(g)) {
+    // TMA descriptor of the G tensor, built once per (geom, tensor) and cached on the host
+    const std::pair<int, const void*> key(gi, (const void*)gp);
+    auto it = e->gmaps.find(key);
+    if (it == e->gmaps.end()) {
+      GMapBox box;
+      const int rc = ss_umma_build_gmap(gp, gB, gH, gW, G.ld, g, box.bytes);
+      if (rc) return rc;
+      it = e->gmaps.emplace(key, box).first;
+    }
     return ss_launch_conv_wgrad_umma(e->geoms_dev + gi, g,
                                      *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
-                                     gp, gB, gH, gW, gN, e->grads, st);
+                                     it->second.bytes, gN,
+                                     bias_layer >= 0 ? (long long)e->poff[2 * bias_layer + 1] : -1LL,
+                                     e->wg_partial, e->grads, st);
+  }
+  if (bias_layer >= 0) {
+    const int rc = ss_launch_bias_grad(G.p, G.pix(), G.ld, gN, e->grads + e->poff[2 * bias_layer + 1], st);
+    if (rc) return rc;
+  }
   return ss_launch_conv_wgrad_simt(e->geoms_dev + gi, g, gp, gB, gH, gW, gN, e->grads, st);
 }
 
@@ -392,6 +436,11 @@ static WAddr waddr_conv_dgrad(const sshslie_engine* e, int layer, int n_off = 0)
 }
 
 #define PUSH(vec, ...) (vec).push_back([=](cudaStream_t st) -> int { __VA_ARGS__ })
+// weight-gradient work is off the critical path of backward (nothing reads the gradients before the step ends):
+// it is forked onto the engine's side stream and joined at the end of each phase (captured as graph edges)
+#define PUSH_SIDE(vec, ...) \
+  (vec).push_back([=](cudaStream_t main_st) -> int { cudaStream_t st = e->fork(main_st); __VA_ARGS__ })
+#define PUSH_JOIN(vec) (vec).push_back([=](cudaStream_t st) -> int { return e->join(st); })
 
 // forward of one DecompositionNet pass (model.py:49-70).  Returns the geom ids for reuse by the backward pass.
 struct DecompGeoms {
@@ -476,11 +525,10 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
   float** grads = &e->grads;
   const int64_t* poff = e->poff;
   auto bias_grad = [&](const Tens& t, int n, int layer) {
-    PUSH(ops, return ss_launch_bias_grad(t.p, t.pix(), t.ld, n, *grads + poff[2 * layer + 1], st););
+    PUSH_SIDE(ops, return ss_launch_bias_grad(t.p, t.pix(), t.ld, n, *grads + poff[2 * layer + 1], st););
   };
   // recon
-  { const int gi = G.recon; PUSH(ops, return run_wgrad(e, gi, dc8, dc8_n, 0, 0, 1, st);); }
-  bias_grad(dc8, dc8_n, L_D_RECON);
+  { const int gi = G.recon; PUSH_SIDE(ops, return run_wgrad(e, gi, dc8, dc8_n, 0, 0, 1, st, L_D_RECON);); }
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_RECON);
     const int gi = e->add_geom(geom_conv(B, H, W, {{dc8, 0, dc8_n, 0}}, 3, 1, 1, -1, 64, wa));
@@ -488,8 +536,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv7 (no activation): inputs [c5 | c0]
-  { const int gi = G.conv7; PUSH(ops, return run_wgrad(e, gi, g.dc7, 64, 0, 0, 1, st);); }
-  bias_grad(g.dc7, 64, L_D_CONV7);
+  { const int gi = G.conv7; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc7, 64, 0, 0, 1, st, L_D_CONV7);); }
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV7, 0);
     const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc7, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -503,8 +550,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv5 (ReLU already folded into dc5): inputs [dc | c1]
-  { const int gi = G.conv5; PUSH(ops, return run_wgrad(e, gi, g.dc5, 64, 0, 0, 1, st);); }
-  bias_grad(g.dc5, 64, L_D_CONV5);
+  { const int gi = G.conv5; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc5, 64, 0, 0, 1, st, L_D_CONV5);); }
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV5, 0);
     const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc5, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -522,14 +568,13 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     WAddr wa = waddr_conv_dgrad(e, L_D_DECONV);
     const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{g.ddc, 0, 64, 0}}, 3, 2, 1, +1, 128, wa));
     const Tens c3 = d.c3;
-    PUSH(ops, return run_wgrad(e, gi, c3, 128, 0, 0, 1, st););
+    PUSH_SIDE(ops, return run_wgrad(e, gi, c3, 128, 0, 0, 1, st););
     bias_grad(g.ddc, 64, L_D_DECONV);
     Epi ep = epi_bf16(g.dc3, 128); epi_set_mask(ep, d.c3);
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv3
-  { const int gi = G.conv3; PUSH(ops, return run_wgrad(e, gi, g.dc3, 128, 0, 0, 1, st);); }
-  bias_grad(g.dc3, 128, L_D_CONV3);
+  { const int gi = G.conv3; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc3, 128, 0, 0, 1, st, L_D_CONV3);); }
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV3);
     const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{g.dc3, 0, 128, 0}}, 3, 1, 1, -1, 128, wa));
@@ -537,8 +582,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv2 (stride 2): wgrad on its forward geom; dgrad = transposed gather per input parity class, + dc1p, ReLU mask
-  { const int gi = G.conv2; PUSH(ops, return run_wgrad(e, gi, g.dc2, 128, 0, 0, 1, st);); }
-  bias_grad(g.dc2, 128, L_D_CONV2);
+  { const int gi = G.conv2; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc2, 128, 0, 0, 1, st, L_D_CONV2);); }
   for (int q = 0; q < 4; ++q) {
     const int qh = q >> 1, qw = q & 1;
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV2);
@@ -549,8 +593,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv1
-  { const int gi = G.conv1; PUSH(ops, return run_wgrad(e, gi, g.dc1, 64, 0, 0, 1, st);); }
-  bias_grad(g.dc1, 64, L_D_CONV1);
+  { const int gi = G.conv1; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc1, 64, 0, 0, 1, st, L_D_CONV1);); }
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV1);
     const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc1, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -558,10 +601,8 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // shallow 9x9 and conv0 read the pass input
-  { const int gi = G.shallow; PUSH(ops, return run_wgrad(e, gi, g.dsh, 64, 0, 0, 1, st);); }
-  bias_grad(g.dsh, 64, L_D_SHALLOW);
-  { const int gi = G.conv0; PUSH(ops, return run_wgrad(e, gi, g.dc0, 32, 0, 0, 1, st);); }
-  bias_grad(g.dc0, 32, L_D_CONV0);
+  { const int gi = G.shallow; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dsh, 64, 0, 0, 1, st, L_D_SHALLOW);); }
+  { const int gi = G.conv0; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc0, 32, 0, 0, 1, st, L_D_CONV0);); }
   if (need_din) {  // d(input) = dgrad_shallow(dsh) + dgrad_conv0(dc0)
     {
       WAddr wa = waddr_conv_dgrad(e, L_D_SHALLOW);
@@ -760,7 +801,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     {
       const int64_t total = n * 8;
       const int rows_pb = 2;
-      PUSH(Lq, final_wgrad_kernel<<<(unsigned)(((int64_t)B * H + rows_pb - 1) / rows_pb), 576, 0, st>>>(
+      PUSH_SIDE(Lq, final_wgrad_kernel<<<(unsigned)(((int64_t)B * H + rows_pb - 1) / rows_pb), 576, 0, st>>>(
                    dId32, ff.p, e->grads + e->poff[2 * L_I_FINAL], e->grads + e->poff[2 * L_I_FINAL + 1], B, H, W,
                    rows_pb);
                return ss_check_launch("final_wgrad"););
@@ -768,8 +809,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
                    dId32, e->params + e->poff[2 * L_I_FINAL], dff.p, H, W, total);
                return ss_check_launch("final_dgrad"););
     }
-    PUSH(Lq, return run_wgrad(e, g_fus, dff, 64, 0, 0, 1, st););
-    PUSH(Lq, return ss_launch_bias_grad(dff.p, dff.pix(), 64, 64, e->grads + e->poff[2 * L_I_FUSION + 1], st););
+    PUSH_SIDE(Lq, return run_wgrad(e, g_fus, dff, 64, 0, 0, 1, st, L_I_FUSION););
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_FUSION);
       const int gi = e->add_geom(geom_conv(B, H, W, {{dff, 0, 64, 0}}, 1, 1, 0, -1, 192, wa));
@@ -778,8 +818,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     PUSH(Lq, return ss_launch_concat_bwd(dfg.p, r3.p, dr3.p, p2.p, p1.p, B, H, W, st););
     // deconv3
-    PUSH(Lq, return run_wgrad(e, g_d3, dr3, 64, 0, 0, 1, st););
-    PUSH(Lq, return ss_launch_bias_grad(dr3.p, dr3.pix(), 64, 64, e->grads + e->poff[2 * L_I_DECONV3 + 1], st););
+    PUSH_SIDE(Lq, return run_wgrad(e, g_d3, dr3, 64, 0, 0, 1, st, L_I_DECONV3););
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_DECONV3);
       const int gi = e->add_geom(geom_conv(B, H, W, {{dr3, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -788,8 +827,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     PUSH(Lq, return ss_launch_pool2(du3.p, p2.p, r2.p, da1p.p, dr2.p, nullptr, B, H / 2, W / 2, st););
     // deconv2
-    PUSH(Lq, return run_wgrad(e, g_d2, dr2, 64, 0, 0, 1, st););
-    PUSH(Lq, return ss_launch_bias_grad(dr2.p, dr2.pix(), 64, 64, e->grads + e->poff[2 * L_I_DECONV2 + 1], st););
+    PUSH_SIDE(Lq, return run_wgrad(e, g_d2, dr2, 64, 0, 0, 1, st, L_I_DECONV2););
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_DECONV2);
       const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{dr2, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -798,8 +836,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     PUSH(Lq, return ss_launch_pool2(du2.p, p1.p, r1.p, da2p.p, dr1.p, nullptr, B, H / 4, W / 4, st););
     // deconv1
-    PUSH(Lq, return run_wgrad(e, g_d1, dr1, 64, 0, 0, 1, st););
-    PUSH(Lq, return ss_launch_bias_grad(dr1.p, dr1.pix(), 64, 64, e->grads + e->poff[2 * L_I_DECONV1 + 1], st););
+    PUSH_SIDE(Lq, return run_wgrad(e, g_d1, dr1, 64, 0, 0, 1, st, L_I_DECONV1););
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_DECONV1);
       const int gi = e->add_geom(geom_conv(B, H / 4, W / 4, {{dr1, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -815,8 +852,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
                       {L_I_CONV1, g_i1, da1, a0, da0, Tens(), false}};
     for (int i = 0; i < 3; ++i) {
       const S2 s = s2[i];
-      PUSH(Lq, return run_wgrad(e, s.gfwd, s.dy, 64, 0, 0, 1, st););
-      PUSH(Lq, return ss_launch_bias_grad(s.dy.p, s.dy.pix(), 64, 64, e->grads + e->poff[2 * s.layer + 1], st););
+      PUSH_SIDE(Lq, return run_wgrad(e, s.gfwd, s.dy, 64, 0, 0, 1, st, s.layer););
       for (int q = 0; q < 4; ++q) {
         const int qh = q >> 1, qw = q & 1;
         WAddr wa = waddr_conv_dgrad(e, s.layer);
@@ -832,19 +868,20 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
       }
     }
     // conv0 of the illumination net reads cat[R, I]
-    PUSH(Lq, return run_wgrad(e, g_i0, da0, 64, 0, 0, 1, st););
-    PUSH(Lq, return ss_launch_bias_grad(da0.p, da0.pix(), 64, 64, e->grads + e->poff[2 * L_I_CONV0 + 1], st););
+    PUSH_SIDE(Lq, return run_wgrad(e, g_i0, da0, 64, 0, 0, 1, st, L_I_CONV0););
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_CONV0);
       const int gi = e->add_geom(geom_conv(B, H, W, {{da0, 0, 64, 0}}, 3, 1, 1, -1, C + 1, wa));
       Epi ep = epi_bf16(dRI, (C + 1 + 15) / 16 * 16);
       PUSH(Lq, return run_gather(e, gi, ep, -1, st););
     }
+    PUSH_JOIN(Lq);
 
     // ---- backward, pass 1 -------------------------------------------------------------------
     auto& B1 = e->ops_bwd1;
     PUSH(B1, return ss_launch_head_bwd(dR32, e->R32, dRI.p, 128, dI32, e->I32, dc8.p, 128, B, C, H, W, st););
     plan_decomp_bwd(e, B1, X, d1, G1, dc8, C + 1, gr, false);
+    PUSH_JOIN(B1);
   }
 
   if ((int)e->geoms.size() > 128) {
@@ -860,6 +897,15 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     e->pack_start[i + 1] = e->pack_start[i] + (int)((elems + 255) / 256);
   }
   e->pack_blocks = e->pack_start.back();
+  if (e->train) {
+    size_t mx = 0;
+    for (size_t i = 0; i < e->geoms.size(); ++i) {
+      const size_t a = ss_umma_wgrad_partial_floats(e->geoms[i], 128), b = ss_umma_wgrad_partial_floats(e->geoms[i], 64);
+      mx = std::max(mx, std::max(a, b));
+    }
+    e->wg_partial_floats = mx;
+    e->wg_partial = e->falloc((int64_t)mx);
+  }
   e->ws_bytes = e->cursor;
   return SSHSLIE_OK;
 }
@@ -907,7 +953,13 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
   *out = e;
   return SSHSLIE_OK;
 }
-extern "C" void sshslie_engine_destroy(sshslie_engine* e) { delete e; }
+extern "C" void sshslie_engine_destroy(sshslie_engine* e) {
+  if (!e) return;
+  if (e->side) cudaStreamDestroy(e->side);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  delete e;
+}
 extern "C" int64_t sshslie_engine_workspace_bytes(const sshslie_engine* e) { return e ? e->ws_bytes : 0; }
 
 extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t workspace_bytes, void* stream) {
@@ -918,6 +970,15 @@ extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t w
   }
   cudaStream_t st = (cudaStream_t)stream;
   e->bound = false;
+  e->gmaps.clear();
+  if (!e->side) {
+    if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      ss_set_error("bind: cannot create the side stream: %s", cudaGetErrorString(cudaGetLastError()));
+      return SSHSLIE_ERR_CUDA;
+    }
+  }
   int rc = build_plan(e, (unsigned char*)workspace);
   if (rc != SSHSLIE_OK) return rc;
   e->ws = (unsigned char*)workspace;
@@ -1024,6 +1085,7 @@ extern "C" int64_t sshslie_conv2d_scratch_bytes(int B, int Cin, int Cout, int H,
   bytes += big * pad64(Cout) * 2 + 1024;
   bytes += (int64_t)sizeof(ConvGeom) * 8 + 4096;
   bytes += 4 * ((int64_t)(pad64(Cin) + pad64(Cout)) * k * k * pad64(Cin > Cout ? Cin : Cout) * 2 + 1024);
+  bytes += (int64_t)148 * 512 * 128 * 4 + 1024;     // split-K partials of the tcgen05 wgrad: <= 148 CTAs x all TMEM
   return bytes + (1 << 16);
 }
 
@@ -1118,6 +1180,10 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
     g.wp = (bf16*)e->alloc(elems * sizeof(bf16));
     e->pack_start[i + 1] = e->pack_start[i] + (int)((elems + 255) / 256);
   }
+  if (kind == 2 && impl == 1) {
+    e->wg_partial_floats = ss_umma_wgrad_partial_floats(e->geoms[0], gN);
+    e->wg_partial = e->falloc((int64_t)e->wg_partial_floats);
+  }
   if (e->cursor > scratch_bytes) { ss_set_error("sshslie_conv2d: scratch overflow"); return SSHSLIE_ERR_WORKSPACE; }
   const size_t msz = ss_umma_maps_size();
   e->maps_blob.assign(e->geoms.size() * msz, 0);
@@ -1186,6 +1252,8 @@ extern "C" SSHSLIE_API int sshslie_profile_step(sshslie_engine* e, const float* 
   e->x = x; e->params = params;
   g_prof_rows.clear();
   g_prof_on = true;
+  const bool saved_side = e->use_side;
+  e->use_side = false;
   int rc = run_ops_profiled(e->ops_fwd, st, "fwd");
   if (!rc && e->train && cfg && grads && losses) {
     e->grads = grads; e->losses = losses; e->cfg = *cfg;
@@ -1193,6 +1261,7 @@ extern "C" SSHSLIE_API int sshslie_profile_step(sshslie_engine* e, const float* 
     if (!rc) rc = run_ops_profiled(e->ops_bwd1, st, "pass1_bwd");
   }
   g_prof_on = false;
+  e->use_side = saved_side;
   return rc ? rc : (int)g_prof_rows.size();
 }
 extern "C" SSHSLIE_API int sshslie_profile_row(int i, char* name, int name_cap, float* ms, double* flops,

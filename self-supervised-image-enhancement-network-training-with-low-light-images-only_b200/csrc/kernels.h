@@ -19,8 +19,11 @@ int ss_umma_wgrad_supported(const ConvGeom& g);
 int ss_umma_build_maps(const ConvGeom& g, UmmaMaps* maps);     // needs final device pointers
 int ss_launch_conv_gather_umma(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const Epi& epi,
                                cudaStream_t st);
-int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const bf16* G,
-                              int64_t gB, int64_t gH, int64_t gW, int gN, float* grads, cudaStream_t st);
+int ss_umma_build_gmap(const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld_extent, const ConvGeom& g,
+                       void* out_map /* 128 bytes, 64-byte aligned */);
+int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const void* gmap,
+                              int gN, long long bias_off, float* partial, float* grads, cudaStream_t st);
+size_t ss_umma_wgrad_partial_floats(const ConvGeom& g, int gN);
 size_t ss_umma_maps_size();
 
 // elementwise.cu

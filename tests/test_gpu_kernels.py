@@ -73,8 +73,9 @@ def test_conv_dgrad(case, impl):
     torch.testing.assert_close(dx, dx_ref, rtol=2 ** -7, atol=2e-3 * float(dx_ref.abs().max()))
 
 
-@pytest.mark.parametrize("case", CONV_CASES[:8], ids=[c[0] for c in CONV_CASES[:8]])
-def test_conv_wgrad(case):
+@pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES[:9] + CONV_CASES[11:], ids=[c[0] for c in CONV_CASES[:9] + CONV_CASES[11:]])
+def test_conv_wgrad(case, impl):
     """fp32 output, bf16 operands: only summation order differs -> rtol 1e-3 of the largest entry."""
     from gpu_util import conv2d, bf16_round
     name, Cin, Cout, k, stride, tr, H, W, B = case
@@ -84,7 +85,7 @@ def test_conv_wgrad(case):
     dy = bf16_round(torch.randn(yref.shape, generator=torch.Generator().manual_seed(5))).cuda()
     (dw_ref,) = torch.autograd.grad(yref, w, dy)
     dw = torch.zeros_like(dw_ref)
-    conv2d(2, 0, tr, x.detach(), dw, None, dy, B, Cin, Cout, H, W, k, stride, relu=False)
+    conv2d(2, impl, tr, x.detach(), dw, None, dy, B, Cin, Cout, H, W, k, stride, relu=False)
     torch.testing.assert_close(dw, dw_ref, rtol=1e-3, atol=1e-3 * float(dw_ref.abs().max()))
 
 
