@@ -14,6 +14,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -29,6 +31,14 @@ struct alignas(64) UmmaMaps {
   CUtensorMap w;
 };
 size_t ss_umma_maps_size() { return sizeof(UmmaMaps); }
+static int g_pdl = -1;
+int ss_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("SSHSLIE_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -91,6 +101,10 @@ SS_DEVINL void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 SS_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// programmatic dependent launch: let the next kernel's prologue overlap this kernel / wait for the previous kernel's
+// results.  Both are no-ops when the kernel was launched without the PDL attribute.
+SS_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+SS_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 SS_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 SS_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 SS_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -149,7 +163,8 @@ conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
+  pdl_launch_dependents();
+  {   // the plan (ConvGeom) is written once at bind time, never by a kernel: safe to read before pdl_wait()
     const int* src = reinterpret_cast<const int*>(gp);
     int* dst = reinterpret_cast<int*>(&g);
     for (int i = threadIdx.x; i < (int)(sizeof(ConvGeom) / 4); i += blockDim.x) dst[i] = src[i];
@@ -176,6 +191,7 @@ conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();      // everything below reads or writes tensors produced by earlier kernels
 
   // tile -> (b, oh0, ow0)
   const int tiles_w = (g.OW + g.tw - 1) / g.tw, tiles_h = (g.OH + g.th - 1) / g.th;
@@ -331,7 +347,18 @@ int ss_launch_conv_gather_umma(const ConvGeom* g_dev, const ConvGeom& g, const U
     }
     attr_set = true;
   }
-  conv_gather_umma_kernel<<<tiles, UM_THREADS, smem, st>>>(g_dev, maps, epi, cols);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(tiles);
+  cfg.blockDim = dim3(UM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ss_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, conv_gather_umma_kernel, g_dev, maps, epi, cols);
   return ss_check_launch("conv_gather_umma");
 }
 

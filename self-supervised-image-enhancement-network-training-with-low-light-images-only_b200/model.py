@@ -109,32 +109,59 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self._owner = [owner]
         self._step = 0
+        self._state_ready = False
         self.grad_scale = 1.0
 
     def _ensure_state(self):
+        """(Re)attach the per-parameter state entries to the flat moment buffers."""
         own = self._owner[0]
         own._ensure_flat()
         if own._flat_m is None or own._flat_m.device != own._flat.device:
             own._flat_m = torch.zeros_like(own._flat)
             own._flat_v = torch.zeros_like(own._flat)
+            self._state_ready = False
+        if self._state_ready and self._state_flat is own._flat_m:
+            return
         for p, (off, n) in zip(own._plist, own._pranges):
             st = self.state[p]
-            if "exp_avg" not in st or st["exp_avg"].data_ptr() != own._flat_m.data_ptr() + 4 * off:
-                if "exp_avg" in st:   # loaded from a checkpoint: copy into the flat buffers
-                    own._flat_m[off:off + n].copy_(st["exp_avg"].reshape(-1))
-                    own._flat_v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
-                    self._step = max(self._step, int(st.get("step", 0)))
-                st["exp_avg"] = own._flat_m[off:off + n].view(p.shape)
-                st["exp_avg_sq"] = own._flat_v[off:off + n].view(p.shape)
+            if "exp_avg" in st and st["exp_avg"].data_ptr() != own._flat_m.data_ptr() + 4 * off:
+                own._flat_m[off:off + n].copy_(st["exp_avg"].reshape(-1))          # loaded from a checkpoint
+                own._flat_v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                self._step = max(self._step, int(st.get("step", 0)))
+            st["exp_avg"] = own._flat_m[off:off + n].view(p.shape)
+            st["exp_avg_sq"] = own._flat_v[off:off + n].view(p.shape)
             st["step"] = torch.tensor(float(self._step))
+        self._state_ready = True
+        self._state_flat = own._flat_m
+
+    def zero_grad(self, set_to_none=True):
+        if set_to_none:
+            for p in self._owner[0]._plist:
+                p.grad = None
+        else:
+            super().zero_grad(set_to_none=False)
+
+    def _launch(self, lo, hi):
+        own = self._owner[0]
+        group = self.param_groups[0]
+        b1, b2 = group["betas"]
+        stream = ctypes.c_void_p(torch.cuda.current_stream(own._flat.device).cuda_stream)
+        L.check(L.load().sshslie_adam_step(
+            ctypes.c_void_p(own._flat.data_ptr() + 4 * lo), ctypes.c_void_p(own._flat_grad.data_ptr() + 4 * lo),
+            ctypes.c_void_p(own._flat_m.data_ptr() + 4 * lo), ctypes.c_void_p(own._flat_v.data_ptr() + 4 * lo),
+            hi - lo, float(group["lr"]), float(b1), float(b2), float(group["eps"]), self._step,
+            float(self.grad_scale), stream), "sshslie_adam_step")
 
     @torch.no_grad()
     def step(self, closure=None):
         own = self._owner[0]
         self._ensure_state()
         self._step += 1
-        group = self.param_groups[0]
-        # contiguous ranges of parameters that received a gradient (frozen decomposition_net -> only the tail)
+        views = own._grad_views
+        if views is not None and all(p.grad is v for p, v in zip(own._plist, views)):
+            self._launch(0, own._nparams)            # every gradient is the finished view of the flat buffer
+            return None
+        # general path: contiguous ranges of parameters that received a gradient (frozen decomposition_net -> tail)
         ranges = []
         for p, (off, n) in zip(own._plist, own._pranges):
             if p.grad is None:
@@ -145,18 +172,16 @@ class FusedAdam(torch.optim.Optimizer):
                 ranges[-1][1] = off + n
             else:
                 ranges.append([off, off + n])
-        lib = L.load()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(own._flat.device).cuda_stream)
-        b1, b2 = group["betas"]
         for lo, hi in ranges:
-            L.check(lib.sshslie_adam_step(
-                ctypes.c_void_p(own._flat.data_ptr() + 4 * lo), ctypes.c_void_p(own._flat_grad.data_ptr() + 4 * lo),
-                ctypes.c_void_p(own._flat_m.data_ptr() + 4 * lo), ctypes.c_void_p(own._flat_v.data_ptr() + 4 * lo),
-                hi - lo, float(group["lr"]), float(b1), float(b2), float(group["eps"]), self._step,
-                float(self.grad_scale), stream), "sshslie_adam_step")
-        for p in own._plist:
-            self.state[p]["step"] = torch.tensor(float(self._step))
+            self._launch(lo, hi)
         return None
+
+    def state_dict(self):
+        if self._owner[0]._plist[0].is_cuda:
+            self._ensure_state()
+            for st in self.state.values():
+                st["step"] = torch.tensor(float(self._step))
+        return super().state_dict()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
@@ -164,37 +189,38 @@ class FusedAdam(torch.optim.Optimizer):
         for st in self.state.values():
             if "step" in st:
                 self._step = max(self._step, int(st["step"]))
+        self._state_ready = False
         self._ensure_state()
 
 
 class _LossFn(torch.autograd.Function):
-    """Forward runs compute_loss AND backward on the GPU; backward returns the finished gradient views."""
+    """compute_loss already ran forward AND backward on the GPU.  `loss.backward()` lands here once and hands the
+    finished gradient views to the parameters (p.grad = view, or += when a gradient is already there), instead of
+    routing 46 tensors through autograd's AccumulateGrad nodes."""
 
     @staticmethod
-    def forward(ctx, owner_box, *params):
-        own = owner_box[0]
+    def forward(ctx, anchor, owner_box):
         ctx.owner_box = owner_box
-        ctx.need = [p.requires_grad for p in params]
-        return own._losses_dev[0].clone()
+        return owner_box[0]._losses_dev[0].clone()
 
     @staticmethod
     def backward(ctx, gout):
         own = ctx.owner_box[0]
-        grads = []
-        unit = None
-        for need, (off, n), p in zip(ctx.need, own._pranges, own._plist):
-            if not need:
-                grads.append(None)
+        scale = 1.0
+        if gout is not None and gout.numel() == 1:
+            g = float(gout)
+            if g != 1.0:
+                scale = g
+        views = own._grad_views
+        for p, v in zip(own._plist, views):
+            if not p.requires_grad:
                 continue
-            g = own._flat_grad[off:off + n].view(p.shape)
-            grads.append(g)
-        if gout is not None:
-            unit = float(gout) if gout.numel() == 1 and not gout.is_cuda else None
-            if unit is None:
-                unit = float(gout.item())
-            if unit != 1.0:
-                grads = [None if g is None else g * unit for g in grads]
-        return (None, *grads)
+            gv = v if scale == 1.0 else v * scale
+            if p.grad is None:
+                p.grad = gv
+            else:
+                p.grad = p.grad + gv
+        return None, None
 
 
 class LazyLosses(dict):
@@ -311,6 +337,7 @@ class LowLightEnhance(nn.Module):
         self._pranges = list(zip(offs, sizes))
         self._nparams = total
         self._flat = self._flat_grad = self._flat_m = self._flat_v = None
+        self._grad_views = None
         self._engines = {}
         self._losses_dev = None
         self.use_cuda_graph = True
@@ -343,6 +370,9 @@ class LowLightEnhance(nn.Module):
                 p.data = flat[off:off + n].view(p.shape)
         self._flat = flat
         self._flat_grad = torch.zeros_like(flat)
+        self._grad_views = [self._flat_grad[off:off + n].view(p.shape) for p, (off, n) in
+                            zip(self._plist, self._pranges)]
+        self._anchor = torch.zeros((), device=p0.device, requires_grad=True)
         self._losses_dev = torch.zeros(8, dtype=torch.float32, device=p0.device)
         self._engines = {}
 
@@ -410,8 +440,8 @@ class LowLightEnhance(nn.Module):
         else:
             self._launch_loss_and_grad(eng)
         self.last_outputs = (eng.R, eng.I, eng.Id, eng.S)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self._plist):
-            total = _LossFn.apply(self._box, *self._plist)
+        if torch.is_grad_enabled():
+            total = _LossFn.apply(self._anchor, self._box)
         else:
             total = self._losses_dev[0].clone()
         return total, LazyLosses(self._losses_dev[:7].clone())
