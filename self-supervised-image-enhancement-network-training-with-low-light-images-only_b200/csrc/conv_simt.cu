@@ -32,13 +32,12 @@ __global__ void __launch_bounds__(128) conv_gather_simt_kernel(const ConvGeom* _
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  const int Ktot = g.nslabs * SS_SLAB;
   for (int s = 0; s < g.nslabs; ++s) {
     __syncthreads();
     {  // 16 rows x 64 bf16 = 128 x 16 bytes
       const int r = threadIdx.x >> 3, q = threadIdx.x & 7;
       reinterpret_cast<uint4*>(wsm)[threadIdx.x] =
-          *reinterpret_cast<const uint4*>(g.wp + (size_t)(n0 + r) * Ktot + s * SS_SLAB + q * 8);
+          *reinterpret_cast<const uint4*>(g.wp + ((size_t)s * g.Npad + n0 + r) * SS_SLAB + q * 8);
     }
     __syncthreads();
     const Slab sl = g.slab[s];
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvGeom* __res
   const Slab sl = g->slab[s];
   float w = 0.f;
   if (n < g->N && c < sl.wcn) w = __ldg(params + g->w_off + (int64_t)n * g->w_sN + sl.woff + (int64_t)c * g->w_sC);
-  g->wp[idx] = f2bf(w);
+  g->wp[((size_t)s * g->Npad + n) * SS_SLAB + c] = f2bf(w);   // slab-major: one slab = Npad x 64 contiguous bf16
 }
 
 int ss_launch_pack_weights(const ConvGeom* geoms_dev, const int* block_start_dev, int njobs, int total_blocks,

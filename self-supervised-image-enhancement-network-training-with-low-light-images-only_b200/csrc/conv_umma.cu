@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -29,6 +30,7 @@
 struct alignas(64) UmmaMaps {
   CUtensorMap src[SS_MAX_SRC];
   CUtensorMap w;
+  CUtensorMap halo[SS_MAX_SRC];   // same views, box = one halo window (HALO_TW+2p) x (HALO_TH+2p) x 64 ch
 };
 size_t ss_umma_maps_size() { return sizeof(UmmaMaps); }
 static int g_pdl = -1;
@@ -78,6 +80,24 @@ SS_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// whole-warp wait with ONE polling lane: 128 epilogue threads hammering try_wait on the same barrier slow the
+// SM's barrier unit down for the MMA warp's commits and the producer's arrivals (measured: 0.4 us per K-slab)
+SS_DEVINL void mbar_wait_warp(uint32_t bar, uint32_t parity, unsigned sleep_ns) {
+  if ((threadIdx.x & 31) == 0) {
+    if (!mbar_try_wait(bar, parity)) {
+      const long long t0 = clock64();
+      while (!mbar_try_wait(bar, parity)) {
+        if (sleep_ns) __nanosleep(sleep_ns);
+        if (clock64() - t0 > UM_WAIT_CYCLES) {
+          printf("sshslie: mbarrier wait timed out (block %d warp %d bar %u parity %u)\n", (int)blockIdx.x,
+                 (int)(threadIdx.x >> 5), bar, parity);
+          __trap();
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
 SS_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -115,6 +135,18 @@ SS_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one elected lane of a CONVERGED warp (the MMA warp runs its loop warp-uniformly so that descriptors stay in uniform
+// registers; issuing tcgen05.mma under `if (lane == 0)` makes ptxas wrap every MMA in an ELECT/R2UR waterfall loop)
+SS_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+SS_DEVINL uint32_t uniform32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 SS_DEVINL void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -213,29 +245,28 @@ conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
         const uint32_t fb = smem_u32(&full_bar[st]);
         mbar_expect_tx(fb, stage_bytes);
         tma_load_4d(a_dst, &maps.src[sl.src], fb, sl.c0, ow0 + sl.dw, oh0 + sl.dh, b);
-        tma_load_2d(a_dst + UM_A_BYTES, &maps.w, fb, s * SS_SLAB, 0);
+        tma_load_2d(a_dst + UM_A_BYTES, &maps.w, fb, 0, s * Npad);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, Npad, 0, 0);
-      for (int s = 0; s < g.nslabs; ++s) {
-        const int st = s % UM_STAGES;
-        const uint32_t ph = (uint32_t)(s / UM_STAGES) & 1u;
-        mbar_wait(smem_u32(&full_bar[st]), ph);
-        tc_fence_after();
-        const uint32_t a_addr = dyn_base + (uint32_t)st * stage_bytes;
-        const uint32_t b_addr = a_addr + UM_A_BYTES;
+    // ===== MMA issuer: whole warp converged, one elected lane issues =====
+    const uint32_t idesc = make_idesc(128, Npad, 0, 0);
+    const uint32_t tm = uniform32(tmem_base), base = uniform32(dyn_base);
+    for (int s = 0; s < g.nslabs; ++s) {
+      const int st = s % UM_STAGES;
+      const uint32_t ph = (uint32_t)(s / UM_STAGES) & 1u;
+      mbar_wait_warp(smem_u32(&full_bar[st]), ph, 0);
+      tc_fence_after();
+      const uint32_t a_addr = base + (uint32_t)st * stage_bytes;
+      const uint64_t ad0 = make_sdesc(a_addr, 16, 1024);
+      const uint64_t bd0 = make_sdesc(a_addr + UM_A_BYTES, 16, 1024);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_sdesc(a_addr + k * 32, 16, 1024);
-          const uint64_t bd = make_sdesc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (s > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k) umma_bf16(tm, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, (s > 0 || k > 0) ? 1u : 0u);
         umma_commit(smem_u32(&empty_bar[st]));      // frees the stage when these MMAs retire
+        if (s == g.nslabs - 1) umma_commit(smem_u32(&accum_bar));
       }
-      umma_commit(smem_u32(&accum_bar));            // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
@@ -243,7 +274,7 @@ conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
     const int row = quarter * 32 + lane;
     const int oh = oh0 + row / g.tw, ow = ow0 + row % g.tw;
     const bool ok = oh < g.OH && ow < g.OW;
-    mbar_wait(smem_u32(&accum_bar), 0);
+    mbar_wait_warp(smem_u32(&accum_bar), 0, 200);
     tc_fence_after();
     for (int n0 = 0; n0 < Npad; n0 += 16) {
       float v[16];
@@ -254,6 +285,164 @@ conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather GEMM with HALO REUSE (stride-1 taps):  the per-tap activation windows of a tile overlap almost entirely,
+// so instead of one TMA load per tap the CTA loads ONE halo window per (source, 64-channel slab) —
+// (16+2p) x (8+2p) pixels x 64 ch — and points the UMMA A-descriptor of tap (dh,dw) INTO it:
+//     start = halo + ((dh+p) * pitch + (dw+p)) * 128 B,   SBO = pitch * 128 B  (one 8-pixel output row per group)
+// (the 128B swizzle is a function of the shared-memory address, for TMA writes and UMMA reads alike, so a start
+// that is 128B- but not 1024B-aligned still addresses consistently; `bo_mode` selects the descriptor base_offset).
+// Only the weight slabs stream through the ring, and T pixel tiles per CTA share each weight slab, which turns the
+// kernel from L2-feed-bound (24 KB per 4 MMAs) into MMA-bound (8 KB per 4*T MMAs).
+// ---------------------------------------------------------------------------------------------
+#define HALO_TW 8
+#define HALO_TH 16
+#define HALO_MAX_T 4
+#define HALO_MAX_STAGES 16
+
+struct HaloArgs {
+  int nh;                  // distinct (source, channel-slab) halo windows per tile
+  int src[SS_MAX_SRC];
+  int c0[SS_MAX_SRC];
+  int pad;                 // p = max |dh|,|dw|
+  int T;                   // pixel tiles per CTA
+  int halo_bytes;          // one window, rounded up to 1024
+  int bo_mode;             // 0: base_offset = 0 ; 1: base_offset = (start >> 7) & 7
+  int tmem_cols;
+  int n_tiles;
+  int stages;              // depth of the weight-slab ring (the only operand that streams)
+  int debug;               // timing experiments only (wrong results): 1 = every tap reads the window at offset 0
+};
+
+SS_DEVINL uint64_t make_sdesc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, int bo_mode) {
+  uint64_t d = make_sdesc(smem_addr, lbo_bytes, sbo_bytes);
+  if (bo_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps maps, Epi epi, HaloArgs ha) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ ConvGeom g;
+  __shared__ __align__(8) uint64_t full_bar[HALO_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[HALO_MAX_STAGES];
+  __shared__ __align__(8) uint64_t halo_bar[HALO_MAX_T];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  {
+    const int* src = reinterpret_cast<const int*>(gp);
+    int* dst = reinterpret_cast<int*>(&g);
+    for (int i = threadIdx.x; i < (int)(sizeof(ConvGeom) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  __syncthreads();
+  const int Npad = g.Npad;
+  const uint32_t b_bytes = (uint32_t)Npad * 128u;
+  const uint32_t ring_base = dyn_base + (uint32_t)(ha.T * ha.nh * ha.halo_bytes);
+  const int pitch = HALO_TW + 2 * ha.pad;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&maps.halo[s]);
+    tma_prefetch_desc(&maps.w);
+    for (int s = 0; s < ha.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int t = 0; t < HALO_MAX_T; ++t) mbar_init(smem_u32(&halo_bar[t]), 1);
+    mbar_init(smem_u32(&accum_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)ha.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+
+  const int tiles_w = g.OW / HALO_TW, tiles_h = (g.OH + HALO_TH - 1) / HALO_TH;
+  const int t_first = blockIdx.x * ha.T;
+  const int nt = min(ha.T, ha.n_tiles - t_first);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int t = 0; t < nt; ++t) {
+        int ti = t_first + t;
+        const int twi = ti % tiles_w; ti /= tiles_w;
+        const int thi = ti % tiles_h;
+        const int b = ti / tiles_h;
+        const uint32_t hb = smem_u32(&halo_bar[t]);
+        if (ha.debug & 32) { mbar_arrive(hb); continue; }
+        mbar_expect_tx(hb, (uint32_t)ha.nh * (uint32_t)((HALO_TH + 2 * ha.pad) * pitch * 128));
+        for (int h = 0; h < ha.nh; ++h)
+          tma_load_4d(dyn_base + (uint32_t)((t * ha.nh + h) * ha.halo_bytes), &maps.halo[ha.src[h]], hb, ha.c0[h],
+                      twi * HALO_TW - ha.pad, thi * HALO_TH - ha.pad, b);
+      }
+      for (int s = 0; s < g.nslabs && !(ha.debug & 4); ++s) {
+        const int st = s % ha.stages;
+        mbar_wait(smem_u32(&empty_bar[st]), (((uint32_t)(s / ha.stages)) & 1u) ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[st]);
+        mbar_expect_tx(fb, b_bytes);
+        tma_load_2d(ring_base + (uint32_t)st * b_bytes, &maps.w, fb, 0, s * Npad);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, Npad, 0, 0);
+    const uint32_t tm = uniform32(tmem_base), base = uniform32(dyn_base), rbase = uniform32(ring_base);
+    for (int s = 0; s < g.nslabs; ++s) {
+      const int st = s % ha.stages;
+      const Slab sl = g.slab[s];
+      int h = 0;
+      for (int i = 0; i < ha.nh; ++i)
+        if (ha.src[i] == sl.src && ha.c0[i] == sl.c0) h = i;
+      if (!(ha.debug & 4)) mbar_wait_warp(smem_u32(&full_bar[st]), ((uint32_t)(s / ha.stages)) & 1u, 0);
+      if (s == 0)
+        for (int t = 0; t < nt; ++t) mbar_wait_warp(smem_u32(&halo_bar[t]), 0, 0);
+      if (!(ha.debug & 8)) tc_fence_after();
+      const uint32_t tap_off = (ha.debug & 1) ? 0u : (uint32_t)(((sl.dh + ha.pad) * pitch + (sl.dw + ha.pad)) * 128);
+      const uint64_t bd0 = make_sdesc(rbase + (uint32_t)st * b_bytes, 16, 1024);
+      const uint32_t a0 = base + (uint32_t)(h * ha.halo_bytes) + tap_off;
+      if (elect_one()) {
+        // k outer, tile inner: consecutive MMAs accumulate into DIFFERENT TMEM tiles, so the dependent-accumulate
+        // latency of one narrow (N = 64) MMA is hidden behind the MMAs of the other tiles
+        const uint64_t ad0 = make_sdesc_bo(a0, 16, (uint32_t)pitch * 128u, ha.bo_mode);
+        const uint64_t tstep = (uint64_t)((ha.nh * ha.halo_bytes) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          for (int t = 0; t < nt && !(ha.debug & 2); ++t)
+            umma_bf16(tm + (uint32_t)(t * Npad), ad0 + (uint64_t)t * tstep + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k),
+                      idesc, (s > 0 || k > 0) ? 1u : 0u);
+        if (!(ha.debug & 16)) umma_commit(smem_u32(&empty_bar[st]));
+        if (s == g.nslabs - 1) umma_commit(smem_u32(&accum_bar));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait_warp(smem_u32(&accum_bar), 0, 200);
+    tc_fence_after();
+    for (int t = 0; t < nt; ++t) {
+      int ti = t_first + t;
+      const int twi = ti % tiles_w; ti /= tiles_w;
+      const int thi = ti % tiles_h;
+      const int b = ti / tiles_h;
+      const int oh = thi * HALO_TH + (row >> 3), ow = twi * HALO_TW + (row & 7);
+      const bool ok = oh < g.OH;
+      for (int n0 = 0; n0 < Npad; n0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Npad + n0), v);
+        if (ok) epi_apply16(epi, b, oh, ow, n0, g.N, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)ha.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,6 +475,62 @@ int ss_umma_supported(const ConvGeom& g) {
   return 1;
 }
 
+static int halo_args(const ConvGeom& g, HaloArgs* out) {
+  HaloArgs ha;
+  memset(&ha, 0, sizeof(ha));
+  if (g.OW % HALO_TW) return 0;
+  int pad = 0;
+  for (int i = 0; i < g.nslabs; ++i) {
+    const Slab& sl = g.slab[i];
+    pad = std::max(pad, std::max(abs((int)sl.dh), abs((int)sl.dw)));
+    int h = -1;
+    for (int j = 0; j < ha.nh; ++j)
+      if (ha.src[j] == sl.src && ha.c0[j] == sl.c0) h = j;
+    if (h < 0) {
+      if (ha.nh == SS_MAX_SRC) return 0;
+      ha.src[ha.nh] = sl.src; ha.c0[ha.nh] = sl.c0; ++ha.nh;
+    }
+  }
+  if (pad > 4) return 0;
+  ha.pad = pad;
+  const int rows = (HALO_TH + 2 * pad) * (HALO_TW + 2 * pad);
+  ha.halo_bytes = (rows * 128 + 1023) / 1024 * 1024;
+  const int ring = 6 * g.Npad * 128;                  // smallest ring we accept when sizing T
+  int T = HALO_MAX_T;
+  while (T > 1 && (T * ha.nh * ha.halo_bytes + ring > 200 * 1024 || T * g.Npad > 512)) --T;
+  if (T * ha.nh * ha.halo_bytes + ring > 200 * 1024 || T * g.Npad > 512) return 0;
+  ha.n_tiles = g.B * ((g.OH + HALO_TH - 1) / HALO_TH) * (g.OW / HALO_TW);
+  const int T0 = T;        // largest T the shared memory / TMEM budget allows
+  // keep at least ~one wave of CTAs
+  while (T > 1 && (ha.n_tiles + T - 1) / T < 120) --T;
+  {
+    const char* te = getenv("SSHSLIE_HALO_T");
+    if (te && atoi(te) >= 1 && atoi(te) <= T0) T = atoi(te);
+  }
+  ha.T = T;
+  int stages = (200 * 1024 - T * ha.nh * ha.halo_bytes) / (g.Npad * 128);
+  if (stages > HALO_MAX_STAGES) stages = HALO_MAX_STAGES;
+  if (stages > g.nslabs) stages = std::max(2, g.nslabs);
+  {
+    const char* se = getenv("SSHSLIE_HALO_STAGES");
+    if (se && atoi(se) >= 2 && atoi(se) <= stages) stages = atoi(se);
+    const char* de = getenv("SSHSLIE_HALO_DEBUG");
+    ha.debug = de ? atoi(de) : 0;
+  }
+  ha.stages = stages;
+  int cols = 32;
+  while (cols < T * g.Npad) cols <<= 1;
+  ha.tmem_cols = cols;
+  const char* e = getenv("SSHSLIE_HALO_BO");
+  ha.bo_mode = (e && e[0] == '1') ? 1 : 0;
+  *out = ha;
+  return 1;
+}
+int ss_umma_halo_supported(const ConvGeom& g) {
+  HaloArgs ha;
+  return ss_umma_supported(g) && halo_args(g, &ha);
+}
+
 static int encode_src(const SrcView& v, int ld_extent, int tw, int th, int B, CUtensorMap* out) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return SSHSLIE_ERR_CUDA;
@@ -310,14 +555,20 @@ int ss_umma_build_maps(const ConvGeom& g, UmmaMaps* maps) {
     int ext = 64;
     for (int i = 0; i < g.nslabs; ++i)
       if (g.slab[i].src == s && g.slab[i].c0 + 64 > ext) ext = g.slab[i].c0 + 64;
-    const int rc = encode_src(g.src[s], ext, g.tw, g.th, g.B, &maps->src[s]);
+    int rc = encode_src(g.src[s], ext, g.tw, g.th, g.B, &maps->src[s]);
     if (rc) return rc;
+    HaloArgs ha;
+    if (halo_args(g, &ha)) {
+      rc = encode_src(g.src[s], ext, HALO_TW + 2 * ha.pad, HALO_TH + 2 * ha.pad, g.B, &maps->halo[s]);
+      if (rc) return rc;
+    }
   }
   EncodeTiledFn enc = get_encode();
   if (!enc) return SSHSLIE_ERR_CUDA;
+  // packed weights are slab-major: [nslabs][Npad][64] bf16, so one slab is ONE contiguous Npad x 128 B block
   const cuuint64_t Ktot = (cuuint64_t)g.nslabs * SS_SLAB;
-  cuuint64_t dims[2] = {Ktot, (cuuint64_t)g.Npad};
-  cuuint64_t strides[1] = {Ktot * 2};
+  cuuint64_t dims[2] = {64, (cuuint64_t)g.Npad * g.nslabs};
+  cuuint64_t strides[1] = {128};
   cuuint32_t box[2] = {64, (cuuint32_t)g.Npad};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&maps->w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)g.wp, dims, strides, box, estr,
@@ -484,43 +735,45 @@ conv_wgrad_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, wa.N, 1, 1);
-      int it = 0;
-      for (int ti = 0; ti < ntiles; ++ti) {
-        const int gs = ti & 1;
-        mbar_wait(smem_u32(&g_full[gs]), ((uint32_t)(ti >> 1)) & 1u);
-        for (int p = 0; p < npairs; ++p, ++it) {
-          const int st = it % WG_STAGES;
-          mbar_wait(smem_u32(&a_full[st]), ((uint32_t)(it / WG_STAGES)) & 1u);
-          tc_fence_after();
-          const uint32_t a_addr = dyn_base + st * WG_STAGE_BYTES;
-          const uint32_t b_addr = g_base + gs * WG_G_BYTES;
+    const uint32_t idesc = make_idesc(128, wa.N, 1, 1);
+    const uint32_t tm = uniform32(tmem_base), base = uniform32(dyn_base), gb = uniform32(g_base),
+                   ob = uniform32(ones_base);
+    int it = 0;
+    for (int ti = 0; ti < ntiles; ++ti) {
+      const int gs = ti & 1;
+      mbar_wait_warp(smem_u32(&g_full[gs]), ((uint32_t)(ti >> 1)) & 1u, 0);
+      const uint64_t bd0 = make_sdesc(gb + gs * WG_G_BYTES, UM_A_BYTES, 1024);       // 1 or 2 G atoms
+      for (int p = 0; p < npairs; ++p, ++it) {
+        const int st = it % WG_STAGES;
+        mbar_wait_warp(smem_u32(&a_full[st]), ((uint32_t)(it / WG_STAGES)) & 1u, 0);
+        tc_fence_after();
+        const uint64_t ad0 = make_sdesc(base + st * WG_STAGE_BYTES, UM_A_BYTES, 1024);  // 2 slab atoms, LBO = one tile
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t ad = make_sdesc(a_addr + k * 2048, UM_A_BYTES, 1024);   // 2 slab atoms, LBO = one tile
-            const uint64_t bd = make_sdesc(b_addr + k * 2048, UM_A_BYTES, 1024);   // 1 or 2 G atoms
-            umma_bf16(tmem_base + (uint32_t)(p * wa.N), ad, bd, idesc, (ti > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 8; ++k)      // K step = 16 pixel rows = 2048 B = 128 descriptor units
+            umma_bf16(tm + (uint32_t)(p * wa.N), ad0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), idesc,
+                      (ti > 0 || k > 0) ? 1u : 0u);
           umma_commit(smem_u32(&a_empty[st]));
         }
+        __syncwarp();
+      }
+      if (elect_one()) {
         if (do_bias) {
-          const uint32_t b_addr = g_base + gs * WG_G_BYTES;
+          const uint64_t od0 = make_sdesc(ob, 0, 1024);                                // both M atoms = the ones tile
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t ad = make_sdesc(ones_base + k * 2048, 0, 1024);          // both M atoms = the ones tile
-            const uint64_t bd = make_sdesc(b_addr + k * 2048, UM_A_BYTES, 1024);
-            umma_bf16(tmem_base + (uint32_t)(npairs * wa.N), ad, bd, idesc, (ti > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tm + (uint32_t)(npairs * wa.N), od0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), idesc,
+                      (ti > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(smem_u32(&g_empty[gs]));
+        if (ti == ntiles - 1) umma_commit(smem_u32(&accum_bar));
       }
-      umma_commit(smem_u32(&accum_bar));
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    mbar_wait(smem_u32(&accum_bar), 0);
+    mbar_wait_warp(smem_u32(&accum_bar), 0, 200);
     tc_fence_after();
     // partial[split][group][block][n][row]: lanes = consecutive rows -> 128-byte coalesced stores, no atomics
     float* out = partial + ((size_t)(blockIdx.x * wa.groups + group) * wa.blocks_per_cta) * (size_t)wa.N * 128;
@@ -538,6 +791,38 @@ conv_wgrad_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)wa.tmem_cols);
+}
+
+int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g, const UmmaMaps& maps, const Epi& epi,
+                               cudaStream_t st) {
+  HaloArgs ha;
+  if (!halo_args(g, &ha)) {
+    ss_set_error("conv_gather_halo: geometry not eligible");
+    return SSHSLIE_ERR_ARG;
+  }
+  const size_t smem = (size_t)ha.T * ha.nh * ha.halo_bytes + (size_t)ha.stages * g.Npad * 128 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_gather_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
+        cudaSuccess) {
+      ss_set_error("conv_gather_halo: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      return SSHSLIE_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((ha.n_tiles + ha.T - 1) / ha.T);
+  cfg.blockDim = dim3(UM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ss_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, conv_gather_halo_kernel, g_dev, maps, epi, ha);
+  return ss_check_launch("conv_gather_halo");
 }
 
 int ss_umma_wgrad_supported(const ConvGeom& g) { return ss_umma_supported(g) && g.N <= 128; }
@@ -644,4 +929,71 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
   dim3 rgrid(wa.blocks_per_cta, wa.groups, wa.N / 8);
   conv_wgrad_reduce_kernel<<<rgrid, 128, 0, st>>>(g_dev, partial, wa, grads);
   return ss_check_launch("conv_wgrad_reduce");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05.mma issue-rate probe (tools/umma_probe.py): a chain of n_mma bf16 MMAs (M=128, N, K=16) on operands already
+// resident in shared memory (contents irrelevant), cycling over n_acc TMEM accumulators; reports cycles per MMA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int n_mma, int n_acc, int commit_every,
+                                                             long long* __restrict__ out) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar2;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < (16384 + 256 * 128) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_dyn + (base - smem_u32(smem_dyn)))[i] = 0x3C003C00u;
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    mbar_init(smem_u32(&bar2), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = uniform32(tmem_base_smem);
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(128, N, 0, 0);
+    const uint64_t ad0 = make_sdesc(base, 16, 1024), bd0 = make_sdesc(base + 16384, 16, 1024);
+    long long t0 = 0, t1 = 0;
+    uint32_t phase = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      const uint32_t amask = (uint32_t)(n_acc - 1);          // n_acc is a power of two
+      for (int gi = 0; gi < n_mma / 4; ++gi) {
+        const uint32_t d = tm + ((uint32_t)gi & amask) * (uint32_t)N;
+        const uint32_t accum = gi >= n_acc ? 1u : 0u;
+        umma_bf16(d, ad0, bd0, idesc, accum);
+        umma_bf16(d, ad0 + 2, bd0 + 2, idesc, 1u);
+        umma_bf16(d, ad0 + 4, bd0 + 4, idesc, 1u);
+        umma_bf16(d, ad0 + 6, bd0 + 6, idesc, 1u);
+        if (commit_every) umma_commit(smem_u32(&bar2));      // like a stage release: nobody waits on it
+      }
+      umma_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), phase);
+      t1 = clock64();
+      out[blockIdx.x] = t1 - t0;
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tm, 512);
+}
+
+extern "C" SSHSLIE_API int sshslie_umma_probe(int N, int n_mma, int n_acc, int commit_every, long long* out_cycles,
+                                              int n_ctas, void* stream) {
+  if (N < 16 || N > 256 || (N % 16) || n_acc < 1 || n_acc * N > 512 || !out_cycles) {
+    ss_set_error("sshslie_umma_probe: bad argument");
+    return SSHSLIE_ERR_ARG;
+  }
+  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  umma_probe_kernel<<<n_ctas, 128, 16384 + 256 * 128 + 1024, (cudaStream_t)stream>>>(N, n_mma, n_acc, commit_every,
+                                                                                    out_cycles);
+  return ss_check_launch("umma_probe");
 }

@@ -6,6 +6,7 @@
 // forward and backward launch sequences.  Running a step only enqueues those launches on the caller's stream.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <functional>
@@ -242,6 +243,7 @@ static ConvGeom geom_conv(int B, int OH, int OW, const std::vector<SrcSpec>& src
                           int N, const WAddr& wa) {
   ConvGeom g = geom_init(B, OH, OW, N, wa);
   if (stride == 1) {
+    g.halo_ok = 1;
     for (size_t s = 0; s < srcs.size(); ++s) g.src[g.nsrc++] = view_full(srcs[s].t);
     for (int kh = 0; kh < k; ++kh)
       for (int kw = 0; kw < k; ++kw)
@@ -366,13 +368,17 @@ static double geom_flops(const ConvGeom& g) {
 static std::string geom_label(const sshslie_engine* e, int gi, const char* kind) {
   const int l = gi < (int)e->geom_layer.size() ? e->geom_layer[gi] : -1;
   std::string s = std::string(kind) + ":" + (l >= 0 && l < L_COUNT ? kLayerNames[l] : "layer");
-  s += e->geom_umma[gi] ? "[tcgen05]" : "[simt]";
+  s += e->geom_umma[gi] == 2 ? "[tcgen05-halo]" : (e->geom_umma[gi] ? "[tcgen05]" : "[simt]");
   return s;
 }
 static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaStream_t st) {
   if (bias_layer >= 0) epi.bias = e->params + e->poff[2 * bias_layer + 1];
   const ConvGeom& g = e->geoms[gi];
   prof_note(geom_label(e, gi, e->geom_role[gi] ? "dgrad" : "fwd"), geom_flops(g), 0);
+  if (e->geom_umma[gi] == 2)
+    return ss_launch_conv_gather_halo(e->geoms_dev + gi, g,
+                                      *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
+                                      epi, st);
   if (e->geom_umma[gi])
     return ss_launch_conv_gather_umma(e->geoms_dev + gi, g,
                                       *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
@@ -990,7 +996,9 @@ extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t w
     if (!e->force_simt && ss_umma_supported(e->geoms[i])) {
       rc = ss_umma_build_maps(e->geoms[i], reinterpret_cast<UmmaMaps*>(e->maps_blob.data() + i * msz));
       if (rc != SSHSLIE_OK) return rc;
-      e->geom_umma[i] = 1;
+      const char* he = getenv("SSHSLIE_HALO");
+      const bool halo_on = (he && he[0] == '1');   // opt-in: correct, but not yet faster than the per-tap kernel
+      e->geom_umma[i] = (halo_on && e->geoms[i].halo_ok && ss_umma_halo_supported(e->geoms[i])) ? 2 : 1;
     }
   }
   for (auto& zr : e->zero_ranges)
@@ -1180,7 +1188,7 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
     g.wp = (bf16*)e->alloc(elems * sizeof(bf16));
     e->pack_start[i + 1] = e->pack_start[i] + (int)((elems + 255) / 256);
   }
-  if (kind == 2 && impl == 1) {
+  if (kind == 2 && impl >= 1) {
     e->wg_partial_floats = ss_umma_wgrad_partial_floats(e->geoms[0], gN);
     e->wg_partial = e->falloc((int64_t)e->wg_partial_floats);
   }
@@ -1188,11 +1196,11 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
   const size_t msz = ss_umma_maps_size();
   e->maps_blob.assign(e->geoms.size() * msz, 0);
   for (size_t i = 0; i < e->geoms.size(); ++i) {
-    if (impl == 1) {
-      if (!ss_umma_supported(e->geoms[i])) { ss_set_error("sshslie_conv2d: shape not taken by the tcgen05 kernel"); return SSHSLIE_ERR_ARG; }
+    if (impl >= 1) {
+      if (!ss_umma_supported(e->geoms[i]) || (impl == 2 && !ss_umma_halo_supported(e->geoms[i]))) { ss_set_error("sshslie_conv2d: shape not taken by the tcgen05 kernel"); return SSHSLIE_ERR_ARG; }
       int rc = ss_umma_build_maps(e->geoms[i], reinterpret_cast<UmmaMaps*>(e->maps_blob.data() + i * msz));
       if (rc) return rc;
-      e->geom_umma[i] = 1;
+      e->geom_umma[i] = (char)impl;
     }
   }
   cudaMemcpyAsync(e->geoms_dev, e->geoms.data(), e->geoms.size() * sizeof(ConvGeom), cudaMemcpyHostToDevice, st);

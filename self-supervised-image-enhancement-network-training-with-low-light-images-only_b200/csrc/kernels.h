@@ -16,6 +16,9 @@ int ss_launch_pack_weights(const ConvGeom* geoms_dev, const int* block_start_dev
 struct UmmaMaps;   // host-built CUtensorMaps of one geom (opaque here)
 int ss_umma_supported(const ConvGeom& g);
 int ss_umma_wgrad_supported(const ConvGeom& g);
+int ss_umma_halo_supported(const ConvGeom& g);
+int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const Epi& epi,
+                               cudaStream_t st);
 int ss_umma_build_maps(const ConvGeom& g, UmmaMaps* maps);     // needs final device pointers
 int ss_launch_conv_gather_umma(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const Epi& epi,
                                cudaStream_t st);

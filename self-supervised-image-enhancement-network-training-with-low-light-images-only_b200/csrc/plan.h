@@ -6,7 +6,7 @@
 //   out[b, oh, ow, n] = sum over K-slabs s, j<64 of  A_s[b, oh+dh_s, ow+dw_s, c0_s + j] * Wp[n][s*64 + j]
 //
 // where A_s is a (possibly parity-strided) view of a bf16 NHWC activation tensor, zero outside its bounds,
-// and Wp is the bf16 weight matrix packed in slab order.  Strided convolutions read 4 parity views of their
+// and Wp is the bf16 weight matrix packed slab-major ([slab][n][64]: one slab is one contiguous TMA box).  Strided convolutions read 4 parity views of their
 // input; transposed convolutions are 4 geoms, one per output parity class.  The same ConvGeom drives
 //   * the gather GEMM (forward / dgrad)                     — conv_umma.cu (tcgen05) and conv_simt.cu
 //   * the weight-gradient GEMM  dW[n][s*64+j] = sum_pixels G[b,oh,ow,n] * A_s[...]   (same slabs)
@@ -45,10 +45,11 @@ struct ConvGeom {
   // fp32 master weight addressing inside the flat parameter / gradient buffer
   int64_t w_off;              // first element of the weight tensor
   int32_t w_sN, w_sC;         // element strides of the column (n) index and of the inner-channel index
-  // packed bf16 weights  Wp[Npad][nslabs*64]
+  // packed bf16 weights, slab-major: Wp[nslabs][Npad][64]
   bf16* wp;
   // tcgen05 tiling: the 128 GEMM rows of a tile are a (th x tw) block of the OHxOW grid, tw*th == 128
   int tw, th;
+  int halo_ok;                // stride-1 full views: the halo-reuse kernel may take this geom
 };
 
 // Epilogue applied to 16 consecutive columns of one GEMM row (one output pixel).

@@ -89,6 +89,21 @@ def test_conv_wgrad(case, impl):
     torch.testing.assert_close(dw, dw_ref, rtol=1e-3, atol=1e-3 * float(dw_ref.abs().max()))
 
 
+HALO_CASES = [c for c in CONV_CASES if c[4] == 1 and not c[5]]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])
+def test_conv_forward_halo(case):
+    """Halo-reuse tcgen05 kernel (one activation window per tile, A-descriptors pointing into it)."""
+    from gpu_util import conv2d
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    x, w, b = _mk(case)
+    ref = _ref_conv(x, w, b, k, stride, tr, relu=True)
+    y = torch.empty_like(ref)
+    conv2d(0, 2, tr, x, w, b, y, B, Cin, Cout, H, W, k, stride, relu=True)
+    torch.testing.assert_close(y, ref, rtol=2 ** -7, atol=2e-3)
+
+
 def _loss_inputs(B, C, H, W, seed=0):
     g = torch.Generator().manual_seed(seed)
     x = torch.rand(B, C, H, W, generator=g) * 0.3
