@@ -297,6 +297,7 @@ conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
 // Only the weight slabs stream through the ring, and T pixel tiles per CTA share each weight slab, which turns the
 // kernel from L2-feed-bound (24 KB per 4 MMAs) into MMA-bound (8 KB per 4*T MMAs).
 // ---------------------------------------------------------------------------------------------
+__device__ long long g_dbg[16];   // timing breadcrumbs of block 0 (SSHSLIE_HALO_DEBUG & 64), read by sshslie_debug_read
 #define HALO_TW 8
 #define HALO_TH 16
 #define HALO_MAX_T 4
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps maps, Epi epi, HaloArgs ha) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ ConvGeom g;
+  __shared__ uint32_t slab_aoff[SS_MAX_SLABS];     // per slab: byte offset of its A window inside tile 0's halo block
   __shared__ __align__(8) uint64_t full_bar[HALO_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[HALO_MAX_STAGES];
   __shared__ __align__(8) uint64_t halo_bar[HALO_MAX_T];
@@ -333,6 +335,7 @@ conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ts0 = clock64();
   pdl_launch_dependents();
   {
     const int* src = reinterpret_cast<const int*>(gp);
@@ -341,15 +344,25 @@ conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
   }
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   __syncthreads();
-  const int Npad = g.Npad;
+  const int Npad = g.Npad, nslabs = g.nslabs;
   const uint32_t b_bytes = (uint32_t)Npad * 128u;
-  const uint32_t ring_base = dyn_base + (uint32_t)(ha.T * ha.nh * ha.halo_bytes);
-  const int pitch = HALO_TW + 2 * ha.pad;
-
+  const int T = ha.T, nh = ha.nh, pad = ha.pad, stages = ha.stages, halo_bytes = ha.halo_bytes;
+  const uint32_t ring_base = dyn_base + (uint32_t)(T * nh * halo_bytes);
+  const int pitch = HALO_TW + 2 * pad;
+  // everything the MMA loop needs per slab is resolved here, once, by all threads: the loop itself must stay a
+  // handful of instructions (measured: a 120-instruction loop body costs ~1500 cycles per slab, 4x the MMA time)
+  for (int s = threadIdx.x; s < nslabs; s += blockDim.x) {
+    const Slab sl = g.slab[s];
+    int h = 0;
+    for (int i = 0; i < nh; ++i)
+      if (ha.src[i] == sl.src && ha.c0[i] == sl.c0) h = i;
+    slab_aoff[s] = (ha.debug & 1) ? (uint32_t)(h * halo_bytes)
+                                  : (uint32_t)(h * halo_bytes + ((sl.dh + pad) * pitch + (sl.dw + pad)) * 128);
+  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&maps.halo[s]);
     tma_prefetch_desc(&maps.w);
-    for (int s = 0; s < ha.stages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
@@ -362,11 +375,13 @@ conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const long long ts1 = clock64();
   pdl_wait();
+  const long long ts2 = clock64();
 
   const int tiles_w = g.OW / HALO_TW, tiles_h = (g.OH + HALO_TH - 1) / HALO_TH;
-  const int t_first = blockIdx.x * ha.T;
-  const int nt = min(ha.T, ha.n_tiles - t_first);
+  const int t_first = blockIdx.x * T;
+  const int nt = min(T, ha.n_tiles - t_first);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -377,55 +392,63 @@ conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
         const int b = ti / tiles_h;
         const uint32_t hb = smem_u32(&halo_bar[t]);
         if (ha.debug & 32) { mbar_arrive(hb); continue; }
-        mbar_expect_tx(hb, (uint32_t)ha.nh * (uint32_t)((HALO_TH + 2 * ha.pad) * pitch * 128));
-        for (int h = 0; h < ha.nh; ++h)
-          tma_load_4d(dyn_base + (uint32_t)((t * ha.nh + h) * ha.halo_bytes), &maps.halo[ha.src[h]], hb, ha.c0[h],
-                      twi * HALO_TW - ha.pad, thi * HALO_TH - ha.pad, b);
+        mbar_expect_tx(hb, (uint32_t)nh * (uint32_t)((HALO_TH + 2 * pad) * pitch * 128));
+        for (int h = 0; h < nh; ++h)
+          tma_load_4d(dyn_base + (uint32_t)((t * nh + h) * halo_bytes), &maps.halo[ha.src[h]], hb, ha.c0[h],
+                      twi * HALO_TW - pad, thi * HALO_TH - pad, b);
       }
-      for (int s = 0; s < g.nslabs && !(ha.debug & 4); ++s) {
-        const int st = s % ha.stages;
-        mbar_wait(smem_u32(&empty_bar[st]), (((uint32_t)(s / ha.stages)) & 1u) ^ 1u);
+      uint32_t st = 0, ph = 1;
+      for (int s = 0; s < nslabs && !(ha.debug & 4); ++s) {
+        mbar_wait(smem_u32(&empty_bar[st]), ph);
         const uint32_t fb = smem_u32(&full_bar[st]);
         mbar_expect_tx(fb, b_bytes);
-        tma_load_2d(ring_base + (uint32_t)st * b_bytes, &maps.w, fb, 0, s * Npad);
+        tma_load_2d(ring_base + st * b_bytes, &maps.w, fb, 0, s * Npad);
+        if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc(128, Npad, 0, 0);
-    const uint32_t tm = uniform32(tmem_base), base = uniform32(dyn_base), rbase = uniform32(ring_base);
-    for (int s = 0; s < g.nslabs; ++s) {
-      const int st = s % ha.stages;
-      const Slab sl = g.slab[s];
-      int h = 0;
-      for (int i = 0; i < ha.nh; ++i)
-        if (ha.src[i] == sl.src && ha.c0[i] == sl.c0) h = i;
-      if (!(ha.debug & 4)) mbar_wait_warp(smem_u32(&full_bar[st]), ((uint32_t)(s / ha.stages)) & 1u, 0);
-      if (s == 0)
-        for (int t = 0; t < nt; ++t) mbar_wait_warp(smem_u32(&halo_bar[t]), 0, 0);
+    const uint32_t tm = uniform32(tmem_base);
+    // descriptor words: hi is constant; lo = (start >> 4) | (LBO >> 4) << 16, advanced by plain 32-bit adds
+    const uint32_t a_hi = (uint32_t)(make_sdesc(0, 16, (uint32_t)pitch * 128u) >> 32);
+    const uint32_t b_hi = (uint32_t)(make_sdesc(0, 16, 1024) >> 32);
+    const uint32_t a_lo0 = uniform32(((dyn_base >> 4) & 0x3FFFu) | (1u << 16));
+    const uint32_t b_lo0 = uniform32(((ring_base >> 4) & 0x3FFFu) | (1u << 16));
+    const uint32_t tstep = (uint32_t)((nh * halo_bytes) >> 4), bstep = b_bytes >> 4;
+    for (int t = 0; t < nt; ++t) mbar_wait_warp(smem_u32(&halo_bar[t]), 0, 0);
+    uint32_t st = 0, ph = 0;
+    for (int s = 0; s < nslabs; ++s) {
+      if (!(ha.debug & 4)) mbar_wait_warp(smem_u32(&full_bar[st]), ph, 0);
       if (!(ha.debug & 8)) tc_fence_after();
-      const uint32_t tap_off = (ha.debug & 1) ? 0u : (uint32_t)(((sl.dh + ha.pad) * pitch + (sl.dw + ha.pad)) * 128);
-      const uint64_t bd0 = make_sdesc(rbase + (uint32_t)st * b_bytes, 16, 1024);
-      const uint32_t a0 = base + (uint32_t)(h * ha.halo_bytes) + tap_off;
+      // warp-uniform on purpose (shfl): ptxas then keeps the descriptor arithmetic in the uniform datapath and the
+      // MMAs issue back to back instead of paying an R2UR round trip per operand per MMA
+      const uint32_t a_lo = uniform32(a_lo0 + (slab_aoff[s] >> 4));
+      const uint32_t b_lo = uniform32(b_lo0 + st * bstep);
       if (elect_one()) {
-        // k outer, tile inner: consecutive MMAs accumulate into DIFFERENT TMEM tiles, so the dependent-accumulate
-        // latency of one narrow (N = 64) MMA is hidden behind the MMAs of the other tiles
-        const uint64_t ad0 = make_sdesc_bo(a0, 16, (uint32_t)pitch * 128u, ha.bo_mode);
-        const uint64_t tstep = (uint64_t)((ha.nh * ha.halo_bytes) >> 4);
+        // k outer, tile inner: consecutive MMAs accumulate into different TMEM tiles
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           for (int t = 0; t < nt && !(ha.debug & 2); ++t)
-            umma_bf16(tm + (uint32_t)(t * Npad), ad0 + (uint64_t)t * tstep + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k),
-                      idesc, (s > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tm + (uint32_t)(t * Npad), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)t * tstep + 2u * k),
+                      ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k), idesc, (s > 0 || k > 0) ? 1u : 0u);
         if (!(ha.debug & 16)) umma_commit(smem_u32(&empty_bar[st]));
-        if (s == g.nslabs - 1) umma_commit(smem_u32(&accum_bar));
+        if (s == nslabs - 1) umma_commit(smem_u32(&accum_bar));
       }
-      __syncwarp();
+      if (!(ha.debug & 128)) __syncwarp();
+      if ((ha.debug & 64) && blockIdx.x == 0 && lane == 0) {
+        if (s == 0) g_dbg[3] = clock64() - ts0;
+        if (s == nslabs - 1) g_dbg[4] = clock64() - ts0;
+      }
+      if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
     }
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    mbar_wait_warp(smem_u32(&accum_bar), 0, 200);
+    mbar_wait_warp(smem_u32(&accum_bar), 0, (ha.debug & 256) ? 5000u : 200u);
     tc_fence_after();
+    if ((ha.debug & 64) && blockIdx.x == 0 && threadIdx.x == 64) {
+      g_dbg[0] = nslabs; g_dbg[1] = ts1 - ts0; g_dbg[2] = ts2 - ts0; g_dbg[5] = clock64() - ts0;
+    }
     for (int t = 0; t < nt; ++t) {
       int ti = t_first + t;
       const int twi = ti % tiles_w; ti /= tiles_w;
@@ -440,6 +463,7 @@ conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
       }
     }
   }
+  if ((ha.debug & 64) && blockIdx.x == 0 && threadIdx.x == 64) g_dbg[6] = clock64() - ts0;
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)ha.tmem_cols);
@@ -937,14 +961,14 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
 // resident in shared memory (contents irrelevant), cycling over n_acc TMEM accumulators; reports cycles per MMA.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int n_mma, int n_acc, int commit_every,
-                                                             long long* __restrict__ out) {
+                                                             long long* __restrict__ out, int a_off, int a_sbo) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(8) uint64_t bar2;
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5;
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  for (int i = threadIdx.x; i < (16384 + 256 * 128) / 4; i += blockDim.x)
+  for (int i = threadIdx.x; i < (65536 + 256 * 128) / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(smem_dyn + (base - smem_u32(smem_dyn)))[i] = 0x3C003C00u;
   fence_proxy_async();
   if (threadIdx.x == 0) {
@@ -959,7 +983,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int n_mma, in
   const uint32_t tm = uniform32(tmem_base_smem);
   if (warp == 0) {
     const uint32_t idesc = make_idesc(128, N, 0, 0);
-    const uint64_t ad0 = make_sdesc(base, 16, 1024), bd0 = make_sdesc(base + 16384, 16, 1024);
+    const uint64_t ad0 = make_sdesc(base + (uint32_t)a_off, 16, (uint32_t)a_sbo), bd0 = make_sdesc(base + 65536, 16, 1024);
     long long t0 = 0, t1 = 0;
     uint32_t phase = 0;
     if (elect_one()) {
@@ -988,12 +1012,21 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int n_mma, in
 
 extern "C" SSHSLIE_API int sshslie_umma_probe(int N, int n_mma, int n_acc, int commit_every, long long* out_cycles,
                                               int n_ctas, void* stream) {
+  // A-operand placement experiments: SSHSLIE_PROBE_AOFF (byte offset of the window, multiple of 128) and
+  // SSHSLIE_PROBE_SBO (byte stride between 8-row groups; 16 groups must fit in 64 KB)
+  const char* ao = getenv("SSHSLIE_PROBE_AOFF");
+  const char* sb = getenv("SSHSLIE_PROBE_SBO");
+  const int a_off = ao ? atoi(ao) : 0, a_sbo = sb ? atoi(sb) : 1024;
   if (N < 16 || N > 256 || (N % 16) || n_acc < 1 || n_acc * N > 512 || !out_cycles) {
     ss_set_error("sshslie_umma_probe: bad argument");
     return SSHSLIE_ERR_ARG;
   }
-  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  umma_probe_kernel<<<n_ctas, 128, 16384 + 256 * 128 + 1024, (cudaStream_t)stream>>>(N, n_mma, n_acc, commit_every,
-                                                                                    out_cycles);
+  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  umma_probe_kernel<<<n_ctas, 128, 65536 + 256 * 128 + 1024, (cudaStream_t)stream>>>(N, n_mma, n_acc, commit_every,
+                                                                                    out_cycles, a_off, a_sbo);
   return ss_check_launch("umma_probe");
+}
+
+extern "C" SSHSLIE_API int sshslie_debug_read(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_dbg, sizeof(long long) * 16) == cudaSuccess ? SSHSLIE_OK : SSHSLIE_ERR_CUDA;
 }

@@ -12,13 +12,14 @@ import sshslie_b200 as S  # noqa: E402
 lib = S.lib.load()
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+print("AOFF", os.environ.get("SSHSLIE_PROBE_AOFF"), "SBO", os.environ.get("SSHSLIE_PROBE_SBO"))
 print(f"{'N':>4s} {'n_acc':>5s} {'commit_every':>12s} {'ctas':>5s} {'cycles/MMA':>10s} {'ideal(N/2)':>10s}")
-for ctas in (1, 148):
-    for N in (64, 128, 256):
-        for n_acc in (1, 2, 4):
+for ctas in (148,):
+    for N in (64, 128):
+        for n_acc in (1,):
             if n_acc * N > 512:
                 continue
-            for ce in (0, 1):
+            for ce in (1,):
                 n = 2048
                 for _ in range(2):
                     S.lib.check(lib.sshslie_umma_probe(N, n, n_acc, ce, S.lib.ptr(out), ctas, st), "probe")
