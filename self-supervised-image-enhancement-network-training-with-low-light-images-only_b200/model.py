@@ -480,7 +480,10 @@ class LowLightEnhance(nn.Module):
 
     def _dp_step(self, eng):
         import torch.distributed as dist
-        n_dec = self._pranges[18][0]                 # first illum_adjust_net parameter (decomposition has 9x2 tensors)
+        from . import parallel as P
+        offs = [o for o, _ in self._pranges]
+        sizes = [n for _, n in self._pranges]
+        dec, ill = P.bucket_ranges(offs, sizes)
         cur = torch.cuda.current_stream(self._flat.device)
         eng.calls += 1
         if self.use_cuda_graph and eng.graph is None and eng.calls >= 3:
@@ -498,13 +501,12 @@ class LowLightEnhance(nn.Module):
         ev.record(cur)
         with torch.cuda.stream(self._dp_stream):
             self._dp_stream.wait_event(ev)
-            dist.all_reduce(self._flat_grad[n_dec:], group=self.dp_group)     # bucket 1: illum_adjust_net, overlaps
-            dist.all_reduce(self._losses_dev, group=self.dp_group)            # with the pass-1 backward below
+            P.allreduce_bucket(self._flat_grad, ill, self.dp_group)           # overlaps the pass-1 backward below
+            dist.all_reduce(self._losses_dev, group=self.dp_group)
         run(2)                                       # pass-1 decomposition backward
-        dist.all_reduce(self._flat_grad[:n_dec], group=self.dp_group)         # bucket 2: decomposition_net
+        P.allreduce_bucket(self._flat_grad, dec, self.dp_group)
         cur.wait_stream(self._dp_stream)
-        self._flat_grad.mul_(1.0 / self._dp_world)                            # p.grad = mean over ranks
-        self._losses_dev.mul_(1.0 / self._dp_world)
+        P.finish_mean(self._flat_grad, self._losses_dev, self._dp_world)      # p.grad = mean over ranks
 
     # ------------------------------------------------------------------ loops (host glue, model.py:236-443)
     def train_model(self, train_data_path, eval_data_path, batch_size, patch_size, num_epochs, start_lr, ckpt_dir,

@@ -1,0 +1,57 @@
+"""world_size-2 CPU (gloo) test of the data-parallel host logic: bucket layout + all-reduce + mean, on the same code the
+NCCL path runs (sshslie_b200/parallel.py), and bench.py's reference arm under a 2-rank launch."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sshslie_b200 as S
+    from sshslie_b200 import parallel as P
+    total, offs, sizes = S.lib.param_table(64)
+    dec, ill = P.bucket_ranges(offs, sizes)
+    assert dec == (0, 849121) and ill == (849121, 1141922)          # SURVEY.md §8e parameter split
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(total, generator=g)
+    losses = torch.full((8,), float(rank + 1))
+    mine = flat.clone()
+    P.allreduce_bucket(flat, ill)                                     # bucket 1 first (ready mid-backward)
+    assert torch.equal(flat[:dec[1]], mine[:dec[1]])                  # decomposition slice untouched so far
+    P.allreduce_bucket(flat, dec)
+    dist.all_reduce(losses)
+    P.finish_mean(flat, losses, world)
+    others = [torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    ref = sum(others) / world
+    torch.testing.assert_close(flat, ref, rtol=1e-6, atol=1e-6)
+    assert abs(float(losses[0]) - 1.5) < 1e-6
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_mean_gloo(tmp_path):
+    mp.spawn(_worker, args=(2, 29531, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_bench_reference_arm_two_ranks():
+    """`bench.py --impl reference` under a 2-rank launch: rank 0 alone runs and prints ONE JSON line."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "patches/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
