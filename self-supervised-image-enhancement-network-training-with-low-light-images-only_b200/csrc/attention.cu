@@ -321,19 +321,13 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* P, const int6
 int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const float* P, float* G, const int64_t* poff,
                           AttnBuffers bf, int B, int L, cudaStream_t st) {
   const int T = B * L;
-  const int gl = (T + 15) / 16, gw = (T + 63) / 64;
-  // y = W2 h + b2 ; t = x + y
-  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(dt, nullptr, bf.h, G + poff[8], G + poff[9], T);
+  const int gl = (T + 15) / 16;
+  // data-gradient chain only; the five weight gradients run in ss_attention_backward_weights (side stream)
   linear_bwd_data_kernel<<<gl, 256, 0, st>>>(dt, P + poff[8], nullptr, bf.dh, T, 0);          // dh (pre-mask)
-  // h = relu(W1 o + b1): mask by h > 0
-  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(bf.dh, bf.h, bf.o, G + poff[6], G + poff[7], T);
-  linear_bwd_data_kernel<<<gl, 256, 0, st>>>(bf.dh, P + poff[6], bf.h, bf.d_o, T, 0);         // dO
+  linear_bwd_data_kernel<<<gl, 256, 0, st>>>(bf.dh, P + poff[6], bf.h, bf.d_o, T, 0);         // dO (h = relu: mask)
   dim3 ga((L + 127) / 128, AT_HEADS, B);
   attn_bwd_q_kernel<<<ga, 128, 0, st>>>(bf.q, bf.k, bf.v, bf.o, bf.d_o, bf.lse, bf.dq, bf.Dv, L);
   attn_bwd_kv_kernel<<<ga, 128, 0, st>>>(bf.q, bf.k, bf.v, bf.d_o, bf.lse, bf.Dv, bf.dk, bf.dv, L);
-  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(bf.dq, nullptr, bf.x, G + poff[0], G + poff[1], T);
-  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(bf.dk, nullptr, bf.x, G + poff[2], G + poff[3], T);
-  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(bf.dv, nullptr, bf.x, G + poff[4], G + poff[5], T);
   // dx = dt (residual) + dq Wq + dk Wk + dv Wv
   const int64_t n = (int64_t)T * AT_D;
   cudaMemcpyAsync(bf.dx, dt, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -341,6 +335,20 @@ int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const floa
   linear_bwd_data_kernel<<<gl, 256, 0, st>>>(bf.dk, P + poff[2], nullptr, bf.dx, T, 1);
   linear_bwd_data_kernel<<<gl, 256, 0, st>>>(bf.dv, P + poff[4], nullptr, bf.dx, T, 1);
   mask_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bf.dx, a3, da3, n);
-  ss_count_launches(13);
+  ss_count_launches(8);
   return ss_check_launch("attention_backward");
+}
+
+// dW, db of the five Linear layers (reads dt, dh, dq, dk, dv produced by ss_attention_backward)
+int ss_attention_backward_weights(const float* dt, float* G, const int64_t* poff, AttnBuffers bf, int B, int L,
+                                  cudaStream_t st) {
+  const int T = B * L;
+  const int gw = (T + 63) / 64;
+  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(dt, nullptr, bf.h, G + poff[8], G + poff[9], T);       // ff_linear2
+  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(bf.dh, bf.h, bf.o, G + poff[6], G + poff[7], T);       // ff_linear1
+  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(bf.dq, nullptr, bf.x, G + poff[0], G + poff[1], T);
+  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(bf.dk, nullptr, bf.x, G + poff[2], G + poff[3], T);
+  linear_bwd_weight_kernel<<<gw, 256, 0, st>>>(bf.dv, nullptr, bf.x, G + poff[4], G + poff[5], T);
+  ss_count_launches(4);
+  return ss_check_launch("attention_backward_weights");
 }

@@ -422,14 +422,17 @@ conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
       if (!(ha.debug & 8)) tc_fence_after();
       // warp-uniform on purpose (shfl): ptxas then keeps the descriptor arithmetic in the uniform datapath and the
       // MMAs issue back to back instead of paying an R2UR round trip per operand per MMA
-      const uint32_t a_lo = uniform32(a_lo0 + (slab_aoff[s] >> 4));
-      const uint32_t b_lo = uniform32(b_lo0 + st * bstep);
+      // timing-bisect switches (wrong results): 512 = every slab reads window 0, 1024 = every slab reads ring stage 0,
+      // 2048 = every tile reads tile 0's halo
+      const uint32_t a_lo = uniform32(a_lo0 + ((ha.debug & 512) ? 0u : (slab_aoff[s] >> 4)));
+      const uint32_t b_lo = uniform32(b_lo0 + ((ha.debug & 1024) ? 0u : st * bstep));
+      const uint32_t tstep_eff = (ha.debug & 2048) ? 0u : tstep;
       if (elect_one()) {
         // k outer, tile inner: consecutive MMAs accumulate into different TMEM tiles
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           for (int t = 0; t < nt && !(ha.debug & 2); ++t)
-            umma_bf16(tm + (uint32_t)(t * Npad), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)t * tstep + 2u * k),
+            umma_bf16(tm + (uint32_t)(t * Npad), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)t * tstep_eff + 2u * k),
                       ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k), idesc, (s > 0 || k > 0) ? 1u : 0u);
         if (!(ha.debug & 16)) umma_commit(smem_u32(&empty_bar[st]));
         if (s == nslabs - 1) umma_commit(smem_u32(&accum_bar));

@@ -777,9 +777,12 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     const int64_t np = e->nparams;
     PUSH(Lq, return cudaMemsetAsync(e->grads, 0, np * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
     PUSH(Lq, return cudaMemsetAsync(e->sums_dev, 0, 16 * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
-    PUSH(Lq, return ss_pixel_losses(e->x, e->R32, e->I32, e->Id32, Re32, e->cfg, B, C, H, W, e->sums_dev, dR32, dI32,
+    // algorithmic HBM bytes: 24.25 MiB per patch for the 5-term loss + gradients, 12 MiB for the Fourier term
+    PUSH(Lq, prof_note("loss:pixel_terms+grads", 0, 24.25 * 1048576.0 * B);
+             return ss_pixel_losses(e->x, e->R32, e->I32, e->Id32, Re32, e->cfg, B, C, H, W, e->sums_dev, dR32, dI32,
                                     dId32, dS32, dRe32, st););
-    PUSH(Lq, return sshslie_fourier_loss(e->x, e->S32, e->mask_dev, dS32, e->sums_dev + 9, B * C, H, W,
+    PUSH(Lq, prof_note("loss:fourier_fft+grad", 0, 12.0 * 1048576.0 * B);
+             return sshslie_fourier_loss(e->x, e->S32, e->mask_dev, dS32, e->sums_dev + 9, B * C, H, W,
                                          (float)(e->cfg.c_loss_fourier / ((double)B * C * H * W)), st););
     PUSH(Lq, return ss_launch_finalize_losses(e->sums_dev, &e->cfg, e->losses, B, C, H, W, st););
 
@@ -851,6 +854,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     PUSH(Lq, return ss_launch_pool2(du1.p, nullptr, nullptr, nullptr, nullptr, dt32, B, H / 8, W / 8, st););
     PUSH(Lq, return ss_attention_backward(dt32, a3.p, da3.p, e->params, e->grads, apoff, ab, B, L, st););
+    PUSH_SIDE(Lq, return ss_attention_backward_weights(dt32, e->grads, apoff, ab, B, L, st););
     // conv3 / conv2 / conv1 (stride 2): wgrad on the forward geom, dgrad per input parity class (+ skip gradient)
     struct S2 { int layer, gfwd; Tens dy, x_in, dx, addp; bool mask; };
     const S2 s2[3] = {{L_I_CONV3, g_i3, da3, a2, da2, da2p, true},

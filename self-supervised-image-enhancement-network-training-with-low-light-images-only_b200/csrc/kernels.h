@@ -58,6 +58,9 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* params, const
 int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const float* params, float* grads,
                           const int64_t* poff, AttnBuffers bufs, int B, int L, cudaStream_t st);
 
+int ss_attention_backward_weights(const float* dt, float* grads, const int64_t* poff, AttnBuffers bufs, int B, int L,
+                                  cudaStream_t st);
+
 // loss.cu / fft_loss.cu / adam.cu : see include/sshslie_b200.h (exported directly)
 int ss_pixel_losses(const float* x, const float* R, const float* I, const float* Id, const float* Re,
                     const sshslie_loss_cfg& cfg, int B, int C, int H, int W, float* sums, float* dR, float* dI,
