@@ -205,6 +205,27 @@ def bf16_storage(t, name=None):
     return _RoundBf16.apply(t)
 
 
+class _RoundBf16Pair(torch.autograd.Function):
+    """hi + lo bf16 storage (~16 mantissa bits) forward, bf16 gradient backward."""
+
+    @staticmethod
+    def forward(ctx, t):
+        hi = t.to(torch.bfloat16).to(torch.float32)
+        return hi + (t - hi).to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+HI_LO_TENSORS = ("RI", "a0", "r3", "d3", "ff")      # full-resolution tensors feeding final_conv (DESIGN.md §4)
+
+
+def cuda_storage(t, name=None):
+    """Storage precision of the CUDA path: bf16 everywhere except the HI_LO_TENSORS, which are kept as bf16 pairs."""
+    return _RoundBf16Pair.apply(t) if name in HI_LO_TENSORS else _RoundBf16.apply(t)
+
+
 def bf16_weights(p: Params) -> Params:
     """Conv weights as the tensor cores see them (bf16); biases and Linear layers stay fp32."""
     return OrderedDict((k, _RoundBf16.apply(v) if (k.endswith("weight") and v.dim() == 4) else v)

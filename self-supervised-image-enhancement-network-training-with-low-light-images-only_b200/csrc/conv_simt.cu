@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const ConvGeom* __
     }
   }
   const int n = nb + tn;
-  if (n < g.N) {
+  if (n < g.N && !sl.no_wgrad) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = tq * 8 + j;

@@ -894,7 +894,7 @@ __global__ void __launch_bounds__(128) conv_wgrad_reduce_kernel(const ConvGeom* 
   const int j = row & 63;
   if (s >= s_end) return;
   const Slab sl = gp->slab[s];
-  if (j >= sl.wcn) return;
+  if (j >= sl.wcn || sl.no_wgrad) return;
   float* dst = grads + gp->w_off + sl.woff + (int64_t)j * gp->w_sC;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {

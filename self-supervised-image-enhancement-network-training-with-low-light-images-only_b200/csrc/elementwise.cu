@@ -94,7 +94,7 @@ int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// fg[b,y,x,:] = [ (r1+a2)[y/4,x/4] | (r2+a1)[y/2,x/2] | (r3+a0)[y,x] ]   192 channels  [model.py:168-172]
+// fg[b,y,x,:] = [ (r1+a2)[y/4,x/4] | (r2+a1)[y/2,x/2] | hi(r3+a0)[y,x] | lo(r3+a0)[y,x] ]   256 channels  [model.py:168-172]
 // ---------------------------------------------------------------------------------------------
 SS_DEVINL uint4 add8(const uint4& p, const uint4& q) {
   float f[8], g[8];
@@ -109,7 +109,8 @@ SS_DEVINL uint4 add8(const uint4& p, const uint4& q) {
 }
 __global__ void fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __restrict__ a2,
                                    const uint4* __restrict__ r2, const uint4* __restrict__ a1,
-                                   const uint4* __restrict__ r3, const uint4* __restrict__ a0, uint4* __restrict__ fg,
+                                   const uint4* __restrict__ r3, const uint4* __restrict__ r3l,
+                                   const uint4* __restrict__ a0, const uint4* __restrict__ a0l, uint4* __restrict__ fg,
                                    int H, int W, int64_t total /* B*H*W*24 */) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -119,25 +120,43 @@ __global__ void fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __
   const int64_t t = pix / W;
   const int y = (int)(t % H);
   const int64_t b = t / H;
-  uint4 v;
   if (q < 8) {
     const int64_t s = ((b * (H / 4) + y / 4) * (W / 4) + x / 4) * 8 + q;
-    v = add8(r1[s], a2[s]);
+    fg[pix * 32 + q] = add8(r1[s], a2[s]);
   } else if (q < 16) {
     const int64_t s = ((b * (H / 2) + y / 2) * (W / 2) + x / 2) * 8 + (q - 8);
-    v = add8(r2[s], a1[s]);
+    fg[pix * 32 + q] = add8(r2[s], a1[s]);
   } else {
+    // full-resolution block d3 = deconv3 + conv0 in ~16-bit mantissa: hi -> channels [128,192), residual -> [192,256)
     const int64_t s = pix * 8 + (q - 16);
-    v = add8(r3[s], a0[s]);
+    float f[8], g[8], hsum[8];
+    unpack8(r3[s], f);
+    unpack8(a0[s], g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hsum[j] = f[j] + g[j];
+    if (r3l) {
+      unpack8(r3l[s], f);
+      unpack8(a0l[s], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hsum[j] += f[j] + g[j];
+    }
+    uint4 hi, lo;
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = hsum[j] - bf2f(f2bf(hsum[j]));
+    hi.x = pack2(hsum[0], hsum[1]); hi.y = pack2(hsum[2], hsum[3]); hi.z = pack2(hsum[4], hsum[5]); hi.w = pack2(hsum[6], hsum[7]);
+    lo.x = pack2(r[0], r[1]); lo.y = pack2(r[2], r[3]); lo.z = pack2(r[4], r[5]); lo.w = pack2(r[6], r[7]);
+    fg[pix * 32 + q] = hi;
+    fg[pix * 32 + q + 8] = lo;
   }
-  fg[i] = v;
 }
 int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
-                          const bf16* a0, bf16* fg, int B, int H, int W, cudaStream_t st) {
+                          const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W,
+                          cudaStream_t st) {
   const int64_t total = (int64_t)B * H * W * 24;
   fuse_concat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      (const uint4*)r1, (const uint4*)a2, (const uint4*)r2, (const uint4*)a1, (const uint4*)r3, (const uint4*)a0,
-      (uint4*)fg, H, W, total);
+      (const uint4*)r1, (const uint4*)a2, (const uint4*)r2, (const uint4*)a1, (const uint4*)r3, (const uint4*)r3l,
+      (const uint4*)a0, (const uint4*)a0l, (uint4*)fg, H, W, total);
   EW_CHECK("fuse_concat");
 }
 

@@ -102,7 +102,7 @@ struct Tens {          // bf16 NHWC tensor
   int B = 0, H = 0, W = 0, ld = 0;
   int64_t pix() const { return (int64_t)B * H * W; }
 };
-struct SrcSpec { Tens t; int c_off; int c_cnt; int wc_off; };
+struct SrcSpec { Tens t; int c_off; int c_cnt; int wc_off; int lo = 0; };
 struct WAddr { int64_t w_off; int sN, sC, sKH, sKW; };
 
 struct GeomOp {        // one lowered GEMM: geometry + (for gathers) epilogue template
@@ -216,7 +216,7 @@ static void geom_add_slabs(ConvGeom& g, int src, int dh, int dw, const SrcSpec& 
   const int ns = (s.c_cnt + SS_SLAB - 1) / SS_SLAB;
   for (int i = 0; i < ns; ++i) {
     Slab& sl = g.slab[g.nslabs++];
-    sl.src = (int8_t)src; sl.dh = (int8_t)dh; sl.dw = (int8_t)dw; sl.wcn_hi = 0;
+    sl.src = (int8_t)src; sl.dh = (int8_t)dh; sl.dw = (int8_t)dw; sl.no_wgrad = (int8_t)s.lo;
     sl.c0 = (int16_t)(s.c_off + i * SS_SLAB);
     const int rem = s.c_cnt - i * SS_SLAB;
     sl.wcn = (int16_t)(rem < SS_SLAB ? rem : SS_SLAB);
@@ -650,7 +650,8 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   // ---- tensors -----------------------------------------------------------------------------
   Tens X = e->talloc(B, H, W, 64);
   e->R32 = e->falloc(n * C); e->I32 = e->falloc(n); e->Id32 = e->falloc(n); e->S32 = e->falloc(n * C);
-  Tens RI = e->talloc(B, H, W, 128, true);
+  // cat[R, I] as the illumination net reads it: [R hi (64) | I, 63 zero lanes | R lo (64)]  (hi+lo: DESIGN.md §4)
+  Tens RI = e->talloc(B, H, W, 192, true);
   auto decomp_bufs = [&]() {
     DecompBufs d;
     d.c0 = e->talloc(B, H, W, 64, true);
@@ -662,9 +663,10 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   DecompBufs d1 = decomp_bufs();
   Tens a0 = e->talloc(B, H, W, 64), a1 = e->talloc(B, H / 2, W / 2, 64), a2 = e->talloc(B, H / 4, W / 4, 64),
        a3 = e->talloc(B, H / 8, W / 8, 64), tt = e->talloc(B, H / 8, W / 8, 64);
+  Tens a0l = e->talloc(B, H, W, 64), r3l = e->talloc(B, H, W, 64), ffl = e->talloc(B, H, W, 64);   // bf16 residuals
   Tens u1 = e->talloc(B, H / 4, W / 4, 64), r1 = e->talloc(B, H / 4, W / 4, 64), u2 = e->talloc(B, H / 2, W / 2, 64),
        r2 = e->talloc(B, H / 2, W / 2, 64), u3 = e->talloc(B, H, W, 64), r3 = e->talloc(B, H, W, 64);
-  Tens fg = e->talloc(B, H, W, 192), ff = e->talloc(B, H, W, 64);
+  Tens fg = e->talloc(B, H, W, 256), ff = e->talloc(B, H, W, 64);
   const int L = (H / 8) * (W / 8);
   const int64_t T64 = (int64_t)B * L * 64;
   AttnBuffers ab;
@@ -687,7 +689,8 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   }
   Epi head1;
   memset(&head1, 0, sizeof(head1));
-  head1.mode = EPI_HEAD; head1.R32 = e->R32; head1.I32 = e->I32; head1.RI = RI.p; head1.ri_c = 128;
+  head1.mode = EPI_HEAD; head1.R32 = e->R32; head1.I32 = e->I32; head1.RI = RI.p; head1.ri_c = 192;
+  head1.ri_lo_off = 128;
   head1.C = C; head1.H = H; head1.W = W;
   DecompGeoms G1 = plan_decomp_fwd(e, F, X, d1, head1);
 
@@ -695,8 +698,8 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   int g_i0, g_i1, g_i2, g_i3, g_d1, g_d2, g_d3, g_fus, g_fin;
   {
     WAddr wa = waddr_conv_fwd(e, L_I_CONV0);
-    g_i0 = e->add_geom(geom_conv(B, H, W, {{RI, 0, C + 1, 0}}, 3, 1, 1, +1, 64, wa));
-    Epi ep = epi_bf16(a0, 64);
+    g_i0 = e->add_geom(geom_conv(B, H, W, {{RI, 0, C + 1, 0}, {RI, 128, C, 0, 1}}, 3, 1, 1, +1, 64, wa));
+    Epi ep = epi_bf16(a0, 64); ep.out_lo = a0l.p;
     PUSH(F, return run_gather(e, g_i0, ep, L_I_CONV0, st););
   }
   {
@@ -737,19 +740,19 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   {
     WAddr wa = waddr_conv_fwd(e, L_I_DECONV3);
     g_d3 = e->add_geom(geom_conv(B, H, W, {{u3, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
-    Epi ep = epi_bf16(r3, 64); ep.relu = 1;
+    Epi ep = epi_bf16(r3, 64); ep.relu = 1; ep.out_lo = r3l.p;
     PUSH(F, return run_gather(e, g_d3, ep, L_I_DECONV3, st););
   }
-  PUSH(F, return ss_launch_fuse_concat(r1.p, a2.p, r2.p, a1.p, r3.p, a0.p, fg.p, B, H, W, st););
+  PUSH(F, return ss_launch_fuse_concat(r1.p, a2.p, r2.p, a1.p, r3.p, r3l.p, a0.p, a0l.p, fg.p, B, H, W, st););
   {
     WAddr wa = waddr_conv_fwd(e, L_I_FUSION);
-    g_fus = e->add_geom(geom_conv(B, H, W, {{fg, 0, 192, 0}}, 1, 1, 0, +1, 64, wa));
-    Epi ep = epi_bf16(ff, 64);
+    g_fus = e->add_geom(geom_conv(B, H, W, {{fg, 0, 192, 0}, {fg, 192, 64, 128, 1}}, 1, 1, 0, +1, 64, wa));
+    Epi ep = epi_bf16(ff, 64); ep.out_lo = ffl.p;
     PUSH(F, return run_gather(e, g_fus, ep, L_I_FUSION, st););
   }
   {
     WAddr wa = waddr_conv_fwd(e, L_I_FINAL);
-    g_fin = e->add_geom(geom_conv(B, H, W, {{ff, 0, 64, 0}}, 3, 1, 1, +1, 1, wa));
+    g_fin = e->add_geom(geom_conv(B, H, W, {{ff, 0, 64, 0}, {ffl, 0, 64, 0, 1}}, 3, 1, 1, +1, 1, wa));
     Epi ep;
     memset(&ep, 0, sizeof(ep));
     ep.mode = EPI_PLANE32; ep.plane32 = e->Id32; ep.H = H; ep.W = W;

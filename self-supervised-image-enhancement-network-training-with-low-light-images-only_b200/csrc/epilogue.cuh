@@ -36,6 +36,17 @@ SS_DEVINL void epi_apply16(const Epi& e, int b, int oh, int ow, int n0, int N, f
     hi.x = pack2(v[8], v[9]);  hi.y = pack2(v[10], v[11]); hi.z = pack2(v[12], v[13]); hi.w = pack2(v[14], v[15]);
     *reinterpret_cast<uint4*>(p) = lo;
     *reinterpret_cast<uint4*>(p + 8) = hi;
+    if (e.out_lo) {   // residual of the bf16 rounding: consumers read hi and lo as two K-slabs with the same weights
+      float r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = v[i] - bf2f(f2bf(v[i]));
+      bf16* q = e.out_lo + b * e.oB + oh * e.oH + ow * e.oW + n0;
+      uint4 l0, l1;
+      l0.x = pack2(r[0], r[1]);  l0.y = pack2(r[2], r[3]);  l0.z = pack2(r[4], r[5]);   l0.w = pack2(r[6], r[7]);
+      l1.x = pack2(r[8], r[9]);  l1.y = pack2(r[10], r[11]); l1.z = pack2(r[12], r[13]); l1.w = pack2(r[14], r[15]);
+      *reinterpret_cast<uint4*>(q) = l0;
+      *reinterpret_cast<uint4*>(q + 8) = l1;
+    }
   } else if (e.mode == EPI_HEAD) {
     const int64_t pix = ((int64_t)b * e.H + oh) * e.W + ow;
 #pragma unroll
@@ -56,6 +67,17 @@ SS_DEVINL void epi_apply16(const Epi& e, int b, int oh, int ow, int n0, int N, f
       hi.x = pack2(v[8], v[9]);  hi.y = pack2(v[10], v[11]); hi.z = pack2(v[12], v[13]); hi.w = pack2(v[14], v[15]);
       *reinterpret_cast<uint4*>(p) = lo;
       *reinterpret_cast<uint4*>(p + 8) = hi;
+      if (e.ri_lo_off > 0 && n0 < e.C) {
+        float r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = (n0 + i < e.C) ? v[i] - bf2f(f2bf(v[i])) : 0.f;
+        bf16* q = p + e.ri_lo_off;
+        uint4 l0, l1;
+        l0.x = pack2(r[0], r[1]);  l0.y = pack2(r[2], r[3]);  l0.z = pack2(r[4], r[5]);   l0.w = pack2(r[6], r[7]);
+        l1.x = pack2(r[8], r[9]);  l1.y = pack2(r[10], r[11]); l1.z = pack2(r[12], r[13]); l1.w = pack2(r[14], r[15]);
+        *reinterpret_cast<uint4*>(q) = l0;
+        *reinterpret_cast<uint4*>(q + 8) = l1;
+      }
     }
   } else {  // EPI_PLANE32
     if (n0 == 0) e.plane32[((int64_t)b * e.H + oh) * e.W + ow] = v[0];

@@ -34,7 +34,8 @@ int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, i
 int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, int W, int ldi, cudaStream_t st);
 int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, cudaStream_t st);
 int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
-                          const bf16* a0, bf16* fg, int B, int H, int W, cudaStream_t st);
+                          const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W,
+                          cudaStream_t st);
 int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
                      cudaStream_t st);
 int ss_launch_s_bwd(const float* dS32, const bf16* dSb, const float* R, const float* I, const float* Id, float* dR32,

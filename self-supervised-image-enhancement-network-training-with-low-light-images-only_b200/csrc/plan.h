@@ -30,7 +30,8 @@ struct SrcView {
 struct Slab {
   int8_t src;                 // index into ConvGeom::src
   int8_t dh, dw;              // pixel offset in view coordinates
-  int8_t wcn_hi;              // unused
+  int8_t no_wgrad;            // 1: residual (lo) slab of a hi+lo pair — shares its weights with the hi slab, so the
+                              //    weight gradient skips it (its term is 2^-9 of the hi term and would alias dW)
   int16_t c0;                 // channel offset inside the source tensor
   int16_t wcn;                // how many of the 64 channels carry real weights (rest are zero)
   int32_t woff;               // weight element offset for (tap, first inner channel): kh*sH + kw*sW + wc0*sC
@@ -63,6 +64,7 @@ struct Epi {
   int relu;
   int mode;
   bf16* out;                  // EPI_BF16: NHWC (strided) bf16 output, columns [0, n_store)
+  bf16* out_lo;               // optional: bf16(v - float(bf16(v))) at the same strides -> hi+lo carries ~16 mantissa bits
   int64_t oB, oH, oW;
   int n_store;
   // EPI_HEAD: sigmoid; columns [0,C) -> R32 (B,C,H,W) fp32 and RI (NHWC bf16, stride ri_c); column C -> I32, RI[C]
@@ -70,6 +72,7 @@ struct Epi {
   float* I32;
   bf16* RI;
   int ri_c;
+  int ri_lo_off;              // > 0: also store the bf16 residual of R at RI[pix*ri_c + ri_lo_off + n]
   int C, H, W;
   // EPI_PLANE32: column 0 -> plane32[(b*H + oh)*W + ow]
   float* plane32;

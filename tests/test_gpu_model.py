@@ -2,10 +2,10 @@
 B200 against the CPU oracle on the same seeded inputs, and against the fixtures recorded from the unmodified
 reference.  Tolerances (bf16 tensor-core operands, fp32 accumulate, fp32 heads and loss kernels):
   outputs R/I/S  <= 5e-3 abs,  I_delta <= 4e-3 abs
-  loss terms     <= 2e-2 relative, except L_I_smooth_delta <= 0.2 relative: that term averages |forward differences|
-                 of I_delta (~1e-3) and the per-pixel bf16 rounding of the full-resolution activations feeding
-                 final_conv is white noise of the same order, which biases a mean of absolute differences upwards
-                 (the reference itself under CPU bf16 autocast shows +16 %; DESIGN.md "precision")
+  loss terms     <= 2e-2 relative, except L_I_smooth_delta <= 5e-2 relative: that term averages |forward differences|
+                 of I_delta (~1e-3), so per-pixel rounding noise of the activations feeding final_conv biases it upwards.
+                 With plain bf16 storage it is +17 % (the reference under CPU bf16 autocast: +16 %); the CUDA
+                 path therefore stores the four full-resolution tensors on that path as bf16 hi+lo pairs
   gradients      cosine >= 0.995 over the full 1.14M-vector and per-tensor cosine >= 0.97
 """
 import os
@@ -16,7 +16,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-LOSS_RTOL = {"L_I_smooth_delta": 0.2}
+LOSS_RTOL = {"L_I_smooth_delta": 0.05}
 
 
 def _coefs():
@@ -79,10 +79,13 @@ def test_loss_and_grads_match_oracle(case, impl):
     torch.cuda.synchronize()
     p = O.init_params(41)
     l32, g32, _ = O.loss_and_grads(p, x, coef)
-    l16, g16, _ = O.loss_and_grads(p, x, coef, q=O.bf16_storage)
+    l16, g16, _ = O.loss_and_grads(p, x, coef, q=O.cuda_storage)
     for k in O.LOSS_KEYS:
         np.testing.assert_allclose(losses[k], l32[k], rtol=LOSS_RTOL.get(k, 2e-2), atol=1e-5, err_msg=k)
-        np.testing.assert_allclose(losses[k], l16[k], rtol=2e-3, atol=1e-6, err_msg=k + " (bf16-storage oracle)")
+        # the storage emulation is exact for plain-bf16 tensors; the hi+lo tensors differ in detail (I has no lo part,
+        # conv1 of the illumination net reads only the hi half), which only L_I_smooth_delta can see
+        np.testing.assert_allclose(losses[k], l16[k], rtol=2e-2 if k == "L_I_smooth_delta" else 2e-3, atol=1e-6,
+                                   err_msg=k + " (storage-precision oracle)")
     np.testing.assert_allclose(float(loss.detach()), l32["total_loss"], rtol=2e-2)
     G = {k: prm.grad.detach().cpu() for k, prm in m.named_parameters()}
     cat = lambda d: torch.cat([d[k].flatten() for k in G])

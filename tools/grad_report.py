@@ -31,7 +31,7 @@ def main():
     torch.cuda.synchronize()
     p = O.init_params(41)
     l32, g32, _ = O.loss_and_grads(p, x, coef)
-    l16, g16, _ = O.loss_and_grads(p, x, coef, q=O.bf16_storage)
+    l16, g16, _ = O.loss_and_grads(p, x, coef, q=O.cuda_storage)
     out = []
     out.append(f"case B={B} size={size} coef={cname} simt={simt}")
     for k in O.LOSS_KEYS:
