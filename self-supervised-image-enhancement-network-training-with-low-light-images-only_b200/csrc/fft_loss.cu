@@ -6,13 +6,13 @@
 //
 // Both real images ride ONE complex transform: z = x + i*s, so X_k = (Z_k + conj(Z_-k))/2 and
 // S_k = (Z_k - conj(Z_-k))/(2i).  The HxW complex tile lives in shared memory (128 KB at 128x128);
-// forward = radix-2 decimation-in-frequency along W then H (natural in, bit-reversed out), the spectrum is
+// forward = decimation-in-frequency along W then H, two radix-2 levels fused per sweep (natural in, bit-reversed out), the spectrum is
 // consumed in bit-reversed positions, and the inverse runs decimation-in-time (bit-reversed in, natural out),
 // so no reordering pass exists.  Algorithmic HBM traffic: read x, s (2 planes), read+write dS (1 plane each).
 #include "common.cuh"
 #include "kernels.h"
 
-#define FFT_THREADS 512
+#define FFT_THREADS 1024
 
 SS_DEVINL float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 SS_DEVINL int brev(int v, int bits) { return (int)(__brev((unsigned)v) >> (32 - bits)); }
@@ -20,25 +20,28 @@ SS_DEVINL int brev(int v, int bits) { return (int)(__brev((unsigned)v) >> (32 - 
 // one radix-2 stage over the whole tile along the W axis (rows) or the H axis (columns)
 //   dif:  a' = a + b ; b' = (a - b) * tw        dit:  b *= tw ; a' = a + b ; b' = a - b
 template <bool ALONG_W, bool DIT, bool INV>
-SS_DEVINL void fft_stage(float2* z, const float2* tw, int H, int W, int half, int n_axis) {
-  const int nbf = H * W / 2;
-  const int tstep = n_axis / (2 * half);
+SS_DEVINL void fft_stage(float2* z, const float2* tw, int H, int W, int lgW, int lg_half, int lg_axis) {
+  // all sizes are powers of two: index math is shifts and masks only (runtime div/mod was 80 % of the instructions)
+  const int nbf = (H * W) >> 1;
+  const int half = 1 << lg_half;
+  const int lg_tstep = lg_axis - 1 - lg_half;
+#pragma unroll 2
   for (int t = threadIdx.x; t < nbf; t += FFT_THREADS) {
     int i0, i1, pos;
     if (ALONG_W) {
-      const int row = t / (W / 2), j = t - row * (W / 2);
-      const int grp = j / half;
-      pos = j - grp * half;
-      i0 = row * W + grp * 2 * half + pos;
+      const int row = t >> (lgW - 1), j = t & ((W >> 1) - 1);
+      const int grp = j >> lg_half;
+      pos = j & (half - 1);
+      i0 = (row << lgW) + (grp << (lg_half + 1)) + pos;
       i1 = i0 + half;
     } else {
-      const int col = t % W, j = t / W;          // consecutive lanes -> consecutive columns (conflict-free)
-      const int grp = j / half;
-      pos = j - grp * half;
-      i0 = (grp * 2 * half + pos) * W + col;
-      i1 = i0 + half * W;
+      const int col = t & (W - 1), j = t >> lgW;      // consecutive lanes -> consecutive columns (conflict-free)
+      const int grp = j >> lg_half;
+      pos = j & (half - 1);
+      i0 = (((grp << (lg_half + 1)) + pos) << lgW) + col;
+      i1 = i0 + (half << lgW);
     }
-    float2 w = tw[pos * tstep];
+    float2 w = tw[pos << lg_tstep];
     if (INV) w.y = -w.y;
     float2 a = z[i0], b = z[i1];
     if (DIT) {
@@ -51,6 +54,68 @@ SS_DEVINL void fft_stage(float2* z, const float2* tw, int H, int W, int half, in
     }
   }
   __syncthreads();
+}
+
+// two radix-2 levels fused in registers (a radix-4 pass): halves the shared-memory sweeps and barriers.
+//   DIF: levels (h, h/2) with lg_h = lg_first;   DIT: levels (h, 2h) with lg_h = lg_first.
+template <bool ALONG_W, bool DIT, bool INV>
+SS_DEVINL void fft_stage2(float2* z, const float2* tw, int H, int W, int lgW, int lg_first, int lg_axis) {
+  const int nq = (H * W) >> 2;
+  const int es = ALONG_W ? 1 : W;                       // element stride along the transformed axis
+#pragma unroll 2
+  for (int t = threadIdx.x; t < nq; t += FFT_THREADS) {
+    int line, j;
+    if (ALONG_W) { line = (t >> (lgW - 2)) << lgW; j = t & ((W >> 2) - 1); }
+    else { line = t & (W - 1); j = t >> lgW; }
+    if (!DIT) {
+      const int h = 1 << lg_first, hh = h >> 1;         // levels h then h/2
+      const int grp = j >> (lg_first - 1), pos = j & (hh - 1);
+      const int base = line + ((grp << (lg_first + 1)) + pos) * es;
+      const int lt1 = lg_axis - 1 - lg_first;           // twiddle stride of level h; level h/2 uses lt1 + 1
+      float2 w1a = tw[pos << lt1], w1b = tw[(pos + hh) << lt1], w2 = tw[pos << (lt1 + 1)];
+      if (INV) { w1a.y = -w1a.y; w1b.y = -w1b.y; w2.y = -w2.y; }
+      const float2 e0 = z[base], e1 = z[base + hh * es], e2 = z[base + h * es], e3 = z[base + (h + hh) * es];
+      const float2 a0 = make_float2(e0.x + e2.x, e0.y + e2.y);
+      const float2 a2 = cmul(make_float2(e0.x - e2.x, e0.y - e2.y), w1a);
+      const float2 a1 = make_float2(e1.x + e3.x, e1.y + e3.y);
+      const float2 a3 = cmul(make_float2(e1.x - e3.x, e1.y - e3.y), w1b);
+      z[base] = make_float2(a0.x + a1.x, a0.y + a1.y);
+      z[base + hh * es] = cmul(make_float2(a0.x - a1.x, a0.y - a1.y), w2);
+      z[base + h * es] = make_float2(a2.x + a3.x, a2.y + a3.y);
+      z[base + (h + hh) * es] = cmul(make_float2(a2.x - a3.x, a2.y - a3.y), w2);
+    } else {
+      const int h = 1 << lg_first;                      // levels h then 2h
+      const int grp = j >> lg_first, pos = j & (h - 1);
+      const int base = line + ((grp << (lg_first + 2)) + pos) * es;
+      const int lt1 = lg_axis - 1 - lg_first;           // level h; level 2h uses lt1 - 1
+      float2 w1 = tw[pos << lt1], w2a = tw[pos << (lt1 - 1)], w2b = tw[(pos + h) << (lt1 - 1)];
+      if (INV) { w1.y = -w1.y; w2a.y = -w2a.y; w2b.y = -w2b.y; }
+      const float2 e0 = z[base], e1 = cmul(z[base + h * es], w1), e2 = z[base + 2 * h * es],
+                   e3 = cmul(z[base + 3 * h * es], w1);
+      const float2 a0 = make_float2(e0.x + e1.x, e0.y + e1.y), a1 = make_float2(e0.x - e1.x, e0.y - e1.y);
+      const float2 a2 = cmul(make_float2(e2.x + e3.x, e2.y + e3.y), w2a);
+      const float2 a3 = cmul(make_float2(e2.x - e3.x, e2.y - e3.y), w2b);
+      z[base] = make_float2(a0.x + a2.x, a0.y + a2.y);
+      z[base + 2 * h * es] = make_float2(a0.x - a2.x, a0.y - a2.y);
+      z[base + h * es] = make_float2(a1.x + a3.x, a1.y + a3.y);
+      z[base + 3 * h * es] = make_float2(a1.x - a3.x, a1.y - a3.y);
+    }
+  }
+  __syncthreads();
+}
+
+// full 1-D transform along one axis of the tile: pairs of levels fused, one single level if the count is odd
+template <bool ALONG_W, bool DIT, bool INV>
+SS_DEVINL void fft_axis(float2* z, const float2* tw, int H, int W, int lgW, int lg_axis) {
+  if (!DIT) {
+    int lh = lg_axis - 1;
+    for (; lh >= 1; lh -= 2) fft_stage2<ALONG_W, false, INV>(z, tw, H, W, lgW, lh, lg_axis);
+    if (lh == 0) fft_stage<ALONG_W, false, INV>(z, tw, H, W, lgW, 0, lg_axis);
+  } else {
+    int lh = 0;
+    for (; lh + 1 < lg_axis; lh += 2) fft_stage2<ALONG_W, true, INV>(z, tw, H, W, lgW, lh, lg_axis);
+    if (lh < lg_axis) fft_stage<ALONG_W, true, INV>(z, tw, H, W, lgW, lh, lg_axis);
+  }
 }
 
 __global__ void __launch_bounds__(FFT_THREADS, 1)
@@ -80,13 +145,13 @@ fourier_loss_kernel(const float* __restrict__ x, const float* __restrict__ s, co
   __syncthreads();
 
   // forward: DIF along W, then along H
-  for (int half = W / 2; half >= 1; half >>= 1) fft_stage<true, false, false>(z, twW, H, W, half, W);
-  for (int half = H / 2; half >= 1; half >>= 1) fft_stage<false, false, false>(z, twH, H, W, half, H);
+  fft_axis<true, false, false>(z, twW, H, W, lgW, lgW);
+  fft_axis<false, false, false>(z, twH, H, W, lgW, lgH);
 
   // spectrum pass: position (ph,pw) holds frequency (brev(ph), brev(pw)); pair it with -k
   float lsum = 0.f;
   for (int p = threadIdx.x; p < H * W; p += FFT_THREADS) {
-    const int ph = p / W, pw = p - ph * W;
+    const int ph = p >> lgW, pw = p & (W - 1);
     const int ky = brev(ph, lgH), kx = brev(pw, lgW);
     const int nky = (H - ky) & (H - 1), nkx = (W - kx) & (W - 1);
     const int pn = brev(nky, lgH) * W + brev(nkx, lgW);
@@ -114,8 +179,8 @@ fourier_loss_kernel(const float* __restrict__ x, const float* __restrict__ s, co
   if (dS == nullptr) return;
 
   // inverse: DIT along H then W with conjugated twiddles (bit-reversed in, natural out)
-  for (int half = 1; half <= H / 2; half <<= 1) fft_stage<false, true, true>(z, twH, H, W, half, H);
-  for (int half = 1; half <= W / 2; half <<= 1) fft_stage<true, true, true>(z, twW, H, W, half, W);
+  fft_axis<false, true, true>(z, twH, H, W, lgW, lgH);
+  fft_axis<true, true, true>(z, twW, H, W, lgW, lgW);
 
   float* dp = dS + img * H * W;
   for (int i = threadIdx.x; i < H * W; i += FFT_THREADS) dp[i] += grad_scale * z[i].x;

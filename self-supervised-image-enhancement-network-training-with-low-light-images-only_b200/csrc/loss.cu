@@ -7,8 +7,9 @@
 //   6,7 L_I_smooth_delta mean(|dx Id| exp(-a2 |dx R_c|)) + same in y, Id broadcast over c  model.py:450-454
 //   8 L_spectral_cons    mean |S[c+1] - S[c]|,  S = R*(Id + I)                            model.py:475-481, 233
 //
-// One thread owns one pixel (b,h,w) and walks the band axis twice: pass A builds the band-mean edge weights of
-// term 1/2 for its four incident edges, pass B accumulates the term sums and writes every gradient by GATHER
+// Eight threads own one pixel (b,h,w), each walking one eighth of the band axis twice: pass A builds the band-mean edge
+// weights of term 1/2 for the four incident edges (combined through shared memory), pass B accumulates the term sums and
+// writes every gradient by GATHER
 // (each pixel collects the contributions of the <=4 forward-difference edges it takes part in).
 // Gradients are written already multiplied by c_loss_x / count (d total_loss / d tensor).
 #include "common.cuh"
@@ -22,30 +23,51 @@ struct PixLossArgs {
   float k_rec, k_ilx, k_ily, k_rf, k_rfx, k_rfy, k_idx, k_idy, k_sp;   // c_loss / count per term
 };
 
-__global__ void __launch_bounds__(128) pixel_losses_kernel(PixLossArgs p) {
+#define PL_CHUNKS 8      // the band axis is split over 8 threads per pixel: 8x the parallelism of one-thread-per-pixel
+#define PL_WX 128        // pixels of one image row handled by a block
+
+SS_DEVINL float block_sum_2d(float v, float* red, int tid, int nthreads) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  if (tid < 32) {
+    v = (tid < ((nthreads + 31) >> 5)) ? red[tid] : 0.f;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// blockDim = (WX, 8): threadIdx.x = pixel along the row (coalesced plane reads), threadIdx.y = band chunk.
+// grid = (ceil(W / WX), H, B)
+__global__ void __launch_bounds__(PL_WX* PL_CHUNKS) pixel_losses_kernel(PixLossArgs p) {
+  __shared__ float part[PL_CHUNKS][4][PL_WX];
   __shared__ float red[32];
   const int W = p.W, H = p.H, C = p.C;
   const int HW = H * W;
-  const int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = pix < (int64_t)p.B * HW;
+  const int tx = threadIdx.x, k = threadIdx.y;
+  const int tid = k * blockDim.x + tx, nthreads = blockDim.x * blockDim.y;
+  const int w = blockIdx.x * blockDim.x + tx, h = blockIdx.y, b = blockIdx.z;
+  const bool active = w < W;
+  const int cpc = (C + PL_CHUNKS - 1) / PL_CHUNKS;
+  const int c_begin = k * cpc, c_end = min(C, c_begin + cpc);
   float s[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) s[i] = 0.f;
 
-  if (active) {
-    const int b = (int)(pix / HW);
-    const int hw = (int)(pix - (int64_t)b * HW);
-    const int h = hw / W, w = hw - h * W;
-    const bool hasR = w + 1 < W, hasL = w > 0, hasD = h + 1 < H, hasU = h > 0;
-    const float* Rb = p.R + (int64_t)b * C * HW + hw;
-    const float* Eb = p.Re + (int64_t)b * C * HW + hw;
-    const float* xb = p.x + (int64_t)b * C * HW + hw;
-    const float* Ib = p.I + (int64_t)b * HW + hw;
-    const float* Db = p.Id + (int64_t)b * HW + hw;
+  const int hw = h * W + (active ? w : 0);
+  const int64_t pix = (int64_t)b * HW + hw;
+  const bool hasR = w + 1 < W, hasL = w > 0, hasD = h + 1 < H, hasU = h > 0;
+  const float* Rb = p.R + (int64_t)b * C * HW + hw;
+  const float* Eb = p.Re + (int64_t)b * C * HW + hw;
+  const float* xb = p.x + (int64_t)b * C * HW + hw;
+  const float* Ib = p.I + (int64_t)b * HW + hw;
+  const float* Db = p.Id + (int64_t)b * HW + hw;
 
-    // ---- pass A: band means of |dR| on the four incident edges --------------------------------
-    float mR = 0.f, mL = 0.f, mD = 0.f, mU = 0.f;
-    for (int c = 0; c < C; ++c) {
+  // ---- pass A: band means of |dR| on the four incident edges (partial over this thread's chunk) -------------
+  float mR = 0.f, mL = 0.f, mD = 0.f, mU = 0.f;
+  if (active) {
+    for (int c = c_begin; c < c_end; ++c) {
       const float* r = Rb + (int64_t)c * HW;
       const float r0 = r[0];
       if (hasR) mR += fabsf(r[1] - r0);
@@ -53,52 +75,53 @@ __global__ void __launch_bounds__(128) pixel_losses_kernel(PixLossArgs p) {
       if (hasD) mD += fabsf(r[W] - r0);
       if (hasU) mU += fabsf(r0 - r[-W]);
     }
+  }
+  part[k][0][tx] = mR; part[k][1][tx] = mL; part[k][2][tx] = mD; part[k][3][tx] = mU;
+  __syncthreads();
+  mR = mL = mD = mU = 0.f;
+#pragma unroll
+  for (int i = 0; i < PL_CHUNKS; ++i) {
+    mR += part[i][0][tx]; mL += part[i][1][tx]; mD += part[i][2][tx]; mU += part[i][3][tx];
+  }
+  __syncthreads();
+
+  float gI = 0.f, gId = 0.f;
+  if (active) {
     const float invC = 1.f / (float)C;
     const float wR = __expf(-p.a1 * mR * invC), wL = __expf(-p.a1 * mL * invC);
     const float wD = __expf(-p.a1 * mD * invC), wU = __expf(-p.a1 * mU * invC);
-
-    // illumination differences on the four edges
     const float i0 = Ib[0], d0 = Db[0];
     const float iR = hasR ? Ib[1] - i0 : 0.f, iL = hasL ? i0 - Ib[-1] : 0.f;
     const float iD = hasD ? Ib[W] - i0 : 0.f, iU = hasU ? i0 - Ib[-W] : 0.f;
     const float dRt = hasR ? Db[1] - d0 : 0.f, dLt = hasL ? d0 - Db[-1] : 0.f;
     const float dDt = hasD ? Db[W] - d0 : 0.f, dUt = hasU ? d0 - Db[-W] : 0.f;
-
-    // term 1/2 sums (each edge counted once, by its left/upper pixel) and dI from that term
-    if (hasR) s[1] += wR * fabsf(iR);
-    if (hasD) s[2] += wD * fabsf(iD);
-    float gI = p.k_ilx * (wL * sgnf(iL) - wR * sgnf(iR)) + p.k_ily * (wU * sgnf(iU) - wD * sgnf(iD));
-    float gId = 0.f;
-    // coefficients of d/dR_c through the band-mean weights: + on the far side of an edge, - on the near side
+    if (k == 0) {   // band-independent parts, once per pixel
+      if (hasR) s[1] += wR * fabsf(iR);
+      if (hasD) s[2] += wD * fabsf(iD);
+      gI = p.k_ilx * (wL * sgnf(iL) - wR * sgnf(iR)) + p.k_ily * (wU * sgnf(iU) - wD * sgnf(iD));
+    }
     const float cR = p.k_ilx * wR * fabsf(iR) * p.a1 * invC, cL = p.k_ilx * wL * fabsf(iL) * p.a1 * invC;
     const float cD = p.k_ily * wD * fabsf(iD) * p.a1 * invC, cU = p.k_ily * wU * fabsf(iU) * p.a1 * invC;
-
     const float gain = d0 + i0;
-    float s_prev = 0.f;
-    float r_next = Rb[0];
-    // ---- pass B ---------------------------------------------------------------------------------
-    for (int c = 0; c < C; ++c) {
+    float s_prev = (c_begin > 0) ? Rb[(int64_t)(c_begin - 1) * HW] * gain : 0.f;
+    float r_next = (c_begin < C) ? Rb[(int64_t)c_begin * HW] : 0.f;
+    // ---- pass B over this thread's bands --------------------------------------------------------------------
+    for (int c = c_begin; c < c_end; ++c) {
       const int64_t off = (int64_t)c * HW;
       const float* r = Rb + off;
       const float* e = Eb + off;
       const float r0 = r_next;
       if (c + 1 < C) r_next = r[HW];
       const float e0 = e[0];
-      float gR = 0.f, gE = 0.f;
-
-      // reconstruction
+      float gR = 0.f;
       const float u = r0 * i0 - xb[off];
       s[0] += fabsf(u);
       const float gu = p.k_rec * sgnf(u);
       gR += gu * i0;
       gI += gu * r0;
-
-      // fidelity, plain
       const float q0 = r0 - e0;
       s[3] += fabsf(q0);
       float gq = p.k_rf * sgnf(q0);
-
-      // edges
       if (hasR) {
         const float dr = r[1] - r0;
         const float dq = (r[1] - e[1]) - q0;
@@ -136,8 +159,6 @@ __global__ void __launch_bounds__(128) pixel_losses_kernel(PixLossArgs p) {
         gId += p.k_idy * sgnf(dUt) * ex;
       }
       gR += gq;
-      gE -= gq;
-
       // spectral smoothness on S = R*(Id+I):  dS_c = k (sgn(S_c - S_{c-1}) - sgn(S_{c+1} - S_c))
       const float s0 = r0 * gain;
       float gS = 0.f;
@@ -148,18 +169,25 @@ __global__ void __launch_bounds__(128) pixel_losses_kernel(PixLossArgs p) {
         gS -= sgnf(sn - s0);
       }
       s_prev = s0;
-
-      if (p.dR) p.dR[(int64_t)b * C * HW + hw + off] = gR;
-      if (p.dRe) p.dRe[(int64_t)b * C * HW + hw + off] = gE;
-      if (p.dS) p.dS[(int64_t)b * C * HW + hw + off] = p.k_sp * gS;
+      const int64_t o = (int64_t)b * C * HW + hw + off;
+      if (p.dR) p.dR[o] = gR;
+      if (p.dRe) p.dRe[o] = -gq;
+      if (p.dS) p.dS[o] = p.k_sp * gS;
     }
-    if (p.dI) p.dI[pix] = gI;
-    if (p.dId) p.dId[pix] = gId;
+  }
+  part[k][0][tx] = gI; part[k][1][tx] = gId;
+  __syncthreads();
+  if (active && k == 0) {
+    float a = 0.f, d = 0.f;
+#pragma unroll
+    for (int i = 0; i < PL_CHUNKS; ++i) { a += part[i][0][tx]; d += part[i][1][tx]; }
+    if (p.dI) p.dI[pix] = a;
+    if (p.dId) p.dId[pix] = d;
   }
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
-    const float t = block_sum(s[i], red);
-    if (threadIdx.x == 0) atomicAdd(p.sums + i, t);
+    const float t = block_sum_2d(s[i], red, tid, nthreads);
+    if (tid == 0) atomicAdd(p.sums + i, t);
   }
 }
 
@@ -183,8 +211,9 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
   p.k_idx = (float)(cfg.c_loss_i_smooth_delta / (nx1 * C));
   p.k_idy = (float)(cfg.c_loss_i_smooth_delta / (ny1 * C));
   p.k_sp = (float)(cfg.c_loss_spectral_cons / ((double)B * (C - 1) * H * W));
-  const int64_t npix = (int64_t)B * H * W;
-  pixel_losses_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, st>>>(p);
+  const int wx = W < PL_WX ? W : PL_WX;
+  dim3 grid((W + wx - 1) / wx, H, B), block(wx, PL_CHUNKS);
+  pixel_losses_kernel<<<grid, block, 0, st>>>(p);
   return ss_check_launch("pixel_losses");
 }
 
