@@ -862,32 +862,39 @@ int ss_umma_build_gmap(const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld
 }
 
 // second stage: dW[n][slab, j] += sum over pixel splits of the partial accumulators (deterministic, no atomics)
-// grid = (blocks_per_cta, groups, N/8); block = 128 threads = the 128 accumulator rows
-__global__ void __launch_bounds__(128) conv_wgrad_reduce_kernel(const ConvGeom* __restrict__ gp,
-                                                                const float* __restrict__ partial, WgradArgs wa,
-                                                                float* __restrict__ grads) {
+// grid = (blocks_per_cta, groups, N/8); block = (128, 8): threadIdx.x = accumulator row, threadIdx.y strides the splits.
+// Each thread sums every 8th split for 8 columns, the 8 partial sums per column meet in shared memory, and thread
+// (row, q) finishes column n0 + q — 8x the parallelism and 1/8 the dependent-load depth of one thread per row.
+__global__ void __launch_bounds__(1024) conv_wgrad_reduce_kernel(const ConvGeom* __restrict__ gp,
+                                                                 const float* __restrict__ partial, WgradArgs wa,
+                                                                 float* __restrict__ grads) {
+  __shared__ float red[8][8][128];
   const int blk = blockIdx.x, group = blockIdx.y, n0 = blockIdx.z * 8;
-  const int row = threadIdx.x;
+  const int row = threadIdx.x, q = threadIdx.y;
   const int s_begin = group * wa.slabs_per_group;
   const int s_end = min(gp->nslabs, s_begin + wa.slabs_per_group);
   const int npairs = (s_end - s_begin + 1) / 2;
   const bool is_bias = (blk == npairs) && (group == 0) && (wa.bias_off >= 0);
-  if (blk > npairs || (blk == npairs && !is_bias)) return;
+  if (blk > npairs || (blk == npairs && !is_bias)) return;       // block-uniform
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   const size_t cta_stride = (size_t)wa.groups * wa.blocks_per_cta * wa.N * 128;
-  const float* p = partial + ((size_t)group * wa.blocks_per_cta + blk) * (size_t)wa.N * 128 + (size_t)n0 * 128 + row;
-  for (int sp = 0; sp < wa.splits; ++sp, p += cta_stride) {
+  const float* p = partial + ((size_t)group * wa.blocks_per_cta + blk) * (size_t)wa.N * 128 + (size_t)n0 * 128 + row +
+                   (size_t)q * cta_stride;
+  for (int sp = q; sp < wa.splits; sp += 8, p += 8 * cta_stride) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += p[(size_t)i * 128];
   }
-  if (is_bias) {
-    if (row == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (n0 + i < wa.gN) grads[wa.bias_off + n0 + i] += acc[i];
-    }
+  for (int i = 0; i < 8; ++i) red[q][i][row] = acc[i];
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tot += red[j][q][row];              // fixed order -> deterministic
+  const int n = n0 + q;
+  if (is_bias) {
+    if (row == 0 && n < wa.gN) grads[wa.bias_off + n] += tot;
     return;
   }
   const int s = s_begin + 2 * blk + (row >> 6);
@@ -895,12 +902,7 @@ __global__ void __launch_bounds__(128) conv_wgrad_reduce_kernel(const ConvGeom* 
   if (s >= s_end) return;
   const Slab sl = gp->slab[s];
   if (j >= sl.wcn || sl.no_wgrad) return;
-  float* dst = grads + gp->w_off + sl.woff + (int64_t)j * gp->w_sC;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int n = n0 + i;
-    if (n < gp->N && n < wa.gN) dst[(int64_t)n * gp->w_sN] += acc[i];
-  }
+  if (n < gp->N && n < wa.gN) grads[gp->w_off + sl.woff + (int64_t)j * gp->w_sC + (int64_t)n * gp->w_sN] += tot;
 }
 
 static void wgrad_plan(const ConvGeom& g, int gN, long long bias_off, WgradArgs* out) {
@@ -954,7 +956,7 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
   int rc = ss_check_launch("conv_wgrad_umma");
   if (rc) return rc;
   dim3 rgrid(wa.blocks_per_cta, wa.groups, wa.N / 8);
-  conv_wgrad_reduce_kernel<<<rgrid, 128, 0, st>>>(g_dev, partial, wa, grads);
+  conv_wgrad_reduce_kernel<<<rgrid, dim3(128, 8), 0, st>>>(g_dev, partial, wa, grads);
   return ss_check_launch("conv_wgrad_reduce");
 }
 
