@@ -188,8 +188,12 @@ int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, c
 __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvGeom* __restrict__ geoms,
                                                            const int* __restrict__ block_start, int njobs,
                                                            const float* __restrict__ params) {
-  int j = 0;
-  while (j + 1 < njobs && (int)blockIdx.x >= block_start[j + 1]) ++j;
+  int lo = 0, hi = njobs - 1;           // last job whose first block is <= blockIdx.x (block_start is ascending)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int)blockIdx.x >= block_start[mid]) lo = mid; else hi = mid - 1;
+  }
+  const int j = lo;
   const ConvGeom* g = geoms + j;
   const int Ktot = g->nslabs * SS_SLAB;
   const int64_t idx = (int64_t)(blockIdx.x - block_start[j]) * 256 + threadIdx.x;

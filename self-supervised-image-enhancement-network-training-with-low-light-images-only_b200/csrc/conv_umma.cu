@@ -184,9 +184,8 @@ SS_DEVINL uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
 // ---------------------------------------------------------------------------------------------
 // gather GEMM kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UM_THREADS, 1)
-conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps maps, Epi epi,
-                        int tmem_cols) {
+SS_DEVINL void conv_gather_umma_body(const ConvGeom* __restrict__ gp, const UmmaMaps& maps, const Epi& epi,
+                                     int tmem_cols, int tile_index) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ ConvGeom g;
   __shared__ __align__(8) uint64_t full_bar[UM_STAGES];
@@ -227,7 +226,7 @@ conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
 
   // tile -> (b, oh0, ow0)
   const int tiles_w = (g.OW + g.tw - 1) / g.tw, tiles_h = (g.OH + g.th - 1) / g.th;
-  int t = blockIdx.x;
+  int t = tile_index;
   const int twi = t % tiles_w; t /= tiles_w;
   const int thi = t % tiles_h;
   const int b = t / tiles_h;
@@ -285,6 +284,26 @@ conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps maps, Epi epi,
+                        int tmem_cols) {
+  conv_gather_umma_body(gp, maps, epi, tmem_cols, blockIdx.x);
+}
+
+// the four output-parity classes of a transposed / strided-dgrad layer in ONE launch: blockIdx.y = class (qh, qw).
+// The classes are four consecutive ConvGeoms with their own weight packs; their outputs interleave in the same tensor.
+struct alignas(64) UmmaMaps4 { UmmaMaps m[4]; };
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_gather_umma4_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps4 maps, Epi epi,
+                         int tmem_cols) {
+  const int q = blockIdx.y, qh = q >> 1, qw = q & 1;
+  Epi e = epi;
+  e.out += qh * (e.oH >> 1) + qw * (e.oW >> 1);
+  if (e.add) e.add += qh * (e.aH >> 1) + qw * (e.aW >> 1);
+  if (e.mask) e.mask += qh * (e.mH >> 1) + qw * (e.mW >> 1);
+  conv_gather_umma_body(gp + q, maps.m[q], e, tmem_cols, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -818,6 +837,40 @@ conv_wgrad_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)wa.tmem_cols);
+}
+
+int ss_launch_conv_gather_umma4(const ConvGeom* g_dev, const ConvGeom* g4, const UmmaMaps* maps4, const Epi& epi,
+                                cudaStream_t st) {
+  const ConvGeom& g = g4[0];
+  const int tiles = g.B * ((g.OH + g.th - 1) / g.th) * ((g.OW + g.tw - 1) / g.tw);
+  int cols = 32;
+  while (cols < g.Npad) cols <<= 1;
+  const size_t smem = (size_t)UM_STAGES * (UM_A_BYTES + (size_t)g.Npad * 128) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_gather_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+        cudaSuccess) {
+      ss_set_error("conv_gather_umma4: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      return SSHSLIE_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  UmmaMaps4 m4;
+  for (int q = 0; q < 4; ++q) m4.m[q] = maps4[q];
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(tiles, 4);
+  cfg.blockDim = dim3(UM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ss_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, conv_gather_umma4_kernel, g_dev, m4, epi, cols);
+  ss_count_launches(0);
+  return ss_check_launch("conv_gather_umma4");
 }
 
 int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g, const UmmaMaps& maps, const Epi& epi,

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <array>
 #include <functional>
 #include <map>
 #include <string>
@@ -385,6 +386,28 @@ static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaSt
                                       epi, st);
   return ss_launch_conv_gather_simt(e->geoms_dev + gi, g, epi, st);
 }
+// four parity classes (consecutive geoms gi0..gi0+3, same tile grid, same Npad) in one launch when all are on tcgen05
+static int run_gather4(sshslie_engine* e, int gi0, const Epi* epis, int bias_layer, cudaStream_t st) {
+  bool merged = true;
+  for (int q = 0; q < 4; ++q)
+    merged = merged && e->geom_umma[gi0 + q] == 1 && e->geoms[gi0 + q].Npad == e->geoms[gi0].Npad;
+  if (!merged) {
+    for (int q = 0; q < 4; ++q) {
+      const int rc = run_gather(e, gi0 + q, epis[q], bias_layer, st);
+      if (rc) return rc;
+    }
+    return SSHSLIE_OK;
+  }
+  Epi epi = epis[0];
+  if (bias_layer >= 0) epi.bias = e->params + e->poff[2 * bias_layer + 1];
+  double fl = 0;
+  for (int q = 0; q < 4; ++q) fl += geom_flops(e->geoms[gi0 + q]);
+  prof_note(geom_label(e, gi0, e->geom_role[gi0] ? "dgrad" : "fwd") + "x4", fl, 0);
+  return ss_launch_conv_gather_umma4(e->geoms_dev + gi0, &e->geoms[gi0],
+                                     reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi0 * ss_umma_maps_size()),
+                                     epi, st);
+}
+
 static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, int qw, int scale, cudaStream_t st,
                      int bias_layer = -1) {
   const ConvGeom& g = e->geoms[gi];
@@ -491,13 +514,17 @@ static DecompGeoms plan_decomp_fwd(sshslie_engine* e, std::vector<sshslie_engine
     const int gi = G.conv3;
     PUSH(ops, return run_gather(e, gi, ep, L_D_CONV3, st););
   }
-  for (int q = 0; q < 4; ++q) {  // ConvTranspose 3x3 s2 p1 op1: 128 -> 64, four output parity classes
-    const int qh = q >> 1, qw = q & 1;
-    WAddr wa = waddr_conv_fwd(e, L_D_DECONV);
-    G.deconv[q] = e->add_geom(geom_tconv_class(B, H / 2, W / 2, {d.c3, 0, 128, 0}, 3, 1, qh, qw, 64, wa));
-    Epi ep = epi_bf16(d.dc, 64, qh, qw, 2); ep.relu = 1;
-    const int gi = G.deconv[q];
-    PUSH(ops, return run_gather(e, gi, ep, L_D_DECONV, st););
+  {  // ConvTranspose 3x3 s2 p1 op1: 128 -> 64, four output parity classes, one launch
+    Epi eps[4];
+    for (int q = 0; q < 4; ++q) {
+      const int qh = q >> 1, qw = q & 1;
+      WAddr wa = waddr_conv_fwd(e, L_D_DECONV);
+      G.deconv[q] = e->add_geom(geom_tconv_class(B, H / 2, W / 2, {d.c3, 0, 128, 0}, 3, 1, qh, qw, 64, wa));
+      eps[q] = epi_bf16(d.dc, 64, qh, qw, 2); eps[q].relu = 1;
+    }
+    const int gi0 = G.deconv[0];
+    const std::array<Epi, 4> ea = {eps[0], eps[1], eps[2], eps[3]};
+    PUSH(ops, return run_gather4(e, gi0, ea.data(), L_D_DECONV, st););
   }
   {  // conv5 on cat[deconv, conv1]
     WAddr wa = waddr_conv_fwd(e, L_D_CONV5);
@@ -589,14 +616,20 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
   }
   // conv2 (stride 2): wgrad on its forward geom; dgrad = transposed gather per input parity class, + dc1p, ReLU mask
   { const int gi = G.conv2; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc2, 128, 0, 0, 1, st, L_D_CONV2);); }
-  for (int q = 0; q < 4; ++q) {
-    const int qh = q >> 1, qw = q & 1;
-    WAddr wa = waddr_conv_dgrad(e, L_D_CONV2);
-    const int gi = e->add_geom(geom_tconv_class(B, H / 2, W / 2, {g.dc2, 0, 128, 0}, 3, 1, qh, qw, 64, wa));
-    Epi ep = epi_bf16(g.dc1, 64, qh, qw, 2);
-    epi_set_add(ep, g.dc1p, 0, qh, qw, 2);
-    epi_set_mask(ep, d.c1, qh, qw, 2);
-    PUSH(ops, return run_gather(e, gi, ep, -1, st););
+  {
+    Epi eps[4];
+    int gi0 = -1;
+    for (int q = 0; q < 4; ++q) {
+      const int qh = q >> 1, qw = q & 1;
+      WAddr wa = waddr_conv_dgrad(e, L_D_CONV2);
+      const int gi = e->add_geom(geom_tconv_class(B, H / 2, W / 2, {g.dc2, 0, 128, 0}, 3, 1, qh, qw, 64, wa));
+      if (q == 0) gi0 = gi;
+      eps[q] = epi_bf16(g.dc1, 64, qh, qw, 2);
+      epi_set_add(eps[q], g.dc1p, 0, qh, qw, 2);
+      epi_set_mask(eps[q], d.c1, qh, qw, 2);
+    }
+    const std::array<Epi, 4> ea = {eps[0], eps[1], eps[2], eps[3]};
+    PUSH(ops, return run_gather4(e, gi0, ea.data(), -1, st););
   }
   // conv1
   { const int gi = G.conv1; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc1, 64, 0, 0, 1, st, L_D_CONV1);); }
@@ -866,19 +899,23 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     for (int i = 0; i < 3; ++i) {
       const S2 s = s2[i];
       PUSH_SIDE(Lq, return run_wgrad(e, s.gfwd, s.dy, 64, 0, 0, 1, st, s.layer););
+      Epi eps[4];
+      int gi0 = -1;
       for (int q = 0; q < 4; ++q) {
         const int qh = q >> 1, qw = q & 1;
         WAddr wa = waddr_conv_dgrad(e, s.layer);
         const int gi = e->add_geom(geom_tconv_class(B, s.dy.H, s.dy.W, {s.dy, 0, 64, 0}, 3, 1, qh, qw, 64, wa));
-        Epi ep = epi_bf16(s.dx, 64, qh, qw, 2);
+        if (q == 0) gi0 = gi;
+        eps[q] = epi_bf16(s.dx, 64, qh, qw, 2);
         if (s.mask) {
-          epi_set_add(ep, s.addp, 0, qh, qw, 2);
-          epi_set_mask(ep, s.x_in, qh, qw, 2);
+          epi_set_add(eps[q], s.addp, 0, qh, qw, 2);
+          epi_set_mask(eps[q], s.x_in, qh, qw, 2);
         } else {
-          epi_set_add(ep, dfg, 128, qh, qw, 2);     // d(a0) also receives dfg[...,128:192] (deconv3 + conv0 skip)
+          epi_set_add(eps[q], dfg, 128, qh, qw, 2);     // d(a0) also receives dfg[...,128:192] (deconv3 + conv0 skip)
         }
-        PUSH(Lq, return run_gather(e, gi, ep, -1, st););
       }
+      const std::array<Epi, 4> ea = {eps[0], eps[1], eps[2], eps[3]};
+      PUSH(Lq, return run_gather4(e, gi0, ea.data(), -1, st););
     }
     // conv0 of the illumination net reads cat[R, I]
     PUSH_SIDE(Lq, return run_wgrad(e, g_i0, da0, 64, 0, 0, 1, st, L_I_CONV0););

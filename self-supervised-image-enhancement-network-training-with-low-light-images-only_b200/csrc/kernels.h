@@ -15,6 +15,8 @@ int ss_launch_pack_weights(const ConvGeom* geoms_dev, const int* block_start_dev
 // conv_umma.cu (tcgen05 / TMEM / TMA)
 struct UmmaMaps;   // host-built CUtensorMaps of one geom (opaque here)
 int ss_umma_supported(const ConvGeom& g);
+int ss_launch_conv_gather_umma4(const ConvGeom* g_dev, const ConvGeom* g4_host, const UmmaMaps* maps4_host,
+                                const Epi& epi_class0, cudaStream_t st);
 int ss_umma_wgrad_supported(const ConvGeom& g);
 int ss_umma_halo_supported(const ConvGeom& g);
 int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const Epi& epi,
