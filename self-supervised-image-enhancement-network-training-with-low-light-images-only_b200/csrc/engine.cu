@@ -156,28 +156,35 @@ struct sshslie_engine {
   float* mask_dev = nullptr;
   float* sums_dev = nullptr;
   float* wg_partial = nullptr;           // split-K partial accumulators of the tcgen05 wgrad (largest op)
+  float* wg_partial2 = nullptr;          // second buffer for the second side stream
   size_t wg_partial_floats = 0;
   int64_t* attn_poff_dummy = nullptr;
 
-  // side stream for weight gradients (created at bind; host objects only)
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool side_dirty = false, use_side = true;
+  // two side streams for weight gradients (created at bind; host objects only): consecutive wgrad launches alternate
+  // between them, each with its own split-K partial buffer
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  bool side_dirty[2] = {false, false}, use_side = true;
+  int side_rr = 0;
   cudaStream_t fork(cudaStream_t main_st) {
-    if (!use_side || !side) return main_st;
+    if (!use_side || !side[0]) return main_st;
+    const int i = (side_rr++) & 1;
     cudaEventRecord(ev_fork, main_st);
-    cudaStreamWaitEvent(side, ev_fork, 0);
-    side_dirty = true;
-    return side;
+    cudaStreamWaitEvent(side[i], ev_fork, 0);
+    side_dirty[i] = true;
+    return side[i];
   }
   int join(cudaStream_t main_st) {
-    if (side_dirty) {
-      cudaEventRecord(ev_join, side);
-      cudaStreamWaitEvent(main_st, ev_join, 0);
-      side_dirty = false;
-    }
+    for (int i = 0; i < 2; ++i)
+      if (side_dirty[i]) {
+        cudaEventRecord(ev_join[i], side[i]);
+        cudaStreamWaitEvent(main_st, ev_join[i], 0);
+        side_dirty[i] = false;
+      }
+    side_rr = 0;
     return SSHSLIE_OK;
   }
+  float* partial_for(cudaStream_t st) const { return (side[1] && st == side[1]) ? wg_partial2 : wg_partial; }
 
   // per-call state read by the recorded launches
   const float* x = nullptr;
@@ -432,7 +439,7 @@ static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, i
                                      *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
                                      it->second.bytes, gN,
                                      bias_layer >= 0 ? (long long)e->poff[2 * bias_layer + 1] : -1LL,
-                                     e->wg_partial, e->grads, st);
+                                     e->partial_for(st), e->grads, st);
   }
   if (bias_layer >= 0) {
     const int rc = ss_launch_bias_grad(G.p, G.pix(), G.ld, gN, e->grads + e->poff[2 * bias_layer + 1], st);
@@ -955,6 +962,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     e->wg_partial_floats = mx;
     e->wg_partial = e->falloc((int64_t)mx);
+    e->wg_partial2 = e->falloc((int64_t)mx);
   }
   e->ws_bytes = e->cursor;
   return SSHSLIE_OK;
@@ -1005,9 +1013,11 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
 }
 extern "C" void sshslie_engine_destroy(sshslie_engine* e) {
   if (!e) return;
-  if (e->side) cudaStreamDestroy(e->side);
+  for (int i = 0; i < 2; ++i) {
+    if (e->side[i]) cudaStreamDestroy(e->side[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  if (e->ev_join) cudaEventDestroy(e->ev_join);
   delete e;
 }
 extern "C" int64_t sshslie_engine_workspace_bytes(const sshslie_engine* e) { return e ? e->ws_bytes : 0; }
@@ -1021,11 +1031,13 @@ extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t w
   cudaStream_t st = (cudaStream_t)stream;
   e->bound = false;
   e->gmaps.clear();
-  if (!e->side) {
-    if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-      ss_set_error("bind: cannot create the side stream: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!e->side[0]) {
+    bool ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      ss_set_error("bind: cannot create the side streams: %s", cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
   }
