@@ -10,73 +10,6 @@
 #define AT_HEADS 4
 #define AT_HD 16
 
-// ---------------------------------------------------------------------------------------------
-// Y[t, o] = sum_i X[t, i] * W[o, i] + b[o]   (+relu) (+res[t,o]);  X given as fp32 or bf16
-// block = 256 threads: 64 outputs x 4 tokens per pass, 16 tokens per block
-// ---------------------------------------------------------------------------------------------
-template <bool XBF16>
-__global__ void __launch_bounds__(256) linear_fwd_kernel(const void* __restrict__ Xv, const float* __restrict__ Wt,
-                                                         const float* __restrict__ bias, float* __restrict__ Y,
-                                                         const float* __restrict__ res, float* __restrict__ xcopy,
-                                                         int T, int relu) {
-  __shared__ float Ws[AT_D][AT_D + 1];
-  __shared__ float Xs[16][AT_D];
-  const int t0 = blockIdx.x * 16;
-  for (int i = threadIdx.x; i < AT_D * AT_D; i += 256) Ws[i >> 6][i & 63] = Wt[i];
-  for (int i = threadIdx.x; i < 16 * AT_D; i += 256) {
-    const int t = t0 + (i >> 6);
-    float v = 0.f;
-    if (t < T) {
-      v = XBF16 ? bf2f(reinterpret_cast<const bf16*>(Xv)[(int64_t)t * AT_D + (i & 63)])
-                : reinterpret_cast<const float*>(Xv)[(int64_t)t * AT_D + (i & 63)];
-      if (xcopy) xcopy[(int64_t)t * AT_D + (i & 63)] = v;
-    }
-    Xs[i >> 6][i & 63] = v;
-  }
-  __syncthreads();
-  const int o = threadIdx.x & 63;
-  for (int tt = threadIdx.x >> 6; tt < 16; tt += 4) {
-    const int t = t0 + tt;
-    if (t >= T) break;
-    float acc = bias[o];
-#pragma unroll 16
-    for (int i = 0; i < AT_D; ++i) acc = fmaf(Xs[tt][i], Ws[o][i], acc);
-    if (relu) acc = fmaxf(acc, 0.f);
-    if (res) acc += res[(int64_t)t * AT_D + o];
-    Y[(int64_t)t * AT_D + o] = acc;
-  }
-}
-
-// dX[t, i] (+)= sum_o dY[t, o] * W[o, i]     (optionally dY is first masked by Hmask > 0: ReLU backward)
-__global__ void __launch_bounds__(256) linear_bwd_data_kernel(const float* __restrict__ dY, const float* __restrict__ Wt,
-                                                              const float* __restrict__ hmask, float* __restrict__ dX,
-                                                              int T, int accumulate) {
-  __shared__ float Ws[AT_D][AT_D + 1];
-  __shared__ float Ys[16][AT_D];
-  const int t0 = blockIdx.x * 16;
-  for (int i = threadIdx.x; i < AT_D * AT_D; i += 256) Ws[i >> 6][i & 63] = Wt[i];
-  for (int i = threadIdx.x; i < 16 * AT_D; i += 256) {
-    const int t = t0 + (i >> 6);
-    float v = 0.f;
-    if (t < T) {
-      v = dY[(int64_t)t * AT_D + (i & 63)];
-      if (hmask && !(hmask[(int64_t)t * AT_D + (i & 63)] > 0.f)) v = 0.f;
-    }
-    Ys[i >> 6][i & 63] = v;
-  }
-  __syncthreads();
-  const int ii = threadIdx.x & 63;
-  for (int tt = threadIdx.x >> 6; tt < 16; tt += 4) {
-    const int t = t0 + tt;
-    if (t >= T) break;
-    float acc = 0.f;
-#pragma unroll 16
-    for (int o = 0; o < AT_D; ++o) acc = fmaf(Ys[tt][o], Ws[o][ii], acc);
-    if (accumulate) acc += dX[(int64_t)t * AT_D + ii];
-    dX[(int64_t)t * AT_D + ii] = acc;
-  }
-}
-
 // dW[o, i] += sum_t dY[t,o] * X[t,i] ;  db[o] += sum_t dY[t,o]   (dY optionally masked by hmask > 0)
 // grid.x = token chunks of 64; block 256 = 64 (i) x 4 (o phase); atomics into the flat gradient buffer
 __global__ void __launch_bounds__(256) linear_bwd_weight_kernel(const float* __restrict__ dY,
