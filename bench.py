@@ -262,8 +262,15 @@ def run_ours(args):
     else:
         gb = top[3] / (top_ms * 1e-3) / 1e9 if top[3] else 0.0
         roof = {"bound": "hbm", "achieved": gb, "peak": pk["hbm"], "unit": "GB/s", "frac": gb / pk["hbm"]}
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = tj.get(top_name.split("/", 1)[1])
+    except Exception:
+        pass
     roof.update({"kernel": top_name, "ms_per_launch": top_ms, "share_of_step": top_ms / total_prof,
-                 "traffic": None, "peak_source": pk["source"],
+                 "traffic": traffic, "algorithmic_flops_per_launch": top[2], "algorithmic_bytes_per_launch": top[3],
+                 "peak_source": pk["source"],
                  "timing": "cudaEvent pairs around each launch group, eager steps after the timed region"})
     patches = world * BATCH_PER_GPU * K
     value = patches / (ms_dev * 1e-3)

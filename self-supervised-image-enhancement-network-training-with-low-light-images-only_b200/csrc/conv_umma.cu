@@ -436,8 +436,12 @@ conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
     const uint32_t tstep = (uint32_t)((nh * halo_bytes) >> 4), bstep = b_bytes >> 4;
     for (int t = 0; t < nt; ++t) mbar_wait_warp(smem_u32(&halo_bar[t]), 0, 0);
     uint32_t st = 0, ph = 0;
+    long long c_wait = 0, c_issue = 0, c_sync = 0;
     for (int s = 0; s < nslabs; ++s) {
+      const long long q0 = clock64();
       if (!(ha.debug & 4)) mbar_wait_warp(smem_u32(&full_bar[st]), ph, 0);
+      const long long q1 = clock64();
+      c_wait += q1 - q0;
       if (!(ha.debug & 8)) tc_fence_after();
       // warp-uniform on purpose (shfl): ptxas then keeps the descriptor arithmetic in the uniform datapath and the
       // MMAs issue back to back instead of paying an R2UR round trip per operand per MMA
@@ -456,10 +460,16 @@ conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__
         if (!(ha.debug & 16)) umma_commit(smem_u32(&empty_bar[st]));
         if (s == nslabs - 1) umma_commit(smem_u32(&accum_bar));
       }
+      const long long q2 = clock64();
+      c_issue += q2 - q1;
       if (!(ha.debug & 128)) __syncwarp();
+      c_sync += clock64() - q2;
       if ((ha.debug & 64) && blockIdx.x == 0 && lane == 0) {
         if (s == 0) g_dbg[3] = clock64() - ts0;
-        if (s == nslabs - 1) g_dbg[4] = clock64() - ts0;
+        if (s == nslabs - 1) {
+          g_dbg[4] = clock64() - ts0;
+          g_dbg[7] = c_wait; g_dbg[8] = c_issue; g_dbg[9] = c_sync;
+        }
       }
       if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
     }
