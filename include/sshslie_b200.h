@@ -105,6 +105,12 @@ SSHSLIE_API int sshslie_profile_step(sshslie_engine* e, const float* x, const fl
 SSHSLIE_API long long sshslie_launch_count(void);
 SSHSLIE_API int sshslie_profile_row(int i, char* name, int name_cap, float* ms, double* flops, double* bytes);
 
+/* On-device patch pipeline replacing the numpy crop + augmentation + H2D of train_model (model.py:301-312, utils.py:7-34).
+ * cubes_dev: device array of B pointers to resident HWC fp32 cubes (one per sample); meta_dev: B x {h, w, x0, y0, mode}
+ * int32 (x0, y0, mode drawn by the host in the reference's order); out: (B, C, ps, ps) fp32.  Bit-exact copy. */
+SSHSLIE_API int sshslie_gather_patches(const float* const* cubes_dev, const int* meta_dev, float* out, int B, int C,
+                           int patch_size, void* stream);
+
 /* ---- single kernels, exported for kernel-level parity tests and profiling ---- */
 
 /* fourier_spectrum_loss (model.py:456-473) forward + d/dS.  x,S,dS: (n_img,H,W) fp32 planes, H and W

@@ -457,3 +457,48 @@ int ss_launch_finalize_losses(const float* sums, const sshslie_loss_cfg* cfg, fl
   finalize_losses_kernel<<<1, 32, 0, st>>>(sums, *cfg, losses, B, C, H, W);
   EW_CHECK("finalize_losses");
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// on-device patch pipeline: the reference crops + augments every training patch in numpy and ships
+// 4 MiB per patch over PCIe (model.py:301-312).  Here the normalised cubes stay resident in HBM (HWC fp32, as load_hsi
+// returns them) and one kernel does crop -> one of the 8 dihedral variants (utils.py:7-34: np.rot90(k) then optional
+// np.flipud) -> HWC-to-NCHW for the whole batch.  meta[b] = {h, w, x0, y0, mode}: the host still draws x0, y0, mode with
+// numpy in the reference's order, so runs are reproducible against it.  Pure copy: bit-exact.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gather_patches_kernel(const float* const* __restrict__ cubes,
+                                                             const int* __restrict__ meta, float* __restrict__ out,
+                                                             int C, int ps) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ps) return;
+  const int w = meta[b * 5 + 1], x0 = meta[b * 5 + 2], y0 = meta[b * 5 + 3], mode = meta[b * 5 + 4];
+  const int k = mode >> 1, flip = mode & 1, n1 = ps - 1;
+  const int ii = flip ? n1 - i : i;                 // undo flipud (applied last)
+  int si, sj;                                       // source pixel inside the un-augmented patch
+  if (k == 0) { si = ii; sj = j; }
+  else if (k == 1) { si = j; sj = n1 - ii; }        // np.rot90(P)[i, j] = P[j, n-1-i]
+  else if (k == 2) { si = n1 - ii; sj = n1 - j; }
+  else { si = n1 - j; sj = ii; }
+  const float* src = cubes[b] + ((int64_t)(x0 + si) * w + (y0 + sj)) * C;   // crop = cube[x0:x0+ps, y0:y0+ps, :]
+  float* dst = out + (((int64_t)b * C) * ps + i) * ps + j;
+  const int64_t plane = (int64_t)ps * ps;
+  for (int c = 0; c < C; c += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
+    dst[(c + 0) * plane] = v.x;
+    dst[(c + 1) * plane] = v.y;
+    dst[(c + 2) * plane] = v.z;
+    dst[(c + 3) * plane] = v.w;
+  }
+}
+
+extern "C" int sshslie_gather_patches(const float* const* cubes_dev, const int* meta_dev, float* out, int B, int C,
+                                      int patch_size, void* stream) {
+  if (!cubes_dev || !meta_dev || !out || B < 1 || C < 4 || (C % 4) || patch_size < 1) {
+    ss_set_error("sshslie_gather_patches: bad argument");
+    return SSHSLIE_ERR_ARG;
+  }
+  dim3 grid((patch_size + 127) / 128, patch_size, B);
+  gather_patches_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(cubes_dev, meta_dev, out, C, patch_size);
+  return ss_check_launch("gather_patches");
+}

@@ -266,6 +266,49 @@ class LazyLosses(dict):
         return dict.__repr__(self)
 
 
+class DevicePatchSampler:
+    """Resident training cubes + one-kernel crop/augment/transposition (sshslie_gather_patches).
+
+    Draws (x, y, mode) per sample with numpy in the reference's order (model.py:306-308), so a seeded run picks the same
+    patches as the reference; only the pixel work moves to the GPU."""
+
+    def __init__(self, cubes_hwc, batch_size, patch_size, channels, device):
+        self.cubes = [torch.from_numpy(np.ascontiguousarray(c, dtype=np.float32)).to(device) for c in cubes_hwc]
+        self.shapes = [c.shape for c in cubes_hwc]
+        self.B, self.ps, self.C, self.device = batch_size, patch_size, channels, device
+        self.ptrs_host = torch.empty(batch_size, dtype=torch.int64).pin_memory()
+        self.meta_host = torch.empty(batch_size, 5, dtype=torch.int32).pin_memory()
+        self.ptrs = torch.empty(batch_size, dtype=torch.int64, device=device)
+        self.meta = torch.empty(batch_size, 5, dtype=torch.int32, device=device)
+        self.out = torch.empty(batch_size, channels, patch_size, patch_size, device=device)
+        self._copied = None                    # event: the pinned staging buffers have been read by the last H2D
+
+    def sample(self, batch_id):
+        n = len(self.cubes)
+        if self._copied is not None:
+            self._copied.synchronize()         # do not overwrite pinned metadata an in-flight copy still reads
+        for i in range(self.B):
+            idx = (batch_id * self.B + i) % n
+            h, w, _ = self.shapes[idx]
+            x = np.random.randint(0, h - self.ps)
+            y = np.random.randint(0, w - self.ps)
+            mode = np.random.randint(0, 8)
+            self.ptrs_host[i] = self.cubes[idx].data_ptr()
+            self.meta_host[i] = torch.tensor([h, w, x, y, mode], dtype=torch.int32)
+        return self.gather()
+
+    def gather(self):
+        self.ptrs.copy_(self.ptrs_host, non_blocking=True)
+        self.meta.copy_(self.meta_host, non_blocking=True)
+        if self._copied is None:
+            self._copied = torch.cuda.Event()
+        self._copied.record()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        L.check(L.load().sshslie_gather_patches(L.ptr(self.ptrs), L.ptr(self.meta), L.ptr(self.out), self.B, self.C,
+                                                self.ps, stream), "sshslie_gather_patches")
+        return self.out
+
+
 class _Engine:
     """One bound sshslie_engine + its workspace and static I/O buffers for a (B, H, W, train) shape."""
 
@@ -523,7 +566,9 @@ class LowLightEnhance(nn.Module):
                                   max_val=self.global_max, min_val=self.global_min) for f in eval_files]
         num_batches = len(train_low_data) // batch_size
         dev = self._plist[0].device
-        pinned = torch.empty(batch_size, self.input_channels, patch_size, patch_size).pin_memory()
+        # crop + augmentation + HWC->NCHW run on the device from resident cubes (x, y, mode still drawn by numpy in the
+        # reference's order, model.py:306-308); the reference's per-batch numpy work and 4 MiB/patch H2D are gone
+        sampler = DevicePatchSampler(train_low_data, batch_size, patch_size, self.input_channels, dev)
         for epoch in range(num_epochs):
             if getattr(self, 'freeze_decom_epochs', 0) > 0:
                 if epoch < self.freeze_decom_epochs:
@@ -542,17 +587,9 @@ class LowLightEnhance(nn.Module):
             cur = {k: 0 for k in LOSS_KEYS}
             count = 0
             for batch_id in range(num_batches):
-                batch = np.zeros((batch_size, patch_size, patch_size, self.input_channels), dtype=np.float32)
-                for i in range(batch_size):
-                    idx = (batch_id * batch_size + i) % len(train_low_data)
-                    h, w, _ = train_low_data[idx].shape
-                    x = np.random.randint(0, h - patch_size)
-                    y = np.random.randint(0, w - patch_size)
-                    mode = np.random.randint(0, 8)
-                    batch[i] = data_augmentation(train_low_data[idx][x:x + patch_size, y:y + patch_size, :], mode)
-                pinned.copy_(torch.from_numpy(batch).permute(0, 3, 1, 2))
+                batch = sampler.sample(batch_id)
                 self.optimizer.zero_grad()
-                loss, batch_losses = self.compute_loss(pinned if dev.type == 'cuda' else pinned.to(dev))
+                loss, batch_losses = self.compute_loss(batch)
                 loss.backward()
                 self.optimizer.step()
                 for k in LOSS_KEYS:

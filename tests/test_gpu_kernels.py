@@ -209,3 +209,51 @@ def test_adam_step():
                                           0.999, 1e-8, step, 1.0, stream()), "adam")
         torch.cuda.synchronize()
         torch.testing.assert_close(pd.cpu(), p["w"], rtol=1e-5, atol=1e-6)
+
+
+def test_gather_patches_bit_exact():
+    """On-device crop + dihedral augmentation + HWC->NCHW (sshslie_gather_patches) against the numpy path of the
+    reference's train loop (model.py:301-312, utils.py:7-34): a pure copy, so bit-exact, all 8 modes, ragged cubes."""
+    import sshslie_b200  # noqa: F401
+    from sshslie_b200.model import DevicePatchSampler
+    from sshslie_b200.utils import data_augmentation
+    rng = np.random.default_rng(5)
+    shapes = [(160, 144), (129, 200), (140, 131)]
+    cubes = [rng.random((h, w, 64), dtype=np.float32) for h, w in shapes]
+    ps, B = 128, 8
+    s = DevicePatchSampler(cubes, B, ps, 64, torch.device("cuda"))
+    expect = np.zeros((B, ps, ps, 64), dtype=np.float32)
+    for i in range(B):
+        idx = i % len(cubes)
+        h, w = shapes[idx]
+        x, y = int(rng.integers(0, h - ps)), int(rng.integers(0, w - ps))
+        s.ptrs_host[i] = s.cubes[idx].data_ptr()
+        s.meta_host[i] = torch.tensor([h, w, x, y, i], dtype=torch.int32)      # mode = i covers all 8 variants
+        expect[i] = data_augmentation(cubes[idx][x:x + ps, y:y + ps, :], i)
+    out = s.gather()
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), np.ascontiguousarray(expect.transpose(0, 3, 1, 2)))
+
+
+def test_patch_sampler_follows_reference_rng_order():
+    """sample() draws x, y, mode per sample in the reference's order (model.py:306-308): same seed -> same patches."""
+    import sshslie_b200  # noqa: F401
+    from sshslie_b200.model import DevicePatchSampler
+    from sshslie_b200.utils import data_augmentation
+    rng = np.random.default_rng(6)
+    cubes = [rng.random((150, 140, 64), dtype=np.float32) for _ in range(3)]
+    ps, B = 128, 2
+    s = DevicePatchSampler(cubes, B, ps, 64, torch.device("cuda"))
+    np.random.seed(41)
+    got = [s.sample(b).cpu().numpy().copy() for b in range(2)]
+    np.random.seed(41)
+    for b in range(2):
+        batch = np.zeros((B, ps, ps, 64), dtype=np.float32)
+        for i in range(B):
+            idx = (b * B + i) % len(cubes)
+            h, w, _ = cubes[idx].shape
+            x = np.random.randint(0, h - ps)
+            y = np.random.randint(0, w - ps)
+            mode = np.random.randint(0, 8)
+            batch[i] = data_augmentation(cubes[idx][x:x + ps, y:y + ps, :], mode)
+        assert np.array_equal(got[b], batch.transpose(0, 3, 1, 2))

@@ -79,3 +79,18 @@ def test_half_spectrum_identity():
     fa, fb = torch.fft.rfft2(a).abs(), torch.fft.rfft2(b).abs()
     half = (w * (fa - fb).abs()).sum() / a.numel()
     np.testing.assert_allclose(float(half), float(full), rtol=1e-5)
+
+
+# the 8 dihedral variants of arange(9).reshape(3,3), recorded from the unmodified reference (utils.py:7-34)
+AUG_GOLDEN = [[0, 1, 2, 3, 4, 5, 6, 7, 8], [6, 7, 8, 3, 4, 5, 0, 1, 2], [2, 5, 8, 1, 4, 7, 0, 3, 6],
+              [0, 3, 6, 1, 4, 7, 2, 5, 8], [8, 7, 6, 5, 4, 3, 2, 1, 0], [2, 1, 0, 5, 4, 3, 8, 7, 6],
+              [6, 3, 0, 7, 4, 1, 8, 5, 2], [8, 5, 2, 7, 4, 1, 6, 3, 0]]
+
+
+def test_data_augmentation_modes():
+    """Host restatement of utils.py:7-34 (the checker of the on-device patch gather) against the recorded table."""
+    import sshslie_b200  # noqa: F401
+    from sshslie_b200.utils import data_augmentation
+    a = np.arange(9).reshape(3, 3, 1)
+    for mode in range(8):
+        assert data_augmentation(a, mode)[:, :, 0].flatten().tolist() == AUG_GOLDEN[mode]
