@@ -136,6 +136,10 @@ SSHSLIE_API int sshslie_conv2d(int kind, int impl, int transposed, float* x, flo
                    int B, int Cin, int Cout, int H, int W, int k, int stride, int relu,
                    void* scratch, int64_t scratch_bytes, void* stream);
 
+/* with SSHSLIE_CONV2D_TIMING=n in the environment, sshslie_conv2d repeats the layer's launches n times between two
+ * CUDA events; this returns the mean device time (ms) of the last such call (tools/conv_bench.py) */
+SSHSLIE_API float sshslie_conv2d_last_ms(void);
+
 /* tcgen05.mma issue-rate microbenchmark (tools/umma_probe.py); out_cycles[n_ctas] receives the elapsed SM cycles */
 SSHSLIE_API int sshslie_umma_probe(int N, int n_mma, int n_acc, int commit_every, long long* out_cycles,
                        int n_ctas, void* stream);

@@ -312,186 +312,208 @@ conv_gather_umma4_kernel(const ConvGeom* __restrict__ gp, const __grid_constant_
 // (16+2p) x (8+2p) pixels x 64 ch — and points the UMMA A-descriptor of tap (dh,dw) INTO it:
 //     start = halo + ((dh+p) * pitch + (dw+p)) * 128 B,   SBO = pitch * 128 B  (one 8-pixel output row per group)
 // (the 128B swizzle is a function of the shared-memory address, for TMA writes and UMMA reads alike, so a start
-// that is 128B- but not 1024B-aligned still addresses consistently; `bo_mode` selects the descriptor base_offset).
-// Only the weight slabs stream through the ring, and T pixel tiles per CTA share each weight slab, which turns the
-// kernel from L2-feed-bound (24 KB per 4 MMAs) into MMA-bound (8 KB per 4*T MMAs).
+// that is 128B- but not 1024B-aligned still addresses consistently; descriptor base_offset stays 0 — verified on B200).
+// Only the weight slabs stream, HG slabs per ring stage: the MMA warp pays ONE barrier wait / fence / commit per
+// 4*HG*T MMAs (the per-slab version of this kernel spent 3x the MMA time in that bookkeeping), and T pixel tiles per
+// CTA share each weight slab.  L2->SM traffic per MMA drops from 6 KB (per-tap kernel) to 2 KB / T.
 // ---------------------------------------------------------------------------------------------
-__device__ long long g_dbg[16];   // timing breadcrumbs of block 0 (SSHSLIE_HALO_DEBUG & 64), read by sshslie_debug_read
+__device__ long long g_dbg[16];   // timing breadcrumbs of block 0 (SSHSLIE_HALO_DEBUG=64), read by sshslie_debug_read
 #define HALO_TW 8
 #define HALO_TH 16
 #define HALO_MAX_T 4
-#define HALO_MAX_STAGES 16
+#define HALO_MAX_STAGES 8
 
 struct HaloArgs {
   int nh;                  // distinct (source, channel-slab) halo windows per tile
   int src[SS_MAX_SRC];
   int c0[SS_MAX_SRC];
   int pad;                 // p = max |dh|,|dw|
-  int T;                   // pixel tiles per CTA
+  int T;                   // pixel tiles per CTA (template parameter of the kernel)
   int halo_bytes;          // one window, rounded up to 1024
-  int bo_mode;             // 0: base_offset = 0 ; 1: base_offset = (start >> 7) & 7
   int tmem_cols;
   int n_tiles;
-  int stages;              // depth of the weight-slab ring (the only operand that streams)
-  int debug;               // timing experiments only (wrong results): 1 = every tap reads the window at offset 0
+  int stages;              // depth of the weight ring (the only operand that streams)
+  int G;                   // weight slabs per ring stage
+  int debug;               // 64: block 0 leaves cycle breadcrumbs in g_dbg
+  int nslabs, Npad, N, OH, OW;
+  uint16_t aoff[SS_MAX_SLABS + 3];   // per slab: (byte offset of its A window inside tile 0's halo block) >> 4.
+                                     // Lives in the kernel's constant bank: the MMA loop reads it with uniform loads.
 };
 
-SS_DEVINL uint64_t make_sdesc_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, int bo_mode) {
-  uint64_t d = make_sdesc(smem_addr, lbo_bytes, sbo_bytes);
-  if (bo_mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
-  return d;
+SS_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <int T>
 __global__ void __launch_bounds__(UM_THREADS, 1)
-conv_gather_halo_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps maps, Epi epi, HaloArgs ha) {
+conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ Epi epi,
+                        const __grid_constant__ HaloArgs ha) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ ConvGeom g;
-  __shared__ uint32_t slab_aoff[SS_MAX_SLABS];     // per slab: byte offset of its A window inside tile 0's halo block
   __shared__ __align__(8) uint64_t full_bar[HALO_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[HALO_MAX_STAGES];
-  __shared__ __align__(8) uint64_t halo_bar[HALO_MAX_T];
+  __shared__ __align__(8) uint64_t halo_bar;
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ts0 = clock64();
+  const long long ts0 = (ha.debug & 64) ? clock64() : 0;
   pdl_launch_dependents();
-  {
-    const int* src = reinterpret_cast<const int*>(gp);
-    int* dst = reinterpret_cast<int*>(&g);
-    for (int i = threadIdx.x; i < (int)(sizeof(ConvGeom) / 4); i += blockDim.x) dst[i] = src[i];
-  }
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  __syncthreads();
-  const int Npad = g.Npad, nslabs = g.nslabs;
+  const int Npad = ha.Npad, nslabs = ha.nslabs;
   const uint32_t b_bytes = (uint32_t)Npad * 128u;
-  const int T = ha.T, nh = ha.nh, pad = ha.pad, stages = ha.stages, halo_bytes = ha.halo_bytes;
+  const int nh = ha.nh, pad = ha.pad, stages = ha.stages, halo_bytes = ha.halo_bytes, G = ha.G;
   const uint32_t ring_base = dyn_base + (uint32_t)(T * nh * halo_bytes);
+  const uint32_t stage_bytes = (uint32_t)G * b_bytes;
   const int pitch = HALO_TW + 2 * pad;
-  // everything the MMA loop needs per slab is resolved here, once, by all threads: the loop itself must stay a
-  // handful of instructions (measured: a 120-instruction loop body costs ~1500 cycles per slab, 4x the MMA time)
-  for (int s = threadIdx.x; s < nslabs; s += blockDim.x) {
-    const Slab sl = g.slab[s];
-    int h = 0;
-    for (int i = 0; i < nh; ++i)
-      if (ha.src[i] == sl.src && ha.c0[i] == sl.c0) h = i;
-    slab_aoff[s] = (ha.debug & 1) ? (uint32_t)(h * halo_bytes)
-                                  : (uint32_t)(h * halo_bytes + ((sl.dh + pad) * pitch + (sl.dw + pad)) * 128);
-  }
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&maps.halo[s]);
-    tma_prefetch_desc(&maps.w);
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+  const int tiles_w = ha.OW / HALO_TW, tiles_h = (ha.OH + HALO_TH - 1) / HALO_TH;
+  const int t_first = blockIdx.x * T;            // the launcher guarantees n_tiles % T == 0
+  const int n_iter = (nslabs + G - 1) / G;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // this thread owns every barrier's initialisation AND the first requests, so the loads are in flight before the
+      // rest of the CTA has finished its prologue (TMEM allocation, __syncthreads)
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(&halo_bar), 1);
+      mbar_init(smem_u32(&accum_bar), 1);
+      fence_barrier_init();
+      pdl_wait();      // halo windows (and, in single-layer calls, the packed weights) come from earlier kernels
+      const uint32_t hb = smem_u32(&halo_bar);
+      mbar_expect_tx(hb, (uint32_t)(T * nh) * (uint32_t)((HALO_TH + 2 * pad) * pitch * 128));
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        int ti = t_first + t;
+        const int twi = ti % tiles_w; ti /= tiles_w;
+        const int thi = ti % tiles_h;
+        const int b = ti / tiles_h;
+        for (int h = 0; h < nh; ++h)
+          tma_load_4d(dyn_base + (uint32_t)((t * nh + h) * halo_bytes), &maps.halo[ha.src[h]], hb, ha.c0[h],
+                      twi * HALO_TW - pad, thi * HALO_TH - pad, b);
+      }
+      {  // first weight stage
+        const int cnt = min(G, nslabs);
+        const uint32_t fb = smem_u32(&full_bar[0]);
+        mbar_expect_tx(fb, (uint32_t)cnt * b_bytes);
+        for (int q = 0; q < cnt; ++q) tma_load_2d(ring_base + (uint32_t)q * b_bytes, &maps.w, fb, 0, q * Npad);
+      }
     }
-    for (int t = 0; t < HALO_MAX_T; ++t) mbar_init(smem_u32(&halo_bar[t]), 1);
-    mbar_init(smem_u32(&accum_bar), 1);
-    fence_barrier_init();
+    __syncwarp();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)ha.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const long long ts1 = clock64();
-  pdl_wait();
-  const long long ts2 = clock64();
-
-  const int tiles_w = g.OW / HALO_TW, tiles_h = (g.OH + HALO_TH - 1) / HALO_TH;
-  const int t_first = blockIdx.x * T;
-  const int nt = min(T, ha.n_tiles - t_first);
+  const long long ts1 = (ha.debug & 64) ? clock64() : 0;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int t = 0; t < nt; ++t) {
-        int ti = t_first + t;
-        const int twi = ti % tiles_w; ti /= tiles_w;
-        const int thi = ti % tiles_h;
-        const int b = ti / tiles_h;
-        const uint32_t hb = smem_u32(&halo_bar[t]);
-        if (ha.debug & 32) { mbar_arrive(hb); continue; }
-        mbar_expect_tx(hb, (uint32_t)nh * (uint32_t)((HALO_TH + 2 * pad) * pitch * 128));
-        for (int h = 0; h < nh; ++h)
-          tma_load_4d(dyn_base + (uint32_t)((t * nh + h) * halo_bytes), &maps.halo[ha.src[h]], hb, ha.c0[h],
-                      twi * HALO_TW - pad, thi * HALO_TH - pad, b);
-      }
-      uint32_t st = 0, ph = 1;
-      for (int s = 0; s < nslabs && !(ha.debug & 4); ++s) {
-        mbar_wait(smem_u32(&empty_bar[st]), ph);
-        const uint32_t fb = smem_u32(&full_bar[st]);
-        mbar_expect_tx(fb, b_bytes);
-        tma_load_2d(ring_base + st * b_bytes, &maps.w, fb, 0, s * Npad);
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t st = (stages > 1) ? 1u : 0u, ph = (stages > 1) ? 1u : 0u;      // stage 0 was requested in the prologue
+      for (int it = 1; it < n_iter; ++it) {
+        mbar_wait(empty0 + 8u * st, ph);
+        const int s0 = it * G;
+        const int cnt = min(G, nslabs - s0);
+        const uint32_t fb = full0 + 8u * st;
+        mbar_expect_tx(fb, (uint32_t)cnt * b_bytes);
+        for (int q = 0; q < cnt; ++q)
+          tma_load_2d(ring_base + st * stage_bytes + (uint32_t)q * b_bytes, &maps.w, fb, 0, (s0 + q) * Npad);
         if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
+    // ===== MMA issuer.  Everything in this loop is warp-uniform (kernel parameters, shuffled bases, loop counters) so
+    // that ptxas keeps descriptors and barrier addresses in uniform registers: ~10 instructions per slab of 4*T MMAs.
     const uint32_t idesc = make_idesc(128, Npad, 0, 0);
     const uint32_t tm = uniform32(tmem_base);
-    // descriptor words: hi is constant; lo = (start >> 4) | (LBO >> 4) << 16, advanced by plain 32-bit adds
     const uint32_t a_hi = (uint32_t)(make_sdesc(0, 16, (uint32_t)pitch * 128u) >> 32);
     const uint32_t b_hi = (uint32_t)(make_sdesc(0, 16, 1024) >> 32);
     const uint32_t a_lo0 = uniform32(((dyn_base >> 4) & 0x3FFFu) | (1u << 16));
     const uint32_t b_lo0 = uniform32(((ring_base >> 4) & 0x3FFFu) | (1u << 16));
-    const uint32_t tstep = (uint32_t)((nh * halo_bytes) >> 4), bstep = b_bytes >> 4;
-    for (int t = 0; t < nt; ++t) mbar_wait_warp(smem_u32(&halo_bar[t]), 0, 0);
+    const uint32_t full0 = uniform32(smem_u32(&full_bar[0])), empty0 = uniform32(smem_u32(&empty_bar[0]));
+    const uint32_t accb = uniform32(smem_u32(&accum_bar));
+    const uint32_t tstep = (uint32_t)((nh * halo_bytes) >> 4), bstep = b_bytes >> 4, sstep = stage_bytes >> 4;
+    long long c_wait = 0;
+    mbar_wait_warp(uniform32(smem_u32(&halo_bar)), 0, 0);
+    if ((ha.debug & 64) && blockIdx.x == 0 && lane == 0) g_dbg[2] = clock64() - ts0;
     uint32_t st = 0, ph = 0;
-    long long c_wait = 0, c_issue = 0, c_sync = 0;
-    for (int s = 0; s < nslabs; ++s) {
-      const long long q0 = clock64();
-      if (!(ha.debug & 4)) mbar_wait_warp(smem_u32(&full_bar[st]), ph, 0);
-      const long long q1 = clock64();
-      c_wait += q1 - q0;
-      if (!(ha.debug & 8)) tc_fence_after();
-      // warp-uniform on purpose (shfl): ptxas then keeps the descriptor arithmetic in the uniform datapath and the
-      // MMAs issue back to back instead of paying an R2UR round trip per operand per MMA
-      // timing-bisect switches (wrong results): 512 = every slab reads window 0, 1024 = every slab reads ring stage 0,
-      // 2048 = every tile reads tile 0's halo
-      const uint32_t a_lo = uniform32(a_lo0 + ((ha.debug & 512) ? 0u : (slab_aoff[s] >> 4)));
-      const uint32_t b_lo = uniform32(b_lo0 + ((ha.debug & 1024) ? 0u : st * bstep));
-      const uint32_t tstep_eff = (ha.debug & 2048) ? 0u : tstep;
+    int s = 0;
+#pragma unroll 1
+    for (int it = 0; it < n_iter; ++it) {
+      const long long q0 = (ha.debug & 64) ? clock64() : 0;
+      mbar_wait_warp(full0 + 8u * st, ph, 0);
+      if (ha.debug & 64) c_wait += clock64() - q0;
+      tc_fence_after();
+      uint32_t b_lo = b_lo0 + st * sstep;
+      const int s_end = min(s + G, nslabs);
       if (elect_one()) {
-        // k outer, tile inner: consecutive MMAs accumulate into different TMEM tiles
+#pragma unroll 1
+        for (; s < s_end; ++s, b_lo += bstep) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)ha.aoff[s];
+          const uint32_t acc0 = (s > 0) ? 1u : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          for (int t = 0; t < nt && !(ha.debug & 2); ++t)
-            umma_bf16(tm + (uint32_t)(t * Npad), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)t * tstep_eff + 2u * k),
-                      ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k), idesc, (s > 0 || k > 0) ? 1u : 0u);
-        if (!(ha.debug & 16)) umma_commit(smem_u32(&empty_bar[st]));
-        if (s == nslabs - 1) umma_commit(smem_u32(&accum_bar));
-      }
-      const long long q2 = clock64();
-      c_issue += q2 - q1;
-      if (!(ha.debug & 128)) __syncwarp();
-      c_sync += clock64() - q2;
-      if ((ha.debug & 64) && blockIdx.x == 0 && lane == 0) {
-        if (s == 0) g_dbg[3] = clock64() - ts0;
-        if (s == nslabs - 1) {
-          g_dbg[4] = clock64() - ts0;
-          g_dbg[7] = c_wait; g_dbg[8] = c_issue; g_dbg[9] = c_sync;
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int t = 0; t < T; ++t)      // k outer, tile inner: consecutive MMAs hit different accumulators
+              umma_bf16(tm + (uint32_t)(t * Npad), ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)t * tstep + 2u * k),
+                        ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + 2u * k), idesc, k > 0 ? 1u : acc0);
         }
+        umma_commit(empty0 + 8u * st);
+        if (it == n_iter - 1) umma_commit(accb);
+      }
+      s = s_end;
+      __syncwarp();
+      if ((ha.debug & 64) && blockIdx.x == 0 && lane == 0) {
+        if (it == 0) g_dbg[3] = clock64() - ts0;
+        if (it == n_iter - 1) { g_dbg[4] = clock64() - ts0; g_dbg[7] = c_wait; }
       }
       if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
     }
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    mbar_wait_warp(smem_u32(&accum_bar), 0, (ha.debug & 256) ? 5000u : 200u);
+    pdl_wait();     // the epilogue reads residual / mask tensors and overwrites buffers earlier kernels may still read
+    mbar_wait_warp(smem_u32(&accum_bar), 0, 100u);
     tc_fence_after();
     if ((ha.debug & 64) && blockIdx.x == 0 && threadIdx.x == 64) {
-      g_dbg[0] = nslabs; g_dbg[1] = ts1 - ts0; g_dbg[2] = ts2 - ts0; g_dbg[5] = clock64() - ts0;
+      g_dbg[0] = nslabs; g_dbg[1] = ts1 - ts0; g_dbg[5] = clock64() - ts0;
     }
-    for (int t = 0; t < nt; ++t) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
       int ti = t_first + t;
       const int twi = ti % tiles_w; ti /= tiles_w;
       const int thi = ti % tiles_h;
       const int b = ti / tiles_h;
       const int oh = thi * HALO_TH + (row >> 3), ow = twi * HALO_TW + (row & 7);
-      const bool ok = oh < g.OH;
-      for (int n0 = 0; n0 < Npad; n0 += 16) {
+      const bool ok = oh < ha.OH;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Npad);
+      int n0 = 0;
+      for (; n0 + 32 <= Npad; n0 += 32) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)n0, v);
+        if (ok) {
+          epi_apply16(epi, b, oh, ow, n0, ha.N, v);
+          epi_apply16(epi, b, oh, ow, n0 + 16, ha.N, v + 16);
+        }
+      }
+      if (n0 < Npad) {
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Npad + n0), v);
-        if (ok) epi_apply16(epi, b, oh, ow, n0, g.N, v);
+        tmem_ld16(trow + (uint32_t)n0, v);
+        if (ok) epi_apply16(epi, b, oh, ow, n0, ha.N, v);
       }
     }
   }
@@ -531,6 +553,11 @@ int ss_umma_supported(const ConvGeom& g) {
   return 1;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+#define HALO_SMEM_BUDGET (200 * 1024)
 static int halo_args(const ConvGeom& g, HaloArgs* out) {
   HaloArgs ha;
   memset(&ha, 0, sizeof(ha));
@@ -551,34 +578,49 @@ static int halo_args(const ConvGeom& g, HaloArgs* out) {
   ha.pad = pad;
   const int rows = (HALO_TH + 2 * pad) * (HALO_TW + 2 * pad);
   ha.halo_bytes = (rows * 128 + 1023) / 1024 * 1024;
-  const int ring = 6 * g.Npad * 128;                  // smallest ring we accept when sizing T
-  int T = HALO_MAX_T;
-  while (T > 1 && (T * ha.nh * ha.halo_bytes + ring > 200 * 1024 || T * g.Npad > 512)) --T;
-  if (T * ha.nh * ha.halo_bytes + ring > 200 * 1024 || T * g.Npad > 512) return 0;
   ha.n_tiles = g.B * ((g.OH + HALO_TH - 1) / HALO_TH) * (g.OW / HALO_TW);
-  const int T0 = T;        // largest T the shared memory / TMEM budget allows
-  // keep at least ~one wave of CTAs
-  while (T > 1 && (ha.n_tiles + T - 1) / T < 120) --T;
+  const int b_bytes = g.Npad * 128;
+  // slabs per ring stage: <= 32 KB of weights (16*T MMAs per barrier round at Npad = 64), balanced over the rounds, and
+  // small enough that halo + two stages stay under half an SM's shared memory (two co-resident CTAs when T = 1)
+  int G = std::max(1, (32 * 1024) / b_bytes);
+  while (G > 1 && ha.nh * ha.halo_bytes + 2 * G * b_bytes > 108 * 1024) --G;
+  G = std::min(G, g.nslabs);
   {
-    const char* te = getenv("SSHSLIE_HALO_T");
-    if (te && atoi(te) >= 1 && atoi(te) <= T0) T = atoi(te);
+    const int rounds = (g.nslabs + G - 1) / G;
+    G = (g.nslabs + rounds - 1) / rounds;
   }
+  G = std::max(1, std::min(16, env_int("SSHSLIE_HALO_G", G)));
+  ha.G = G;
+  const int min_ring = 2 * G * b_bytes;
+  // tiles per CTA: small problems keep T = 1 (two CTAs per SM overlap each other's prologue / epilogue); when there
+  // are more than ~4 waves of tiles, T = 2 halves the weight traffic per MMA
+  int T = (ha.n_tiles >= 8 * 148) ? 2 : 1;
+  T = std::max(1, std::min(HALO_MAX_T, env_int("SSHSLIE_HALO_T", T)));
+  if (T > 2) T = 2;
+  while (T > 1 && (T * ha.nh * ha.halo_bytes + min_ring > HALO_SMEM_BUDGET || T * g.Npad > 512 || (ha.n_tiles % T))) --T;
+  if (T * ha.nh * ha.halo_bytes + min_ring > HALO_SMEM_BUDGET || T * g.Npad > 512) return 0;
   ha.T = T;
-  int stages = (200 * 1024 - T * ha.nh * ha.halo_bytes) / (g.Npad * 128);
-  if (stages > HALO_MAX_STAGES) stages = HALO_MAX_STAGES;
-  if (stages > g.nslabs) stages = std::max(2, g.nslabs);
-  {
-    const char* se = getenv("SSHSLIE_HALO_STAGES");
-    if (se && atoi(se) >= 2 && atoi(se) <= stages) stages = atoi(se);
-    const char* de = getenv("SSHSLIE_HALO_DEBUG");
-    ha.debug = de ? atoi(de) : 0;
-  }
+  const int n_iter = (g.nslabs + G - 1) / G;
+  // ring depth: what fits next to the halo windows; with T = 1 stay under half an SM so that two CTAs are co-resident
+  const int budget = (T == 1) ? std::max(T * ha.nh * ha.halo_bytes + min_ring, 108 * 1024) : HALO_SMEM_BUDGET;
+  int stages = (budget - T * ha.nh * ha.halo_bytes) / (G * b_bytes);
+  stages = std::max(2, std::min(stages, std::min(HALO_MAX_STAGES, std::max(2, n_iter))));
+  stages = std::max(2, std::min(HALO_MAX_STAGES, env_int("SSHSLIE_HALO_STAGES", stages)));
+  if (T * ha.nh * ha.halo_bytes + stages * G * b_bytes > 220 * 1024 - 2048) return 0;
   ha.stages = stages;
+  ha.debug = env_int("SSHSLIE_HALO_DEBUG", 0);
+  ha.nslabs = g.nslabs; ha.Npad = g.Npad; ha.N = g.N; ha.OH = g.OH; ha.OW = g.OW;
+  const int pitch = HALO_TW + 2 * pad;
+  for (int i = 0; i < g.nslabs; ++i) {
+    const Slab& sl = g.slab[i];
+    int h = 0;
+    for (int j = 0; j < ha.nh; ++j)
+      if (ha.src[j] == sl.src && ha.c0[j] == sl.c0) h = j;
+    ha.aoff[i] = (uint16_t)((h * ha.halo_bytes + ((sl.dh + pad) * pitch + (sl.dw + pad)) * 128) >> 4);
+  }
   int cols = 32;
   while (cols < T * g.Npad) cols <<= 1;
   ha.tmem_cols = cols;
-  const char* e = getenv("SSHSLIE_HALO_BO");
-  ha.bo_mode = (e && e[0] == '1') ? 1 : 0;
   *out = ha;
   return 1;
 }
@@ -885,16 +927,19 @@ int ss_launch_conv_gather_umma4(const ConvGeom* g_dev, const ConvGeom* g4, const
 
 int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g, const UmmaMaps& maps, const Epi& epi,
                                cudaStream_t st) {
+  (void)g_dev;
   HaloArgs ha;
   if (!halo_args(g, &ha)) {
     ss_set_error("conv_gather_halo: geometry not eligible");
     return SSHSLIE_ERR_ARG;
   }
-  const size_t smem = (size_t)ha.T * ha.nh * ha.halo_bytes + (size_t)ha.stages * g.Npad * 128 + 1024;
+  const size_t smem = (size_t)ha.T * ha.nh * ha.halo_bytes + (size_t)ha.stages * ha.G * g.Npad * 128 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_gather_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
-        cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_gather_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(conv_gather_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
+            cudaSuccess) {
       ss_set_error("conv_gather_halo: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
@@ -902,7 +947,7 @@ int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g, const U
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((ha.n_tiles + ha.T - 1) / ha.T);
+  cfg.gridDim = dim3(ha.n_tiles / ha.T);
   cfg.blockDim = dim3(UM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -911,7 +956,8 @@ int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g, const U
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ss_pdl_enabled() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_gather_halo_kernel, g_dev, maps, epi, ha);
+  if (ha.T == 2) cudaLaunchKernelEx(&cfg, conv_gather_halo_kernel<2>, maps, epi, ha);
+  else cudaLaunchKernelEx(&cfg, conv_gather_halo_kernel<1>, maps, epi, ha);
   return ss_check_launch("conv_gather_halo");
 }
 
@@ -1023,6 +1069,298 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
   return ss_check_launch("conv_wgrad_reduce");
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient with HALO REUSE (stride-1 layers).  Same GEMM as conv_wgrad_umma_kernel — D[(tap pair, channel)][n]
+// += A_pair^T . G over the pixels of a 16x8 tile, both operands MN-major — but the A operand of EVERY tap of the
+// tile is read from ONE halo window (as in conv_gather_halo_kernel): per pixel tile a CTA loads the window(s) and the
+// G tile once (65 KB for the 9x9 layer) and then issues all of its <= 7 tap pairs x 8 MMAs from shared memory, instead of
+// streaming 32 KB per pair.  The two taps of a pair are the two 64-row halves of M: LBO = distance of their windows.
+// One barrier round per pixel tile (56-64 MMAs); descriptor words come from the kernel's constant bank.
+// ---------------------------------------------------------------------------------------------
+#define WGH_MAX_PAIRS 48
+struct WgHaloArgs {
+  int nh;
+  int src[SS_MAX_SRC];
+  int c0[SS_MAX_SRC];
+  int pad, halo_bytes;
+  int N, gN, g_atoms;          // UMMA N (64 / 128), valid gradient channels, 64-channel atoms of G per tile
+  int tmem_cols;
+  long long bias_off;          // >= 0: group 0 also produces db (ones^T . G)
+  int n_tiles, tiles_per_cta, splits, groups, pairs_per_group, npairs, blocks_per_cta;
+  int stages, stage_bytes;
+  int OH, OW;
+  uint32_t pair_lo[WGH_MAX_PAIRS];   // (window offset of slab a) >> 4  |  ((offset of slab b - offset of slab a) >> 4) << 16
+  uint8_t pair_a[WGH_MAX_PAIRS];     // slab indices of the two M halves (pair_b = 255: none)
+  uint8_t pair_b[WGH_MAX_PAIRS];
+};
+
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ CUtensorMap gmap,
+                       const __grid_constant__ WgHaloArgs wa, float* __restrict__ partial) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[4];
+  __shared__ __align__(8) uint64_t empty_bar[4];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const int nh = wa.nh, pad = wa.pad, stages = wa.stages;
+  const uint32_t halo_bytes = (uint32_t)wa.halo_bytes, stage_bytes = (uint32_t)wa.stage_bytes;
+  const uint32_t ones_base = dyn_base + (uint32_t)stages * stage_bytes;
+  const int pitch = HALO_TW + 2 * pad;
+  const int group = blockIdx.y;
+  const bool do_bias = (wa.bias_off >= 0) && (group == 0);
+  const int p_begin = group * wa.pairs_per_group;
+  const int p_end = min(wa.npairs, p_begin + wa.pairs_per_group);
+  const int t_begin = blockIdx.x * wa.tiles_per_cta;
+  const int t_end = min(wa.n_tiles, t_begin + wa.tiles_per_cta);
+  const int ntiles = t_end - t_begin;           // >= 1 by construction of the grid
+  const int tiles_w = wa.OW / HALO_TW, tiles_h = (wa.OH + HALO_TH - 1) / HALO_TH;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(smem_u32(&full_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), 1);
+      }
+      mbar_init(smem_u32(&accum_bar), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+  } else if (do_bias) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem_dyn + (ones_base - smem_u32(smem_dyn)));
+    for (int i = threadIdx.x - 32; i < WG_ONES_BYTES / 4; i += UM_THREADS - 32) ones[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)wa.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      const uint32_t tx = (uint32_t)nh * (uint32_t)((HALO_TH + 2 * pad) * pitch * 128) + (uint32_t)wa.g_atoms * UM_A_BYTES;
+      uint32_t st = 0, ph = 1;
+      for (int ti = 0; ti < ntiles; ++ti) {
+        int t = t_begin + ti;
+        const int twi = t % tiles_w; t /= tiles_w;
+        const int thi = t % tiles_h;
+        const int b = t / tiles_h;
+        mbar_wait(empty0 + 8u * st, ph);
+        const uint32_t fb = full0 + 8u * st;
+        const uint32_t dst = dyn_base + st * stage_bytes;
+        mbar_expect_tx(fb, tx);
+        for (int h = 0; h < nh; ++h)
+          tma_load_4d(dst + (uint32_t)h * halo_bytes, &maps.halo[wa.src[h]], fb, wa.c0[h], twi * HALO_TW - pad,
+                      thi * HALO_TH - pad, b);
+        for (int a = 0; a < wa.g_atoms; ++a)
+          tma_load_4d(dst + (uint32_t)nh * halo_bytes + (uint32_t)a * UM_A_BYTES, &gmap, fb, a * 64, twi * HALO_TW,
+                      thi * HALO_TH, b);
+        if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, wa.N, 1, 1);
+    const uint32_t tm = uniform32(tmem_base);
+    // A: two 64-channel atoms (the two taps), LBO per pair; K groups of 8 pixels = tile rows, SBO = pitch * 128 B
+    const uint32_t a_hi = (uint32_t)(make_sdesc(0, 0, (uint32_t)pitch * 128u) >> 32);
+    const uint32_t b_hi = (uint32_t)(make_sdesc(0, 0, 1024) >> 32);
+    const uint32_t base_lo = uniform32((dyn_base >> 4) & 0x3FFFu);
+    const uint32_t g_rel = (uint32_t)((nh * halo_bytes) >> 4) | ((uint32_t)(UM_A_BYTES >> 4) << 16);   // G atoms: LBO = one tile
+    const uint32_t ones_lo = uniform32((ones_base >> 4) & 0x3FFFu);
+    const uint32_t full0 = uniform32(smem_u32(&full_bar[0])), empty0 = uniform32(smem_u32(&empty_bar[0]));
+    const uint32_t accb = uniform32(smem_u32(&accum_bar));
+    const uint32_t sstep = stage_bytes >> 4;
+    const uint32_t kstep = (uint32_t)(2 * pitch * 128) >> 4;      // 16 pixels = two tile rows
+    const uint32_t N = (uint32_t)wa.N;
+    uint32_t st = 0, ph = 0;
+#pragma unroll 1
+    for (int ti = 0; ti < ntiles; ++ti) {
+      mbar_wait_warp(full0 + 8u * st, ph, 0);
+      tc_fence_after();
+      const uint32_t s_lo = base_lo + st * sstep;
+      const uint32_t acc0 = (ti > 0) ? 1u : 0u;
+      if (elect_one()) {
+        const uint64_t bd0 = ((uint64_t)b_hi << 32) | (uint64_t)(s_lo + g_rel);
+        uint32_t tcol = tm;
+#pragma unroll 1
+        for (int p = p_begin; p < p_end; ++p, tcol += N) {
+          const uint64_t ad0 = ((uint64_t)a_hi << 32) | (uint64_t)(s_lo + wa.pair_lo[p]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tcol, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(128 * k), idesc, k > 0 ? 1u : acc0);
+        }
+        if (do_bias) {
+          const uint64_t od0 = ((uint64_t)b_hi << 32) | (uint64_t)ones_lo;      // both M atoms = the ones tile (LBO 0)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tcol, od0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), idesc, k > 0 ? 1u : acc0);
+        }
+        umma_commit(empty0 + 8u * st);
+        if (ti == ntiles - 1) umma_commit(accb);
+      }
+      __syncwarp();
+      if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait_warp(smem_u32(&accum_bar), 0, 200);
+    tc_fence_after();
+    // partial[split][group][block][n][row]: lanes = consecutive rows -> 128-byte coalesced stores, no atomics
+    float* out = partial + ((size_t)(blockIdx.x * wa.groups + group) * wa.blocks_per_cta) * (size_t)wa.N * 128;
+    const int nblocks = (p_end - p_begin) + (do_bias ? 1 : 0);
+    for (int p = 0; p < nblocks; ++p) {
+      for (int n0 = 0; n0 < wa.N; n0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p * wa.N + n0), v);
+        float* o = out + ((size_t)p * wa.N + n0) * 128 + row;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[(size_t)i * 128] = v[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)wa.tmem_cols);
+}
+
+// second stage for the halo kernel: same partial layout as conv_wgrad_reduce_kernel, slab mapping through the pair table
+__global__ void __launch_bounds__(1024) conv_wgrad_halo_reduce_kernel(const ConvGeom* __restrict__ gp,
+                                                                      const float* __restrict__ partial,
+                                                                      const __grid_constant__ WgHaloArgs wa,
+                                                                      float* __restrict__ grads) {
+  __shared__ float red[8][8][128];
+  const int blk = blockIdx.x, group = blockIdx.y, n0 = blockIdx.z * 8;
+  const int row = threadIdx.x, q = threadIdx.y;
+  const int p_begin = group * wa.pairs_per_group;
+  const int p_end = min(wa.npairs, p_begin + wa.pairs_per_group);
+  const int np = p_end - p_begin;
+  const bool is_bias = (blk == np) && (group == 0) && (wa.bias_off >= 0);
+  if (blk > np || (blk == np && !is_bias)) return;       // block-uniform
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const size_t cta_stride = (size_t)wa.groups * wa.blocks_per_cta * wa.N * 128;
+  const float* p = partial + ((size_t)group * wa.blocks_per_cta + blk) * (size_t)wa.N * 128 + (size_t)n0 * 128 + row +
+                   (size_t)q * cta_stride;
+  for (int sp = q; sp < wa.splits; sp += 8, p += 8 * cta_stride) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += p[(size_t)i * 128];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[q][i][row] = acc[i];
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tot += red[j][q][row];              // fixed order -> deterministic
+  const int n = n0 + q;
+  if (is_bias) {
+    if (row == 0 && n < wa.gN) grads[wa.bias_off + n] += tot;
+    return;
+  }
+  const int s = (row >> 6) ? (int)wa.pair_b[p_begin + blk] : (int)wa.pair_a[p_begin + blk];
+  const int j = row & 63;
+  if (s == 255) return;
+  const Slab sl = gp->slab[s];
+  if (j >= sl.wcn) return;
+  if (n < gp->N && n < wa.gN) grads[gp->w_off + sl.woff + (int64_t)j * gp->w_sC + (int64_t)n * gp->w_sN] += tot;
+}
+
+static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHaloArgs* out) {
+  HaloArgs ha;
+  if (!g.halo_ok || !ss_umma_supported(g) || g.N > 128 || !halo_args(g, &ha)) return 0;
+  WgHaloArgs wa;
+  memset(&wa, 0, sizeof(wa));
+  wa.nh = ha.nh;
+  for (int i = 0; i < SS_MAX_SRC; ++i) { wa.src[i] = ha.src[i]; wa.c0[i] = ha.c0[i]; }
+  wa.pad = ha.pad; wa.halo_bytes = ha.halo_bytes;
+  wa.gN = gN; wa.bias_off = bias_off;
+  wa.N = (gN > 64) ? 128 : 64;
+  wa.g_atoms = wa.N / 64;
+  wa.OH = g.OH; wa.OW = g.OW;
+  // tap pairs over the slabs that carry weights of their own (residual "lo" slabs are skipped), lower window first
+  int slabs[SS_MAX_SLABS], ns = 0;
+  for (int i = 0; i < g.nslabs; ++i)
+    if (!g.slab[i].no_wgrad) slabs[ns++] = i;
+  wa.npairs = (ns + 1) / 2;
+  if (wa.npairs > WGH_MAX_PAIRS) return 0;
+  for (int p = 0; p < wa.npairs; ++p) {
+    int a = slabs[2 * p], b = (2 * p + 1 < ns) ? slabs[2 * p + 1] : -1;
+    if (b >= 0 && ha.aoff[b] < ha.aoff[a]) std::swap(a, b);
+    wa.pair_a[p] = (uint8_t)a;
+    wa.pair_b[p] = (uint8_t)(b >= 0 ? b : 255);
+    const uint32_t lbo = (b >= 0) ? (uint32_t)(ha.aoff[b] - ha.aoff[a]) : 0u;
+    if (lbo > 0x3FFFu) return 0;
+    wa.pair_lo[p] = (uint32_t)ha.aoff[a] | (lbo << 16);
+  }
+  const int max_pairs = 512 / wa.N - 1;                 // one accumulator block is reserved for the bias row
+  wa.groups = (wa.npairs + max_pairs - 1) / max_pairs;
+  wa.pairs_per_group = (wa.npairs + wa.groups - 1) / wa.groups;
+  wa.groups = (wa.npairs + wa.pairs_per_group - 1) / wa.pairs_per_group;
+  wa.blocks_per_cta = wa.pairs_per_group + 1;
+  wa.n_tiles = ha.n_tiles;
+  // split the pixel axis: every CTA should own >= 4 pixel tiles (the split-K partials cost 32 KB x blocks per CTA)
+  int splits = (wa.n_tiles + 3) / 4;
+  splits = std::min(splits, std::max(1, 148 / wa.groups));
+  splits = std::max(1, env_int("SSHSLIE_WGH_SPLITS", splits));
+  wa.tiles_per_cta = (wa.n_tiles + splits - 1) / splits;
+  wa.splits = (wa.n_tiles + wa.tiles_per_cta - 1) / wa.tiles_per_cta;
+  int cols = 32;
+  while (cols < wa.blocks_per_cta * wa.N) cols <<= 1;
+  wa.tmem_cols = cols;
+  wa.stage_bytes = wa.nh * wa.halo_bytes + wa.g_atoms * UM_A_BYTES;
+  int stages = (int)((216 * 1024 - WG_ONES_BYTES) / wa.stage_bytes);
+  stages = std::min(4, stages);
+  if (stages < 2) return 0;
+  wa.stages = stages;
+  *out = wa;
+  return 1;
+}
+int ss_umma_wgrad_halo_supported(const ConvGeom& g, int gN) {
+  WgHaloArgs wa;
+  return wgrad_halo_plan(g, gN, -1, &wa);
+}
+size_t ss_umma_wgrad_halo_partial_floats(const ConvGeom& g, int gN) {
+  WgHaloArgs wa;
+  if (!wgrad_halo_plan(g, gN, 0, &wa)) return 0;
+  return (size_t)wa.splits * wa.groups * wa.blocks_per_cta * wa.N * 128;
+}
+int ss_umma_build_gmap_halo(const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld_extent, const ConvGeom& g,
+                            void* out_map) {
+  SrcView v;
+  v.base = G; v.sB = gB; v.sH = gH; v.sW = gW; v.H = g.OH; v.W = g.OW;
+  return encode_src(v, ld_extent, HALO_TW, HALO_TH, g.B, reinterpret_cast<CUtensorMap*>(out_map));
+}
+int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const UmmaMaps& maps, const void* gmap, int gN,
+                              long long bias_off, float* partial, float* grads, cudaStream_t st) {
+  WgHaloArgs wa;
+  if (!wgrad_halo_plan(g, gN, bias_off, &wa)) {
+    ss_set_error("conv_wgrad_halo: geometry not eligible");
+    return SSHSLIE_ERR_ARG;
+  }
+  const size_t smem = (size_t)wa.stages * wa.stage_bytes + WG_ONES_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
+        cudaSuccess) {
+      ss_set_error("conv_wgrad_halo: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      return SSHSLIE_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(wa.splits, wa.groups);
+  conv_wgrad_halo_kernel<<<grid, UM_THREADS, smem, st>>>(maps, *reinterpret_cast<const CUtensorMap*>(gmap), wa, partial);
+  int rc = ss_check_launch("conv_wgrad_halo");
+  if (rc) return rc;
+  dim3 rgrid(wa.blocks_per_cta, wa.groups, wa.N / 8);
+  conv_wgrad_halo_reduce_kernel<<<rgrid, dim3(128, 8), 0, st>>>(g_dev, partial, wa, grads);
+  return ss_check_launch("conv_wgrad_halo_reduce");
+}
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05.mma issue-rate probe (tools/umma_probe.py): a chain of n_mma bf16 MMAs (M=128, N, K=16) on operands already

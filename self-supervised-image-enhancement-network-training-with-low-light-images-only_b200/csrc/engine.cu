@@ -118,6 +118,7 @@ struct sshslie_engine {
   int B, C, H, W, flags;
   std::map<std::pair<int, const void*>, GMapBox> gmaps;   // wgrad G-tensor TMA descriptors
   bool train, force_simt;
+  bool wgrad_halo = true;               // SSHSLIE_WGRAD_HALO=0 keeps the per-tap weight-gradient kernel
   int64_t ws_bytes = 0;
   unsigned char* ws = nullptr;
   bool bound = false;
@@ -424,6 +425,21 @@ static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, i
     std::string lbl = geom_label(e, gi, "wgrad");
     if (!(e->geom_umma[gi] && ss_umma_wgrad_supported(g))) lbl.replace(lbl.find('['), std::string::npos, "[simt]");
     prof_note(lbl, geom_flops(g) * (double)gN / (double)g.N, 0);
+  }
+  if (e->geom_umma[gi] == 2 && e->wgrad_halo && ss_umma_wgrad_halo_supported(g, gN)) {
+    const std::pair<int, const void*> key(gi | 0x10000, (const void*)gp);
+    auto it = e->gmaps.find(key);
+    if (it == e->gmaps.end()) {
+      GMapBox box;
+      const int rc = ss_umma_build_gmap_halo(gp, gB, gH, gW, G.ld, g, box.bytes);
+      if (rc) return rc;
+      it = e->gmaps.emplace(key, box).first;
+    }
+    return ss_launch_conv_wgrad_halo(e->geoms_dev + gi, g,
+                                     *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
+                                     it->second.bytes, gN,
+                                     bias_layer >= 0 ? (long long)e->poff[2 * bias_layer + 1] : -1LL,
+                                     e->partial_for(st), e->grads, st);
   }
   if (e->geom_umma[gi] && ss_umma_wgrad_supported(g)) {
     // TMA descriptor of the G tensor, built once per (geom, tensor) and cached on the host
@@ -959,6 +975,9 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     for (size_t i = 0; i < e->geoms.size(); ++i) {
       const size_t a = ss_umma_wgrad_partial_floats(e->geoms[i], 128), b = ss_umma_wgrad_partial_floats(e->geoms[i], 64);
       mx = std::max(mx, std::max(a, b));
+      if (e->geoms[i].halo_ok)
+        mx = std::max(mx, std::max(ss_umma_wgrad_halo_partial_floats(e->geoms[i], 128),
+                                   ss_umma_wgrad_halo_partial_floats(e->geoms[i], 64)));
     }
     e->wg_partial_floats = mx;
     e->wg_partial = e->falloc((int64_t)mx);
@@ -1003,6 +1022,10 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
   e->B = batch; e->C = channels; e->H = height; e->W = width; e->flags = flags;
   e->train = (flags & SSHSLIE_FLAG_TRAIN) != 0;
   e->force_simt = (flags & SSHSLIE_FLAG_FORCE_SIMT) != 0;
+  {
+    const char* we = getenv("SSHSLIE_WGRAD_HALO");
+    e->wgrad_halo = !(we && we[0] == '0');
+  }
   layer_shapes(channels, e->shapes);
   e->nparams = sshslie_param_table(channels, e->poff, e->psize);
   memset(&e->cfg, 0, sizeof(e->cfg));
@@ -1053,7 +1076,7 @@ extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t w
       rc = ss_umma_build_maps(e->geoms[i], reinterpret_cast<UmmaMaps*>(e->maps_blob.data() + i * msz));
       if (rc != SSHSLIE_OK) return rc;
       const char* he = getenv("SSHSLIE_HALO");
-      const bool halo_on = (he && he[0] == '1');   // opt-in: correct, but not yet faster than the per-tap kernel
+      const bool halo_on = !(he && he[0] == '0');  // halo-reuse kernels for every stride-1 layer; SSHSLIE_HALO=0 = per-tap
       e->geom_umma[i] = (halo_on && e->geoms[i].halo_ok && ss_umma_halo_supported(e->geoms[i])) ? 2 : 1;
     }
   }
@@ -1140,6 +1163,8 @@ extern "C" int sshslie_loss_and_grad(sshslie_engine* e, const float* x, const fl
 // single-layer entry point for kernel-level parity tests (tests/test_gpu_conv.py)
 // ---------------------------------------------------------------------------------------------
 static int pad64(int c) { return (c + 63) / 64 * 64; }
+static float g_conv2d_last_ms = 0.f;
+extern "C" SSHSLIE_API float sshslie_conv2d_last_ms(void) { return g_conv2d_last_ms; }
 
 extern "C" int64_t sshslie_conv2d_scratch_bytes(int B, int Cin, int Cout, int H, int W, int k, int stride) {
   (void)k;
@@ -1245,7 +1270,8 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
     e->pack_start[i + 1] = e->pack_start[i] + (int)((elems + 255) / 256);
   }
   if (kind == 2 && impl >= 1) {
-    e->wg_partial_floats = ss_umma_wgrad_partial_floats(e->geoms[0], gN);
+    e->wg_partial_floats = std::max(ss_umma_wgrad_partial_floats(e->geoms[0], gN),
+                                    ss_umma_wgrad_halo_partial_floats(e->geoms[0], gN));
     e->wg_partial = e->falloc((int64_t)e->wg_partial_floats);
   }
   if (e->cursor > scratch_bytes) { ss_set_error("sshslie_conv2d: scratch overflow"); return SSHSLIE_ERR_WORKSPACE; }
@@ -1271,6 +1297,27 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
     }
   } else {
     rc = run_wgrad(e, 0, *gt, gN, 0, 0, 1, st);
+  }
+  // SSHSLIE_CONV2D_TIMING=n: repeat the layer's own launches n times between two events (tools/conv_bench.py)
+  if (const char* te = getenv("SSHSLIE_CONV2D_TIMING")) {
+    const int reps = atoi(te);
+    if (reps > 0 && !rc) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+      for (int r = 0; r < reps && !rc; ++r) {
+        if (kind != 2) for (size_t j = 0; j < jobs.size() && !rc; ++j) rc = run_gather(e, jobs[j].gi, jobs[j].ep, -1, st);
+        else rc = run_wgrad(e, 0, *gt, gN, 0, 0, 1, st);
+      }
+      cudaEventRecord(b, st);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      g_conv2d_last_ms = ms / (float)reps;
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+    }
   }
   if (cudaStreamSynchronize(st) != cudaSuccess) {   // the plan lives on this stack frame: finish before returning
     ss_set_error("sshslie_conv2d: %s", cudaGetErrorString(cudaGetLastError()));

@@ -30,6 +30,13 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g_host, con
                               int gN, long long bias_off, float* partial, float* grads, cudaStream_t st);
 size_t ss_umma_wgrad_partial_floats(const ConvGeom& g, int gN);
 size_t ss_umma_maps_size();
+// halo-reuse weight gradient (stride-1 layers): G tiles are 16x8 like the halo tiles
+int ss_umma_wgrad_halo_supported(const ConvGeom& g, int gN);
+size_t ss_umma_wgrad_halo_partial_floats(const ConvGeom& g, int gN);
+int ss_umma_build_gmap_halo(const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld_extent, const ConvGeom& g,
+                            void* out_map);
+int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const void* gmap,
+                              int gN, long long bias_off, float* partial, float* grads, cudaStream_t st);
 
 // elementwise.cu
 int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st);

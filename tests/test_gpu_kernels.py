@@ -90,6 +90,22 @@ def test_conv_wgrad(case, impl):
 
 
 HALO_CASES = [c for c in CONV_CASES if c[4] == 1 and not c[5]]
+WGRAD_HALO_CASES = [c for c in HALO_CASES if c[2] <= 128 and c[0] != "c3_64_1"]
+
+
+@pytest.mark.parametrize("case", WGRAD_HALO_CASES, ids=[c[0] for c in WGRAD_HALO_CASES])
+def test_conv_wgrad_halo(case):
+    """Halo-reuse weight gradient (MN-major A descriptors pointing into one activation window per tile)."""
+    from gpu_util import conv2d, bf16_round
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    x, w, b = _mk(case)
+    w.requires_grad_(True)
+    yref = _ref_conv(x, w, None, k, stride, tr, relu=False)
+    dy = bf16_round(torch.randn(yref.shape, generator=torch.Generator().manual_seed(5))).cuda()
+    (dw_ref,) = torch.autograd.grad(yref, w, dy)
+    dw = torch.zeros_like(dw_ref)
+    conv2d(2, 2, tr, x.detach(), dw, None, dy, B, Cin, Cout, H, W, k, stride, relu=False)
+    torch.testing.assert_close(dw, dw_ref, rtol=1e-3, atol=1e-3 * float(dw_ref.abs().max()))
 
 
 @pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])

@@ -24,5 +24,5 @@ for (k, B) in [(3, 2), (9, 2), (9, 8)]:
     buf = (ctypes.c_longlong * 16)()
     lib.sshslie_debug_read(buf)
     v = list(buf)
-    print(f"k={k} B={B}: nslabs={v[0]} prologue={v[1]} after_pdl_wait={v[2]} slab0_done={v[3]} last_slab_issued={v[4]} "
-          f"accum_seen={v[5]} epilogue_done={v[6]} | loop: wait={v[7]} fence+issue={v[8]} syncwarp={v[9]}")
+    print(f"k={k} B={B}: nslabs={v[0]} prologue={v[1]} halo_ready={v[2]} iter0_issued={v[3]} last_iter_issued={v[4]} "
+          f"accum_seen={v[5]} epilogue_done={v[6]} | MMA warp cycles waiting on weight stages={v[7]}")
