@@ -594,7 +594,7 @@ static int halo_args(const ConvGeom& g, HaloArgs* out) {
   const int min_ring = 2 * G * b_bytes;
   // tiles per CTA: small problems keep T = 1 (two CTAs per SM overlap each other's prologue / epilogue); when there
   // are more than ~4 waves of tiles, T = 2 halves the weight traffic per MMA
-  int T = (ha.n_tiles >= 8 * 148) ? 2 : 1;
+  int T = 1;      // measured: two co-resident T = 1 CTAs per SM beat one T = 2 CTA at every size of this network
   T = std::max(1, std::min(HALO_MAX_T, env_int("SSHSLIE_HALO_T", T)));
   if (T > 2) T = 2;
   while (T > 1 && (T * ha.nh * ha.halo_bytes + min_ring > HALO_SMEM_BUDGET || T * g.Npad > 512 || (ha.n_tiles % T))) --T;
@@ -602,7 +602,11 @@ static int halo_args(const ConvGeom& g, HaloArgs* out) {
   ha.T = T;
   const int n_iter = (g.nslabs + G - 1) / G;
   // ring depth: what fits next to the halo windows; with T = 1 stay under half an SM so that two CTAs are co-resident
-  const int budget = (T == 1) ? std::max(T * ha.nh * ha.halo_bytes + min_ring, 108 * 1024) : HALO_SMEM_BUDGET;
+  int budget = (T == 1) ? std::max(T * ha.nh * ha.halo_bytes + min_ring, 108 * 1024) : HALO_SMEM_BUDGET;
+  // when halo + two stages fit a THIRD of an SM, stop there: the next kernel's CTAs (programmatic dependent launch) can
+  // then become resident and finish their prologue while this kernel's last CTAs drain
+  if (T == 1 && env_int("SSHSLIE_HALO_OCC3", 1) && ha.nh * ha.halo_bytes + min_ring <= 73 * 1024)
+    budget = ha.nh * ha.halo_bytes + min_ring;
   int stages = (budget - T * ha.nh * ha.halo_bytes) / (G * b_bytes);
   stages = std::max(2, std::min(stages, std::min(HALO_MAX_STAGES, std::max(2, n_iter))));
   stages = std::max(2, std::min(HALO_MAX_STAGES, env_int("SSHSLIE_HALO_STAGES", stages)));
@@ -1079,6 +1083,8 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
 // One barrier round per pixel tile (56-64 MMAs); descriptor words come from the kernel's constant bank.
 // ---------------------------------------------------------------------------------------------
 #define WGH_MAX_PAIRS 48
+#define WGH_ONES_BYTES 2048
+#define WGH_MAX_GROUP_PAIRS 7          // 512 TMEM columns / N = 64, minus the bias block
 struct WgHaloArgs {
   int nh;
   int src[SS_MAX_SRC];
@@ -1130,8 +1136,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     }
     __syncwarp();
   } else if (do_bias) {
+    // an all-ones operand: two 8 x 128 B K-atoms (one MMA's K = 16); LBO = 0 makes both M atoms alias them and every
+    // K step re-reads them
     uint32_t* ones = reinterpret_cast<uint32_t*>(smem_dyn + (ones_base - smem_u32(smem_dyn)));
-    for (int i = threadIdx.x - 32; i < WG_ONES_BYTES / 4; i += UM_THREADS - 32) ones[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    for (int i = threadIdx.x - 32; i < WGH_ONES_BYTES / 4; i += UM_THREADS - 32) ones[i] = 0x3F803F80u;   // bf16 1.0 pairs
     fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)wa.tmem_cols);
@@ -1177,6 +1185,13 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     const uint32_t sstep = stage_bytes >> 4;
     const uint32_t kstep = (uint32_t)(2 * pitch * 128) >> 4;      // 16 pixels = two tile rows
     const uint32_t N = (uint32_t)wa.N;
+    // the group's pair words never change: keep them in (uniform) registers.  MMAs are issued k-outer / pair-inner so
+    // that consecutive MMAs accumulate into DIFFERENT TMEM tiles (back-to-back MMAs on one accumulator serialise on its
+    // read-modify-write latency)
+    const int np = p_end - p_begin;
+    uint32_t plo[WGH_MAX_GROUP_PAIRS];
+#pragma unroll
+    for (int p = 0; p < WGH_MAX_GROUP_PAIRS; ++p) plo[p] = wa.pair_lo[min(p_begin + p, WGH_MAX_PAIRS - 1)];
     uint32_t st = 0, ph = 0;
 #pragma unroll 1
     for (int ti = 0; ti < ntiles; ++ti) {
@@ -1186,19 +1201,16 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       const uint32_t acc0 = (ti > 0) ? 1u : 0u;
       if (elect_one()) {
         const uint64_t bd0 = ((uint64_t)b_hi << 32) | (uint64_t)(s_lo + g_rel);
-        uint32_t tcol = tm;
-#pragma unroll 1
-        for (int p = p_begin; p < p_end; ++p, tcol += N) {
-          const uint64_t ad0 = ((uint64_t)a_hi << 32) | (uint64_t)(s_lo + wa.pair_lo[p]);
+        const uint64_t od0 = ((uint64_t)b_hi << 32) | (uint64_t)ones_lo;        // LBO = 0: both M atoms alias; same K atoms each step
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tcol, ad0 + (uint64_t)(k * kstep), bd0 + (uint64_t)(128 * k), idesc, k > 0 ? 1u : acc0);
-        }
-        if (do_bias) {
-          const uint64_t od0 = ((uint64_t)b_hi << 32) | (uint64_t)ones_lo;      // both M atoms = the ones tile (LBO 0)
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t acc = k > 0 ? 1u : acc0;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tcol, od0 + (uint64_t)(128 * k), bd0 + (uint64_t)(128 * k), idesc, k > 0 ? 1u : acc0);
+          for (int p = 0; p < WGH_MAX_GROUP_PAIRS; ++p)
+            if (p < np)
+              umma_bf16(tm + (uint32_t)p * N, ((uint64_t)a_hi << 32) | (uint64_t)(s_lo + plo[p] + (uint32_t)k * kstep),
+                        bd0 + (uint64_t)(128 * k), idesc, acc);
+          if (do_bias) umma_bf16(tm + (uint32_t)np * N, od0, bd0 + (uint64_t)(128 * k), idesc, acc);
         }
         umma_commit(empty0 + 8u * st);
         if (ti == ntiles - 1) umma_commit(accb);
@@ -1305,7 +1317,8 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   wa.blocks_per_cta = wa.pairs_per_group + 1;
   wa.n_tiles = ha.n_tiles;
   // split the pixel axis: every CTA should own >= 4 pixel tiles (the split-K partials cost 32 KB x blocks per CTA)
-  int splits = (wa.n_tiles + 3) / 4;
+  const int min_tiles = std::max(1, env_int("SSHSLIE_WGH_MIN_TILES", 8));
+  int splits = (wa.n_tiles + min_tiles - 1) / min_tiles;
   splits = std::min(splits, std::max(1, 148 / wa.groups));
   splits = std::max(1, env_int("SSHSLIE_WGH_SPLITS", splits));
   wa.tiles_per_cta = (wa.n_tiles + splits - 1) / splits;
@@ -1314,9 +1327,13 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   while (cols < wa.blocks_per_cta * wa.N) cols <<= 1;
   wa.tmem_cols = cols;
   wa.stage_bytes = wa.nh * wa.halo_bytes + wa.g_atoms * UM_A_BYTES;
-  int stages = (int)((216 * 1024 - WG_ONES_BYTES) / wa.stage_bytes);
-  stages = std::min(4, stages);
-  if (stages < 2) return 0;
+  // two stages when that keeps the CTA under half an SM's shared memory (a forward / dgrad CTA of the main stream can
+  // then share the SM with a weight-gradient CTA of the side stream), else whatever fits, at most three
+  int stages = (int)((216 * 1024 - WGH_ONES_BYTES) / wa.stage_bytes);
+  stages = std::min(3, stages);
+  if (2 * wa.stage_bytes + WGH_ONES_BYTES <= 108 * 1024) stages = 2;
+  stages = std::min(4, std::max(1, env_int("SSHSLIE_WGH_STAGES", stages)));
+  if (stages < 2 || stages * wa.stage_bytes + WGH_ONES_BYTES > 216 * 1024) return 0;
   wa.stages = stages;
   *out = wa;
   return 1;
@@ -1343,7 +1360,7 @@ int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const Um
     ss_set_error("conv_wgrad_halo: geometry not eligible");
     return SSHSLIE_ERR_ARG;
   }
-  const size_t smem = (size_t)wa.stages * wa.stage_bytes + WG_ONES_BYTES + 1024;
+  const size_t smem = (size_t)wa.stages * wa.stage_bytes + WGH_ONES_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=

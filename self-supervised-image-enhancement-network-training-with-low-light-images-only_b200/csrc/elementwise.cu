@@ -200,7 +200,8 @@ int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32
 // backward of S = R*(Id + I):  dS = dS32 (loss terms) + dSb (second decomposition pass, bf16 NHWC)
 //   dR32 += dS*(Id+I) ;  t = sum_c dS*R ;  dId32 += t ;  dI32 += t        (block = 32 pixels x all channels)
 // ---------------------------------------------------------------------------------------------
-__global__ void s_bwd_kernel(const float* __restrict__ dS32, const bf16* __restrict__ dSb, const float* __restrict__ R,
+__global__ void s_bwd_kernel(const float* __restrict__ dS32, const float* __restrict__ dSf32,
+                             const bf16* __restrict__ dSb, const float* __restrict__ R,
                              const float* __restrict__ I, const float* __restrict__ Id, float* __restrict__ dR32,
                              float* __restrict__ dI32, float* __restrict__ dId32, int C, int HW) {
   __shared__ float tile[32][33];
@@ -221,7 +222,7 @@ __global__ void s_bwd_kernel(const float* __restrict__ dS32, const bf16* __restr
       const int c = c0 + i;
       if (c < C) {
         const int64_t a = ((int64_t)b * C + c) * HW + hw0 + threadIdx.x;
-        const float ds = dS32[a] + tile[i][threadIdx.x];
+        const float ds = dS32[a] + (dSf32 ? dSf32[a] : 0.f) + tile[i][threadIdx.x];
         dR32[a] += ds * gain;
         t = fmaf(ds, R[a], t);
       }
@@ -237,10 +238,10 @@ __global__ void s_bwd_kernel(const float* __restrict__ dS32, const bf16* __restr
     dI32[p0 + threadIdx.x] += s;
   }
 }
-int ss_launch_s_bwd(const float* dS32, const bf16* dSb, const float* R, const float* I, const float* Id, float* dR32,
-                    float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st) {
-  s_bwd_kernel<<<(unsigned)((int64_t)B * H * W / 32), dim3(32, 8), 0, st>>>(dS32, dSb, R, I, Id, dR32, dI32, dId32, C,
-                                                                           H * W);
+int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, const float* R, const float* I,
+                    const float* Id, float* dR32, float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st) {
+  s_bwd_kernel<<<(unsigned)((int64_t)B * H * W / 32), dim3(32, 8), 0, st>>>(dS32, dSf32, dSb, R, I, Id, dR32, dI32,
+                                                                           dId32, C, H * W);
   EW_CHECK("s_bwd");
 }
 

@@ -113,11 +113,13 @@ struct GeomOp {        // one lowered GEMM: geometry + (for gathers) epilogue te
 };
 
 struct alignas(64) GMapBox { unsigned char bytes[128]; };
+#define SS_MAX_SIDE 4
 
 struct sshslie_engine {
   int B, C, H, W, flags;
   std::map<std::pair<int, const void*>, GMapBox> gmaps;   // wgrad G-tensor TMA descriptors
   bool train, force_simt;
+  bool skip_wgrad = false;
   bool wgrad_halo = true;               // SSHSLIE_WGRAD_HALO=0 keeps the per-tap weight-gradient kernel
   int64_t ws_bytes = 0;
   unsigned char* ws = nullptr;
@@ -156,27 +158,29 @@ struct sshslie_engine {
   int pack_blocks = 0;
   float* mask_dev = nullptr;
   float* sums_dev = nullptr;
-  float* wg_partial = nullptr;           // split-K partial accumulators of the tcgen05 wgrad (largest op)
-  float* wg_partial2 = nullptr;          // second buffer for the second side stream
+  // split-K partial accumulators of the tcgen05 wgrad (sized for the largest op), one buffer per side stream
+  float* wg_partial[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};
   size_t wg_partial_floats = 0;
   int64_t* attn_poff_dummy = nullptr;
 
-  // two side streams for weight gradients (created at bind; host objects only): consecutive wgrad launches alternate
-  // between them, each with its own split-K partial buffer
-  cudaStream_t side[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
-  bool side_dirty[2] = {false, false}, use_side = true;
+  // side streams for weight gradients (created at bind; host objects only): consecutive wgrad launches rotate over
+  // them, each with its own split-K partial buffer.  In the backward phases the weight-gradient kernels add up to more
+  // device time than the data-gradient chain they hide behind, so two streams were not enough to keep up with it.
+  int n_side = SS_MAX_SIDE;
+  cudaStream_t side[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};
+  bool side_dirty[SS_MAX_SIDE] = {false, false, false, false}, use_side = true;
   int side_rr = 0;
   cudaStream_t fork(cudaStream_t main_st) {
     if (!use_side || !side[0]) return main_st;
-    const int i = (side_rr++) & 1;
+    const int i = (side_rr++) % n_side;
     cudaEventRecord(ev_fork, main_st);
     cudaStreamWaitEvent(side[i], ev_fork, 0);
     side_dirty[i] = true;
     return side[i];
   }
   int join(cudaStream_t main_st) {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < n_side; ++i)
       if (side_dirty[i]) {
         cudaEventRecord(ev_join[i], side[i]);
         cudaStreamWaitEvent(main_st, ev_join[i], 0);
@@ -185,7 +189,11 @@ struct sshslie_engine {
     side_rr = 0;
     return SSHSLIE_OK;
   }
-  float* partial_for(cudaStream_t st) const { return (side[1] && st == side[1]) ? wg_partial2 : wg_partial; }
+  float* partial_for(cudaStream_t st) const {
+    for (int i = 1; i < n_side; ++i)
+      if (side[i] && st == side[i]) return wg_partial[i];
+    return wg_partial[0];
+  }
 
   // per-call state read by the recorded launches
   const float* x = nullptr;
@@ -418,6 +426,7 @@ static int run_gather4(sshslie_engine* e, int gi0, const Epi* epis, int bias_lay
 
 static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, int qw, int scale, cudaStream_t st,
                      int bias_layer = -1) {
+  if (e->skip_wgrad) return SSHSLIE_OK;      // timing experiments only (SSHSLIE_SKIP_WGRAD=1): gradients are wrong
   const ConvGeom& g = e->geoms[gi];
   const bf16* gp = G.p + (int64_t)qh * G.W * G.ld + (int64_t)qw * G.ld;
   const int64_t gB = (int64_t)G.H * G.W * G.ld, gH = (int64_t)scale * G.W * G.ld, gW = (int64_t)scale * G.ld;
@@ -831,18 +840,22 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     Epi head2;
     memset(&head2, 0, sizeof(head2));
     head2.mode = EPI_HEAD; head2.R32 = Re32; head2.C = C; head2.H = H; head2.W = W;
+    // The Fourier term needs only x and S: it runs on a side stream BESIDE the second decomposition pass, writes its
+    // gradient into a plane of its own (dSf32, summed in s_bwd) and is joined before the loss values are finalised.
+    float* dSf32 = e->falloc(n * C);
+    PUSH(Lq, return cudaMemsetAsync(e->sums_dev, 0, 16 * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
+    PUSH_SIDE(Lq, prof_note("loss:fourier_fft+grad", 0, 12.0 * 1048576.0 * B);
+                  return ss_fourier_loss(e->x, e->S32, e->mask_dev, dSf32, e->sums_dev + 9, B * C, H, W,
+                                         (float)(e->cfg.c_loss_fourier / ((double)B * C * H * W)), 0, st););
     DecompGeoms G2 = plan_decomp_fwd(e, Lq, Sb, d2, head2);          // model.py:546
 
     const int64_t np = e->nparams;
     PUSH(Lq, return cudaMemsetAsync(e->grads, 0, np * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
-    PUSH(Lq, return cudaMemsetAsync(e->sums_dev, 0, 16 * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
     // algorithmic HBM bytes: 24.25 MiB per patch for the 5-term loss + gradients, 12 MiB for the Fourier term
     PUSH(Lq, prof_note("loss:pixel_terms+grads", 0, 24.25 * 1048576.0 * B);
              return ss_pixel_losses(e->x, e->R32, e->I32, e->Id32, Re32, e->cfg, B, C, H, W, e->sums_dev, dR32, dI32,
                                     dId32, dS32, dRe32, st););
-    PUSH(Lq, prof_note("loss:fourier_fft+grad", 0, 12.0 * 1048576.0 * B);
-             return sshslie_fourier_loss(e->x, e->S32, e->mask_dev, dS32, e->sums_dev + 9, B * C, H, W,
-                                         (float)(e->cfg.c_loss_fourier / ((double)B * C * H * W)), st););
+    PUSH_JOIN(Lq);
     PUSH(Lq, return ss_launch_finalize_losses(e->sums_dev, &e->cfg, e->losses, B, C, H, W, st););
 
     // backward, pass 2 (R_enh branch).  I_enh is unused (model.py:546) -> only C gradient columns.
@@ -855,7 +868,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     PUSH(Lq, return ss_launch_head_bwd(dRe32, Re32, nullptr, 0, nullptr, nullptr, dc8.p, 128, B, C, H, W, st););
     plan_decomp_bwd(e, Lq, Sb, d2, G2, dc8, C, gr, true);
     // S = R*(Id+I)
-    PUSH(Lq, return ss_launch_s_bwd(dS32, gr.din.p, e->R32, e->I32, e->Id32, dR32, dI32, dId32, B, C, H, W, st););
+    PUSH(Lq, return ss_launch_s_bwd(dS32, dSf32, gr.din.p, e->R32, e->I32, e->Id32, dR32, dI32, dId32, B, C, H, W, st););
 
     // IllumAdjustmentNet backward
     Tens dff = e->talloc(B, H, W, 64), dfg = e->talloc(B, H, W, 192), dr3 = e->talloc(B, H, W, 64),
@@ -980,8 +993,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
                                    ss_umma_wgrad_halo_partial_floats(e->geoms[i], 64)));
     }
     e->wg_partial_floats = mx;
-    e->wg_partial = e->falloc((int64_t)mx);
-    e->wg_partial2 = e->falloc((int64_t)mx);
+    for (int i = 0; i < SS_MAX_SIDE; ++i) e->wg_partial[i] = e->falloc((int64_t)mx);
   }
   e->ws_bytes = e->cursor;
   return SSHSLIE_OK;
@@ -1025,6 +1037,12 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
   {
     const char* we = getenv("SSHSLIE_WGRAD_HALO");
     e->wgrad_halo = !(we && we[0] == '0');
+    const char* sk = getenv("SSHSLIE_SKIP_WGRAD");
+    e->skip_wgrad = (sk && sk[0] == '1');
+    const char* ns = getenv("SSHSLIE_NO_SIDE");
+    if (ns && ns[0] == '1') e->use_side = false;
+    const char* nsd = getenv("SSHSLIE_SIDE_STREAMS");
+    if (nsd && atoi(nsd) >= 1 && atoi(nsd) <= SS_MAX_SIDE) e->n_side = atoi(nsd);
   }
   layer_shapes(channels, e->shapes);
   e->nparams = sshslie_param_table(channels, e->poff, e->psize);
@@ -1036,7 +1054,7 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
 }
 extern "C" void sshslie_engine_destroy(sshslie_engine* e) {
   if (!e) return;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < SS_MAX_SIDE; ++i) {
     if (e->side[i]) cudaStreamDestroy(e->side[i]);
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
   }
@@ -1056,7 +1074,7 @@ extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t w
   e->gmaps.clear();
   if (!e->side[0]) {
     bool ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; ++i)
+    for (int i = 0; i < SS_MAX_SIDE && ok; ++i)
       ok = cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) == cudaSuccess &&
            cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
@@ -1251,6 +1269,13 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
     if (rc) return rc;
     const int64_t wn = (int64_t)Cin * Cout * k * k;
     cudaMemsetAsync(w, 0, (size_t)wn * sizeof(float), st);
+    if (bias) {   // kind 2: `bias` receives db (addressed relative to the gradient base like a layer's bias slice)
+      cudaMemsetAsync(const_cast<float*>(bias), 0, (size_t)Cout * sizeof(float), st);
+      float* lo = (bias < w) ? const_cast<float*>(bias) : w;      // offsets must be non-negative: rebase on the lower pointer
+      e->grads = lo;
+      e->poff[0] = (int64_t)(w - lo);
+      e->poff[1] = (int64_t)(bias - lo);
+    }
     if (!transposed) {
       WAddr wa = waddr_conv_fwd(e, 0);
       e->add_geom(geom_conv(B, Hout, Wout, {{tin, 0, Cin, 0}}, k, stride, pad, +1, Cout, wa));
@@ -1272,7 +1297,7 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
   if (kind == 2 && impl >= 1) {
     e->wg_partial_floats = std::max(ss_umma_wgrad_partial_floats(e->geoms[0], gN),
                                     ss_umma_wgrad_halo_partial_floats(e->geoms[0], gN));
-    e->wg_partial = e->falloc((int64_t)e->wg_partial_floats);
+    e->wg_partial[0] = e->falloc((int64_t)e->wg_partial_floats);
   }
   if (e->cursor > scratch_bytes) { ss_set_error("sshslie_conv2d: scratch overflow"); return SSHSLIE_ERR_WORKSPACE; }
   const size_t msz = ss_umma_maps_size();
@@ -1296,7 +1321,7 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
       else rc = ss_launch_nhwc16_to_nchw32(tin.p, y, B, Cin, Hin, Win, tin.ld, st);
     }
   } else {
-    rc = run_wgrad(e, 0, *gt, gN, 0, 0, 1, st);
+    rc = run_wgrad(e, 0, *gt, gN, 0, 0, 1, st, (bias && !transposed) ? 0 : -1);
   }
   // SSHSLIE_CONV2D_TIMING=n: repeat the layer's own launches n times between two events (tools/conv_bench.py)
   if (const char* te = getenv("SSHSLIE_CONV2D_TIMING")) {
@@ -1308,7 +1333,7 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
       cudaEventRecord(a, st);
       for (int r = 0; r < reps && !rc; ++r) {
         if (kind != 2) for (size_t j = 0; j < jobs.size() && !rc; ++j) rc = run_gather(e, jobs[j].gi, jobs[j].ep, -1, st);
-        else rc = run_wgrad(e, 0, *gt, gN, 0, 0, 1, st);
+        else rc = run_wgrad(e, 0, *gt, gN, 0, 0, 1, st, (bias && !transposed) ? 0 : -1);
       }
       cudaEventRecord(b, st);
       cudaEventSynchronize(b);

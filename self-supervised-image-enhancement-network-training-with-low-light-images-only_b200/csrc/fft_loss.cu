@@ -121,7 +121,7 @@ SS_DEVINL void fft_axis(float2* z, const float2* tw, int H, int W, int lgW, int 
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 fourier_loss_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ mask,
                     float* __restrict__ dS, float* __restrict__ sum_out, int H, int W, int lgH, int lgW,
-                    float grad_scale) {
+                    float grad_scale, int accumulate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* z = reinterpret_cast<float2*>(smem_raw);                    // H*W
   float2* twW = z + H * W;                                            // W/2
@@ -183,7 +183,11 @@ fourier_loss_kernel(const float* __restrict__ x, const float* __restrict__ s, co
   fft_axis<true, true, true>(z, twW, H, W, lgW, lgW);
 
   float* dp = dS + img * H * W;
-  for (int i = threadIdx.x; i < H * W; i += FFT_THREADS) dp[i] += grad_scale * z[i].x;
+  if (accumulate) {
+    for (int i = threadIdx.x; i < H * W; i += FFT_THREADS) dp[i] += grad_scale * z[i].x;
+  } else {
+    for (int i = threadIdx.x; i < H * W; i += FFT_THREADS) dp[i] = grad_scale * z[i].x;
+  }
 }
 
 static int ilog2_exact(int v) {
@@ -192,8 +196,10 @@ static int ilog2_exact(int v) {
   return ((1 << l) == v) ? l : -1;
 }
 
-extern "C" int sshslie_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out,
-                                    int n_img, int H, int W, float grad_scale, void* stream) {
+// accumulate = 1: dS += gradient (the exported entry point); 0: dS = gradient (the engine gives the term its own plane so
+// that it can run beside the second decomposition pass instead of after the pixel-space terms)
+int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out, int n_img, int H,
+                    int W, float grad_scale, int accumulate, cudaStream_t stream) {
   const int lgH = ilog2_exact(H), lgW = ilog2_exact(W);
   if (!x || !S || !mask || !sum_out || n_img < 1 || lgH < 3 || lgW < 3 || H > 128 || W > 128) {
     ss_set_error("sshslie_fourier_loss: H and W must be powers of two in [8,128] (got %dx%d)", H, W);
@@ -210,7 +216,11 @@ extern "C" int sshslie_fourier_loss(const float* x, const float* S, const float*
     }
     attr_set = true;
   }
-  fourier_loss_kernel<<<n_img, FFT_THREADS, smem, (cudaStream_t)stream>>>(x, S, mask, dS, sum_out, H, W, lgH, lgW,
-                                                                         grad_scale);
+  fourier_loss_kernel<<<n_img, FFT_THREADS, smem, stream>>>(x, S, mask, dS, sum_out, H, W, lgH, lgW, grad_scale,
+                                                            accumulate);
   return ss_check_launch("fourier_loss");
+}
+extern "C" int sshslie_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out,
+                                    int n_img, int H, int W, float grad_scale, void* stream) {
+  return ss_fourier_loss(x, S, mask, dS, sum_out, n_img, H, W, grad_scale, 1, (cudaStream_t)stream);
 }

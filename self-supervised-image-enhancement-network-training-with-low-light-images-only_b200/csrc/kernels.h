@@ -47,8 +47,10 @@ int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const 
                           cudaStream_t st);
 int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
                      cudaStream_t st);
-int ss_launch_s_bwd(const float* dS32, const bf16* dSb, const float* R, const float* I, const float* Id, float* dR32,
-                    float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st);
+int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, const float* R, const float* I,
+                    const float* Id, float* dR32, float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st);
+int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out, int n_img, int H,
+                    int W, float grad_scale, int accumulate, cudaStream_t stream);
 int ss_launch_head_bwd(const float* dR32, const float* R32, const bf16* dRI, int ld_dri, const float* dI32,
                        const float* I32, bf16* dc8, int ld_out, int B, int C, int H, int W, cudaStream_t st);
 int ss_launch_concat_bwd(const bf16* dfg, const bf16* r3, bf16* dr3, bf16* p2, bf16* p1, int B, int H, int W,

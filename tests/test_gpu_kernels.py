@@ -104,8 +104,11 @@ def test_conv_wgrad_halo(case):
     dy = bf16_round(torch.randn(yref.shape, generator=torch.Generator().manual_seed(5))).cuda()
     (dw_ref,) = torch.autograd.grad(yref, w, dy)
     dw = torch.zeros_like(dw_ref)
-    conv2d(2, 2, tr, x.detach(), dw, None, dy, B, Cin, Cout, H, W, k, stride, relu=False)
+    db = torch.zeros(Cout, device="cuda")
+    conv2d(2, 2, tr, x.detach(), dw, db, dy, B, Cin, Cout, H, W, k, stride, relu=False)
     torch.testing.assert_close(dw, dw_ref, rtol=1e-3, atol=1e-3 * float(dw_ref.abs().max()))
+    db_ref = dy.sum(dim=(0, 2, 3))                     # the fused ones^T . G bias row
+    torch.testing.assert_close(db, db_ref, rtol=1e-3, atol=1e-3 * float(db_ref.abs().max()))
 
 
 @pytest.mark.parametrize("case", HALO_CASES, ids=[c[0] for c in HALO_CASES])

@@ -19,4 +19,12 @@ with torch.no_grad():
     for _ in range(n):
         R, I, Id, S_ = m.forward(x)
 torch.cuda.synchronize()
-print("ok", float(S_.mean()))
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+with torch.no_grad():
+    for _ in range(n):
+        m.forward(x)
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / n
+print(f"ok mean(S)={float(S_.mean()):.5f}  {ms:.3f} ms/forward  {B * 64 * size * size / ms / 1e3:.0f} Mvoxel/s")
