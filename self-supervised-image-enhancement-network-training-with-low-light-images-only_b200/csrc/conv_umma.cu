@@ -1084,6 +1084,7 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
 // ---------------------------------------------------------------------------------------------
 #define WGH_MAX_PAIRS 48
 #define WGH_ONES_BYTES 2048
+#define WGH_ISSUERS 1                    // 2 = pairs split over two issuing warps: measured, no gain (see below)
 #define WGH_MAX_GROUP_PAIRS 7          // 512 TMEM columns / N = 64, minus the bias block
 struct WgHaloArgs {
   int nh;
@@ -1096,6 +1097,7 @@ struct WgHaloArgs {
   int n_tiles, tiles_per_cta, splits, groups, pairs_per_group, npairs, blocks_per_cta;
   int stages, stage_bytes;
   int OH, OW;
+  int debug;                   // 64: block (0,0) leaves cycle breadcrumbs in g_dbg
   uint32_t pair_lo[WGH_MAX_PAIRS];   // (window offset of slab a) >> 4  |  ((offset of slab b - offset of slab a) >> 4) << 16
   uint8_t pair_a[WGH_MAX_PAIRS];     // slab indices of the two M halves (pair_b = 255: none)
   uint8_t pair_b[WGH_MAX_PAIRS];
@@ -1111,6 +1113,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dbg = (wa.debug & 64) && blockIdx.x == 0 && blockIdx.y == 0;
+  const long long ts0 = dbg ? clock64() : 0;
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int nh = wa.nh, pad = wa.pad, stages = wa.stages;
   const uint32_t halo_bytes = (uint32_t)wa.halo_bytes, stage_bytes = (uint32_t)wa.stage_bytes;
@@ -1129,9 +1133,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     if (lane == 0) {
       for (int s = 0; s < stages; ++s) {
         mbar_init(smem_u32(&full_bar[s]), 1);
-        mbar_init(smem_u32(&empty_bar[s]), 1);
+        mbar_init(smem_u32(&empty_bar[s]), WGH_ISSUERS);
       }
-      mbar_init(smem_u32(&accum_bar), 1);
+      mbar_init(smem_u32(&accum_bar), WGH_ISSUERS);
       fence_barrier_init();
     }
     __syncwarp();
@@ -1171,7 +1175,11 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == WGH_ISSUERS) {
+    // Measured on B200 (tools/wgrad_breadcrumbs.py): this loop runs at ~50 clk per M128 N64 K16 MMA, the shared-memory
+    // operand-read limit of SS-mode MMAs at N = 64 (tools/umma_probe.py: 48 clk, same for K- and MN-major operands).
+    // Neither issuing from two warps (WGH_ISSUERS = 2) nor interleaving accumulators changed that.
+    const int issuer = (warp == 1) ? 0 : 1;
     const uint32_t idesc = make_idesc(128, wa.N, 1, 1);
     const uint32_t tm = uniform32(tmem_base);
     // A: two 64-channel atoms (the two taps), LBO per pair; K groups of 8 pixels = tile rows, SBO = pitch * 128 B
@@ -1186,16 +1194,19 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     const uint32_t kstep = (uint32_t)(2 * pitch * 128) >> 4;      // 16 pixels = two tile rows
     const uint32_t N = (uint32_t)wa.N;
     // the group's pair words never change: keep them in (uniform) registers.  MMAs are issued k-outer / pair-inner so
-    // that consecutive MMAs accumulate into DIFFERENT TMEM tiles (back-to-back MMAs on one accumulator serialise on its
-    // read-modify-write latency)
+    // that consecutive MMAs accumulate into different TMEM tiles
     const int np = p_end - p_begin;
     uint32_t plo[WGH_MAX_GROUP_PAIRS];
 #pragma unroll
     for (int p = 0; p < WGH_MAX_GROUP_PAIRS; ++p) plo[p] = wa.pair_lo[min(p_begin + p, WGH_MAX_PAIRS - 1)];
     uint32_t st = 0, ph = 0;
+    long long c_wait = 0;
+    if (dbg && lane == 0 && issuer == 0) g_dbg[1] = clock64() - ts0;
 #pragma unroll 1
     for (int ti = 0; ti < ntiles; ++ti) {
+      const long long q0 = dbg ? clock64() : 0;
       mbar_wait_warp(full0 + 8u * st, ph, 0);
+      if (dbg) c_wait += clock64() - q0;
       tc_fence_after();
       const uint32_t s_lo = base_lo + st * sstep;
       const uint32_t acc0 = (ti > 0) ? 1u : 0u;
@@ -1207,22 +1218,28 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
           const uint32_t acc = k > 0 ? 1u : acc0;
 #pragma unroll
           for (int p = 0; p < WGH_MAX_GROUP_PAIRS; ++p)
-            if (p < np)
+            if (p < np && (p % WGH_ISSUERS) == issuer)
               umma_bf16(tm + (uint32_t)p * N, ((uint64_t)a_hi << 32) | (uint64_t)(s_lo + plo[p] + (uint32_t)k * kstep),
                         bd0 + (uint64_t)(128 * k), idesc, acc);
-          if (do_bias) umma_bf16(tm + (uint32_t)np * N, od0, bd0 + (uint64_t)(128 * k), idesc, acc);
+          if (do_bias && issuer == WGH_ISSUERS - 1) umma_bf16(tm + (uint32_t)np * N, od0, bd0 + (uint64_t)(128 * k), idesc, acc);
         }
         umma_commit(empty0 + 8u * st);
         if (ti == ntiles - 1) umma_commit(accb);
       }
       __syncwarp();
+      if (dbg && lane == 0 && issuer == 0) {
+        if (ti == 0) g_dbg[3] = clock64() - ts0;
+        if (ti == ntiles - 1) { g_dbg[4] = clock64() - ts0; g_dbg[7] = c_wait; g_dbg[0] = ntiles; }
+      }
       if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
     }
-  } else {
+  }
+  if (warp >= 2) {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     mbar_wait_warp(smem_u32(&accum_bar), 0, 200);
     tc_fence_after();
+    if (dbg && threadIdx.x == 96) g_dbg[5] = clock64() - ts0;
     // partial[split][group][block][n][row]: lanes = consecutive rows -> 128-byte coalesced stores, no atomics
     float* out = partial + ((size_t)(blockIdx.x * wa.groups + group) * wa.blocks_per_cta) * (size_t)wa.N * 128;
     const int nblocks = (p_end - p_begin) + (do_bias ? 1 : 0);
@@ -1236,6 +1253,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       }
     }
   }
+  if (dbg && threadIdx.x == 96) g_dbg[6] = clock64() - ts0;
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)wa.tmem_cols);
@@ -1295,6 +1313,7 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   wa.N = (gN > 64) ? 128 : 64;
   wa.g_atoms = wa.N / 64;
   wa.OH = g.OH; wa.OW = g.OW;
+  wa.debug = env_int("SSHSLIE_HALO_DEBUG", 0);
   // tap pairs over the slabs that carry weights of their own (residual "lo" slabs are skipped), lower window first
   int slabs[SS_MAX_SLABS], ns = 0;
   for (int i = 0; i < g.nslabs; ++i)
@@ -1384,7 +1403,8 @@ int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const Um
 // resident in shared memory (contents irrelevant), cycling over n_acc TMEM accumulators; reports cycles per MMA.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int n_mma, int n_acc, int commit_every,
-                                                             long long* __restrict__ out, int a_off, int a_sbo) {
+                                                             long long* __restrict__ out, int a_off, int a_sbo,
+                                                             int mn_major, int distinct) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ __align__(8) uint64_t bar2;
@@ -1405,8 +1425,13 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int n_mma, in
   tc_fence_after();
   const uint32_t tm = uniform32(tmem_base_smem);
   if (warp == 0) {
-    const uint32_t idesc = make_idesc(128, N, 0, 0);
-    const uint64_t ad0 = make_sdesc(base + (uint32_t)a_off, 16, (uint32_t)a_sbo), bd0 = make_sdesc(base + 65536, 16, 1024);
+    // mn_major = 1: both operands MN-major as in the weight-gradient kernels (A = two 64-wide atoms 16 KB apart, K steps of
+    // 2 KB); distinct = 1: every group of 4 MMAs reads a different 8 KB of A (128 B further on), like the halo taps
+    const uint32_t idesc = make_idesc(128, N, mn_major, mn_major);
+    const uint64_t ad0 = mn_major ? make_sdesc(base + (uint32_t)a_off, 16384, (uint32_t)a_sbo)
+                                  : make_sdesc(base + (uint32_t)a_off, 16, (uint32_t)a_sbo);
+    const uint64_t bd0 = mn_major ? make_sdesc(base + 65536, 16384, 1024) : make_sdesc(base + 65536, 16, 1024);
+    const uint64_t kadv = mn_major ? 128u : 2u;
     long long t0 = 0, t1 = 0;
     uint32_t phase = 0;
     if (elect_one()) {
@@ -1415,10 +1440,11 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(int N, int n_mma, in
       for (int gi = 0; gi < n_mma / 4; ++gi) {
         const uint32_t d = tm + ((uint32_t)gi & amask) * (uint32_t)N;
         const uint32_t accum = gi >= n_acc ? 1u : 0u;
-        umma_bf16(d, ad0, bd0, idesc, accum);
-        umma_bf16(d, ad0 + 2, bd0 + 2, idesc, 1u);
-        umma_bf16(d, ad0 + 4, bd0 + 4, idesc, 1u);
-        umma_bf16(d, ad0 + 6, bd0 + 6, idesc, 1u);
+        const uint64_t ad = ad0 + (distinct ? (uint64_t)(((uint32_t)gi & 63u) * 8u) : 0u);
+        umma_bf16(d, ad, bd0, idesc, accum);
+        umma_bf16(d, ad + kadv, bd0 + kadv, idesc, 1u);
+        umma_bf16(d, ad + 2 * kadv, bd0 + 2 * kadv, idesc, 1u);
+        umma_bf16(d, ad + 3 * kadv, bd0 + 3 * kadv, idesc, 1u);
         if (commit_every) umma_commit(smem_u32(&bar2));      // like a stage release: nobody waits on it
       }
       umma_commit(smem_u32(&bar));
@@ -1440,13 +1466,15 @@ extern "C" SSHSLIE_API int sshslie_umma_probe(int N, int n_mma, int n_acc, int c
   const char* ao = getenv("SSHSLIE_PROBE_AOFF");
   const char* sb = getenv("SSHSLIE_PROBE_SBO");
   const int a_off = ao ? atoi(ao) : 0, a_sbo = sb ? atoi(sb) : 1024;
+  const int mn_major = env_int("SSHSLIE_PROBE_MN", 0), distinct = env_int("SSHSLIE_PROBE_DISTINCT", 0);
   if (N < 16 || N > 256 || (N % 16) || n_acc < 1 || n_acc * N > 512 || !out_cycles) {
     ss_set_error("sshslie_umma_probe: bad argument");
     return SSHSLIE_ERR_ARG;
   }
   cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   umma_probe_kernel<<<n_ctas, 128, 65536 + 256 * 128 + 1024, (cudaStream_t)stream>>>(N, n_mma, n_acc, commit_every,
-                                                                                    out_cycles, a_off, a_sbo);
+                                                                                    out_cycles, a_off, a_sbo, mn_major,
+                                                                                    distinct);
   return ss_check_launch("umma_probe");
 }
 

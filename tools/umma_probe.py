@@ -12,11 +12,11 @@ import sshslie_b200 as S  # noqa: E402
 lib = S.lib.load()
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-print("AOFF", os.environ.get("SSHSLIE_PROBE_AOFF"), "SBO", os.environ.get("SSHSLIE_PROBE_SBO"))
+print("AOFF", os.environ.get("SSHSLIE_PROBE_AOFF"), "SBO", os.environ.get("SSHSLIE_PROBE_SBO"), "MN", os.environ.get("SSHSLIE_PROBE_MN"), "DISTINCT", os.environ.get("SSHSLIE_PROBE_DISTINCT"))
 print(f"{'N':>4s} {'n_acc':>5s} {'commit_every':>12s} {'ctas':>5s} {'cycles/MMA':>10s} {'ideal(N/2)':>10s}")
 for ctas in (148,):
     for N in (64, 128):
-        for n_acc in (1,):
+        for n_acc in (1, 4):
             if n_acc * N > 512:
                 continue
             for ce in (1,):
