@@ -974,13 +974,30 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     ss_set_error("internal: %d geoms exceed the plan table", (int)e->geoms.size());
     return SSHSLIE_ERR_ARG;
   }
-  // packed weights + pack job table
+  // packed weights + pack job table.  Geoms that read the same weights the same way (the two decomposition passes and
+  // their two backward passes lower every layer twice) share ONE packed copy: only the first is a pack job.
   e->pack_start.assign(e->geoms.size() + 1, 0);
   for (size_t i = 0; i < e->geoms.size(); ++i) {
     ConvGeom& g = e->geoms[i];
     const int64_t elems = (int64_t)g.Npad * g.nslabs * SS_SLAB;
-    g.wp = (bf16*)e->alloc(elems * sizeof(bf16));
-    e->pack_start[i + 1] = e->pack_start[i] + (int)((elems + 255) / 256);
+    int twin = -1;
+    for (size_t j = 0; j < i && twin < 0; ++j) {
+      const ConvGeom& o = e->geoms[j];
+      if (o.w_off != g.w_off || o.w_sN != g.w_sN || o.w_sC != g.w_sC || o.N != g.N || o.Npad != g.Npad ||
+          o.nslabs != g.nslabs)
+        continue;
+      bool same = true;
+      for (int k = 0; k < g.nslabs && same; ++k)
+        same = o.slab[k].woff == g.slab[k].woff && o.slab[k].wcn == g.slab[k].wcn;
+      if (same) twin = (int)j;
+    }
+    if (twin >= 0) {
+      g.wp = e->geoms[twin].wp;
+      e->pack_start[i + 1] = e->pack_start[i];
+    } else {
+      g.wp = (bf16*)e->alloc(elems * sizeof(bf16));
+      e->pack_start[i + 1] = e->pack_start[i] + (int)((elems + 255) / 256);
+    }
   }
   e->pack_blocks = e->pack_start.back();
   if (e->train) {
