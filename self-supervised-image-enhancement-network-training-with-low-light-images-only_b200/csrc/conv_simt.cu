@@ -187,16 +187,17 @@ int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, c
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvGeom* __restrict__ geoms,
                                                            const int* __restrict__ block_start, int njobs,
-                                                           const float* __restrict__ params) {
-  int lo = 0, hi = njobs - 1;           // last job whose first block is <= blockIdx.x (block_start is ascending)
+                                                           const float* __restrict__ params, int first_block) {
+  const int blk = (int)blockIdx.x + first_block;      // a launch may cover only blocks [first_block, ...) of the table
+  int lo = 0, hi = njobs - 1;           // last job whose first block is <= blk (block_start is ascending)
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if ((int)blockIdx.x >= block_start[mid]) lo = mid; else hi = mid - 1;
+    if (blk >= block_start[mid]) lo = mid; else hi = mid - 1;
   }
   const int j = lo;
   const ConvGeom* g = geoms + j;
   const int Ktot = g->nslabs * SS_SLAB;
-  const int64_t idx = (int64_t)(blockIdx.x - block_start[j]) * 256 + threadIdx.x;
+  const int64_t idx = (int64_t)(blk - block_start[j]) * 256 + threadIdx.x;
   if (idx >= (int64_t)g->Npad * Ktot) return;
   const int n = (int)(idx / Ktot);
   const int k = (int)(idx - (int64_t)n * Ktot);
@@ -208,7 +209,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvGeom* __res
 }
 
 int ss_launch_pack_weights(const ConvGeom* geoms_dev, const int* block_start_dev, int njobs, int total_blocks,
-                           const float* params, cudaStream_t st) {
-  pack_weights_kernel<<<total_blocks, 256, 0, st>>>(geoms_dev, block_start_dev, njobs, params);
+                           const float* params, cudaStream_t st, int first_block, int n_blocks) {
+  if (n_blocks < 0) n_blocks = total_blocks - first_block;
+  if (n_blocks <= 0) return SSHSLIE_OK;
+  pack_weights_kernel<<<n_blocks, 256, 0, st>>>(geoms_dev, block_start_dev, njobs, params, first_block);
   return ss_check_launch("pack_weights");
 }

@@ -155,7 +155,7 @@ struct sshslie_engine {
   ConvGeom* geoms_dev = nullptr;
   int* pack_start_dev = nullptr;
   std::vector<int> pack_start;
-  int pack_blocks = 0;
+  int pack_blocks = 0, pack_split = 0;
   float* mask_dev = nullptr;
   float* sums_dev = nullptr;
   // split-K partial accumulators of the tcgen05 wgrad (sized for the largest op), one buffer per side stream
@@ -508,7 +508,7 @@ struct DecompGeoms {
   int conv0, shallow, conv1, conv2, conv3, deconv[4], conv5, conv7, recon;
 };
 static DecompGeoms plan_decomp_fwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>& ops, const Tens& in,
-                                   DecompBufs& d, Epi head_epi) {
+                                   DecompBufs& d, Epi head_epi, bool join_pack = false) {
   const int B = e->B, H = e->H, W = e->W;
   DecompGeoms G;
   {  // conv0: 64 -> 32, ReLU
@@ -524,6 +524,7 @@ static DecompGeoms plan_decomp_fwd(sshslie_engine* e, std::vector<sshslie_engine
     Epi ep = epi_bf16(d.sh, 64);
     const int gi = G.shallow;
     PUSH(ops, return run_gather(e, gi, ep, L_D_SHALLOW, st););
+    if (join_pack) PUSH_JOIN(ops);        // the rest of the packed weights (side stream) is needed from here on
   }
   {
     WAddr wa = waddr_conv_fwd(e, L_D_CONV1);
@@ -746,18 +747,18 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   // ---- forward (model.py:229-234) ----------------------------------------------------------
   auto& F = e->ops_fwd;
   PUSH(F, return ss_launch_nchw32_to_nhwc16(e->x, X.p, B, C, H, W, 64, st););
-  {
-    const int total = e->pack_blocks;   // filled after planning; read at run time through e
-    (void)total;
-    PUSH(F, return ss_launch_pack_weights(e->geoms_dev, e->pack_start_dev, (int)e->geoms.size(), e->pack_blocks,
-                                          e->params, st););
-  }
+  // fp32 master weights -> packed bf16: the first two layers' weights (conv0, 9x9) on the caller's stream, everything
+  // else on a side stream, joined after the 9x9 layer (pack_split = first pack block of the third geom)
+  PUSH(F, return ss_launch_pack_weights(e->geoms_dev, e->pack_start_dev, (int)e->geoms.size(), e->pack_blocks,
+                                        e->params, st, 0, e->pack_split););
+  PUSH_SIDE(F, return ss_launch_pack_weights(e->geoms_dev, e->pack_start_dev, (int)e->geoms.size(), e->pack_blocks,
+                                             e->params, st, e->pack_split, -1););
   Epi head1;
   memset(&head1, 0, sizeof(head1));
   head1.mode = EPI_HEAD; head1.R32 = e->R32; head1.I32 = e->I32; head1.RI = RI.p; head1.ri_c = 192;
   head1.ri_lo_off = 128;
   head1.C = C; head1.H = H; head1.W = W;
-  DecompGeoms G1 = plan_decomp_fwd(e, F, X, d1, head1);
+  DecompGeoms G1 = plan_decomp_fwd(e, F, X, d1, head1, true);
 
   // IllumAdjustmentNet (model.py:143-175)
   int g_i0, g_i1, g_i2, g_i3, g_d1, g_d2, g_d3, g_fus, g_fin;
@@ -1000,6 +1001,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
   }
   e->pack_blocks = e->pack_start.back();
+  e->pack_split = e->geoms.size() > 2 ? e->pack_start[2] : e->pack_blocks;
   if (e->train) {
     size_t mx = 0;
     for (size_t i = 0; i < e->geoms.size(); ++i) {

@@ -10,7 +10,7 @@ int ss_launch_conv_wgrad_simt(const ConvGeom* g_dev, const ConvGeom& g_host, con
                               int64_t gW, int gN, float* grads, cudaStream_t st);
 int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, cudaStream_t st);
 int ss_launch_pack_weights(const ConvGeom* geoms_dev, const int* block_start_dev, int njobs, int total_blocks,
-                           const float* params, cudaStream_t st);
+                           const float* params, cudaStream_t st, int first_block = 0, int n_blocks = -1);
 
 // conv_umma.cu (tcgen05 / TMEM / TMA)
 struct UmmaMaps;   // host-built CUtensorMaps of one geom (opaque here)
