@@ -238,6 +238,51 @@ def run_ours(args):
                  "tflops_model": 391.4e9 / (ms_i * 1e-3) / 1e12,
                  "cpu_baseline": {"value": vox / cpu_s, "unit": "Mvoxel/s", "cores": os.cpu_count() or 1, "kind": "port",
                                   "sample": "1 forward of the same cube (oracle, torch CPU fp32)"}}
+    # BASELINE.json configs[4]: batch sweep (per-GPU batch 8 / 32, same loss weights), CUDA-graph replays, device timed;
+    # plus the per-launch roofline of the 9x9 layer at the largest batch (the kernels leave the launch-latency regime there)
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        sweep = []
+        for bsz in (8, 32):
+            mb = S.LowLightEnhance(input_channels=CHANNELS, lr=1e-3, **O.JYU_COEF).to(dev)
+            xb = O.synthetic_patches(bsz, CHANNELS, SIZE, seed=7).to(dev)
+
+            def stepb():
+                mb.optimizer.zero_grad()
+                loss, _ = mb.compute_loss(xb)
+                loss.backward()
+                mb.optimizer.step()
+            for _ in range(5):
+                stepb()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            a.record()
+            for _ in range(reps):
+                stepb()
+            b_.record()
+            torch.cuda.synchronize()
+            msb = a.elapsed_time(b_) / reps
+            row = {"batch_per_gpu": bsz, "ms_per_step": msb, "patches_per_sec": bsz / (msb * 1e-3),
+                   "tflops_model": bsz * FLOPS_PER_PATCH_FWD_BWD / (msb * 1e-3) / 1e12}
+            if bsz == 32:
+                pr = {}
+                for _ in range(2):
+                    for name, ms, fl, by in mb.profile_step(xb):
+                        if "shallow9x9" in name or "loss:" in name:
+                            a_ = pr.setdefault(name, [0.0, 0, fl, by])
+                            a_[0] += ms
+                            a_[1] += 1
+                pk_ = peaks()
+                row["kernels"] = [
+                    {"kernel": k, "ms_per_launch": v[0] / v[1],
+                     **({"tflops": v[2] / (v[0] / v[1] * 1e-3) / 1e12, "frac_of_bf16_peak": v[2] / (v[0] / v[1] * 1e-3) / 1e12 / pk_["burst"]}
+                        if v[2] > 0 else
+                        {"gbs": v[3] / (v[0] / v[1] * 1e-3) / 1e9, "frac_of_hbm_peak": v[3] / (v[0] / v[1] * 1e-3) / 1e9 / pk_["hbm"]})}
+                    for k, v in sorted(pr.items())]
+            sweep.append(row)
+            del mb, xb
+            torch.cuda.empty_cache()
     cpu = None
     if rank == 0 and world == 1:
         cores = os.cpu_count() or 1
@@ -265,13 +310,19 @@ def run_ours(args):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        traffic = tj.get(top_name.split("/", 1)[1])
+        traffic = tj.get(top_name.split("/", 1)[1].split("[")[0])
     except Exception:
         pass
     roof.update({"kernel": top_name, "ms_per_launch": top_ms, "share_of_step": top_ms / total_prof,
                  "traffic": traffic, "algorithmic_flops_per_launch": top[2], "algorithmic_bytes_per_launch": top[3],
                  "peak_source": pk["source"],
-                 "timing": "cudaEvent pairs around each launch group, eager steps after the timed region"})
+                 "timing": "cudaEvent pair around 4 back-to-back enqueues of the launch group (time / 4), eager steps after "
+                           "the timed region, on the stream the kernels run on (sshslie_profile_step)"})
+    # the same figure for the other instances of the 9x9 layer (forward / data gradient run the gather kernel)
+    roof["other_launches"] = [
+        {"kernel": k, "ms_per_launch": v[0] / v[1], "achieved": v[2] / (v[0] / v[1] * 1e-3) / 1e12,
+         "frac": v[2] / (v[0] / v[1] * 1e-3) / 1e12 / pk["burst"]}
+        for k, v in sorted(prof.items()) if "shallow9x9" in k and k != top_name]
     patches = world * BATCH_PER_GPU * K
     value = patches / (ms_dev * 1e-3)
     e2e = patches / (ms_e2e * 1e-3)
@@ -303,6 +354,8 @@ def run_ours(args):
         "top_kernels_ms": top5,
         "kernel_class_ms_per_step": classes,
     }
+    if sweep:
+        line["batch_sweep"] = sweep
     if cpu:
         line["cpu_baseline"] = cpu
     if infer:
@@ -318,6 +371,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", dest="no_sweep", action="store_true", help="skip the batch-8/32 sweep (configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 10:

@@ -111,6 +111,17 @@ SSHSLIE_API int sshslie_profile_row(int i, char* name, int name_cap, float* ms, 
 SSHSLIE_API int sshslie_gather_patches(const float* const* cubes_dev, const int* meta_dev, float* out, int B, int C,
                            int patch_size, void* stream);
 
+/* Result writer replacing the host-side permute + de-normalisation of test_model / evaluate_model (model.py:421-424,
+ * 381-387): src (C,H,W) fp32 on the device -> dst (H,W,C) fp32; apply != 0: dst = src * scale + offset as two separately
+ * rounded fp32 operations (numpy's S * (max - min) + min: bit-exact). */
+SSHSLIE_API int sshslie_denorm_hwc(const float* src_chw, float* dst_hwc, int C, int H, int W, float scale, float offset,
+                       int apply, void* stream);
+
+/* PSNR / SAM sums of two (H,W,C) fp32 cubes as metrics.py:13-14,31-34 evaluates them through torchmetrics 1.6.2:
+ * sums2[0] = sum of squared differences, sums2[1] = sum over pixels of the spectral angle (radians); device doubles. */
+SSHSLIE_API int sshslie_psnr_sam(const float* pred_hwc, const float* target_hwc, int H, int W, int C, double* sums2,
+                     void* stream);
+
 /* ---- single kernels, exported for kernel-level parity tests and profiling ---- */
 
 /* fourier_spectrum_loss (model.py:456-473) forward + d/dS.  x,S,dS: (n_img,H,W) fp32 planes, H and W

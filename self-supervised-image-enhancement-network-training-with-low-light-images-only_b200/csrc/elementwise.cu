@@ -1,6 +1,7 @@
 // Layout, resampling and head/glue kernels around the conv GEMMs (all HBM-bound, fp32 math).
 //   fp32 tensors: NCHW planes (the reference's layout, consumed by the loss/FFT kernels and returned to the caller)
 //   bf16 tensors: NHWC (the GEMM operand layout), channel stride `ld`
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -502,4 +503,96 @@ extern "C" int sshslie_gather_patches(const float* const* cubes_dev, const int* 
   dim3 grid((patch_size + 127) / 128, patch_size, B);
   gather_patches_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(cubes_dev, meta_dev, out, C, patch_size);
   return ss_check_launch("gather_patches");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// result writer: the reference turns every output into an HWC numpy array on the host and, for S,
+// de-normalises it there: S.squeeze(0).permute(1,2,0).cpu().numpy() * (max - min) + min (model.py:421-424).  Here one
+// kernel does the NCHW -> HWC transposition and the de-normalisation on the device (two separately rounded fp32
+// operations, as numpy does them: bit-exact), so the host only receives the finished cube.
+// ---------------------------------------------------------------------------------------------
+__global__ void denorm_hwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int64_t HW,
+                                  float scale, float offset, int apply) {
+  __shared__ float tile[32][33];
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {          // i = channel, x = pixel (coalesced plane reads)
+    const int c = c0 + i;
+    const int64_t pix = p0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && pix < HW) {
+      v = src[(int64_t)c * HW + pix];
+      if (apply) v = __fadd_rn(__fmul_rn(v, scale), offset);      // never contracted into an FMA
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {          // i = pixel, x = channel (coalesced HWC writes)
+    const int c = c0 + threadIdx.x;
+    const int64_t pix = p0 + i;
+    if (c < C && pix < HW) dst[pix * C + c] = tile[threadIdx.x][i];
+  }
+}
+extern "C" int sshslie_denorm_hwc(const float* src_chw, float* dst_hwc, int C, int H, int W, float scale, float offset,
+                                  int apply, void* stream) {
+  if (!src_chw || !dst_hwc || C < 1 || H < 1 || W < 1) {
+    ss_set_error("sshslie_denorm_hwc: bad argument");
+    return SSHSLIE_ERR_ARG;
+  }
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32));
+  denorm_hwc_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src_chw, dst_hwc, C, HW, scale, offset, apply);
+  return ss_check_launch("denorm_hwc");
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluation metrics on the device: PSNR and SAM as metrics.py:13-14,31-34 call them
+// (torchmetrics 1.6.2 functional semantics, restated - the package is not available offline, parity unpinned):
+//   sums[0] = sum (p - t)^2 over all elements          -> PSNR = 10 log10(range^2 / (sums[0] / n))
+//   sums[1] = sum over pixels of acos(clamp(<p,t> / (|p| |t|), -1, 1))   -> SAM = sums[1] / pixels   (radians)
+// pred / target are HWC fp32 cubes (what save_hsi wrote).  One warp per pixel; fp32 per pixel, fp64 across pixels.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) psnr_sam_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                       int64_t npix, int C, double* __restrict__ sums) {
+  __shared__ double red[2][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double sse = 0.0, ang = 0.0;
+  for (int64_t pix = (int64_t)blockIdx.x * 8 + wid; pix < npix; pix += (int64_t)gridDim.x * 8) {
+    float dot = 0.f, pp = 0.f, tt = 0.f, se = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float a = pred[pix * C + c], b = tgt[pix * C + c];
+      dot = fmaf(a, b, dot);
+      pp = fmaf(a, a, pp);
+      tt = fmaf(b, b, tt);
+      const float d = a - b;
+      se = fmaf(d, d, se);
+    }
+    dot = warp_sum(dot); pp = warp_sum(pp); tt = warp_sum(tt); se = warp_sum(se);
+    if (lane == 0) {
+      sse += (double)se;
+      const float cosv = fminf(fmaxf(dot / (sqrtf(pp) * sqrtf(tt)), -1.f), 1.f);
+      ang += (double)acosf(cosv);
+    }
+  }
+  if (lane == 0) { red[0][wid] = sse; red[1][wid] = ang; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; b += red[1][i]; }
+    atomicAdd(sums, a);
+    atomicAdd(sums + 1, b);
+  }
+}
+extern "C" int sshslie_psnr_sam(const float* pred_hwc, const float* target_hwc, int H, int W, int C, double* sums2,
+                                void* stream) {
+  if (!pred_hwc || !target_hwc || !sums2 || H < 1 || W < 1 || C < 1) {
+    ss_set_error("sshslie_psnr_sam: bad argument");
+    return SSHSLIE_ERR_ARG;
+  }
+  const int64_t npix = (int64_t)H * W;
+  cudaMemsetAsync(sums2, 0, 2 * sizeof(double), (cudaStream_t)stream);
+  const unsigned blocks = (unsigned)std::min<int64_t>((npix + 7) / 8, 148 * 8);
+  psnr_sam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred_hwc, target_hwc, npix, C, sums2);
+  return ss_check_launch("psnr_sam");
 }

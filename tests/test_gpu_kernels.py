@@ -276,3 +276,29 @@ def test_patch_sampler_follows_reference_rng_order():
             mode = np.random.randint(0, 8)
             batch[i] = data_augmentation(cubes[idx][x:x + ps, y:y + ps, :], mode)
         assert np.array_equal(got[b], batch.transpose(0, 3, 1, 2))
+
+
+def test_denorm_hwc_bit_exact():
+    """Result writer: NCHW -> HWC + S*(max-min)+min on the device == the reference's numpy expression (model.py:421-424)."""
+    import sshslie_b200 as S
+    torch.manual_seed(3)
+    m = S.LowLightEnhance(global_min=238.0, global_max=4095.0)
+    x = torch.rand(1, 64, 40, 24, device="cuda") * 1.2 - 0.1
+    got = m._to_hwc_host(x, denorm=True)
+    ref = x.squeeze(0).permute(1, 2, 0).cpu().numpy()
+    ref = ref * (4095.0 - 238.0) + 238.0
+    assert got.dtype == np.float32 and np.array_equal(got, ref)
+    one = torch.rand(1, 1, 40, 24, device="cuda")
+    assert np.array_equal(m._to_hwc_host(one), one.squeeze(0).permute(1, 2, 0).cpu().numpy())
+
+
+def test_psnr_sam_vs_oracle():
+    """PSNR / SAM sums on the device vs the oracle's torch fp32 restatement of the torchmetrics calls: rel 1e-5."""
+    import sshslie_b200 as S
+    from oracle import sshslie_oracle as O
+    g = torch.Generator().manual_seed(11)
+    t = torch.rand(48, 40, 64, generator=g) * 4000 + 238
+    p = t + torch.randn(48, 40, 64, generator=g) * 60
+    ps, sa = S.metrics.psnr_sam(p, t, 4095.0)
+    np.testing.assert_allclose(ps, float(O.psnr(p, t, 4095.0)), rtol=1e-5)
+    np.testing.assert_allclose(sa, float(O.sam(p, t)), rtol=1e-4)

@@ -197,3 +197,25 @@ def test_linearity_of_batch():
         grads.append(torch.cat([p.grad.detach().flatten().clone() for p in m.parameters()]))
     mean12 = 0.5 * (grads[1] + grads[2])
     assert _cos(grads[0], mean12) >= 0.9995
+
+
+def test_backward_autograd_semantics():
+    """`loss.backward()` (the reference's call, model.py:315) hands over the finished gradients without the autograd
+    engine; arithmetic on the loss still goes through autograd: (3 * loss).backward() gives 3x the gradients, and a
+    second backward into existing .grad accumulates."""
+    from oracle import sshslie_oracle as O
+    m = _model(O.JYU_COEF)
+    x = O.synthetic_patches(1, 64, 64, seed=5).cuda()
+    m.optimizer.zero_grad()
+    loss, _ = m.compute_loss(x)
+    loss.backward()
+    g1 = torch.cat([p.grad.detach().flatten() for p in m.parameters()]).clone()
+    m.optimizer.zero_grad()
+    loss, _ = m.compute_loss(x)
+    (3.0 * loss).backward()
+    g3 = torch.cat([p.grad.detach().flatten() for p in m.parameters()]).clone()
+    torch.testing.assert_close(g3, 3.0 * g1, rtol=1e-6, atol=0)
+    loss2, _ = m.compute_loss(x)
+    loss2.backward()                       # accumulates into the existing .grad like autograd would
+    g4 = torch.cat([p.grad.detach().flatten() for p in m.parameters()])
+    torch.testing.assert_close(g4, 4.0 * g1, rtol=1e-5, atol=1e-12)
