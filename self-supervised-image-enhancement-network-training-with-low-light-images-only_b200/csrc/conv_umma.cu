@@ -966,6 +966,10 @@ int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g, const U
 }
 
 int ss_umma_wgrad_supported(const ConvGeom& g) { return ss_umma_supported(g) && g.N <= 128; }
+// profiling aid: 0 = both kernels of a tcgen05 weight gradient (default), 1 = the GEMM kernel only, 2 = the split-K
+// reduce only (sshslie_profile_step times them as separate rows)
+static thread_local int g_wgrad_part = 0;
+void ss_set_wgrad_part(int part) { g_wgrad_part = part; }
 
 int ss_umma_build_gmap(const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld_extent, const ConvGeom& g,
                        void* out_map) {
@@ -1064,10 +1068,13 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
     attr_set = true;
   }
   dim3 grid(wa.splits, wa.groups);
-  conv_wgrad_umma_kernel<<<grid, UM_THREADS, smem, st>>>(g_dev, maps, *reinterpret_cast<const CUtensorMap*>(gmap), wa,
-                                                         partial);
-  int rc = ss_check_launch("conv_wgrad_umma");
-  if (rc) return rc;
+  int rc = SSHSLIE_OK;
+  if (g_wgrad_part != 2) {
+    conv_wgrad_umma_kernel<<<grid, UM_THREADS, smem, st>>>(g_dev, maps, *reinterpret_cast<const CUtensorMap*>(gmap), wa,
+                                                           partial);
+    rc = ss_check_launch("conv_wgrad_umma");
+    if (rc || g_wgrad_part == 1) return rc;
+  }
   dim3 rgrid(wa.blocks_per_cta, wa.groups, wa.N / 8);
   conv_wgrad_reduce_kernel<<<rgrid, dim3(128, 8), 0, st>>>(g_dev, partial, wa, grads);
   return ss_check_launch("conv_wgrad_reduce");
@@ -1103,9 +1110,10 @@ struct WgHaloArgs {
   uint8_t pair_b[WGH_MAX_PAIRS];
 };
 
-__global__ void __launch_bounds__(UM_THREADS, 1)
-conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ CUtensorMap gmap,
-                       const __grid_constant__ WgHaloArgs wa, float* __restrict__ partial) {
+// body shared by the single-layer kernel (arguments in the constant bank) and the grouped kernel (arguments of the CTA's
+// job staged in shared memory, tensor maps in global memory): bx = pixel split, by = pair group
+SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const CUtensorMap* __restrict__ gmap_p,
+                               const WgHaloArgs& wa, float* __restrict__ partial, const int bx, const int by) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[4];
   __shared__ __align__(8) uint64_t empty_bar[4];
@@ -1113,18 +1121,18 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool dbg = (wa.debug & 64) && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool dbg = (wa.debug & 64) && bx == 0 && by == 0;
   const long long ts0 = dbg ? clock64() : 0;
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int nh = wa.nh, pad = wa.pad, stages = wa.stages;
   const uint32_t halo_bytes = (uint32_t)wa.halo_bytes, stage_bytes = (uint32_t)wa.stage_bytes;
   const uint32_t ones_base = dyn_base + (uint32_t)stages * stage_bytes;
   const int pitch = HALO_TW + 2 * pad;
-  const int group = blockIdx.y;
+  const int group = by;
   const bool do_bias = (wa.bias_off >= 0) && (group == 0);
   const int p_begin = group * wa.pairs_per_group;
   const int p_end = min(wa.npairs, p_begin + wa.pairs_per_group);
-  const int t_begin = blockIdx.x * wa.tiles_per_cta;
+  const int t_begin = bx * wa.tiles_per_cta;
   const int t_end = min(wa.n_tiles, t_begin + wa.tiles_per_cta);
   const int ntiles = t_end - t_begin;           // >= 1 by construction of the grid
   const int tiles_w = wa.OW / HALO_TW, tiles_h = (wa.OH + HALO_TH - 1) / HALO_TH;
@@ -1167,10 +1175,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
         const uint32_t dst = dyn_base + st * stage_bytes;
         mbar_expect_tx(fb, tx);
         for (int h = 0; h < nh; ++h)
-          tma_load_4d(dst + (uint32_t)h * halo_bytes, &maps.halo[wa.src[h]], fb, wa.c0[h], twi * HALO_TW - pad,
+          tma_load_4d(dst + (uint32_t)h * halo_bytes, &halo_maps[wa.src[h]], fb, wa.c0[h], twi * HALO_TW - pad,
                       thi * HALO_TH - pad, b);
         for (int a = 0; a < wa.g_atoms; ++a)
-          tma_load_4d(dst + (uint32_t)nh * halo_bytes + (uint32_t)a * UM_A_BYTES, &gmap, fb, a * 64, twi * HALO_TW,
+          tma_load_4d(dst + (uint32_t)nh * halo_bytes + (uint32_t)a * UM_A_BYTES, gmap_p, fb, a * 64, twi * HALO_TW,
                       thi * HALO_TH, b);
         if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
       }
@@ -1180,30 +1188,35 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     // operand-read limit of SS-mode MMAs at N = 64 (tools/umma_probe.py: 48 clk, same for K- and MN-major operands).
     // Neither issuing from two warps (WGH_ISSUERS = 2) nor interleaving accumulators changed that.
     const int issuer = (warp == 1) ? 0 : 1;
-    const uint32_t idesc = make_idesc(128, wa.N, 1, 1);
+    // (in the grouped kernel `wa` lives in shared memory: every loop-invariant word goes through a shuffle once, so that
+    // ptxas can keep descriptors in uniform registers instead of wrapping each UTCHMMA in an R2UR waterfall)
+    const uint32_t idesc = uniform32(make_idesc(128, wa.N, 1, 1));
     const uint32_t tm = uniform32(tmem_base);
     // A: two 64-channel atoms (the two taps), LBO per pair; K groups of 8 pixels = tile rows, SBO = pitch * 128 B
-    const uint32_t a_hi = (uint32_t)(make_sdesc(0, 0, (uint32_t)pitch * 128u) >> 32);
+    const uint32_t a_hi = uniform32((uint32_t)(make_sdesc(0, 0, (uint32_t)pitch * 128u) >> 32));
     const uint32_t b_hi = (uint32_t)(make_sdesc(0, 0, 1024) >> 32);
     const uint32_t base_lo = uniform32((dyn_base >> 4) & 0x3FFFu);
-    const uint32_t g_rel = (uint32_t)((nh * halo_bytes) >> 4) | ((uint32_t)(UM_A_BYTES >> 4) << 16);   // G atoms: LBO = one tile
+    const uint32_t g_rel = uniform32((uint32_t)((nh * halo_bytes) >> 4) | ((uint32_t)(UM_A_BYTES >> 4) << 16));   // G atoms: LBO = one tile
     const uint32_t ones_lo = uniform32((ones_base >> 4) & 0x3FFFu);
     const uint32_t full0 = uniform32(smem_u32(&full_bar[0])), empty0 = uniform32(smem_u32(&empty_bar[0]));
     const uint32_t accb = uniform32(smem_u32(&accum_bar));
-    const uint32_t sstep = stage_bytes >> 4;
-    const uint32_t kstep = (uint32_t)(2 * pitch * 128) >> 4;      // 16 pixels = two tile rows
-    const uint32_t N = (uint32_t)wa.N;
+    const uint32_t sstep = uniform32(stage_bytes >> 4);
+    const uint32_t kstep = uniform32((uint32_t)(2 * pitch * 128) >> 4);      // 16 pixels = two tile rows
+    const uint32_t N = uniform32((uint32_t)wa.N);
+    const uint32_t nstages = uniform32((uint32_t)stages);
+    const int n_t = (int)uniform32((uint32_t)ntiles);
+    const bool bias_u = uniform32(do_bias ? 1u : 0u) != 0u;
     // the group's pair words never change: keep them in (uniform) registers.  MMAs are issued k-outer / pair-inner so
     // that consecutive MMAs accumulate into different TMEM tiles
-    const int np = p_end - p_begin;
+    const int np = (int)uniform32((uint32_t)(p_end - p_begin));
     uint32_t plo[WGH_MAX_GROUP_PAIRS];
 #pragma unroll
-    for (int p = 0; p < WGH_MAX_GROUP_PAIRS; ++p) plo[p] = wa.pair_lo[min(p_begin + p, WGH_MAX_PAIRS - 1)];
+    for (int p = 0; p < WGH_MAX_GROUP_PAIRS; ++p) plo[p] = uniform32(wa.pair_lo[min(p_begin + p, WGH_MAX_PAIRS - 1)]);
     uint32_t st = 0, ph = 0;
     long long c_wait = 0;
     if (dbg && lane == 0 && issuer == 0) g_dbg[1] = clock64() - ts0;
 #pragma unroll 1
-    for (int ti = 0; ti < ntiles; ++ti) {
+    for (int ti = 0; ti < n_t; ++ti) {
       const long long q0 = dbg ? clock64() : 0;
       mbar_wait_warp(full0 + 8u * st, ph, 0);
       if (dbg) c_wait += clock64() - q0;
@@ -1213,7 +1226,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
       if (elect_one()) {
         const uint64_t bd0 = ((uint64_t)b_hi << 32) | (uint64_t)(s_lo + g_rel);
         const uint64_t od0 = ((uint64_t)b_hi << 32) | (uint64_t)ones_lo;        // LBO = 0: both M atoms alias; same K atoms each step
-#pragma unroll
+#pragma unroll 1      // (fully unrolled, the 64 descriptor pairs overflow the uniform register file: spills in the issue loop)
         for (int k = 0; k < 8; ++k) {
           const uint32_t acc = k > 0 ? 1u : acc0;
 #pragma unroll
@@ -1221,17 +1234,17 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
             if (p < np && (p % WGH_ISSUERS) == issuer)
               umma_bf16(tm + (uint32_t)p * N, ((uint64_t)a_hi << 32) | (uint64_t)(s_lo + plo[p] + (uint32_t)k * kstep),
                         bd0 + (uint64_t)(128 * k), idesc, acc);
-          if (do_bias && issuer == WGH_ISSUERS - 1) umma_bf16(tm + (uint32_t)np * N, od0, bd0 + (uint64_t)(128 * k), idesc, acc);
+          if (bias_u && issuer == WGH_ISSUERS - 1) umma_bf16(tm + (uint32_t)np * N, od0, bd0 + (uint64_t)(128 * k), idesc, acc);
         }
         umma_commit(empty0 + 8u * st);
-        if (ti == ntiles - 1) umma_commit(accb);
+        if (ti == n_t - 1) umma_commit(accb);
       }
       __syncwarp();
       if (dbg && lane == 0 && issuer == 0) {
         if (ti == 0) g_dbg[3] = clock64() - ts0;
         if (ti == ntiles - 1) { g_dbg[4] = clock64() - ts0; g_dbg[7] = c_wait; g_dbg[0] = ntiles; }
       }
-      if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
+      if (++st == nstages) { st = 0; ph ^= 1u; }
     }
   }
   if (warp >= 2) {
@@ -1241,7 +1254,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
     tc_fence_after();
     if (dbg && threadIdx.x == 96) g_dbg[5] = clock64() - ts0;
     // partial[split][group][block][n][row]: lanes = consecutive rows -> 128-byte coalesced stores, no atomics
-    float* out = partial + ((size_t)(blockIdx.x * wa.groups + group) * wa.blocks_per_cta) * (size_t)wa.N * 128;
+    float* out = partial + ((size_t)(bx * wa.groups + group) * wa.blocks_per_cta) * (size_t)wa.N * 128;
     const int nblocks = (p_end - p_begin) + (do_bias ? 1 : 0);
     for (int p = 0; p < nblocks; ++p) {
       for (int n0 = 0; n0 < wa.N; n0 += 32) {
@@ -1259,13 +1272,51 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)wa.tmem_cols);
 }
 
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_constant__ CUtensorMap gmap,
+                       const __grid_constant__ WgHaloArgs wa, float* __restrict__ partial) {
+  wgrad_halo_body(maps.halo, &gmap, wa, partial, (int)blockIdx.x, (int)blockIdx.y);
+}
+
+// ---- grouped launch: the weight gradients of SEVERAL layers in one grid.  At the training batch a single layer's
+// split-K grid (32-64 CTAs) cannot fill 148 SMs and pays its first-load latency, epilogue and launch alone; one grid over
+// the jobs of a backward segment lets the CTAs of different layers share the SMs.  Job descriptors (tensor maps, pair
+// tables, split-K buffer) live in global memory; a CTA finds its job through the small table in the kernel parameters.
+struct alignas(64) WgJob {
+  CUtensorMap halo[SS_MAX_SRC];
+  CUtensorMap gmap;
+  WgHaloArgs wa;
+  float* partial;
+  int geom;                        // index into the plan's geom table (weight addressing of the reduce)
+  int smem_bytes;
+};
+#define WG_GROUP_MAX 12
+struct WgGroupTable {
+  int njobs;
+  int job[WG_GROUP_MAX];
+  int cta_start[WG_GROUP_MAX + 1];
+  int red_start[WG_GROUP_MAX + 1];
+};
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_wgrad_halo_group_kernel(const WgJob* __restrict__ jobs, const __grid_constant__ WgGroupTable tbl) {
+  __shared__ WgHaloArgs swa;
+  int j = 0;
+  while (j + 1 < tbl.njobs && (int)blockIdx.x >= tbl.cta_start[j + 1]) ++j;
+  const WgJob* job = jobs + tbl.job[j];
+  {
+    const int* src = reinterpret_cast<const int*>(&job->wa);
+    int* dst = reinterpret_cast<int*>(&swa);
+    for (int i = threadIdx.x; i < (int)(sizeof(WgHaloArgs) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int local = (int)blockIdx.x - tbl.cta_start[j];
+  wgrad_halo_body(job->halo, &job->gmap, swa, job->partial, local % swa.splits, local / swa.splits);
+}
 // second stage for the halo kernel: same partial layout as conv_wgrad_reduce_kernel, slab mapping through the pair table
-__global__ void __launch_bounds__(1024) conv_wgrad_halo_reduce_kernel(const ConvGeom* __restrict__ gp,
-                                                                      const float* __restrict__ partial,
-                                                                      const __grid_constant__ WgHaloArgs wa,
-                                                                      float* __restrict__ grads) {
+SS_DEVINL void wgrad_halo_reduce_body(const ConvGeom* __restrict__ gp, const float* __restrict__ partial,
+                                      const WgHaloArgs& wa, float* __restrict__ grads, const int blk, const int group,
+                                      const int n0) {
   __shared__ float red[8][8][128];
-  const int blk = blockIdx.x, group = blockIdx.y, n0 = blockIdx.z * 8;
   const int row = threadIdx.x, q = threadIdx.y;
   const int p_begin = group * wa.pairs_per_group;
   const int p_end = min(wa.npairs, p_begin + wa.pairs_per_group);
@@ -1300,6 +1351,34 @@ __global__ void __launch_bounds__(1024) conv_wgrad_halo_reduce_kernel(const Conv
   if (j >= sl.wcn) return;
   if (n < gp->N && n < wa.gN) grads[gp->w_off + sl.woff + (int64_t)j * gp->w_sC + (int64_t)n * gp->w_sN] += tot;
 }
+__global__ void __launch_bounds__(1024) conv_wgrad_halo_reduce_kernel(const ConvGeom* __restrict__ gp,
+                                                                      const float* __restrict__ partial,
+                                                                      const __grid_constant__ WgHaloArgs wa,
+                                                                      float* __restrict__ grads) {
+  wgrad_halo_reduce_body(gp, partial, wa, grads, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z * 8);
+}
+// grouped reduce: blockIdx.x runs over (job, blk, group, n0 / 8)
+__global__ void __launch_bounds__(1024) conv_wgrad_halo_reduce_group_kernel(const ConvGeom* __restrict__ geoms,
+                                                                            const WgJob* __restrict__ jobs,
+                                                                            const __grid_constant__ WgGroupTable tbl,
+                                                                            float* __restrict__ grads) {
+  __shared__ WgHaloArgs swa;
+  int j = 0;
+  while (j + 1 < tbl.njobs && (int)blockIdx.x >= tbl.red_start[j + 1]) ++j;
+  const WgJob* job = jobs + tbl.job[j];
+  {
+    const int* src = reinterpret_cast<const int*>(&job->wa);
+    int* dst = reinterpret_cast<int*>(&swa);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int i = tid; i < (int)(sizeof(WgHaloArgs) / 4); i += blockDim.x * blockDim.y) dst[i] = src[i];
+  }
+  __syncthreads();
+  int local = (int)blockIdx.x - tbl.red_start[j];
+  const int blk = local % swa.blocks_per_cta; local /= swa.blocks_per_cta;
+  const int group = local % swa.groups;
+  const int n0 = (local / swa.groups) * 8;
+  wgrad_halo_reduce_body(geoms + job->geom, job->partial, swa, grads, blk, group, n0);
+}
 
 static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHaloArgs* out) {
   HaloArgs ha;
@@ -1329,7 +1408,13 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
     if (lbo > 0x3FFFu) return 0;
     wa.pair_lo[p] = (uint32_t)ha.aoff[a] | (lbo << 16);
   }
-  const int max_pairs = 512 / wa.N - 1;                 // one accumulator block is reserved for the bias row
+  // TMEM budget of a CTA: all 512 columns (7 pair blocks + the bias block at N = 64).  A smaller budget would let a
+  // forward / dgrad CTA of the main stream allocate tensor memory on the same SM, but it doubles the groups (and the halo
+  // loads) of every small layer: measured at the training batch, 256 columns cost 2.6 % of the step (SSHSLIE_WGH_TMEM).
+  int tmem_cap = env_int("SSHSLIE_WGH_TMEM", 512);
+  if (tmem_cap != 128 && tmem_cap != 256 && tmem_cap != 512) tmem_cap = 512;
+  if (tmem_cap / wa.N < 2) tmem_cap = 2 * wa.N;
+  const int max_pairs = tmem_cap / wa.N - 1;            // one accumulator block is reserved for the bias row
   wa.groups = (wa.npairs + max_pairs - 1) / max_pairs;
   wa.pairs_per_group = (wa.npairs + wa.groups - 1) / wa.groups;
   wa.groups = (wa.npairs + wa.pairs_per_group - 1) / wa.pairs_per_group;
@@ -1390,12 +1475,78 @@ int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const Um
     attr_set = true;
   }
   dim3 grid(wa.splits, wa.groups);
-  conv_wgrad_halo_kernel<<<grid, UM_THREADS, smem, st>>>(maps, *reinterpret_cast<const CUtensorMap*>(gmap), wa, partial);
-  int rc = ss_check_launch("conv_wgrad_halo");
-  if (rc) return rc;
+  int rc = SSHSLIE_OK;
+  if (g_wgrad_part != 2) {
+    conv_wgrad_halo_kernel<<<grid, UM_THREADS, smem, st>>>(maps, *reinterpret_cast<const CUtensorMap*>(gmap), wa, partial);
+    rc = ss_check_launch("conv_wgrad_halo");
+    if (rc || g_wgrad_part == 1) return rc;
+  }
   dim3 rgrid(wa.blocks_per_cta, wa.groups, wa.N / 8);
   conv_wgrad_halo_reduce_kernel<<<rgrid, dim3(128, 8), 0, st>>>(g_dev, partial, wa, grads);
   return ss_check_launch("conv_wgrad_halo_reduce");
+}
+
+size_t ss_wgjob_size() { return sizeof(WgJob); }
+int ss_umma_wgrad_halo_smem(const ConvGeom& g, int gN) {
+  WgHaloArgs wa;
+  if (!wgrad_halo_plan(g, gN, -1, &wa)) return 0;
+  return wa.stages * wa.stage_bytes + WGH_ONES_BYTES + 1024;
+}
+// fills one job descriptor (host copy, uploaded by the engine); returns 0 if the layer is not taken by the halo kernel
+int ss_wgjob_build(const ConvGeom& g, const UmmaMaps& maps, const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld,
+                   int gN, long long bias_off, float* partial, int geom_index, void* out) {
+  WgJob job;
+  memset(&job, 0, sizeof(job));
+  if (!wgrad_halo_plan(g, gN, bias_off, &job.wa)) {
+    ss_set_error("wgrad job: geometry not eligible for the halo kernel");
+    return SSHSLIE_ERR_ARG;
+  }
+  for (int i = 0; i < SS_MAX_SRC; ++i) job.halo[i] = maps.halo[i];
+  const int rc = ss_umma_build_gmap_halo(G, gB, gH, gW, ld, g, &job.gmap);
+  if (rc) return rc;
+  job.partial = partial;
+  job.geom = geom_index;
+  job.smem_bytes = job.wa.stages * job.wa.stage_bytes + WGH_ONES_BYTES + 1024;
+  memcpy(out, &job, sizeof(job));
+  return SSHSLIE_OK;
+}
+int ss_wgjob_smem(const void* job_host) { return reinterpret_cast<const WgJob*>(job_host)->smem_bytes; }
+int ss_launch_wgrad_group(const void* jobs_dev, const void* jobs_host, const int* ids, int n, const ConvGeom* geoms_dev,
+                          float* grads, cudaStream_t st) {
+  if (n < 1 || n > WG_GROUP_MAX) {
+    ss_set_error("wgrad group: %d jobs (1..%d supported)", n, WG_GROUP_MAX);
+    return SSHSLIE_ERR_ARG;
+  }
+  const WgJob* hj = reinterpret_cast<const WgJob*>(jobs_host);
+  WgGroupTable tbl;
+  memset(&tbl, 0, sizeof(tbl));
+  tbl.njobs = n;
+  int smem = 0;
+  for (int i = 0; i < n; ++i) {
+    const WgHaloArgs& wa = hj[ids[i]].wa;
+    tbl.job[i] = ids[i];
+    tbl.cta_start[i + 1] = tbl.cta_start[i] + wa.splits * wa.groups;
+    tbl.red_start[i + 1] = tbl.red_start[i] + wa.blocks_per_cta * wa.groups * (wa.N / 8);
+    smem = std::max(smem, hj[ids[i]].smem_bytes);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_wgrad_halo_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
+        cudaSuccess) {
+      ss_set_error("wgrad group: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      return SSHSLIE_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  int rc = SSHSLIE_OK;
+  if (g_wgrad_part != 2) {
+    conv_wgrad_halo_group_kernel<<<tbl.cta_start[n], UM_THREADS, smem, st>>>(reinterpret_cast<const WgJob*>(jobs_dev), tbl);
+    rc = ss_check_launch("conv_wgrad_halo_group");
+    if (rc || g_wgrad_part == 1) return rc;
+  }
+  conv_wgrad_halo_reduce_group_kernel<<<tbl.red_start[n], dim3(128, 8), 0, st>>>(
+      geoms_dev, reinterpret_cast<const WgJob*>(jobs_dev), tbl, grads);
+  return ss_check_launch("conv_wgrad_halo_reduce_group");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -120,6 +120,15 @@ struct sshslie_engine {
   std::map<std::pair<int, const void*>, GMapBox> gmaps;   // wgrad G-tensor TMA descriptors
   bool train, force_simt;
   bool skip_wgrad = false;
+  // grouped halo weight gradients: jobs recorded while the plan is built, descriptors built at bind, uploaded once
+  struct WgJobRec { int gi; Tens G; int gN; int bias_layer; float* partial; };
+  std::vector<WgJobRec> wg_jobs;
+  std::vector<int> wg_pending;            // job ids waiting for the next flush (plan construction only)
+  std::vector<unsigned char> wg_jobs_host;
+  void* wg_jobs_dev = nullptr;
+  bool group_wgrad = false;               // SSHSLIE_WGRAD_GROUP=1: several layers per launch (measured: no gain)
+  bool halo_on = true;
+  int group_size = 4;                     // pending jobs that trigger a grouped launch (SSHSLIE_WGRAD_GROUP_SIZE)
   bool wgrad_halo = true;               // SSHSLIE_WGRAD_HALO=0 keeps the per-tap weight-gradient kernel
   int64_t ws_bytes = 0;
   unsigned char* ws = nullptr;
@@ -503,6 +512,61 @@ static WAddr waddr_conv_dgrad(const sshslie_engine* e, int layer, int n_off = 0)
   (vec).push_back([=](cudaStream_t main_st) -> int { cudaStream_t st = e->fork(main_st); __VA_ARGS__ })
 #define PUSH_JOIN(vec) (vec).push_back([=](cudaStream_t st) -> int { return e->join(st); })
 
+#define WG_MAX_JOBS 64
+static int run_wgrad_group(sshslie_engine* e, const std::array<int, 12>& ids, int n, cudaStream_t st) {
+  if (e->skip_wgrad) return SSHSLIE_OK;
+  std::string lbl = "wgrad:";
+  double fl = 0;
+  for (int i = 0; i < n; ++i) {
+    const sshslie_engine::WgJobRec& j = e->wg_jobs[ids[i]];
+    const int l = e->geom_layer[j.gi];
+    lbl += (i ? "+" : "");
+    lbl += (l >= 0 && l < L_COUNT) ? kLayerNames[l] : "layer";
+    fl += geom_flops(e->geoms[j.gi]) * (double)j.gN / (double)e->geoms[j.gi].N;
+  }
+  lbl += n > 1 ? "[tcgen05-halo-grouped]" : "[tcgen05-halo]";
+  prof_note(lbl, fl, 0);
+  return ss_launch_wgrad_group(e->wg_jobs_dev, e->wg_jobs_host.data(), ids.data(), n, e->geoms_dev, e->grads, st);
+}
+// push one grouped launch for the pending jobs (side stream)
+static void flush_wgrads(sshslie_engine* e, std::vector<sshslie_engine::OpFn>& ops) {
+  while (!e->wg_pending.empty()) {
+    std::array<int, 12> ids;
+    int n = 0;
+    while (n < 12 && !e->wg_pending.empty()) { ids[n++] = e->wg_pending.front(); e->wg_pending.erase(e->wg_pending.begin()); }
+    PUSH_SIDE(ops, return run_wgrad_group(e, ids, n, st););
+  }
+}
+// a layer's weight gradient: recorded as a job of the next grouped launch when the halo kernel takes it, else launched
+// on its own (stride-2 layers, CUDA-core fallback)
+static void queue_wgrad(sshslie_engine* e, std::vector<sshslie_engine::OpFn>& ops, int gi, const Tens& G, int gN,
+                        int bias_layer) {
+  const ConvGeom& g = e->geoms[gi];
+  const bool eligible = e->group_wgrad && e->halo_on && e->wgrad_halo && !e->force_simt && g.halo_ok &&
+                        ss_umma_halo_supported(g) && ss_umma_wgrad_halo_supported(g, gN) &&
+                        (int)e->wg_jobs.size() < WG_MAX_JOBS;
+  if (!eligible) {
+    PUSH_SIDE(ops, return run_wgrad(e, gi, G, gN, 0, 0, 1, st, bias_layer););
+    return;
+  }
+  sshslie_engine::WgJobRec r;
+  r.gi = gi; r.G = G; r.gN = gN; r.bias_layer = bias_layer;
+  r.partial = e->falloc((int64_t)ss_umma_wgrad_halo_partial_floats(g, gN));
+  const int id = (int)e->wg_jobs.size();
+  e->wg_jobs.push_back(r);
+  // big-footprint jobs (the 9x9 layer: 65 KB per stage; 128-channel layers) go alone: a mixed grid would give every CTA
+  // their footprint
+  const bool big = ss_umma_wgrad_halo_smem(g, gN) > 110 * 1024;     // cannot share an SM with a second CTA anyway
+  if (big) {
+    flush_wgrads(e, ops);
+    e->wg_pending.push_back(id);
+    flush_wgrads(e, ops);
+    return;
+  }
+  e->wg_pending.push_back(id);
+  if ((int)e->wg_pending.size() >= e->group_size) flush_wgrads(e, ops);
+}
+
 // forward of one DecompositionNet pass (model.py:49-70).  Returns the geom ids for reuse by the backward pass.
 struct DecompGeoms {
   int conv0, shallow, conv1, conv2, conv3, deconv[4], conv5, conv7, recon;
@@ -594,7 +658,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH_SIDE(ops, return ss_launch_bias_grad(t.p, t.pix(), t.ld, n, *grads + poff[2 * layer + 1], st););
   };
   // recon
-  { const int gi = G.recon; PUSH_SIDE(ops, return run_wgrad(e, gi, dc8, dc8_n, 0, 0, 1, st, L_D_RECON);); }
+  queue_wgrad(e, ops, G.recon, dc8, dc8_n, L_D_RECON);
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_RECON);
     const int gi = e->add_geom(geom_conv(B, H, W, {{dc8, 0, dc8_n, 0}}, 3, 1, 1, -1, 64, wa));
@@ -602,7 +666,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv7 (no activation): inputs [c5 | c0]
-  { const int gi = G.conv7; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc7, 64, 0, 0, 1, st, L_D_CONV7);); }
+  queue_wgrad(e, ops, G.conv7, g.dc7, 64, L_D_CONV7);
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV7, 0);
     const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc7, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -616,7 +680,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv5 (ReLU already folded into dc5): inputs [dc | c1]
-  { const int gi = G.conv5; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc5, 64, 0, 0, 1, st, L_D_CONV5);); }
+  queue_wgrad(e, ops, G.conv5, g.dc5, 64, L_D_CONV5);
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV5, 0);
     const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc5, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -634,13 +698,13 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     WAddr wa = waddr_conv_dgrad(e, L_D_DECONV);
     const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{g.ddc, 0, 64, 0}}, 3, 2, 1, +1, 128, wa));
     const Tens c3 = d.c3;
-    PUSH_SIDE(ops, return run_wgrad(e, gi, c3, 128, 0, 0, 1, st););
+    queue_wgrad(e, ops, gi, c3, 128, -1);
     bias_grad(g.ddc, 64, L_D_DECONV);
     Epi ep = epi_bf16(g.dc3, 128); epi_set_mask(ep, d.c3);
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv3
-  { const int gi = G.conv3; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc3, 128, 0, 0, 1, st, L_D_CONV3);); }
+  queue_wgrad(e, ops, G.conv3, g.dc3, 128, L_D_CONV3);
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV3);
     const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{g.dc3, 0, 128, 0}}, 3, 1, 1, -1, 128, wa));
@@ -648,7 +712,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv2 (stride 2): wgrad on its forward geom; dgrad = transposed gather per input parity class, + dc1p, ReLU mask
-  { const int gi = G.conv2; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc2, 128, 0, 0, 1, st, L_D_CONV2);); }
+  queue_wgrad(e, ops, G.conv2, g.dc2, 128, L_D_CONV2);
   {
     Epi eps[4];
     int gi0 = -1;
@@ -665,7 +729,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather4(e, gi0, ea.data(), -1, st););
   }
   // conv1
-  { const int gi = G.conv1; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc1, 64, 0, 0, 1, st, L_D_CONV1);); }
+  queue_wgrad(e, ops, G.conv1, g.dc1, 64, L_D_CONV1);
   {
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV1);
     const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc1, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -673,8 +737,8 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // shallow 9x9 and conv0 read the pass input
-  { const int gi = G.shallow; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dsh, 64, 0, 0, 1, st, L_D_SHALLOW);); }
-  { const int gi = G.conv0; PUSH_SIDE(ops, return run_wgrad(e, gi, g.dc0, 32, 0, 0, 1, st, L_D_CONV0);); }
+  queue_wgrad(e, ops, G.shallow, g.dsh, 64, L_D_SHALLOW);
+  queue_wgrad(e, ops, G.conv0, g.dc0, 32, L_D_CONV0);
   if (need_din) {  // d(input) = dgrad_shallow(dsh) + dgrad_conv0(dc0)
     {
       WAddr wa = waddr_conv_dgrad(e, L_D_SHALLOW);
@@ -703,6 +767,8 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   e->ops_fwd.clear();
   e->ops_loss_bwd2_illum.clear();
   e->ops_bwd1.clear();
+  e->wg_jobs.clear();
+  e->wg_pending.clear();
   const int B = e->B, C = e->C, H = e->H, W = e->W;
   const int64_t n = (int64_t)B * H * W;
   const bool train = e->train;
@@ -711,6 +777,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   e->geoms_dev = (ConvGeom*)e->alloc(sizeof(ConvGeom) * 128);
   e->pack_start_dev = (int*)e->alloc(sizeof(int) * 130);
   e->mask_dev = e->falloc((int64_t)H * W);
+  e->wg_jobs_dev = e->alloc((int64_t)ss_wgjob_size() * WG_MAX_JOBS);
   e->sums_dev = e->falloc(16);
 
   // ---- tensors -----------------------------------------------------------------------------
@@ -868,6 +935,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     Tens dc8 = e->talloc(B, H, W, 128, true);
     PUSH(Lq, return ss_launch_head_bwd(dRe32, Re32, nullptr, 0, nullptr, nullptr, dc8.p, 128, B, C, H, W, st););
     plan_decomp_bwd(e, Lq, Sb, d2, G2, dc8, C, gr, true);
+    flush_wgrads(e, Lq);      // pass-2 weight gradients run beside the illumination net's backward chain
     // S = R*(Id+I)
     PUSH(Lq, return ss_launch_s_bwd(dS32, dSf32, gr.din.p, e->R32, e->I32, e->Id32, dR32, dI32, dId32, B, C, H, W, st););
 
@@ -891,7 +959,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
                    dId32, e->params + e->poff[2 * L_I_FINAL], dff.p, H, W, total);
                return ss_check_launch("final_dgrad"););
     }
-    PUSH_SIDE(Lq, return run_wgrad(e, g_fus, dff, 64, 0, 0, 1, st, L_I_FUSION););
+    queue_wgrad(e, Lq, g_fus, dff, 64, L_I_FUSION);
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_FUSION);
       const int gi = e->add_geom(geom_conv(B, H, W, {{dff, 0, 64, 0}}, 1, 1, 0, -1, 192, wa));
@@ -900,7 +968,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     PUSH(Lq, return ss_launch_concat_bwd(dfg.p, r3.p, dr3.p, p2.p, p1.p, B, H, W, st););
     // deconv3
-    PUSH_SIDE(Lq, return run_wgrad(e, g_d3, dr3, 64, 0, 0, 1, st, L_I_DECONV3););
+    queue_wgrad(e, Lq, g_d3, dr3, 64, L_I_DECONV3);
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_DECONV3);
       const int gi = e->add_geom(geom_conv(B, H, W, {{dr3, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -909,7 +977,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     PUSH(Lq, return ss_launch_pool2(du3.p, p2.p, r2.p, da1p.p, dr2.p, nullptr, B, H / 2, W / 2, st););
     // deconv2
-    PUSH_SIDE(Lq, return run_wgrad(e, g_d2, dr2, 64, 0, 0, 1, st, L_I_DECONV2););
+    queue_wgrad(e, Lq, g_d2, dr2, 64, L_I_DECONV2);
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_DECONV2);
       const int gi = e->add_geom(geom_conv(B, H / 2, W / 2, {{dr2, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -918,7 +986,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     PUSH(Lq, return ss_launch_pool2(du2.p, p1.p, r1.p, da2p.p, dr1.p, nullptr, B, H / 4, W / 4, st););
     // deconv1
-    PUSH_SIDE(Lq, return run_wgrad(e, g_d1, dr1, 64, 0, 0, 1, st, L_I_DECONV1););
+    queue_wgrad(e, Lq, g_d1, dr1, 64, L_I_DECONV1);
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_DECONV1);
       const int gi = e->add_geom(geom_conv(B, H / 4, W / 4, {{dr1, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
@@ -935,7 +1003,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
                       {L_I_CONV1, g_i1, da1, a0, da0, Tens(), false}};
     for (int i = 0; i < 3; ++i) {
       const S2 s = s2[i];
-      PUSH_SIDE(Lq, return run_wgrad(e, s.gfwd, s.dy, 64, 0, 0, 1, st, s.layer););
+      queue_wgrad(e, Lq, s.gfwd, s.dy, 64, s.layer);
       Epi eps[4];
       int gi0 = -1;
       for (int q = 0; q < 4; ++q) {
@@ -955,19 +1023,21 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
       PUSH(Lq, return run_gather4(e, gi0, ea.data(), -1, st););
     }
     // conv0 of the illumination net reads cat[R, I]
-    PUSH_SIDE(Lq, return run_wgrad(e, g_i0, da0, 64, 0, 0, 1, st, L_I_CONV0););
+    queue_wgrad(e, Lq, g_i0, da0, 64, L_I_CONV0);
     {
       WAddr wa = waddr_conv_dgrad(e, L_I_CONV0);
       const int gi = e->add_geom(geom_conv(B, H, W, {{da0, 0, 64, 0}}, 3, 1, 1, -1, C + 1, wa));
       Epi ep = epi_bf16(dRI, (C + 1 + 15) / 16 * 16);
       PUSH(Lq, return run_gather(e, gi, ep, -1, st););
     }
+    flush_wgrads(e, Lq);
     PUSH_JOIN(Lq);
 
     // ---- backward, pass 1 -------------------------------------------------------------------
     auto& B1 = e->ops_bwd1;
     PUSH(B1, return ss_launch_head_bwd(dR32, e->R32, dRI.p, 128, dI32, e->I32, dc8.p, 128, B, C, H, W, st););
     plan_decomp_bwd(e, B1, X, d1, G1, dc8, C + 1, gr, false);
+    flush_wgrads(e, B1);
     PUSH_JOIN(B1);
   }
 
@@ -1056,6 +1126,12 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
   {
     const char* we = getenv("SSHSLIE_WGRAD_HALO");
     e->wgrad_halo = !(we && we[0] == '0');
+    const char* gw = getenv("SSHSLIE_WGRAD_GROUP");
+    e->group_wgrad = (gw && gw[0] == '1');
+    const char* gs = getenv("SSHSLIE_WGRAD_GROUP_SIZE");
+    if (gs && atoi(gs) >= 1 && atoi(gs) <= 12) e->group_size = atoi(gs);
+    const char* he0 = getenv("SSHSLIE_HALO");
+    e->halo_on = !(he0 && he0[0] == '0');
     const char* sk = getenv("SSHSLIE_SKIP_WGRAD");
     e->skip_wgrad = (sk && sk[0] == '1');
     const char* ns = getenv("SSHSLIE_NO_SIDE");
@@ -1116,6 +1192,23 @@ extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t w
       const bool halo_on = !(he && he[0] == '0');  // halo-reuse kernels for every stride-1 layer; SSHSLIE_HALO=0 = per-tap
       e->geom_umma[i] = (halo_on && e->geoms[i].halo_ok && ss_umma_halo_supported(e->geoms[i])) ? 2 : 1;
     }
+  }
+  // grouped weight-gradient jobs: descriptors need the final tensor maps and pointers
+  e->wg_jobs_host.assign(e->wg_jobs.size() * ss_wgjob_size(), 0);
+  for (size_t j = 0; j < e->wg_jobs.size(); ++j) {
+    const sshslie_engine::WgJobRec& r = e->wg_jobs[j];
+    const Tens& G = r.G;
+    rc = ss_wgjob_build(e->geoms[r.gi], *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + r.gi * msz), G.p,
+                        (int64_t)G.H * G.W * G.ld, (int64_t)G.W * G.ld, (int64_t)G.ld, G.ld, r.gN,
+                        r.bias_layer >= 0 ? (long long)e->poff[2 * r.bias_layer + 1] : -1LL, r.partial, r.gi,
+                        e->wg_jobs_host.data() + j * ss_wgjob_size());
+    if (rc != SSHSLIE_OK) return rc;
+  }
+  if (!e->wg_jobs_host.empty() &&
+      cudaMemcpyAsync(e->wg_jobs_dev, e->wg_jobs_host.data(), e->wg_jobs_host.size(), cudaMemcpyHostToDevice, st) !=
+          cudaSuccess) {
+    ss_set_error("bind: job table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SSHSLIE_ERR_CUDA;
   }
   for (auto& zr : e->zero_ranges)
     if (cudaMemsetAsync(e->ws + zr.first, 0, (size_t)zr.second, st) != cudaSuccess) {
@@ -1377,33 +1470,52 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
 struct ProfRow { std::string name; float ms; double flops, bytes; };
 static thread_local std::vector<ProfRow> g_prof_rows;
 
-static int run_ops_profiled(std::vector<sshslie_engine::OpFn>& ops, cudaStream_t st, const char* phase) {
-  for (auto& f : ops) {
-    cudaEvent_t a, b;
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
+static int time_op(sshslie_engine::OpFn& f, cudaStream_t st, int reps, float* ms_out) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+  int rc = SSHSLIE_OK;
+  for (int r = 0; r < reps && rc == SSHSLIE_OK; ++r) {
     g_prof_names.clear();
     g_prof_flops = g_prof_bytes = 0;
-    // the op's launches are enqueued `reps` times back to back between the two events and the time divided: one eager
-    // launch + event pair costs ~6-8 us of host/driver latency that the CUDA-graph replay of the real step does not pay
-    // (the repeated ops only disturb values of this profiling pass: gradients accumulate, in-place adds repeat)
-    static const int reps = []() { const char* r = getenv("SSHSLIE_PROFILE_REPS"); return (r && atoi(r) > 0) ? atoi(r) : 4; }();
-    cudaEventRecord(a, st);
-    int rc = SSHSLIE_OK;
-    for (int r = 0; r < reps && rc == SSHSLIE_OK; ++r) {
-      if (r > 0) { g_prof_names.clear(); g_prof_flops = g_prof_bytes = 0; }
-      rc = f(st);
-    }
-    cudaEventRecord(b, st);
-    if (rc != SSHSLIE_OK) return rc;
+    rc = f(st);
+  }
+  cudaEventRecord(b, st);
+  if (rc == SSHSLIE_OK) {
     cudaEventSynchronize(b);
+    cudaEventElapsedTime(ms_out, a, b);
+    *ms_out /= (float)reps;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return rc;
+}
+// Every recorded op is enqueued `reps` times back to back between two events and the time divided: one eager launch +
+// event pair costs ~6-8 us of host/driver latency that the CUDA-graph replay of the real step does not pay (the repeats
+// only disturb values of this profiling pass: gradients accumulate, in-place adds repeat).  A tcgen05 weight gradient
+// is two kernels (GEMM + split-K reduce): they are timed separately and reported as two rows.
+static int run_ops_profiled(std::vector<sshslie_engine::OpFn>& ops, cudaStream_t st, const char* phase) {
+  static const int reps = []() { const char* r = getenv("SSHSLIE_PROFILE_REPS"); return (r && atoi(r) > 0) ? atoi(r) : 4; }();
+  for (auto& f : ops) {
     float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    ms /= (float)reps;
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    g_prof_rows.push_back({std::string(phase) + "/" + (g_prof_names.empty() ? "memop" : g_prof_names), ms, g_prof_flops,
-                           g_prof_bytes});
+    int rc = time_op(f, st, reps, &ms);
+    if (rc != SSHSLIE_OK) return rc;
+    const std::string name = g_prof_names.empty() ? "memop" : g_prof_names;
+    if (name.compare(0, 6, "wgrad:") == 0 && name.find("[tcgen05") != std::string::npos) {
+      const double fl = g_prof_flops;
+      float ms_main = 0, ms_red = 0;
+      ss_set_wgrad_part(1);
+      rc = time_op(f, st, reps, &ms_main);
+      ss_set_wgrad_part(2);
+      if (rc == SSHSLIE_OK) rc = time_op(f, st, reps, &ms_red);
+      ss_set_wgrad_part(0);
+      if (rc != SSHSLIE_OK) return rc;
+      g_prof_rows.push_back({std::string(phase) + "/" + name, ms_main, fl, 0});
+      g_prof_rows.push_back({std::string(phase) + "/" + "splitk_reduce:" + name.substr(6), ms_red, 0, 0});
+      continue;
+    }
+    g_prof_rows.push_back({std::string(phase) + "/" + name, ms, g_prof_flops, g_prof_bytes});
   }
   return SSHSLIE_OK;
 }

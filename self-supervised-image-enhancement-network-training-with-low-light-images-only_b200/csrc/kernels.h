@@ -30,6 +30,15 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g_host, con
                               int gN, long long bias_off, float* partial, float* grads, cudaStream_t st);
 size_t ss_umma_wgrad_partial_floats(const ConvGeom& g, int gN);
 size_t ss_umma_maps_size();
+// grouped halo weight gradients: job descriptors built on the host, uploaded once, launched several per grid
+size_t ss_wgjob_size();
+int ss_umma_wgrad_halo_smem(const ConvGeom& g, int gN);   // dynamic shared memory of the layer's halo wgrad CTA
+int ss_wgjob_build(const ConvGeom& g, const UmmaMaps& maps, const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld,
+                   int gN, long long bias_off, float* partial, int geom_index, void* out_host);
+int ss_wgjob_smem(const void* job_host);
+int ss_launch_wgrad_group(const void* jobs_dev, const void* jobs_host, const int* ids, int n, const ConvGeom* geoms_dev,
+                          float* grads, cudaStream_t st);
+void ss_set_wgrad_part(int part);   // profiling: 0 both kernels, 1 GEMM only, 2 split-K reduce only
 // halo-reuse weight gradient (stride-1 layers): G tiles are 16x8 like the halo tiles
 int ss_umma_wgrad_halo_supported(const ConvGeom& g, int gN);
 size_t ss_umma_wgrad_halo_partial_floats(const ConvGeom& g, int gN);
