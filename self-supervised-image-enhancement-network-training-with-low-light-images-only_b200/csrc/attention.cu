@@ -541,27 +541,6 @@ attn_core_ffn_kernel(const float* __restrict__ X, const float* __restrict__ Q, c
   stage_wt<256>(W1t, AF_WP, 0, P + o1);          // consumed after the head loop
   stage_wt<256>(W2t, AF_WP, 0, P + o2);
   for (int head = 0; head < AT_HEADS; ++head) {
-    __syncthreads();
-    {  // K_h, V_h rows as float4: 4 + 4 loads per thread, all in flight before the first store
-      float4 kv[4], vv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int idx = tid + k * 256;
-        const int j = idx >> 2, d4 = (idx & 3) * 4;
-        kv[k] = vv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < L) {
-          kv[k] = *reinterpret_cast<const float4*>(K + (rowbase + j) * AT_D + head * AT_HD + d4);
-          vv[k] = *reinterpret_cast<const float4*>(V + (rowbase + j) * AT_D + head * AT_HD + d4);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int idx = tid + k * 256;
-        const int j = idx >> 2, d4 = (idx & 3) * 4;
-        *reinterpret_cast<float4*>(Ks + j * AF_KP + d4) = kv[k];
-        *reinterpret_cast<float4*>(Vs + j * AF_KP + d4) = vv[k];
-      }
-    }
     float q[AT_HD];
 #pragma unroll
     for (int d4 = 0; d4 < AT_HD; d4 += 4) {
@@ -569,38 +548,69 @@ attn_core_ffn_kernel(const float* __restrict__ X, const float* __restrict__ Q, c
       if (tq < L) t = *reinterpret_cast<const float4*>(Q + (rowbase + tq) * AT_D + head * AT_HD + d4);
       q[d4] = 0.25f * t.x; q[d4 + 1] = 0.25f * t.y; q[d4 + 2] = 0.25f * t.z; q[d4 + 3] = 0.25f * t.w;   // model.py:110-111
     }
-    __syncthreads();
-    // pass 1: the thread's 16 scores (keys part, part + 16, ...) and their maximum
-    float sc[AF_LMAX / 16];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int jj = 0; jj < AF_LMAX / 16; ++jj) {
-      const int j = jj * 16 + part;
-      float a = 0.f;
-#pragma unroll
-      for (int d4 = 0; d4 < AT_HD; d4 += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(Ks + j * AF_KP + d4);
-        a = fmaf(q[d4], t.x, a); a = fmaf(q[d4 + 1], t.y, a); a = fmaf(q[d4 + 2], t.z, a); a = fmaf(q[d4 + 3], t.w, a);
-      }
-      sc[jj] = (j < L) ? a : -INFINITY;
-      mx = fmaxf(mx, sc[jj]);
-    }
-#pragma unroll
-    for (int sh = 1; sh <= 8; sh <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));   // max over the query's keys
-    // pass 2: p = exp(s - max), o += p v
-    float o[AT_HD], l = 0.f;
+    // running softmax state of (query, head): the maximum is shared by the query's 16 threads (reduced per key tile), so
+    // their partial sums l, o merge by plain addition at the end
+    float m_run = -INFINITY, l = 0.f, o[AT_HD];
 #pragma unroll
     for (int d = 0; d < AT_HD; ++d) o[d] = 0.f;
+    for (int k0 = 0; k0 < L; k0 += AF_LMAX) {      // key tiles of 256 rows (one tile at the training size)
+      __syncthreads();
+      {  // K_h, V_h rows of the tile as float4: 4 + 4 loads per thread, all in flight before the first store
+        float4 kv[4], vv[4];
 #pragma unroll
-    for (int jj = 0; jj < AF_LMAX / 16; ++jj) {
-      const int j = jj * 16 + part;
-      const float pj = __expf(sc[jj] - mx);       // exp(-inf) = 0 for keys beyond L
-      l += pj;
+        for (int k = 0; k < 4; ++k) {
+          const int idx = tid + k * 256;
+          const int j = k0 + (idx >> 2), d4 = (idx & 3) * 4;
+          kv[k] = vv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < L) {
+            kv[k] = *reinterpret_cast<const float4*>(K + (rowbase + j) * AT_D + head * AT_HD + d4);
+            vv[k] = *reinterpret_cast<const float4*>(V + (rowbase + j) * AT_D + head * AT_HD + d4);
+          }
+        }
 #pragma unroll
-      for (int d4 = 0; d4 < AT_HD; d4 += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(Vs + j * AF_KP + d4);
-        o[d4] = fmaf(pj, t.x, o[d4]); o[d4 + 1] = fmaf(pj, t.y, o[d4 + 1]);
-        o[d4 + 2] = fmaf(pj, t.z, o[d4 + 2]); o[d4 + 3] = fmaf(pj, t.w, o[d4 + 3]);
+        for (int k = 0; k < 4; ++k) {
+          const int idx = tid + k * 256;
+          const int j = idx >> 2, d4 = (idx & 3) * 4;
+          *reinterpret_cast<float4*>(Ks + j * AF_KP + d4) = kv[k];
+          *reinterpret_cast<float4*>(Vs + j * AF_KP + d4) = vv[k];
+        }
+      }
+      __syncthreads();
+      // pass 1: the thread's 16 scores of the tile (keys part, part + 16, ...) and the tile maximum
+      float sc[AF_LMAX / 16];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < AF_LMAX / 16; ++jj) {
+        const int j = jj * 16 + part;
+        float a = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < AT_HD; d4 += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(Ks + j * AF_KP + d4);
+          a = fmaf(q[d4], t.x, a); a = fmaf(q[d4 + 1], t.y, a); a = fmaf(q[d4 + 2], t.z, a); a = fmaf(q[d4 + 3], t.w, a);
+        }
+        sc[jj] = (k0 + j < L) ? a : -INFINITY;
+        mx = fmaxf(mx, sc[jj]);
+      }
+#pragma unroll
+      for (int sh = 1; sh <= 8; sh <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));   // over the query's keys
+      const float m_new = fmaxf(m_run, mx);           // finite: every tile holds at least one key
+      const float corr = __expf(m_run - m_new);       // exp(-inf) = 0 on the first tile
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < AT_HD; ++d) o[d] *= corr;
+      m_run = m_new;
+      // pass 2: p = exp(s - max), o += p v
+#pragma unroll
+      for (int jj = 0; jj < AF_LMAX / 16; ++jj) {
+        const int j = jj * 16 + part;
+        const float pj = __expf(sc[jj] - m_new);      // exp(-inf) = 0 for keys beyond L
+        l += pj;
+#pragma unroll
+        for (int d4 = 0; d4 < AT_HD; d4 += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(Vs + j * AF_KP + d4);
+          o[d4] = fmaf(pj, t.x, o[d4]); o[d4 + 1] = fmaf(pj, t.y, o[d4 + 1]);
+          o[d4 + 2] = fmaf(pj, t.z, o[d4 + 2]); o[d4 + 3] = fmaf(pj, t.w, o[d4 + 3]);
+        }
       }
     }
 #pragma unroll
@@ -617,7 +627,7 @@ attn_core_ffn_kernel(const float* __restrict__ X, const float* __restrict__ Q, c
         Ot[(head * AT_HD + d) * AF_TP + qi] = v;
         if (tq < L) O[(rowbase + tq) * AT_D + head * AT_HD + d] = v;
       }
-      if (tq < L) LSE[((int64_t)b * AT_HEADS + head) * L + tq] = mx + __logf(l);
+      if (tq < L) LSE[((int64_t)b * AT_HEADS + head) * L + tq] = m_run + __logf(l);
     }
   }
   __syncthreads();
@@ -885,7 +895,7 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* P, const int6
   if (attn_attrs()) return SSHSLIE_ERR_CUDA;
   const int T = B * L;
   static const bool fused_ok = !(getenv("SSHSLIE_ATTN_FUSED") && getenv("SSHSLIE_ATTN_FUSED")[0] == '0');
-  if (L <= AF_LMAX && fused_ok) {      // training token grid
+  if (fused_ok) {      // register-tiled kernels; keys stream through 256-row tiles (one tile at the training size)
     attn_qkv4_kernel<<<(T + AF_QB - 1) / AF_QB, 192, kSmemQkv4, st>>>(a3, P, poff[0], poff[1], poff[2], poff[3], poff[4],
                                                                      poff[5], bf.x, bf.q, bf.k, bf.v, T);
     dim3 g((L + AF_QB - 1) / AF_QB, B);

@@ -501,10 +501,11 @@ class LowLightEnhance(nn.Module):
             total = self._losses_dev[0].clone()
         return total, LazyLosses(self._losses_dev[:7].clone())
 
-    def profile_step(self, input_low):
-        """One eager training step with device timing per launch group: list of (name, ms, flops, bytes)."""
+    def profile_step(self, input_low, train=True):
+        """One eager training step (train=False: forward only) with device timing per launch group: list of
+        (name, ms, flops, bytes)."""
         self._ensure_flat()
-        eng = self._engine(input_low, train=True)
+        eng = self._engine(input_low, train=train)
         self._stage_input(eng, input_low)
         lib = L.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)

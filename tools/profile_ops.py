@@ -11,6 +11,7 @@ import sshslie_b200 as S  # noqa: E402
 from oracle import sshslie_oracle as O  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+TRAIN = os.environ.get("FORWARD_ONLY", "0") != "1"
 size = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", f"profile_ops_b{B}_{size}.txt")
 torch.manual_seed(41)
@@ -20,7 +21,7 @@ acc = {}
 order = []
 reps = 5
 for r in range(reps + 1):
-    rows = m.profile_step(x)
+    rows = m.profile_step(x, train=TRAIN)
     if r == 0:
         continue
     for i, (name, ms, fl, by) in enumerate(rows):
