@@ -296,33 +296,62 @@ def run_ours(args):
         return
     pk = peaks()
     total_prof = sum(v[0] / v[1] for v in prof.values())
-    # dominant kernel = the single launch group with algorithmic work attached (GEMM FLOPs or HBM bytes) that takes
-    # the longest; multi-kernel groups without a roofline model (the attention block) are listed in top_kernels_ms only
-    cand = {k: v for k, v in prof.items() if v[2] > 0 or v[3] > 0}
-    top_name, top = max(cand.items(), key=lambda kv: kv[1][0] / kv[1][1])
-    top_ms = top[0] / top[1]
-    if top[2] > 0:
-        ach = top[2] / (top_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"]}
-    else:
-        gb = top[3] / (top_ms * 1e-3) / 1e9 if top[3] else 0.0
-        roof = {"bound": "hbm", "achieved": gb, "peak": pk["hbm"], "unit": "GB/s", "frac": gb / pk["hbm"]}
+
+    def kernel_of(name):
+        """profile row -> the CUDA kernel (function) that executes it"""
+        op = name.split("/", 1)[1]
+        if op.startswith("splitk_reduce"):
+            return "conv_wgrad_*_reduce_kernel"
+        if op.startswith("wgrad:"):
+            return "conv_wgrad_halo_kernel" if "halo" in op else ("conv_wgrad_umma_kernel" if "tcgen05" in op else "conv_wgrad_simt_kernel")
+        if op.startswith(("fwd:", "dgrad:")):
+            if "halo" in op:
+                return "conv_gather_halo_kernel"
+            return "conv_gather_umma_kernel" if "tcgen05" in op else "conv_gather_simt_kernel"
+        return {"loss:fourier_fft+grad": "fourier_loss_kernel", "loss:pixel_terms+grads": "pixel_losses_kernel"}.get(op, op)
+
+    # dominant kernel = the kernel function with the largest share of the step's device time (all its launches);
+    # achieved = its algorithmic FLOPs (bytes) over all launches / their total duration
+    byk = {}
+    for name, v in prof.items():
+        a = byk.setdefault(kernel_of(name), [0.0, 0.0, 0.0, 0, None])
+        ms = v[0] / v[1]
+        a[0] += ms
+        a[1] += v[2]
+        a[2] += v[3]
+        a[3] += 1
+        if (v[2] > 0 or v[3] > 0) and (a[4] is None or ms > a[4][1]):
+            a[4] = (name, ms, v[2], v[3])
+
+    def roof_of(ms, flops, nbytes):
+        if flops > 0:
+            ach = flops / (ms * 1e-3) / 1e12
+            return {"bound": "tensor", "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"]}
+        gb = nbytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": gb, "peak": pk["hbm"], "unit": "GB/s", "frac": gb / pk["hbm"]}
+
+    cand = {k: v for k, v in byk.items() if v[1] > 0 or v[2] > 0}
+    top_name, top = max(cand.items(), key=lambda kv: kv[1][0])
+    roof = roof_of(top[0], top[1], top[2])
+    big = top[4]
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        traffic = tj.get(top_name.split("/", 1)[1].split("[")[0])
+        traffic = tj.get(big[0].split("/", 1)[1].split("[")[0])
     except Exception:
         pass
-    roof.update({"kernel": top_name, "ms_per_launch": top_ms, "share_of_step": top_ms / total_prof,
-                 "traffic": traffic, "algorithmic_flops_per_launch": top[2], "algorithmic_bytes_per_launch": top[3],
-                 "peak_source": pk["source"],
-                 "timing": "cudaEvent pair around 4 back-to-back enqueues of the launch group (time / 4), eager steps after "
-                           "the timed region, on the stream the kernels run on (sshslie_profile_step)"})
-    # the same figure for the other instances of the 9x9 layer (forward / data gradient run the gather kernel)
-    roof["other_launches"] = [
-        {"kernel": k, "ms_per_launch": v[0] / v[1], "achieved": v[2] / (v[0] / v[1] * 1e-3) / 1e12,
-         "frac": v[2] / (v[0] / v[1] * 1e-3) / 1e12 / pk["burst"]}
-        for k, v in sorted(prof.items()) if "shallow9x9" in k and k != top_name]
+    roof.update({"kernel": top_name, "launches_per_step": top[3], "ms_per_step": top[0], "ms_per_launch": top[0] / top[3],
+                 "share_of_step": top[0] / total_prof, "algorithmic_flops_per_step": top[1],
+                 "algorithmic_bytes_per_step": top[2],
+                 "largest_launch": dict(roof_of(big[1], big[2], big[3]), kernel=big[0], ms_per_launch=big[1],
+                                        algorithmic_flops_per_launch=big[2], traffic=traffic),
+                 "traffic": traffic, "peak_source": pk["source"],
+                 "timing": "cudaEvent pair around 4 back-to-back enqueues of each launch group (time / 4), eager steps after "
+                           "the timed region, on the stream the kernels run on (sshslie_profile_step); traffic = DRAM bytes of "
+                           "the largest launch from the ncu --set full capture in profiles/"})
+    roof["by_kernel"] = [dict(roof_of(v[0], v[1], v[2]) if (v[1] > 0 or v[2] > 0) else {}, kernel=k, launches_per_step=v[3],
+                              ms_per_step=v[0], share_of_step=v[0] / total_prof)
+                         for k, v in sorted(byk.items(), key=lambda kv: -kv[1][0])[:8]]
     patches = world * BATCH_PER_GPU * K
     value = patches / (ms_dev * 1e-3)
     e2e = patches / (ms_e2e * 1e-3)

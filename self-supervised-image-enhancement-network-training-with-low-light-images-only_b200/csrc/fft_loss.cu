@@ -141,7 +141,30 @@ fourier_loss_kernel(const float* __restrict__ x, const float* __restrict__ s, co
     sincospif(-2.f * (float)i / (float)H, &sn, &cs);
     twH[i] = make_float2(cs, sn);
   }
-  for (int i = threadIdx.x; i < H * W; i += FFT_THREADS) z[i] = make_float2(xp[i], sp[i]);
+  // both planes -> z = x + i s.  Batches of 8 + 8 loads in flight per thread (a load/store loop pays the HBM latency per
+  // iteration), float4 per lane
+  {
+    const float4* x4 = reinterpret_cast<const float4*>(xp);
+    const float4* s4 = reinterpret_cast<const float4*>(sp);
+    const int n4 = (H * W) >> 2;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * FFT_THREADS) {
+      float4 xv[4], sv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * FFT_THREADS;
+        if (i < n4) { xv[k] = __ldg(x4 + i); sv[k] = __ldg(s4 + i); }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * FFT_THREADS;
+        if (i < n4) {
+          float4* zo = reinterpret_cast<float4*>(z + 4 * i);
+          zo[0] = make_float4(xv[k].x, sv[k].x, xv[k].y, sv[k].y);
+          zo[1] = make_float4(xv[k].z, sv[k].z, xv[k].w, sv[k].w);
+        }
+      }
+    }
+  }
   __syncthreads();
 
   // forward: DIF along W, then along H
