@@ -365,6 +365,7 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
   __shared__ __align__(8) uint64_t halo_bar;
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float bias_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ts0 = (ha.debug & 64) ? clock64() : 0;
@@ -486,7 +487,23 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    // While the accumulator is being computed: stage the bias in shared memory (parameters, never written by a kernel
+    // of this step) and pull this thread's rows of the residual / mask tensors towards the SM - otherwise the epilogue
+    // pays two or three dependent L2 / HBM round trips after the last MMA has retired
+    for (int i = (int)threadIdx.x - 64; i < Npad; i += 128) bias_s[i] = (epi.bias && i < ha.N) ? __ldg(epi.bias + i) : 0.f;
     pdl_wait();     // the epilogue reads residual / mask tensors and overwrites buffers earlier kernels may still read
+    {
+      int ti = t_first;
+      const int twi = ti % tiles_w; ti /= tiles_w;
+      const int thi = ti % tiles_h;
+      const int b = ti / tiles_h;
+      const int oh = thi * HALO_TH + (row >> 3), ow = twi * HALO_TW + (row & 7);
+      if (oh < ha.OH) {
+        if (epi.add) asm volatile("prefetch.global.L1 [%0];" ::"l"(epi.add + b * epi.aB + oh * epi.aH + ow * epi.aW));
+        if (epi.mask) asm volatile("prefetch.global.L1 [%0];" ::"l"(epi.mask + b * epi.mB + oh * epi.mH + ow * epi.mW));
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");      // bias_s visible to the four epilogue warps
     mbar_wait_warp(smem_u32(&accum_bar), 0, 100u);
     tc_fence_after();
     if ((ha.debug & 64) && blockIdx.x == 0 && threadIdx.x == 64) {
@@ -506,14 +523,14 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
         float v[32];
         tmem_ld32(trow + (uint32_t)n0, v);
         if (ok) {
-          epi_apply16(epi, b, oh, ow, n0, ha.N, v);
-          epi_apply16(epi, b, oh, ow, n0 + 16, ha.N, v + 16);
+          epi_apply16(epi, b, oh, ow, n0, ha.N, v, bias_s);
+          epi_apply16(epi, b, oh, ow, n0 + 16, ha.N, v + 16, bias_s);
         }
       }
       if (n0 < Npad) {
         float v[16];
         tmem_ld16(trow + (uint32_t)n0, v);
-        if (ok) epi_apply16(epi, b, oh, ow, n0, ha.N, v);
+        if (ok) epi_apply16(epi, b, oh, ow, n0, ha.N, v, bias_s);
       }
     }
   }

@@ -3,8 +3,13 @@
 #pragma once
 #include "common.cuh"
 
-SS_DEVINL void epi_apply16(const Epi& e, int b, int oh, int ow, int n0, int N, float* v /*[16]*/) {
-  if (e.bias) {
+// bias_s: optional shared-memory copy of the bias (zero beyond N), staged while the accumulator is still being computed
+SS_DEVINL void epi_apply16(const Epi& e, int b, int oh, int ow, int n0, int N, float* v /*[16]*/,
+                           const float* bias_s = nullptr) {
+  if (bias_s) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += bias_s[n0 + i];
+  } else if (e.bias) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += (n0 + i < N) ? __ldg(e.bias + n0 + i) : 0.f;
   }
