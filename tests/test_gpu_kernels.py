@@ -302,3 +302,18 @@ def test_psnr_sam_vs_oracle():
     ps, sa = S.metrics.psnr_sam(p, t, 4095.0)
     np.testing.assert_allclose(ps, float(O.psnr(p, t, 4095.0)), rtol=1e-5)
     np.testing.assert_allclose(sa, float(O.sam(p, t)), rtol=1e-4)
+
+
+@pytest.mark.parametrize("case", [c for c in HALO_CASES if c[0] not in ("c3_64_1",)][:7], ids=lambda c: c[0])
+def test_conv_dgrad_halo(case):
+    """Data gradient of stride-1 layers through the halo-reuse kernel (mirrored taps, sign = -1 geometry)."""
+    from gpu_util import conv2d, bf16_round
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    x, w, b = _mk(case)
+    x.requires_grad_(True)
+    yref = _ref_conv(x, w, None, k, stride, tr, relu=False)
+    dy = bf16_round(torch.randn(yref.shape, generator=torch.Generator().manual_seed(3))).cuda()
+    (dx_ref,) = torch.autograd.grad(yref, x, dy)
+    dx = torch.empty_like(dx_ref)
+    conv2d(1, 2, tr, dy, w, None, dx, B, Cin, Cout, H, W, k, stride, relu=False)
+    torch.testing.assert_close(dx, dx_ref, rtol=2 ** -7, atol=2e-3 * float(dx_ref.abs().max()))
