@@ -318,6 +318,15 @@ static void epi_set_add(Epi& e, const Tens& t, int c_off = 0, int qh = 0, int qw
   e.add = t.p + c_off + (int64_t)qh * t.W * t.ld + (int64_t)qw * t.ld;
   e.aB = (int64_t)t.H * t.W * t.ld; e.aH = (int64_t)scale * t.W * t.ld; e.aW = (int64_t)scale * t.ld;
 }
+static void epi_set_split(Epi& e, int n_split, const Tens& out2, int n_store2, const Tens* mask2) {
+  e.n_split = n_split; e.n_store2 = n_store2;
+  e.out2 = out2.p;
+  e.o2B = (int64_t)out2.H * out2.W * out2.ld; e.o2H = (int64_t)out2.W * out2.ld; e.o2W = out2.ld;
+  if (mask2) {
+    e.mask2 = mask2->p;
+    e.m2B = (int64_t)mask2->H * mask2->W * mask2->ld; e.m2H = (int64_t)mask2->W * mask2->ld; e.m2W = mask2->ld;
+  }
+}
 static void epi_set_mask(Epi& e, const Tens& t, int qh = 0, int qw = 0, int scale = 1) {
   e.mask = t.p + (int64_t)qh * t.W * t.ld + (int64_t)qw * t.ld;
   e.mB = (int64_t)t.H * t.W * t.ld; e.mH = (int64_t)scale * t.W * t.ld; e.mW = (int64_t)scale * t.ld;
@@ -667,30 +676,20 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
   }
   // conv7 (no activation): inputs [c5 | c0]
   queue_wgrad(e, ops, G.conv7, g.dc7, 64, L_D_CONV7);
-  {
+  {  // both halves of the concat [c5 (64) | c0 (32)] from ONE GEMM (N = 96): columns 64.. go to dc0 with c0's ReLU mask
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV7, 0);
-    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc7, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc7, 0, 64, 0}}, 3, 1, 1, -1, 96, wa));
     Epi ep = epi_bf16(g.dc5, 64); epi_set_mask(ep, d.c5);
-    PUSH(ops, return run_gather(e, gi, ep, -1, st););
-  }
-  {
-    WAddr wa = waddr_conv_dgrad(e, L_D_CONV7, 64);
-    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc7, 0, 64, 0}}, 3, 1, 1, -1, 32, wa));
-    Epi ep = epi_bf16(g.dc0, 32); epi_set_mask(ep, d.c0);
+    epi_set_split(ep, 64, g.dc0, 32, &d.c0);
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // conv5 (ReLU already folded into dc5): inputs [dc | c1]
   queue_wgrad(e, ops, G.conv5, g.dc5, 64, L_D_CONV5);
-  {
+  {  // concat [deconv (64) | conv1 (64)]: ONE GEMM with N = 128, columns 64.. are the skip gradient dc1p (no mask)
     WAddr wa = waddr_conv_dgrad(e, L_D_CONV5, 0);
-    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc5, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
+    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc5, 0, 64, 0}}, 3, 1, 1, -1, 128, wa));
     Epi ep = epi_bf16(g.ddc, 64); epi_set_mask(ep, d.dc);
-    PUSH(ops, return run_gather(e, gi, ep, -1, st););
-  }
-  {
-    WAddr wa = waddr_conv_dgrad(e, L_D_CONV5, 64);
-    const int gi = e->add_geom(geom_conv(B, H, W, {{g.dc5, 0, 64, 0}}, 3, 1, 1, -1, 64, wa));
-    Epi ep = epi_bf16(g.dc1p, 64);
+    epi_set_split(ep, 64, g.dc1p, 64, nullptr);
     PUSH(ops, return run_gather(e, gi, ep, -1, st););
   }
   // deconv: dgrad = stride-2 conv of ddc (n = 128 input channels); the same geom drives its wgrad with G = c3

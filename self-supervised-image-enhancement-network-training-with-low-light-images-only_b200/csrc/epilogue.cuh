@@ -13,6 +13,25 @@ SS_DEVINL void epi_apply16(const Epi& e, int b, int oh, int ow, int n0, int N, f
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += (n0 + i < N) ? __ldg(e.bias + n0 + i) : 0.f;
   }
+  if (e.mode == EPI_BF16 && e.n_split > 0 && n0 >= e.n_split) {      // second half of a split output: own tensor, own mask
+    const int n1 = n0 - e.n_split;
+    if (n1 >= e.n_store2) return;
+    if (e.mask2) {
+      const bf16* p = e.mask2 + b * e.m2B + oh * e.m2H + ow * e.m2W + n1;
+      float m[16];
+      unpack8(*reinterpret_cast<const uint4*>(p), m);
+      unpack8(*reinterpret_cast<const uint4*>(p + 8), m + 8);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = (m[i] > 0.f) ? v[i] : 0.f;
+    }
+    bf16* p = e.out2 + b * e.o2B + oh * e.o2H + ow * e.o2W + n1;
+    uint4 lo, hi;
+    lo.x = pack2(v[0], v[1]);  lo.y = pack2(v[2], v[3]);  lo.z = pack2(v[4], v[5]);   lo.w = pack2(v[6], v[7]);
+    hi.x = pack2(v[8], v[9]);  hi.y = pack2(v[10], v[11]); hi.z = pack2(v[12], v[13]); hi.w = pack2(v[14], v[15]);
+    *reinterpret_cast<uint4*>(p) = lo;
+    *reinterpret_cast<uint4*>(p + 8) = hi;
+    return;
+  }
   if (e.add) {
     const bf16* p = e.add + b * e.aB + oh * e.aH + ow * e.aW + n0;
     float a[16];

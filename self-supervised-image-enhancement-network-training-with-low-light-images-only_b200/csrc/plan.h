@@ -67,6 +67,14 @@ struct Epi {
   bf16* out_lo;               // optional: bf16(v - float(bf16(v))) at the same strides -> hi+lo carries ~16 mantissa bits
   int64_t oB, oH, oW;
   int n_store;
+  // optional column split (EPI_BF16): columns [n_split, n_split + n_store2) go to a SECOND tensor with its own mask — the
+  // data gradient of a layer whose input is a concat writes both halves of the concat from one GEMM
+  int n_split;                // 0: no split
+  int n_store2;
+  bf16* out2;
+  int64_t o2B, o2H, o2W;
+  const bf16* mask2;
+  int64_t m2B, m2H, m2W;
   // EPI_HEAD: sigmoid; columns [0,C) -> R32 (B,C,H,W) fp32 and RI (NHWC bf16, stride ri_c); column C -> I32, RI[C]
   float* R32;
   float* I32;
