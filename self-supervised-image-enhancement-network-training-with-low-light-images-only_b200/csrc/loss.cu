@@ -12,6 +12,7 @@
 // writes every gradient by GATHER
 // (each pixel collects the contributions of the <=4 forward-difference edges it takes part in).
 // Gradients are written already multiplied by c_loss_x / count (d total_loss / d tensor).
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -191,6 +192,198 @@ __global__ void __launch_bounds__(PL_WX* PL_CHUNKS) pixel_losses_kernel(PixLossA
   }
 }
 
+// Tiled variant (C = 64, W % 16 == 0, H % 4 == 0): one block = a 4 x 16 pixel tile x 8 band chunks (512 threads).  The
+// R and R_enh values of the tile and its one-pixel halo, ALL 64 bands, are staged in shared memory once (every global load
+// of the thread issued before the first store); both band sweeps then read their 5-point stencils from shared memory
+// instead of issuing 16 global loads per element.  grid = (W / 16, H / 4, B)
+#define PT_TW 16
+#define PT_TH 4
+#define PT_PITCH (PT_TW + 2)
+#define PT_PLANE ((PT_TH + 2) * PT_PITCH)
+#define PT_PIX (PT_TW * PT_TH)
+#define PT_C 64
+__global__ void __launch_bounds__(PT_PIX* PL_CHUNKS) pixel_losses_tiled_kernel(PixLossArgs p) {
+  extern __shared__ __align__(16) float pt_smem[];
+  float* Rs = pt_smem;                       // [64][PT_TH + 2][PT_PITCH]
+  float* Es = pt_smem + PT_C * PT_PLANE;
+  __shared__ float part[PL_CHUNKS][4][PT_PIX];
+  __shared__ float red[32];
+  const int W = p.W, H = p.H, C = p.C;
+  const int HW = H * W;
+  const int tx = threadIdx.x, k = threadIdx.y;
+  const int tid = k * blockDim.x + tx, nthreads = blockDim.x * blockDim.y;
+  const int w0 = blockIdx.x * PT_TW, h0 = blockIdx.y * PT_TH, b = blockIdx.z;
+  const int lx = tx & (PT_TW - 1), ly = tx >> 4;
+  const int w = w0 + lx, h = h0 + ly;
+  const bool active = true;
+  {  // stage R and R_enh: (band, row, col) of the haloed tile, zero outside the image
+    constexpr int NEL = PT_C * PT_PLANE;
+    constexpr int PER = (NEL + PT_PIX * PL_CHUNKS - 1) / (PT_PIX * PL_CHUNKS);
+    const float* Rg = p.R + (int64_t)b * C * HW;
+    const float* Eg = p.Re + (int64_t)b * C * HW;
+    float rv[PER], ev[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = tid + q * (PT_PIX * PL_CHUNKS);
+      rv[q] = ev[q] = 0.f;
+      if (i < NEL) {
+        const int c = i / PT_PLANE, rem = i - c * PT_PLANE;
+        const int gy = h0 - 1 + rem / PT_PITCH, gx = w0 - 1 + rem % PT_PITCH;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const int64_t o = (int64_t)c * HW + gy * W + gx;
+          rv[q] = __ldg(Rg + o);
+          ev[q] = __ldg(Eg + o);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = tid + q * (PT_PIX * PL_CHUNKS);
+      if (i < NEL) { Rs[i] = rv[q]; Es[i] = ev[q]; }
+    }
+  }
+  __syncthreads();
+  const int sidx = (ly + 1) * PT_PITCH + (lx + 1);      // this pixel inside a band plane of the staged tile
+  const int cpc = (C + PL_CHUNKS - 1) / PL_CHUNKS;
+  const int c_begin = k * cpc, c_end = min(C, c_begin + cpc);
+  float s[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) s[i] = 0.f;
+
+  const int hw = h * W + (active ? w : 0);
+  const int64_t pix = (int64_t)b * HW + hw;
+  const bool hasR = w + 1 < W, hasL = w > 0, hasD = h + 1 < H, hasU = h > 0;
+  const float* xb = p.x + (int64_t)b * C * HW + hw;
+  const float* Ib = p.I + (int64_t)b * HW + hw;
+  const float* Db = p.Id + (int64_t)b * HW + hw;
+
+  // ---- pass A: band means of |dR| on the four incident edges (partial over this thread's chunk) -------------
+  float mR = 0.f, mL = 0.f, mD = 0.f, mU = 0.f;
+  if (active) {
+    for (int c = c_begin; c < c_end; ++c) {
+      const float* r = Rs + c * PT_PLANE + sidx;
+      const float r0 = r[0];
+      if (hasR) mR += fabsf(r[1] - r0);
+      if (hasL) mL += fabsf(r0 - r[-1]);
+      if (hasD) mD += fabsf(r[PT_PITCH] - r0);
+      if (hasU) mU += fabsf(r0 - r[-PT_PITCH]);
+    }
+  }
+  part[k][0][tx] = mR; part[k][1][tx] = mL; part[k][2][tx] = mD; part[k][3][tx] = mU;
+  __syncthreads();
+  mR = mL = mD = mU = 0.f;
+#pragma unroll
+  for (int i = 0; i < PL_CHUNKS; ++i) {
+    mR += part[i][0][tx]; mL += part[i][1][tx]; mD += part[i][2][tx]; mU += part[i][3][tx];
+  }
+  __syncthreads();
+
+  float gI = 0.f, gId = 0.f;
+  if (active) {
+    const float invC = 1.f / (float)C;
+    const float wR = __expf(-p.a1 * mR * invC), wL = __expf(-p.a1 * mL * invC);
+    const float wD = __expf(-p.a1 * mD * invC), wU = __expf(-p.a1 * mU * invC);
+    const float i0 = Ib[0], d0 = Db[0];
+    const float iR = hasR ? Ib[1] - i0 : 0.f, iL = hasL ? i0 - Ib[-1] : 0.f;
+    const float iD = hasD ? Ib[W] - i0 : 0.f, iU = hasU ? i0 - Ib[-W] : 0.f;
+    const float dRt = hasR ? Db[1] - d0 : 0.f, dLt = hasL ? d0 - Db[-1] : 0.f;
+    const float dDt = hasD ? Db[W] - d0 : 0.f, dUt = hasU ? d0 - Db[-W] : 0.f;
+    if (k == 0) {   // band-independent parts, once per pixel
+      if (hasR) s[1] += wR * fabsf(iR);
+      if (hasD) s[2] += wD * fabsf(iD);
+      gI = p.k_ilx * (wL * sgnf(iL) - wR * sgnf(iR)) + p.k_ily * (wU * sgnf(iU) - wD * sgnf(iD));
+    }
+    const float cR = p.k_ilx * wR * fabsf(iR) * p.a1 * invC, cL = p.k_ilx * wL * fabsf(iL) * p.a1 * invC;
+    const float cD = p.k_ily * wD * fabsf(iD) * p.a1 * invC, cU = p.k_ily * wU * fabsf(iU) * p.a1 * invC;
+    const float gain = d0 + i0;
+    float s_prev = (c_begin > 0) ? Rs[(c_begin - 1) * PT_PLANE + sidx] * gain : 0.f;
+    float r_next = (c_begin < C) ? Rs[c_begin * PT_PLANE + sidx] : 0.f;
+    // ---- pass B over this thread's bands --------------------------------------------------------------------
+    for (int c = c_begin; c < c_end; ++c) {
+      const int64_t off = (int64_t)c * HW;
+      const float* r = Rs + c * PT_PLANE + sidx;
+      const float* e = Es + c * PT_PLANE + sidx;
+      const float r0 = r_next;
+      if (c + 1 < C) r_next = r[PT_PLANE];
+      const float e0 = e[0];
+      float gR = 0.f;
+      const float u = r0 * i0 - xb[off];
+      s[0] += fabsf(u);
+      const float gu = p.k_rec * sgnf(u);
+      gR += gu * i0;
+      gI += gu * r0;
+      const float q0 = r0 - e0;
+      s[3] += fabsf(q0);
+      float gq = p.k_rf * sgnf(q0);
+      if (hasR) {
+        const float dr = r[1] - r0;
+        const float dq = (r[1] - e[1]) - q0;
+        const float ex = __expf(-p.a2 * fabsf(dr));
+        s[4] += fabsf(dq);
+        s[6] += fabsf(dRt) * ex;
+        gq -= p.k_rfx * sgnf(dq);
+        gR += (cR + p.k_idx * fabsf(dRt) * p.a2 * ex) * sgnf(dr);
+        gId -= p.k_idx * sgnf(dRt) * ex;
+      }
+      if (hasL) {
+        const float dr = r0 - r[-1];
+        const float dq = q0 - (r[-1] - e[-1]);
+        const float ex = __expf(-p.a2 * fabsf(dr));
+        gq += p.k_rfx * sgnf(dq);
+        gR -= (cL + p.k_idx * fabsf(dLt) * p.a2 * ex) * sgnf(dr);
+        gId += p.k_idx * sgnf(dLt) * ex;
+      }
+      if (hasD) {
+        const float dr = r[PT_PITCH] - r0;
+        const float dq = (r[PT_PITCH] - e[PT_PITCH]) - q0;
+        const float ex = __expf(-p.a2 * fabsf(dr));
+        s[5] += fabsf(dq);
+        s[7] += fabsf(dDt) * ex;
+        gq -= p.k_rfy * sgnf(dq);
+        gR += (cD + p.k_idy * fabsf(dDt) * p.a2 * ex) * sgnf(dr);
+        gId -= p.k_idy * sgnf(dDt) * ex;
+      }
+      if (hasU) {
+        const float dr = r0 - r[-PT_PITCH];
+        const float dq = q0 - (r[-PT_PITCH] - e[-PT_PITCH]);
+        const float ex = __expf(-p.a2 * fabsf(dr));
+        gq += p.k_rfy * sgnf(dq);
+        gR -= (cU + p.k_idy * fabsf(dUt) * p.a2 * ex) * sgnf(dr);
+        gId += p.k_idy * sgnf(dUt) * ex;
+      }
+      gR += gq;
+      // spectral smoothness on S = R*(Id+I):  dS_c = k (sgn(S_c - S_{c-1}) - sgn(S_{c+1} - S_c))
+      const float s0 = r0 * gain;
+      float gS = 0.f;
+      if (c > 0) gS += sgnf(s0 - s_prev);
+      if (c + 1 < C) {
+        const float sn = r_next * gain;
+        s[8] += fabsf(sn - s0);
+        gS -= sgnf(sn - s0);
+      }
+      s_prev = s0;
+      const int64_t o = (int64_t)b * C * HW + hw + off;
+      if (p.dR) p.dR[o] = gR;
+      if (p.dRe) p.dRe[o] = -gq;
+      if (p.dS) p.dS[o] = p.k_sp * gS;
+    }
+  }
+  part[k][0][tx] = gI; part[k][1][tx] = gId;
+  __syncthreads();
+  if (active && k == 0) {
+    float a = 0.f, d = 0.f;
+#pragma unroll
+    for (int i = 0; i < PL_CHUNKS; ++i) { a += part[i][0][tx]; d += part[i][1][tx]; }
+    if (p.dI) p.dI[pix] = a;
+    if (p.dId) p.dId[pix] = d;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float t = block_sum_2d(s[i], red, tid, nthreads);
+    if (tid == 0) atomicAdd(p.sums + i, t);
+  }
+}
+
 int ss_pixel_losses(const float* x, const float* R, const float* I, const float* Id, const float* Re,
                     const sshslie_loss_cfg& cfg, int B, int C, int H, int W, float* sums, float* dR, float* dI,
                     float* dId, float* dS, float* dRe, cudaStream_t st) {
@@ -211,6 +404,22 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
   p.k_idx = (float)(cfg.c_loss_i_smooth_delta / (nx1 * C));
   p.k_idy = (float)(cfg.c_loss_i_smooth_delta / (ny1 * C));
   p.k_sp = (float)(cfg.c_loss_spectral_cons / ((double)B * (C - 1) * H * W));
+  static const bool tiled_ok = !(getenv("SSHSLIE_LOSS_TILED") && getenv("SSHSLIE_LOSS_TILED")[0] == '0');
+  if (tiled_ok && C == PT_C && (W % PT_TW) == 0 && (H % PT_TH) == 0) {
+    const size_t smem = (size_t)2 * PT_C * PT_PLANE * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(pixel_losses_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess) {
+        ss_set_error("pixel_losses: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+        return SSHSLIE_ERR_CUDA;
+      }
+      attr_set = true;
+    }
+    dim3 grid(W / PT_TW, H / PT_TH, B), block(PT_PIX, PL_CHUNKS);
+    pixel_losses_tiled_kernel<<<grid, block, smem, st>>>(p);
+    return ss_check_launch("pixel_losses_tiled");
+  }
   const int wx = W < PL_WX ? W : PL_WX;
   dim3 grid((W + wx - 1) / wx, H, B), block(wx, PL_CHUNKS);
   pixel_losses_kernel<<<grid, block, 0, st>>>(p);
