@@ -207,7 +207,6 @@ __global__ void __launch_bounds__(PT_PIX* PL_CHUNKS) pixel_losses_tiled_kernel(P
   float* Rs = pt_smem;                       // [64][PT_TH + 2][PT_PITCH]
   float* Es = pt_smem + PT_C * PT_PLANE;
   __shared__ float part[PL_CHUNKS][4][PT_PIX];
-  __shared__ float red[32];
   const int W = p.W, H = p.H, C = p.C;
   const int HW = H * W;
   const int tx = threadIdx.x, k = threadIdx.y;
@@ -377,11 +376,21 @@ __global__ void __launch_bounds__(PT_PIX* PL_CHUNKS) pixel_losses_tiled_kernel(P
     if (p.dI) p.dI[pix] = a;
     if (p.dId) p.dId[pix] = d;
   }
+  // the nine term sums of the block: warp sums -> one shared-memory exchange -> nine atomics (one barrier instead of 18)
+  __shared__ float wred[PT_PIX * PL_CHUNKS / 32][9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
-    const float t = block_sum_2d(s[i], red, tid, nthreads);
-    if (tid == 0) atomicAdd(p.sums + i, t);
+    const float t = warp_sum(s[i]);
+    if ((tid & 31) == 0) wred[tid >> 5][i] = t;
   }
+  __syncthreads();
+  if (tid < 9) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < PT_PIX * PL_CHUNKS / 32; ++wv) t += wred[wv][tid];
+    atomicAdd(p.sums + tid, t);
+  }
+  (void)nthreads;
 }
 
 int ss_pixel_losses(const float* x, const float* R, const float* I, const float* Id, const float* Re,
