@@ -184,10 +184,11 @@ SS_DEVINL uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
 // ---------------------------------------------------------------------------------------------
 // gather GEMM kernel
 // ---------------------------------------------------------------------------------------------
-SS_DEVINL void conv_gather_umma_body(const ConvGeom* __restrict__ gp, const UmmaMaps& maps, const Epi& epi,
-                                     int tmem_cols, int tile_index) {
+// The geometry arrives as a __grid_constant__ kernel parameter (uniform constant-bank loads, no global->shared copy in
+// the prologue); loop-invariant words of the MMA loop are hoisted (barrier addresses, descriptor bases, slab count).
+SS_DEVINL void conv_gather_umma_body(const ConvGeom& g, const UmmaMaps& maps, const Epi& epi, int tmem_cols,
+                                     int tile_index) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ ConvGeom g;
   __shared__ __align__(8) uint64_t full_bar[UM_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[UM_STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
@@ -195,21 +196,13 @@ SS_DEVINL void conv_gather_umma_body(const ConvGeom* __restrict__ gp, const Umma
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
-  {   // the plan (ConvGeom) is written once at bind time, never by a kernel: safe to read before pdl_wait()
-    const int* src = reinterpret_cast<const int*>(gp);
-    int* dst = reinterpret_cast<int*>(&g);
-    for (int i = threadIdx.x; i < (int)(sizeof(ConvGeom) / 4); i += blockDim.x) dst[i] = src[i];
-  }
   // operand ring, 1024-byte aligned (SWIZZLE_128B atom)
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  __syncthreads();
-  const int Npad = g.Npad;
+  const int Npad = g.Npad, nslabs = g.nslabs;
   const uint32_t b_bytes = (uint32_t)Npad * 128u;
   const uint32_t stage_bytes = UM_A_BYTES + b_bytes;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < g.nsrc; ++s) tma_prefetch_desc(&maps.src[s]);
-    tma_prefetch_desc(&maps.w);
     for (int s = 0; s < UM_STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -222,7 +215,6 @@ SS_DEVINL void conv_gather_umma_body(const ConvGeom* __restrict__ gp, const Umma
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();      // everything below reads or writes tensors produced by earlier kernels
 
   // tile -> (b, oh0, ow0)
   const int tiles_w = (g.OW + g.tw - 1) / g.tw, tiles_h = (g.OH + g.th - 1) / g.th;
@@ -235,37 +227,45 @@ SS_DEVINL void conv_gather_umma_body(const ConvGeom* __restrict__ gp, const Umma
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int s = 0; s < g.nslabs; ++s) {
-        const int st = s % UM_STAGES;
-        const uint32_t ph = (uint32_t)(s / UM_STAGES) & 1u;
-        mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1u);
-        const Slab sl = g.slab[s];
-        const uint32_t a_dst = dyn_base + (uint32_t)st * stage_bytes;
-        const uint32_t fb = smem_u32(&full_bar[st]);
+      pdl_wait();      // everything below reads tensors produced by earlier kernels
+      const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+      uint32_t st = 0, ph = 1;
+      for (int s = 0; s < nslabs; ++s) {
+        mbar_wait(empty0 + 8u * st, ph);
+        const uint32_t a_dst = dyn_base + st * stage_bytes;
+        const uint32_t fb = full0 + 8u * st;
         mbar_expect_tx(fb, stage_bytes);
-        tma_load_4d(a_dst, &maps.src[sl.src], fb, sl.c0, ow0 + sl.dw, oh0 + sl.dh, b);
+        tma_load_4d(a_dst, &maps.src[g.slab[s].src], fb, g.slab[s].c0, ow0 + g.slab[s].dw, oh0 + g.slab[s].dh, b);
         tma_load_2d(a_dst + UM_A_BYTES, &maps.w, fb, 0, s * Npad);
+        if (++st == UM_STAGES) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: whole warp converged, one elected lane issues =====
     const uint32_t idesc = make_idesc(128, Npad, 0, 0);
-    const uint32_t tm = uniform32(tmem_base), base = uniform32(dyn_base);
-    for (int s = 0; s < g.nslabs; ++s) {
-      const int st = s % UM_STAGES;
-      const uint32_t ph = (uint32_t)(s / UM_STAGES) & 1u;
-      mbar_wait_warp(smem_u32(&full_bar[st]), ph, 0);
+    const uint32_t tm = uniform32(tmem_base);
+    const uint32_t hi = (uint32_t)(make_sdesc(0, 16, 1024) >> 32);
+    const uint32_t a_lo0 = uniform32(((dyn_base >> 4) & 0x3FFFu) | (1u << 16));
+    const uint32_t b_lo0 = a_lo0 + (UM_A_BYTES >> 4);
+    const uint32_t sstep = stage_bytes >> 4;
+    const uint32_t full0 = uniform32(smem_u32(&full_bar[0])), empty0 = uniform32(smem_u32(&empty_bar[0]));
+    const uint32_t accb = uniform32(smem_u32(&accum_bar));
+    uint32_t st = 0, ph = 0;
+#pragma unroll 1
+    for (int s = 0; s < nslabs; ++s) {
+      mbar_wait_warp(full0 + 8u * st, ph, 0);
       tc_fence_after();
-      const uint32_t a_addr = base + (uint32_t)st * stage_bytes;
-      const uint64_t ad0 = make_sdesc(a_addr, 16, 1024);
-      const uint64_t bd0 = make_sdesc(a_addr + UM_A_BYTES, 16, 1024);
+      const uint32_t a_lo = a_lo0 + st * sstep, b_lo = b_lo0 + st * sstep;
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tm, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), idesc, (s > 0 || k > 0) ? 1u : 0u);
-        umma_commit(smem_u32(&empty_bar[st]));      // frees the stage when these MMAs retire
-        if (s == g.nslabs - 1) umma_commit(smem_u32(&accum_bar));
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm, ((uint64_t)hi << 32) | (uint64_t)(a_lo + 2u * k), ((uint64_t)hi << 32) | (uint64_t)(b_lo + 2u * k),
+                    idesc, (s > 0 || k > 0) ? 1u : 0u);
+        umma_commit(empty0 + 8u * st);      // frees the stage when these MMAs retire
+        if (s == nslabs - 1) umma_commit(accb);
       }
       __syncwarp();
+      if (++st == UM_STAGES) { st = 0; ph ^= 1u; }
     }
   } else {
     // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
@@ -273,7 +273,8 @@ SS_DEVINL void conv_gather_umma_body(const ConvGeom* __restrict__ gp, const Umma
     const int row = quarter * 32 + lane;
     const int oh = oh0 + row / g.tw, ow = ow0 + row % g.tw;
     const bool ok = oh < g.OH && ow < g.OW;
-    mbar_wait_warp(smem_u32(&accum_bar), 0, 200);
+    pdl_wait();        // the epilogue reads residual / mask tensors and overwrites buffers earlier kernels may still read
+    mbar_wait_warp(smem_u32(&accum_bar), 0, 100);
     tc_fence_after();
     for (int n0 = 0; n0 < Npad; n0 += 16) {
       float v[16];
@@ -287,23 +288,24 @@ SS_DEVINL void conv_gather_umma_body(const ConvGeom* __restrict__ gp, const Umma
 }
 
 __global__ void __launch_bounds__(UM_THREADS, 1)
-conv_gather_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps maps, Epi epi,
-                        int tmem_cols) {
-  conv_gather_umma_body(gp, maps, epi, tmem_cols, blockIdx.x);
+conv_gather_umma_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ UmmaMaps maps,
+                        const __grid_constant__ Epi epi, int tmem_cols) {
+  conv_gather_umma_body(g, maps, epi, tmem_cols, blockIdx.x);
 }
 
 // the four output-parity classes of a transposed / strided-dgrad layer in ONE launch: blockIdx.y = class (qh, qw).
 // The classes are four consecutive ConvGeoms with their own weight packs; their outputs interleave in the same tensor.
 struct alignas(64) UmmaMaps4 { UmmaMaps m[4]; };
+struct alignas(16) ConvGeom4 { ConvGeom g[4]; };
 __global__ void __launch_bounds__(UM_THREADS, 1)
-conv_gather_umma4_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps4 maps, Epi epi,
-                         int tmem_cols) {
+conv_gather_umma4_kernel(const __grid_constant__ ConvGeom4 g4, const __grid_constant__ UmmaMaps4 maps,
+                         const __grid_constant__ Epi epi, int tmem_cols) {
   const int q = blockIdx.y, qh = q >> 1, qw = q & 1;
   Epi e = epi;
   e.out += qh * (e.oH >> 1) + qw * (e.oW >> 1);
   if (e.add) e.add += qh * (e.aH >> 1) + qw * (e.aW >> 1);
   if (e.mask) e.mask += qh * (e.mH >> 1) + qw * (e.mW >> 1);
-  conv_gather_umma_body(gp + q, maps.m[q], e, tmem_cols, blockIdx.x);
+  conv_gather_umma_body(g4.g[q], maps.m[q], e, tmem_cols, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -728,7 +730,8 @@ int ss_launch_conv_gather_umma(const ConvGeom* g_dev, const ConvGeom& g, const U
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ss_pdl_enabled() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_gather_umma_kernel, g_dev, maps, epi, cols);
+  (void)g_dev;
+  cudaLaunchKernelEx(&cfg, conv_gather_umma_kernel, g, maps, epi, cols);
   return ss_check_launch("conv_gather_umma");
 }
 
@@ -929,7 +932,9 @@ int ss_launch_conv_gather_umma4(const ConvGeom* g_dev, const ConvGeom* g4, const
     attr_set = true;
   }
   UmmaMaps4 m4;
-  for (int q = 0; q < 4; ++q) m4.m[q] = maps4[q];
+  ConvGeom4 gg;
+  for (int q = 0; q < 4; ++q) { m4.m[q] = maps4[q]; gg.g[q] = g4[q]; }
+  (void)g_dev;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(tiles, 4);
@@ -941,7 +946,7 @@ int ss_launch_conv_gather_umma4(const ConvGeom* g_dev, const ConvGeom* g4, const
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ss_pdl_enabled() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, conv_gather_umma4_kernel, g_dev, m4, epi, cols);
+  cudaLaunchKernelEx(&cfg, conv_gather_umma4_kernel, gg, m4, epi, cols);
   ss_count_launches(0);
   return ss_check_launch("conv_gather_umma4");
 }
