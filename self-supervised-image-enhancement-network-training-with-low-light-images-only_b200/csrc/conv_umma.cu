@@ -765,10 +765,10 @@ struct WgradArgs {
 };
 
 __global__ void __launch_bounds__(UM_THREADS, 1)
-conv_wgrad_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ UmmaMaps maps,
-                       const __grid_constant__ CUtensorMap gmap, WgradArgs wa, float* __restrict__ partial) {
+conv_wgrad_umma_kernel(const __grid_constant__ ConvGeom g, const __grid_constant__ UmmaMaps maps,
+                       const __grid_constant__ CUtensorMap gmap, const __grid_constant__ WgradArgs wa,
+                       float* __restrict__ partial) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ ConvGeom g;
   __shared__ __align__(8) uint64_t a_full[WG_STAGES];
   __shared__ __align__(8) uint64_t a_empty[WG_STAGES];
   __shared__ __align__(8) uint64_t g_full[2];
@@ -777,11 +777,6 @@ conv_wgrad_umma_kernel(const ConvGeom* __restrict__ gp, const __grid_constant__ 
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
-    const int* src = reinterpret_cast<const int*>(gp);
-    int* dst = reinterpret_cast<int*>(&g);
-    for (int i = threadIdx.x; i < (int)(sizeof(ConvGeom) / 4); i += blockDim.x) dst[i] = src[i];
-  }
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t g_base = dyn_base + WG_STAGES * WG_STAGE_BYTES;
   const uint32_t ones_base = g_base + 2 * WG_G_BYTES;
@@ -1092,7 +1087,7 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
   dim3 grid(wa.splits, wa.groups);
   int rc = SSHSLIE_OK;
   if (g_wgrad_part != 2) {
-    conv_wgrad_umma_kernel<<<grid, UM_THREADS, smem, st>>>(g_dev, maps, *reinterpret_cast<const CUtensorMap*>(gmap), wa,
+    conv_wgrad_umma_kernel<<<grid, UM_THREADS, smem, st>>>(g, maps, *reinterpret_cast<const CUtensorMap*>(gmap), wa,
                                                            partial);
     rc = ss_check_launch("conv_wgrad_umma");
     if (rc || g_wgrad_part == 1) return rc;
