@@ -430,14 +430,15 @@ __global__ void __launch_bounds__(128) attn_bwd_kv_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// training token grid (L <= 256): TWO launches instead of three, both register-tiled (4 tokens x 4 outputs per thread,
-// operands as float4 from feature-major shared-memory tiles; the kernels above issue one shared-memory load per FMA and
-// are LDS-bound):
+// forward in TWO launches instead of three, both register-tiled (4 tokens x 4 outputs per thread, operands as float4 from
+// feature-major shared-memory tiles; the older kernels above issue one shared-memory load per FMA and are LDS-bound):
 //   attn_qkv4_kernel      16 tokens per CTA: x = fp32(a3), Q | K | V = x W^T + b
-//   attn_core_ffn_kernel  one CTA per (image, 16 queries): per head, K_h / V_h rows of the image -> shared memory,
-//                         two-pass softmax over 16 keys per thread (16 threads per query), then the FFN of the block
+//   attn_core_ffn_kernel  one CTA per (image, 16 queries): per head, the K_h / V_h rows stream through shared memory in
+//                         256-key tiles (one tile at the training size, 16 at 512x512 inference); two-pass softmax per
+//                         tile over 16 keys per thread (16 threads per query) with a running maximum shared by the
+//                         query's threads; then the FFN of the block
 // A single fused kernel that recomputed K/V per CTA was measured at 67 us (issue-bound on 16 SMs); this split is ~4x
-// less work per SM and uses 32 + 32 SMs.  Saves exactly what the separate kernels save (x, q, k, v, o, lse, h).
+// less work per SM and uses 32 + 32 SMs.  Saves exactly what the older kernels save (x, q, k, v, o, lse, h).
 // ---------------------------------------------------------------------------------------------
 #define AF_QB 16
 #define AF_LMAX 256
