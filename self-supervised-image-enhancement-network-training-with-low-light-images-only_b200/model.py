@@ -395,6 +395,7 @@ class LowLightEnhance(nn.Module):
         self._engines = {}
         self._losses_dev = None
         self.use_cuda_graph = True
+        self.max_cached_engines = 4
         self.force_simt = False
         self.dp_group = None                 # set by enable_data_parallel()
         self._box = [self]
@@ -439,10 +440,14 @@ class LowLightEnhance(nn.Module):
     def _engine(self, x, train):
         B, C, H, W = x.shape
         key = (B, C, H, W, train, self.force_simt)
-        eng = self._engines.get(key)
+        eng = self._engines.pop(key, None)
         if eng is None:
+            # a bound engine owns its workspace (~1 GB for a 512x512 cube): keep the few most recently used shapes only,
+            # so that test_model over cubes of many different sizes does not accumulate workspaces
+            while len(self._engines) >= self.max_cached_engines:
+                self._engines.pop(next(iter(self._engines)))
             eng = _Engine(self._flat.device, B, C, H, W, train, self.force_simt)
-            self._engines[key] = eng
+        self._engines[key] = eng               # (re)insert as most recently used
         return eng
 
     def _stage_input(self, eng, x):

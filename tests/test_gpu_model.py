@@ -299,3 +299,22 @@ def test_reference_fixtures_other_configs(case, golden_dir):
     total_l2 = float(np.sqrt(sum(float(g["grad/" + k + "/l2"]) ** 2 for k, _ in m.named_parameters())))
     got_l2 = float(torch.cat([q.grad.detach().flatten() for q in m.parameters()]).double().norm())
     np.testing.assert_allclose(got_l2, total_l2, rtol=0.05)
+
+
+def test_engine_cache_is_bounded():
+    """test_model over cubes of many sizes must not accumulate workspaces: at most `max_cached_engines` shapes stay bound,
+    and a shape that was evicted is rebuilt transparently."""
+    from oracle import sshslie_oracle as O
+    m = _model(O.JYU_COEF)
+    first = None
+    with torch.no_grad():
+        for H, W in [(32, 32), (32, 48), (48, 32), (40, 40), (64, 32), (32, 64), (32, 32)]:
+            x = _rect_input(1, H, W, 5)
+            R, I, Id, S = m.forward(x.cuda())
+            if (H, W) == (32, 32):
+                if first is None:
+                    first = S.clone()
+                else:
+                    assert torch.equal(first, S)          # rebuilt engine, same deterministic forward
+            assert len(m._engines) <= m.max_cached_engines
+    assert len(m._engines) == m.max_cached_engines
