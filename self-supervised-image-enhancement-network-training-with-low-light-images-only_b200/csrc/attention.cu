@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256) attn_ffn_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) attn_ffn_bwd_kernel(const float* __restrict__ dT, const float* __restrict__ Hh,
                                                            const float* __restrict__ P, int64_t o1, int64_t o2,
                                                            float* __restrict__ dH, float* __restrict__ dO, int T) {
+  SS_PDL_ENTRY();
   extern __shared__ float smf[];
   float (*W1)[AT_D + 1] = reinterpret_cast<float (*)[AT_D + 1]>(smf);
   float (*W2)[AT_D + 1] = W1 + AT_D;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(256) attn_dx_kernel(const float* __restrict__ 
                                                       const float* __restrict__ dK, const float* __restrict__ dV,
                                                       const float* __restrict__ P, int64_t oq, int64_t ok, int64_t ov,
                                                       const bf16* __restrict__ a3, bf16* __restrict__ da3, int T) {
+  SS_PDL_ENTRY();
   extern __shared__ float smf[];
   float (*Wq)[AT_D + 1] = reinterpret_cast<float (*)[AT_D + 1]>(smf);
   float (*Wk)[AT_D + 1] = Wq + AT_D;
@@ -483,6 +485,7 @@ __global__ void __launch_bounds__(192)
 attn_qkv4_kernel(const bf16* __restrict__ a3, const float* __restrict__ P, int64_t oq, int64_t obq, int64_t ok,
                  int64_t obk, int64_t ov, int64_t obv, float* __restrict__ X, float* __restrict__ Q,
                  float* __restrict__ K, float* __restrict__ V, int T) {
+  SS_PDL_ENTRY();
   extern __shared__ __align__(16) float smf[];
   float* Wt = smf;                               // [64][AF_W3P]
   float* Xt = Wt + AT_D * AF_W3P;                // [64][AF_TP]
@@ -528,6 +531,7 @@ attn_core_ffn_kernel(const float* __restrict__ X, const float* __restrict__ Q, c
                      const float* __restrict__ V, const float* __restrict__ P, int64_t o1, int64_t ob1, int64_t o2,
                      int64_t ob2, float* __restrict__ O, float* __restrict__ LSE, float* __restrict__ Hh,
                      bf16* __restrict__ Tout, int L) {
+  SS_PDL_ENTRY();
   extern __shared__ __align__(16) float smf[];
   float* Ks = smf;                               // [256][AF_KP]   one head
   float* Vs = Ks + AF_LMAX * AF_KP;
@@ -725,6 +729,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_q16_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                     const float* __restrict__ O, const float* __restrict__ dO, const float* __restrict__ LSE,
                     float* __restrict__ dQ, float* __restrict__ Dv, int L) {
+  SS_PDL_ENTRY();
   __shared__ __align__(16) float Ks[AF_LMAX * AF_KP];
   __shared__ __align__(16) float Vs[AF_LMAX * AF_KP];
   const int head = blockIdx.y, b = blockIdx.z;
@@ -766,6 +771,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_kv16_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                      const float* __restrict__ dO, const float* __restrict__ LSE, const float* __restrict__ Dv,
                      float* __restrict__ dK, float* __restrict__ dV, int L) {
+  SS_PDL_ENTRY();
   __shared__ __align__(16) float Qs[AF_LMAX * AF_KP];      // 0.25 * Q_h
   __shared__ __align__(16) float Gs[AF_LMAX * AF_KP];      // dO_h
   __shared__ float Ls[AF_LMAX];
@@ -897,10 +903,10 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* P, const int6
   const int T = B * L;
   static const bool fused_ok = !(getenv("SSHSLIE_ATTN_FUSED") && getenv("SSHSLIE_ATTN_FUSED")[0] == '0');
   if (fused_ok) {      // register-tiled kernels; keys stream through 256-row tiles (one tile at the training size)
-    attn_qkv4_kernel<<<(T + AF_QB - 1) / AF_QB, 192, kSmemQkv4, st>>>(a3, P, poff[0], poff[1], poff[2], poff[3], poff[4],
+    ss_launch_pdl(attn_qkv4_kernel, dim3((T + AF_QB - 1) / AF_QB), dim3(192), (size_t)(kSmemQkv4), st, a3, P, poff[0], poff[1], poff[2], poff[3], poff[4],
                                                                      poff[5], bf.x, bf.q, bf.k, bf.v, T);
     dim3 g((L + AF_QB - 1) / AF_QB, B);
-    attn_core_ffn_kernel<<<g, 256, kSmemCore, st>>>(bf.x, bf.q, bf.k, bf.v, P, poff[6], poff[7], poff[8], poff[9], bf.o,
+    ss_launch_pdl(attn_core_ffn_kernel, dim3(g), dim3(256), (size_t)(kSmemCore), st, bf.x, bf.q, bf.k, bf.v, P, poff[6], poff[7], poff[8], poff[9], bf.o,
                                                      bf.lse, bf.h, t_out, L);
     ss_count_launches(1);
     return ss_check_launch("attention_forward_fused");
@@ -922,18 +928,18 @@ int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const floa
   const int T = B * L;
   const int gl = (T + TK - 1) / TK;
   // data-gradient chain only; the five weight gradients run in ss_attention_backward_weights (side stream)
-  attn_ffn_bwd_kernel<<<gl, 256, kSmem2, st>>>(dt, bf.h, P, poff[6], poff[8], bf.dh, bf.d_o, T);
+  ss_launch_pdl(attn_ffn_bwd_kernel, dim3(gl), dim3(256), (size_t)(kSmem2), st, dt, bf.h, P, poff[6], poff[8], bf.dh, bf.d_o, T);
   static const bool fused_ok = !(getenv("SSHSLIE_ATTN_FUSED") && getenv("SSHSLIE_ATTN_FUSED")[0] == '0');
   if (L <= AF_LMAX && fused_ok) {
     dim3 g16((L + 15) / 16, AT_HEADS, B);
-    attn_bwd_q16_kernel<<<g16, 256, 0, st>>>(bf.q, bf.k, bf.v, bf.o, bf.d_o, bf.lse, bf.dq, bf.Dv, L);
-    attn_bwd_kv16_kernel<<<g16, 256, 0, st>>>(bf.q, bf.k, bf.v, bf.d_o, bf.lse, bf.Dv, bf.dk, bf.dv, L);
+    ss_launch_pdl(attn_bwd_q16_kernel, dim3(g16), dim3(256), (size_t)(0), st, bf.q, bf.k, bf.v, bf.o, bf.d_o, bf.lse, bf.dq, bf.Dv, L);
+    ss_launch_pdl(attn_bwd_kv16_kernel, dim3(g16), dim3(256), (size_t)(0), st, bf.q, bf.k, bf.v, bf.d_o, bf.lse, bf.Dv, bf.dk, bf.dv, L);
   } else {
     dim3 ga((L + AT_QB - 1) / AT_QB, AT_HEADS, B);
     attn_bwd_q_kernel<<<ga, 128, 0, st>>>(bf.q, bf.k, bf.v, bf.o, bf.d_o, bf.lse, bf.dq, bf.Dv, L);
     attn_bwd_kv_kernel<<<ga, 128, 0, st>>>(bf.q, bf.k, bf.v, bf.d_o, bf.lse, bf.Dv, bf.dk, bf.dv, L);
   }
-  attn_dx_kernel<<<gl, 256, kSmem3, st>>>(dt, bf.dq, bf.dk, bf.dv, P, poff[0], poff[2], poff[4], a3, da3, T);
+  ss_launch_pdl(attn_dx_kernel, dim3(gl), dim3(256), (size_t)(kSmem3), st, dt, bf.dq, bf.dk, bf.dv, P, poff[0], poff[2], poff[4], a3, da3, T);
   ss_count_launches(3);
   return ss_check_launch("attention_backward");
 }

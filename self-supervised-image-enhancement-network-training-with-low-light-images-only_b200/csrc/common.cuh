@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "plan.h"
 
 #define SS_DEVINL __device__ __forceinline__
@@ -51,3 +52,32 @@ SS_DEVINL float block_sum(float v, float* red /* >= 32 floats of smem */) {
 
 SS_DEVINL float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 SS_DEVINL float sgnf(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch for the small kernels between the conv GEMMs: every kernel of the main chain triggers
+// its dependents at entry and waits for its predecessors before touching global memory, and is launched with the
+// programmatic-stream-serialization attribute - the launch latency and prologue of kernel N+1 then overlap the tail of
+// kernel N (measured on the 3x3 conv: 10.3 -> 7.4 us per dependent launch).  SSHSLIE_PDL=0 turns the attribute off.
+// ---------------------------------------------------------------------------------------------
+int ss_pdl_enabled();
+#define SS_PDL_ENTRY()                                                   \
+  do {                                                                   \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                  \
+  } while (0)
+template <typename K, typename... A>
+static inline void ss_launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ss_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}

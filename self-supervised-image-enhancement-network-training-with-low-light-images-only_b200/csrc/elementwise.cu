@@ -14,6 +14,7 @@
 // x (B,C,H,W) fp32  ->  out (B,H,W,ldo) bf16        [decomposition_net input, model.py:51-52]
 // ---------------------------------------------------------------------------------------------
 __global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int C, int HW, int ldo) {
+  SS_PDL_ENTRY();
   __shared__ float tile[32][33];
   const int64_t p0 = (int64_t)blockIdx.x * 32;          // linear pixel over B*HW
   const int b = (int)(p0 / HW);
@@ -31,7 +32,7 @@ __global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ x, bf16* __res
 }
 int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st) {
   dim3 grid((unsigned)((int64_t)B * H * W / 32), (C + 31) / 32);
-  nchw32_to_nhwc16_kernel<<<grid, dim3(32, 8), 0, st>>>(x, out, C, H * W, ldo);
+  ss_launch_pdl(nchw32_to_nhwc16_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), st, x, out, C, H * W, ldo);
   EW_CHECK("nchw32_to_nhwc16");
 }
 
@@ -63,6 +64,7 @@ int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, in
 // ---------------------------------------------------------------------------------------------
 __global__ void upsample2_add_kernel(const bf16* __restrict__ r, const bf16* __restrict__ a, bf16* __restrict__ out,
                                      int h, int w, int64_t total /* B*h*w*8 vectors of the SOURCE */) {
+  SS_PDL_ENTRY();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int q = (int)(i & 7);
@@ -90,7 +92,7 @@ __global__ void upsample2_add_kernel(const bf16* __restrict__ r, const bf16* __r
 }
 int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, cudaStream_t st) {
   const int64_t total = (int64_t)B * h * w * 8;
-  upsample2_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r, a, out, h, w, total);
+  ss_launch_pdl(upsample2_add_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, r, a, out, h, w, total);
   EW_CHECK("upsample2_add");
 }
 
@@ -113,6 +115,7 @@ __global__ void fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __
                                    const uint4* __restrict__ r3, const uint4* __restrict__ r3l,
                                    const uint4* __restrict__ a0, const uint4* __restrict__ a0l, uint4* __restrict__ fg,
                                    int H, int W, int64_t total /* B*H*W*24 */) {
+  SS_PDL_ENTRY();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int q = (int)(i % 24);
@@ -155,7 +158,7 @@ int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const 
                           const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W,
                           cudaStream_t st) {
   const int64_t total = (int64_t)B * H * W * 24;
-  fuse_concat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+  ss_launch_pdl(fuse_concat_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, 
       (const uint4*)r1, (const uint4*)a2, (const uint4*)r2, (const uint4*)a1, (const uint4*)r3, (const uint4*)r3l,
       (const uint4*)a0, (const uint4*)a0l, (uint4*)fg, H, W, total);
   EW_CHECK("fuse_concat");
@@ -166,6 +169,7 @@ int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const 
 // ---------------------------------------------------------------------------------------------
 __global__ void make_s_kernel(const float* __restrict__ R, const float* __restrict__ I, const float* __restrict__ Id,
                               float* __restrict__ S32, bf16* __restrict__ Sb, int C, int HW) {
+  SS_PDL_ENTRY();
   __shared__ float tile[32][33];
   const int64_t p0 = (int64_t)blockIdx.x * 32;
   const int b = (int)(p0 / HW);
@@ -193,7 +197,7 @@ __global__ void make_s_kernel(const float* __restrict__ R, const float* __restri
 int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
                      cudaStream_t st) {
   dim3 grid((unsigned)((int64_t)B * H * W / 32), (C + 31) / 32);
-  make_s_kernel<<<grid, dim3(32, 8), 0, st>>>(R, I, Id, S32, Sb, C, H * W);
+  ss_launch_pdl(make_s_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), st, R, I, Id, S32, Sb, C, H * W);
   EW_CHECK("make_s");
 }
 
@@ -205,6 +209,7 @@ __global__ void s_bwd_kernel(const float* __restrict__ dS32, const float* __rest
                              const bf16* __restrict__ dSb, const float* __restrict__ R,
                              const float* __restrict__ I, const float* __restrict__ Id, float* __restrict__ dR32,
                              float* __restrict__ dI32, float* __restrict__ dId32, int C, int HW) {
+  SS_PDL_ENTRY();
   __shared__ float tile[32][33];
   __shared__ float part[8][32];
   const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -241,7 +246,7 @@ __global__ void s_bwd_kernel(const float* __restrict__ dS32, const float* __rest
 }
 int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, const float* R, const float* I,
                     const float* Id, float* dR32, float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st) {
-  s_bwd_kernel<<<(unsigned)((int64_t)B * H * W / 32), dim3(32, 8), 0, st>>>(dS32, dSf32, dSb, R, I, Id, dR32, dI32,
+  ss_launch_pdl(s_bwd_kernel, dim3((unsigned)((int64_t)B * H * W / 32)), dim3(dim3(32, 8)), (size_t)(0), st, dS32, dSf32, dSb, R, I, Id, dR32, dI32,
                                                                            dId32, C, H * W);
   EW_CHECK("s_bwd");
 }
@@ -255,6 +260,7 @@ int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, cons
 __global__ void head_bwd_kernel(const float* __restrict__ dR32, const float* __restrict__ R32,
                                 const bf16* __restrict__ dRI, int ld_dri, const float* __restrict__ dI32,
                                 const float* __restrict__ I32, bf16* __restrict__ dc8, int ld_out, int C, int HW) {
+  SS_PDL_ENTRY();
   __shared__ float tg[32][33];   // raw gradient
   __shared__ float tr[32][33];   // sigmoid'(.) = R(1-R)
   const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -294,7 +300,7 @@ __global__ void head_bwd_kernel(const float* __restrict__ dR32, const float* __r
 }
 int ss_launch_head_bwd(const float* dR32, const float* R32, const bf16* dRI, int ld_dri, const float* dI32,
                        const float* I32, bf16* dc8, int ld_out, int B, int C, int H, int W, cudaStream_t st) {
-  head_bwd_kernel<<<(unsigned)((int64_t)B * H * W / 32), dim3(32, 8), 0, st>>>(dR32, R32, dRI, ld_dri, dI32, I32, dc8,
+  ss_launch_pdl(head_bwd_kernel, dim3((unsigned)((int64_t)B * H * W / 32)), dim3(dim3(32, 8)), (size_t)(0), st, dR32, R32, dRI, ld_dri, dI32, I32, dc8,
                                                                               ld_out, C, H * W);
   EW_CHECK("head_bwd");
 }
@@ -308,6 +314,7 @@ int ss_launch_head_bwd(const float* dR32, const float* R32, const bf16* dRI, int
 // ---------------------------------------------------------------------------------------------
 __global__ void concat_bwd_kernel(const uint4* __restrict__ dfg, const uint4* __restrict__ r3, uint4* __restrict__ dr3,
                                   uint4* __restrict__ p2, uint4* __restrict__ p1, int H, int W, int64_t total) {
+  SS_PDL_ENTRY();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int q = (int)(i & 7);
@@ -356,7 +363,7 @@ __global__ void concat_bwd_kernel(const uint4* __restrict__ dfg, const uint4* __
 int ss_launch_concat_bwd(const bf16* dfg, const bf16* r3, bf16* dr3, bf16* p2, bf16* p1, int B, int H, int W,
                          cudaStream_t st) {
   const int64_t total = (int64_t)B * (H / 4) * (W / 4) * 8;
-  concat_bwd_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)dfg, (const uint4*)r3, (uint4*)dr3,
+  ss_launch_pdl(concat_bwd_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), (size_t)(0), st, (const uint4*)dfg, (const uint4*)r3, (uint4*)dr3,
                                                                     (uint4*)p2, (uint4*)p1, H, W, total);
   EW_CHECK("concat_bwd");
 }
@@ -371,6 +378,7 @@ int ss_launch_concat_bwd(const bf16* dfg, const bf16* r3, bf16* dr3, bf16* p2, b
 __global__ void pool2_kernel(const uint4* __restrict__ du, const uint4* __restrict__ addp,
                              const uint4* __restrict__ maskr, uint4* __restrict__ out_sum,
                              uint4* __restrict__ out_masked, float* __restrict__ out32, int h, int w, int64_t total) {
+  SS_PDL_ENTRY();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int q = (int)(i & 7);
@@ -420,7 +428,7 @@ __global__ void pool2_kernel(const uint4* __restrict__ du, const uint4* __restri
 int ss_launch_pool2(const bf16* du, const bf16* addp, const bf16* maskr, bf16* out_sum, bf16* out_masked, float* out32,
                     int B, int h, int w, cudaStream_t st) {
   const int64_t total = (int64_t)B * h * w * 8;
-  pool2_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint4*)du, (const uint4*)addp,
+  ss_launch_pdl(pool2_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), (size_t)(0), st, (const uint4*)du, (const uint4*)addp,
                                                                (const uint4*)maskr, (uint4*)out_sum,
                                                                (uint4*)out_masked, out32, h, w, total);
   EW_CHECK("pool2");
@@ -432,6 +440,7 @@ int ss_launch_pool2(const bf16* du, const bf16* addp, const bf16* maskr, bf16* o
 // ---------------------------------------------------------------------------------------------
 __global__ void finalize_losses_kernel(const float* __restrict__ sums, sshslie_loss_cfg cfg, float* __restrict__ losses,
                                        int B, int C, int H, int W) {
+  SS_PDL_ENTRY();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double n0 = (double)B * C * H * W;
   const double nx1 = (double)B * H * (W - 1), ny1 = (double)B * (H - 1) * W;
@@ -456,7 +465,7 @@ __global__ void finalize_losses_kernel(const float* __restrict__ sums, sshslie_l
 }
 int ss_launch_finalize_losses(const float* sums, const sshslie_loss_cfg* cfg, float* losses, int B, int C, int H, int W,
                               cudaStream_t st) {
-  finalize_losses_kernel<<<1, 32, 0, st>>>(sums, *cfg, losses, B, C, H, W);
+  ss_launch_pdl(finalize_losses_kernel, dim3(1), dim3(32), (size_t)(0), st, sums, *cfg, losses, B, C, H, W);
   EW_CHECK("finalize_losses");
 }
 

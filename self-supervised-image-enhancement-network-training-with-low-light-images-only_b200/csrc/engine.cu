@@ -338,6 +338,7 @@ static void epi_set_mask(Epi& e, const Tens& t, int qh = 0, int qw = 0, int scal
 // dff[pix, c] = sum_taps dId[pix - tap] * w[c][tap]
 __global__ void __launch_bounds__(256) final_dgrad_kernel(const float* __restrict__ dId, const float* __restrict__ w,
                                                           bf16* __restrict__ dff, int H, int W, int64_t total) {
+  SS_PDL_ENTRY();
   __shared__ float ws[64 * 9];
   for (int i = threadIdx.x; i < 576; i += 256) ws[i] = w[i];
   __syncthreads();
@@ -954,7 +955,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
                    dId32, ff.p, e->grads + e->poff[2 * L_I_FINAL], e->grads + e->poff[2 * L_I_FINAL + 1], B, H, W,
                    rows_pb);
                return ss_check_launch("final_wgrad"););
-      PUSH(Lq, final_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      PUSH(Lq, ss_launch_pdl(final_dgrad_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, 
                    dId32, e->params + e->poff[2 * L_I_FINAL], dff.p, H, W, total);
                return ss_check_launch("final_dgrad"););
     }

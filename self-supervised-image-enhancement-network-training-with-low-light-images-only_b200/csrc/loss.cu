@@ -42,6 +42,7 @@ SS_DEVINL float block_sum_2d(float v, float* red, int tid, int nthreads) {
 // blockDim = (WX, 8): threadIdx.x = pixel along the row (coalesced plane reads), threadIdx.y = band chunk.
 // grid = (ceil(W / WX), H, B)
 __global__ void __launch_bounds__(PL_WX* PL_CHUNKS) pixel_losses_kernel(PixLossArgs p) {
+  SS_PDL_ENTRY();
   __shared__ float part[PL_CHUNKS][4][PL_WX];
   __shared__ float red[32];
   const int W = p.W, H = p.H, C = p.C;
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(PL_WX* PL_CHUNKS) pixel_losses_kernel(PixLossA
 #define PT_PIX (PT_TW * PT_TH)
 #define PT_C 64
 __global__ void __launch_bounds__(PT_PIX* PL_CHUNKS) pixel_losses_tiled_kernel(PixLossArgs p) {
+  SS_PDL_ENTRY();
   extern __shared__ __align__(16) float pt_smem[];
   float* Rs = pt_smem;                       // [64][PT_TH + 2][PT_PITCH]
   float* Es = pt_smem + PT_C * PT_PLANE;
@@ -426,12 +428,12 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
       attr_set = true;
     }
     dim3 grid(W / PT_TW, H / PT_TH, B), block(PT_PIX, PL_CHUNKS);
-    pixel_losses_tiled_kernel<<<grid, block, smem, st>>>(p);
+    ss_launch_pdl(pixel_losses_tiled_kernel, dim3(grid), dim3(block), (size_t)(smem), st, p);
     return ss_check_launch("pixel_losses_tiled");
   }
   const int wx = W < PL_WX ? W : PL_WX;
   dim3 grid((W + wx - 1) / wx, H, B), block(wx, PL_CHUNKS);
-  pixel_losses_kernel<<<grid, block, 0, st>>>(p);
+  ss_launch_pdl(pixel_losses_kernel, dim3(grid), dim3(block), (size_t)(0), st, p);
   return ss_check_launch("pixel_losses");
 }
 
