@@ -206,6 +206,7 @@ struct sshslie_engine {
 
   // per-call state read by the recorded launches
   const float* x = nullptr;
+  float *out_R = nullptr, *out_I = nullptr, *out_Id = nullptr, *out_S = nullptr;   // caller's output buffers (may be null)
   const float* params = nullptr;
   float* grads = nullptr;
   float* losses = nullptr;
@@ -756,6 +757,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
   (void)in;
 }
 
+static int copy_outputs(sshslie_engine* e, float* R, float* I, float* Id, float* S, cudaStream_t st);
 static int build_plan(sshslie_engine* e, unsigned char* base) {
   e->base = base;
   e->cursor = 0;
@@ -813,6 +815,12 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
 
   // ---- forward (model.py:229-234) ----------------------------------------------------------
   auto& F = e->ops_fwd;
+  if (train) {
+    // per-step zeroing first: a memset node between two kernels would break their programmatic-dependent-launch edge
+    PUSH(F, return cudaMemsetAsync(e->sums_dev, 0, 16 * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
+    PUSH(F, if (!e->grads) return SSHSLIE_OK;
+            return cudaMemsetAsync(e->grads, 0, e->nparams * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
+  }
   PUSH(F, return ss_launch_nchw32_to_nhwc16(e->x, X.p, B, C, H, W, 64, st););
   // fp32 master weights -> packed bf16: the first two layers' weights (conv0, 9x9) on the caller's stream, everything
   // else on a side stream, joined after the 9x9 layer (pack_split = first pack block of the third geom)
@@ -898,6 +906,10 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     PUSH(F, return ss_launch_make_s(e->R32, e->I32, e->Id32, e->S32, sbp, B, C, H, W, st););
   }
 
+  // the caller's copies of R, I, I_delta, S: final once make_s has run -> copied on a side stream, off the critical path
+  // (joined at the end of the forward for inference, at the end of phase 1 for training)
+  PUSH_SIDE(F, return copy_outputs(e, e->out_R, e->out_I, e->out_Id, e->out_S, st););
+  if (!train) PUSH_JOIN(F);
   if (train) {
     // ---- second decomposition pass on S, losses, backward ------------------------------------
     auto& Lq = e->ops_loss_bwd2_illum;
@@ -911,14 +923,11 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     // The Fourier term needs only x and S: it runs on a side stream BESIDE the second decomposition pass, writes its
     // gradient into a plane of its own (dSf32, summed in s_bwd) and is joined before the loss values are finalised.
     float* dSf32 = e->falloc(n * C);
-    PUSH(Lq, return cudaMemsetAsync(e->sums_dev, 0, 16 * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
     PUSH_SIDE(Lq, prof_note("loss:fourier_fft+grad", 0, 12.0 * 1048576.0 * B);
                   return ss_fourier_loss(e->x, e->S32, e->mask_dev, dSf32, e->sums_dev + 9, B * C, H, W,
                                          (float)(e->cfg.c_loss_fourier / ((double)B * C * H * W)), 0, st););
     DecompGeoms G2 = plan_decomp_fwd(e, Lq, Sb, d2, head2);          // model.py:546
 
-    const int64_t np = e->nparams;
-    PUSH(Lq, return cudaMemsetAsync(e->grads, 0, np * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
     // algorithmic HBM bytes: 24.25 MiB per patch for the 5-term loss + gradients, 12 MiB for the Fourier term
     PUSH(Lq, prof_note("loss:pixel_terms+grads", 0, 24.25 * 1048576.0 * B);
              return ss_pixel_losses(e->x, e->R32, e->I32, e->Id32, Re32, e->cfg, B, C, H, W, e->sums_dev, dR32, dI32,
@@ -1263,8 +1272,10 @@ extern "C" int sshslie_forward(sshslie_engine* e, const float* x, const float* p
   if (!e->bound) { ss_set_error("sshslie_forward: engine not bound to a workspace"); return SSHSLIE_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   e->x = x; e->params = params;
+  e->out_R = R; e->out_I = I; e->out_Id = I_delta; e->out_S = S;
+  if (e->train) e->grads = nullptr;      // forward only on a training engine: nothing to zero
   int rc = run_ops(e->ops_fwd, st);
-  if (!rc) rc = copy_outputs(e, R, I, I_delta, S, st);
+  if (!rc && e->train) rc = e->join(st);
   return rc;
 }
 
@@ -1281,9 +1292,9 @@ extern "C" int sshslie_loss_and_grad(sshslie_engine* e, const float* x, const fl
   e->x = x; e->params = params; e->grads = grads; e->losses = losses; e->cfg = *cfg;
   int rc = SSHSLIE_OK;
   if (phase_mask & 1) {
+    e->out_R = R; e->out_I = I; e->out_Id = I_delta; e->out_S = S;
     rc = run_ops(e->ops_fwd, st);
     if (!rc) rc = run_ops(e->ops_loss_bwd2_illum, st);
-    if (!rc) rc = copy_outputs(e, R, I, I_delta, S, st);
   }
   if (!rc && (phase_mask & 2)) rc = run_ops(e->ops_bwd1, st);
   return rc;
