@@ -188,6 +188,7 @@ int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, c
 __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvGeom* __restrict__ geoms,
                                                            const int* __restrict__ block_start, int njobs,
                                                            const float* __restrict__ params, int first_block) {
+  SS_PDL_ENTRY();
   const int blk = (int)blockIdx.x + first_block;      // a launch may cover only blocks [first_block, ...) of the table
   int lo = 0, hi = njobs - 1;           // last job whose first block is <= blk (block_start is ascending)
   while (lo < hi) {
@@ -212,6 +213,6 @@ int ss_launch_pack_weights(const ConvGeom* geoms_dev, const int* block_start_dev
                            const float* params, cudaStream_t st, int first_block, int n_blocks) {
   if (n_blocks < 0) n_blocks = total_blocks - first_block;
   if (n_blocks <= 0) return SSHSLIE_OK;
-  pack_weights_kernel<<<n_blocks, 256, 0, st>>>(geoms_dev, block_start_dev, njobs, params, first_block);
+  ss_launch_pdl(pack_weights_kernel, dim3(n_blocks), dim3(256), (size_t)0, st, geoms_dev, block_start_dev, njobs, params, first_block);
   return ss_check_launch("pack_weights");
 }
