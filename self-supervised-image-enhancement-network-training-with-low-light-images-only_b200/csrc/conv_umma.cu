@@ -1016,9 +1016,19 @@ __global__ void __launch_bounds__(1024) conv_wgrad_reduce_kernel(const ConvGeom*
   const size_t cta_stride = (size_t)wa.groups * wa.blocks_per_cta * wa.N * 128;
   const float* p = partial + ((size_t)group * wa.blocks_per_cta + blk) * (size_t)wa.N * 128 + (size_t)n0 * 128 + row +
                    (size_t)q * cta_stride;
-  for (int sp = q; sp < wa.splits; sp += 8, p += 8 * cta_stride) {
+  // all loads of up to four splits in flight before their adds (the loop otherwise pays one L2 / HBM round trip per split)
+  for (int sp = q; sp < wa.splits; sp += 32, p += 32 * cta_stride) {
+    float v[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += p[(size_t)i * 128];
+    for (int u = 0; u < 4; ++u) {
+      const bool valid = sp + 8 * u < wa.splits;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u][i] = valid ? __ldg(p + (size_t)u * 8 * cta_stride + (size_t)i * 128) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[u][i];
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[q][i][row] = acc[i];
@@ -1346,9 +1356,19 @@ SS_DEVINL void wgrad_halo_reduce_body(const ConvGeom* __restrict__ gp, const flo
   const size_t cta_stride = (size_t)wa.groups * wa.blocks_per_cta * wa.N * 128;
   const float* p = partial + ((size_t)group * wa.blocks_per_cta + blk) * (size_t)wa.N * 128 + (size_t)n0 * 128 + row +
                    (size_t)q * cta_stride;
-  for (int sp = q; sp < wa.splits; sp += 8, p += 8 * cta_stride) {
+  // all loads of up to four splits in flight before their adds (the loop otherwise pays one L2 / HBM round trip per split)
+  for (int sp = q; sp < wa.splits; sp += 32, p += 32 * cta_stride) {
+    float v[4][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] += p[(size_t)i * 128];
+    for (int u = 0; u < 4; ++u) {
+      const bool valid = sp + 8 * u < wa.splits;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u][i] = valid ? __ldg(p + (size_t)u * 8 * cta_stride + (size_t)i * 128) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[u][i];
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[q][i][row] = acc[i];
