@@ -9,6 +9,7 @@
 // forward = decimation-in-frequency along W then H, two radix-2 levels fused per sweep (natural in, bit-reversed out), the spectrum is
 // consumed in bit-reversed positions, and the inverse runs decimation-in-time (bit-reversed in, natural out),
 // so no reordering pass exists.  Algorithmic HBM traffic: read x, s (2 planes), read+write dS (1 plane each).
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -213,6 +214,174 @@ fourier_loss_kernel(const float* __restrict__ x, const float* __restrict__ s, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 128 x 128 planes (the training patch of every reference config): register FFT.
+// A 128-point line transform is 16 x 8:  k = k1 + 16 k2,  n = j + 8 m
+//     X[k1 + 16 k2] = sum_j W8^(j k2) [ W128^(j k1) sum_m W16^(m k1) x[j + 8 m] ]
+//   step 1  thread (line, j):   16-point DFT over m in registers, twiddle W128^(j k1), stored in place at j + 8 k1
+//   step 2  thread (line, k1):  8-point DFT over j (8 consecutive elements), stored at k1 + 16 k2  -> natural order
+// Lanes run over LINES, so with a row pitch of 129 complex words both the row pass (line = image row, element stride 1)
+// and the column pass (line = column, element stride = pitch) are free of bank conflicts, and the whole 2-D transform is
+// 4 passes x 2 barriers instead of 16 radix-4 sweeps over shared memory.  Natural order in and out (no bit reversal).
+// ---------------------------------------------------------------------------------------------
+#define F128_N 128
+#define F128_PITCH 129
+#define F128_THREADS 1024
+
+template <bool INV>
+SS_DEVINL float2 tw_apply(float2 a, float c, float s_) {      // a * (c - i s) forward, a * (c + i s) inverse
+  const float s2 = INV ? -s_ : s_;
+  return make_float2(a.x * c + a.y * s2, a.y * c - a.x * s2);
+}
+// in-register radix-2 DIF of length N (power of two <= 16) with compile-time twiddles; output index k ends up at
+// position bit-reverse(k): callers read v[BR(k)].
+template <int N, bool INV>
+SS_DEVINL void dft_regs(float2 (&v)[N]) {
+  constexpr float C16[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
+                            0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+  constexpr float S16[8] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f,
+                            1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+#pragma unroll
+  for (int half = N / 2; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int g = 0; g < N; g += 2 * half) {
+#pragma unroll
+      for (int p = 0; p < half; ++p) {
+        const float2 a = v[g + p], b = v[g + p + half];
+        v[g + p] = make_float2(a.x + b.x, a.y + b.y);
+        const float2 d = make_float2(a.x - b.x, a.y - b.y);
+        const int tw = p * (8 / half);                 // W_(2 half)^p = W16^(p * 16 / (2 half))
+        if (tw == 0) v[g + p + half] = d;
+        else if (tw == 4) v[g + p + half] = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+        else v[g + p + half] = tw_apply<INV>(d, C16[tw], S16[tw]);
+      }
+    }
+  }
+}
+SS_DEVINL constexpr int br4(int k) { return ((k & 1) << 3) | ((k & 2) << 1) | ((k & 4) >> 1) | ((k & 8) >> 3); }
+SS_DEVINL constexpr int br3(int k) { return ((k & 1) << 2) | (k & 2) | ((k & 4) >> 2); }
+
+// one pass over all 128 lines: es = element stride along the line, ls = stride between lines (in float2 words)
+template <bool INV>
+SS_DEVINL void fft128_lines(float2* __restrict__ z, const float2* __restrict__ tw128, int es, int ls) {
+  const int line = threadIdx.x & (F128_N - 1), j = threadIdx.x >> 7;          // j = 0..7
+  {
+    float2* base = z + line * ls + j * es;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = base[(8 * m) * es];
+    dft_regs<16, INV>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      float2 r = v[br4(k1)];
+      if (k1 > 0 && j > 0) {
+        const float2 w = tw128[(j * k1) & (F128_N - 1)];      // (cos, sin) of 2 pi j k1 / 128
+        r = tw_apply<INV>(r, w.x, w.y);
+      }
+      base[(8 * k1) * es] = r;                                  // in place: position j + 8 k1
+    }
+  }
+  __syncthreads();
+  float2 u[2][8];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k1 = j + 8 * it;                                  // this thread's two k1 values
+    const float2* src = z + line * ls + (8 * k1) * es;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) u[it][jj] = src[jj * es];
+    dft_regs<8, INV>(u[it]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int k1 = j + 8 * it;
+    float2* dst = z + line * ls + k1 * es;
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) dst[(16 * k2) * es] = u[it][br3(k2)];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(F128_THREADS, 1)
+fourier_loss128_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ mask,
+                       float* __restrict__ dS, float* __restrict__ sum_out, float grad_scale, int accumulate) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* z = reinterpret_cast<float2*>(smem_raw);                    // [128][F128_PITCH]
+  float2* tw128 = z + F128_N * F128_PITCH;                            // (cos, sin)(2 pi i / 128)
+  __shared__ float red[32];
+  constexpr int HW = F128_N * F128_N;
+  const int64_t img = blockIdx.x;
+  const float* xp = x + img * HW;
+  const float* sp = s + img * HW;
+  if (threadIdx.x < F128_N) {
+    float sn, cs;
+    sincospif(2.f * (float)threadIdx.x / (float)F128_N, &sn, &cs);
+    tw128[threadIdx.x] = make_float2(cs, sn);
+  }
+  {  // z = x + i s, all loads in flight before the stores
+    const float4* x4 = reinterpret_cast<const float4*>(xp);
+    const float4* s4 = reinterpret_cast<const float4*>(sp);
+    float4 xv[4], sv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { xv[k] = __ldg(x4 + threadIdx.x + k * F128_THREADS); sv[k] = __ldg(s4 + threadIdx.x + k * F128_THREADS); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = (threadIdx.x + k * F128_THREADS) * 4;             // first of 4 consecutive pixels of a row
+      float2* zo = z + (i >> 7) * F128_PITCH + (i & 127);
+      zo[0] = make_float2(xv[k].x, sv[k].x); zo[1] = make_float2(xv[k].y, sv[k].y);
+      zo[2] = make_float2(xv[k].z, sv[k].z); zo[3] = make_float2(xv[k].w, sv[k].w);
+    }
+  }
+  __syncthreads();
+  fft128_lines<false>(z, tw128, 1, F128_PITCH);        // rows (along W)
+  fft128_lines<false>(z, tw128, F128_PITCH, 1);        // columns (along H)
+
+  // spectrum pass, natural order: frequency (ky, kx) pairs with (-ky, -kx)
+  float lsum = 0.f;
+  for (int p = threadIdx.x; p < HW; p += F128_THREADS) {
+    const int ky = p >> 7, kx = p & 127;
+    const int nky = (F128_N - ky) & 127, nkx = (F128_N - kx) & 127;
+    const int pn = nky * F128_N + nkx;
+    if (pn < p) continue;                        // the pair is owned by its smaller index
+    float2* za = z + ky * F128_PITCH + kx;
+    float2* zc = z + nky * F128_PITCH + nkx;
+    const float2 a = *za, c = *zc;
+    // X_k = (Z_k + conj(Z_-k))/2 ; S_k = (Z_k - conj(Z_-k))/(2i)
+    const float2 X = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+    const float2 S = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));
+    const float ax = sqrtf(X.x * X.x + X.y * X.y);
+    const float as = sqrtf(S.x * S.x + S.y * S.y);
+    const float mk = mask[p], mn = mask[pn];
+    const float diff = ax - as;
+    const float ad = fabsf(diff);
+    lsum += (pn == p) ? mk * ad : (mk + mn) * ad;
+    const float g = (as > 0.f) ? -sgnf(diff) / as : 0.f;
+    *za = make_float2(mk * g * S.x, mk * g * S.y);
+    if (pn != p) *zc = make_float2(mn * g * S.x, -mn * g * S.y);
+  }
+  __syncthreads();
+  {
+    const float t = block_sum(lsum, red);
+    if (threadIdx.x == 0) atomicAdd(sum_out, t);
+  }
+  if (dS == nullptr) return;
+  fft128_lines<true>(z, tw128, F128_PITCH, 1);         // inverse (unnormalised): columns, then rows
+  fft128_lines<true>(z, tw128, 1, F128_PITCH);
+  float* dp = dS + img * HW;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = (threadIdx.x + k * F128_THREADS) * 4;
+    const float2* zi = z + (i >> 7) * F128_PITCH + (i & 127);
+    float4 o = make_float4(grad_scale * zi[0].x, grad_scale * zi[1].x, grad_scale * zi[2].x, grad_scale * zi[3].x);
+    float4* d4 = reinterpret_cast<float4*>(dp + i);
+    if (accumulate) {
+      const float4 old = *d4;
+      o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+    }
+    *d4 = o;
+  }
+}
+
 static int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -227,6 +396,22 @@ int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS
   if (!x || !S || !mask || !sum_out || n_img < 1 || lgH < 3 || lgW < 3 || H > 128 || W > 128) {
     ss_set_error("sshslie_fourier_loss: H and W must be powers of two in [8,128] (got %dx%d)", H, W);
     return SSHSLIE_ERR_ARG;
+  }
+  static const bool reg_fft = !(getenv("SSHSLIE_FFT128") && getenv("SSHSLIE_FFT128")[0] == '0');
+  if (reg_fft && H == F128_N && W == F128_N && ((uintptr_t)x & 15) == 0 && ((uintptr_t)S & 15) == 0 &&
+      (!dS || ((uintptr_t)dS & 15) == 0)) {
+    const size_t smem128 = (size_t)(F128_N * F128_PITCH + F128_N) * sizeof(float2);
+    static bool attr128 = false;
+    if (!attr128) {
+      if (cudaFuncSetAttribute(fourier_loss128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128) !=
+          cudaSuccess) {
+        ss_set_error("sshslie_fourier_loss: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+        return SSHSLIE_ERR_CUDA;
+      }
+      attr128 = true;
+    }
+    fourier_loss128_kernel<<<n_img, F128_THREADS, smem128, stream>>>(x, S, mask, dS, sum_out, grad_scale, accumulate);
+    return ss_check_launch("fourier_loss128");
   }
   const size_t smem = (size_t)H * W * sizeof(float2) + 128 * sizeof(float2);
   static bool attr_set = false;
