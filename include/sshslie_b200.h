@@ -122,6 +122,12 @@ SSHSLIE_API int sshslie_denorm_hwc(const float* src_chw, float* dst_hwc, int C, 
 SSHSLIE_API int sshslie_psnr_sam(const float* pred_hwc, const float* target_hwc, int H, int W, int C, double* sums2,
                      void* stream);
 
+/* SSIM of two (H,W,C) fp32 cubes as metrics.py:16-19 evaluates it through torchmetrics 1.6.2 (the cube unsqueezed to
+ * (1,H,W,C): H is the channel axis, the 11x11 gaussian window, sigma 1.5, slides over the (W, C) plane; c1 = (0.01 range)^2,
+ * c2 = (0.03 range)^2).  sum1[0] = sum of the index over the H x (W-10) x (C-10) averaged outputs; device double. */
+SSHSLIE_API int sshslie_ssim_sum(const float* pred_hwc, const float* target_hwc, int H, int W, int C, float c1, float c2,
+                     double* sum1, void* stream);
+
 /* ---- single kernels, exported for kernel-level parity tests and profiling ---- */
 
 /* fourier_spectrum_loss (model.py:456-473) forward + d/dS.  x,S,dS: (n_img,H,W) fp32 planes, H and W

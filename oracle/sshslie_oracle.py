@@ -359,3 +359,32 @@ def sam(pred_hwc, target_hwc):
     dot = (pred_hwc * target_hwc).sum(-1)
     den = pred_hwc.norm(dim=-1) * target_hwc.norm(dim=-1)
     return torch.acos(torch.clamp(dot / den, -1, 1)).mean()
+
+
+def ssim(pred_hwc, target_hwc, data_range):
+    """torchmetrics structural_similarity_index_measure as metrics.py:16-19 calls it: the (H,W,C) cube is unsqueezed to
+    (1,H,W,C), so H plays the channel role and the 11x11 gaussian window (sigma 1.5, k1 0.01, k2 0.03) slides over the
+    (W, C) plane of every image row; reflect-padded by 5, convolved, cropped by 5 again, mean.  Restated from
+    torchmetrics 1.6.2 `_ssim_update` (package not installable here: PARITY UNPINNED)."""
+    p = pred_hwc.unsqueeze(0).float()
+    t = target_hwc.unsqueeze(0).float()
+    if isinstance(data_range, tuple):
+        p = p.clamp(data_range[0], data_range[1])
+        t = t.clamp(data_range[0], data_range[1])
+        data_range = data_range[1] - data_range[0]
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    ch = p.shape[1]
+    dist = torch.arange(-5.0, 6.0)
+    g = torch.exp(-(dist / 1.5) ** 2 / 2)
+    g = (g / g.sum()).unsqueeze(0)
+    kernel = (g.t() @ g).expand(ch, 1, 11, 11).contiguous()
+    pp = F.pad(p, (5, 5, 5, 5), mode="reflect")
+    tp = F.pad(t, (5, 5, 5, 5), mode="reflect")
+    out = F.conv2d(torch.cat((pp, tp, pp * pp, tp * tp, pp * tp)), kernel, groups=ch)
+    mu_p, mu_t, e_pp, e_tt, e_pt = out.split(1)
+    mu_pp, mu_tt, mu_pt = mu_p * mu_p, mu_t * mu_t, mu_p * mu_t
+    s_pp = torch.clamp(e_pp - mu_pp, min=0.0)
+    s_tt = torch.clamp(e_tt - mu_tt, min=0.0)
+    s_pt = e_pt - mu_pt
+    full = ((2 * mu_pt + c1) * (2 * s_pt + c2)) / ((mu_pp + mu_tt + c1) * (s_pp + s_tt + c2))
+    return full[..., 5:-5, 5:-5].reshape(1, -1).mean(-1)[0]

@@ -605,3 +605,67 @@ extern "C" int sshslie_psnr_sam(const float* pred_hwc, const float* target_hwc, 
   psnr_sam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred_hwc, target_hwc, npix, C, sums2);
   return ss_check_launch("psnr_sam");
 }
+
+
+// SSIM as metrics.py:16-19 evaluates it (torchmetrics on the (1,H,W,C) tensor: H plays the channel role, the 11x11 gaussian
+// window slides over the (W, C) plane of every image row; reflect padding by 5 and the final crop by 5 cancel, so every
+// averaged output is a plain window that lies inside the plane).  One thread per output (h, w, c), c fastest; fp32 per
+// window, fp64 across outputs.  sum[0] += sum of the SSIM index over H x (W-10) x (C-10) outputs.
+__global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, int H,
+                                                   int W, int C, float c1, float c2, double* __restrict__ sum) {
+  __shared__ float gw[11];
+  __shared__ double red[8];
+  if (threadIdx.x < 11) {
+    float tot = 0.f;
+    for (int i = 0; i < 11; ++i) tot += expf(-((float)(i - 5) / 1.5f) * ((float)(i - 5) / 1.5f) / 2.f);
+    gw[threadIdx.x] = expf(-((float)((int)threadIdx.x - 5) / 1.5f) * ((float)((int)threadIdx.x - 5) / 1.5f) / 2.f) / tot;
+  }
+  __syncthreads();
+  const int Wo = W - 10, Co = C - 10;
+  const int64_t total = (int64_t)H * Wo * Co;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Co);
+    const int64_t t = i / Co;
+    const int w = (int)(t % Wo);
+    const int h = (int)(t / Wo);
+    const float* p0 = pred + ((int64_t)h * W + w) * C + c;
+    const float* t0 = tgt + ((int64_t)h * W + w) * C + c;
+    float mp = 0.f, mt = 0.f, epp = 0.f, ett = 0.f, ept = 0.f;
+    for (int dw = 0; dw < 11; ++dw) {
+      const float gy = gw[dw];
+#pragma unroll
+      for (int dc = 0; dc < 11; ++dc) {
+        const float g = gy * gw[dc];
+        const float a = p0[(int64_t)dw * C + dc], b = t0[(int64_t)dw * C + dc];
+        mp = fmaf(g, a, mp);
+        mt = fmaf(g, b, mt);
+        epp = fmaf(g, a * a, epp);
+        ett = fmaf(g, b * b, ett);
+        ept = fmaf(g, a * b, ept);
+      }
+    }
+    const float spp = fmaxf(epp - mp * mp, 0.f), stt = fmaxf(ett - mt * mt, 0.f), spt = ept - mp * mt;
+    acc += (double)(((2.f * mp * mt + c1) * (2.f * spt + c2)) / ((mp * mp + mt * mt + c1) * (spp + stt + c2)));
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    atomicAdd(sum, s);
+  }
+}
+extern "C" int sshslie_ssim_sum(const float* pred_hwc, const float* target_hwc, int H, int W, int C, float c1, float c2,
+                                double* sum1, void* stream) {
+  if (!pred_hwc || !target_hwc || !sum1 || H < 1 || W < 11 || C < 11) {
+    ss_set_error("sshslie_ssim_sum: need W >= 11 and C >= 11 (11x11 window over the (W, C) plane)");
+    return SSHSLIE_ERR_ARG;
+  }
+  cudaMemsetAsync(sum1, 0, sizeof(double), (cudaStream_t)stream);
+  const int64_t total = (int64_t)H * (W - 10) * (C - 10);
+  const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  ssim_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred_hwc, target_hwc, H, W, C, c1, c2, sum1);
+  return ss_check_launch("ssim");
+}

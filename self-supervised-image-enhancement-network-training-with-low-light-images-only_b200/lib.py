@@ -20,7 +20,7 @@ EXPORTS = [
     "sshslie_engine_destroy", "sshslie_engine_workspace_bytes", "sshslie_engine_bind", "sshslie_forward",
     "sshslie_loss_and_grad", "sshslie_adam_step", "sshslie_fourier_loss", "sshslie_pixel_losses",
     "sshslie_conv2d_scratch_bytes", "sshslie_conv2d", "sshslie_profile_step", "sshslie_profile_row",
-    "sshslie_launch_count", "sshslie_umma_probe", "sshslie_debug_read", "sshslie_gather_patches", "sshslie_conv2d_last_ms", "sshslie_denorm_hwc", "sshslie_psnr_sam",
+    "sshslie_launch_count", "sshslie_umma_probe", "sshslie_debug_read", "sshslie_gather_patches", "sshslie_conv2d_last_ms", "sshslie_denorm_hwc", "sshslie_psnr_sam", "sshslie_ssim_sum",
 ]
 
 
@@ -69,6 +69,7 @@ def load():
     lib.sshslie_gather_patches.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.sshslie_denorm_hwc.argtypes = [vp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.sshslie_psnr_sam.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.sshslie_ssim_sum.argtypes = [vp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_float, vp, vp]
     lib.sshslie_launch_count.restype = ctypes.c_longlong
     lib.sshslie_conv2d_last_ms.restype = ctypes.c_float
     lib.sshslie_umma_probe.argtypes = [i32, i32, i32, i32, vp, i32, vp]

@@ -317,3 +317,18 @@ def test_conv_dgrad_halo(case):
     dx = torch.empty_like(dx_ref)
     conv2d(1, 2, tr, dy, w, None, dx, B, Cin, Cout, H, W, k, stride, relu=False)
     torch.testing.assert_close(dx, dx_ref, rtol=2 ** -7, atol=2e-3 * float(dx_ref.abs().max()))
+
+
+def test_ssim_vs_oracle():
+    """SSIM on the device vs the oracle's torch restatement of the torchmetrics call (H as channel axis): rel 1e-4."""
+    import sshslie_b200 as S
+    from oracle import sshslie_oracle as O
+    g = torch.Generator().manual_seed(13)
+    yy, xx = torch.meshgrid(torch.arange(40.0), torch.arange(56.0), indexing="ij")
+    scene = (0.5 + 0.5 * torch.sin(xx / 9.0) * torch.cos(yy / 7.0))[..., None] * (0.4 + 0.6 * torch.rand(64, generator=g))
+    t = 238 + 3000 * scene
+    p = t + torch.randn(40, 56, 64, generator=g) * 80
+    got = S.metrics.ssim(p, t, 4095.0)
+    np.testing.assert_allclose(got, float(O.ssim(p, t, 4095.0)), rtol=1e-4)
+    got2 = S.metrics.ssim(p, t, (238.0, 3000.0))
+    np.testing.assert_allclose(got2, float(O.ssim(p, t, (238.0, 3000.0))), rtol=1e-4)
