@@ -657,14 +657,34 @@ class LowLightEnhance(nn.Module):
         if len(eval_low_data) <= 0:
             print(f"--- No files found for evaluation. Skipping evaluation for epoch {epoch} ---")
             return
+        from . import metrics as M
+        from .utils import load_hsi
         epoch_dir = os.path.join(eval_result_dir, f'epoch_{epoch}')
         os.makedirs(epoch_dir, exist_ok=True)
+        acc, n = [0.0, 0.0, 0.0], 0
         with torch.no_grad():
             for idx, low_im in enumerate(eval_low_data):
+                filename = os.path.basename(eval_files[idx])
                 x = torch.from_numpy(low_im).unsqueeze(0).permute(0, 3, 1, 2)
                 R, I, Id, S = self.forward(x)
-                self._save_outputs(epoch_dir, os.path.basename(eval_files[idx]), R, I, Id, S,
+                self._save_outputs(epoch_dir, filename, R, I, Id, S,
                                    self.save_reflectance, self.save_illumination, self.save_i_delta)
+                # PSNR / SSIM / SAM against the label cube of the same name (model.py:390-397 -> metrics.calc_metrics with
+                # data_max = global_max), on the device.  The reference reads its own output back with key 'ref' although
+                # save_hsi wrote 'data' and so cannot get this far; here the metrics are computed whenever
+                # the label file exists.
+                label_path = os.path.join(label_dir, filename) if label_dir else None
+                if label_path and os.path.exists(label_path) and self.global_max is not None:
+                    label = torch.from_numpy(load_hsi(label_path, matContentHeader='data'))
+                    pred = torch.from_numpy(self._to_hwc_host(S, denorm=True))
+                    ps, sa = M.psnr_sam(pred, label, self.global_max)
+                    acc[0] += ps
+                    acc[1] += M.ssim(pred, label, self.global_max)
+                    acc[2] += sa
+                    n += 1
+        if n > 0:
+            self.eval_metrics[epoch] = {"psnr": acc[0] / n, "ssim": acc[1] / n, "sam": acc[2] / n}
+            print(f"--- Evaluation for epoch {epoch}: PSNR {acc[0] / n:.4f} SSIM {acc[1] / n:.4f} SAM {acc[2] / n:.4f} ---")
 
     def test_model(self, model_dir, test_low_data, test_low_data_names, save_dir, save_reflectance=False,
                    save_illumination=False, save_i_delta=False):

@@ -91,3 +91,28 @@ def test_full_image_inference_512():
     assert (I.cpu() - Ir).abs().max() <= 5e-3
     assert (Id.cpu() - Idr).abs().max() <= 4e-3
     assert (S_.cpu() - Sr).abs().max() <= 5e-3
+
+
+def test_evaluate_model_computes_metrics(tmp_path):
+    """In-training evaluation (model.py:342-403): outputs are written and PSNR / SSIM / SAM against the label cubes land in
+    `eval_metrics[epoch]`, equal to the oracle's restatement of the metrics on the written file."""
+    import scipy.io as sio
+    import sshslie_b200 as S
+    from oracle import sshslie_oracle as O
+    torch.manual_seed(41)
+    gmin, gmax = 238.0, 4095.0
+    m = S.LowLightEnhance(global_min=gmin, global_max=gmax, time_stamp="t").to("cuda")
+    cube = O.synthetic_patches(1, 64, 64, seed=9)[0].permute(1, 2, 0).numpy()
+    label_dir = tmp_path / "label"
+    os.makedirs(label_dir)
+    rng = np.random.default_rng(2)
+    label = (gmin + (gmax - gmin) * np.clip(cube * 3.0 + 0.02 * rng.standard_normal(cube.shape), 0, 1)).astype(np.float32)
+    sio.savemat(str(label_dir / "scene.mat"), {"data": label})
+    out_dir = tmp_path / "eval"
+    m.evaluate_model([cube], ["scene.mat"], str(out_dir), 3, str(label_dir))
+    assert set(m.eval_metrics[3]) == {"psnr", "ssim", "sam"}
+    pred = torch.from_numpy(sio.loadmat(str(out_dir / "epoch_3" / "scene.mat"))["data"])
+    lab = torch.from_numpy(label)
+    np.testing.assert_allclose(m.eval_metrics[3]["psnr"], float(O.psnr(pred, lab, gmax)), rtol=1e-4)
+    np.testing.assert_allclose(m.eval_metrics[3]["sam"], float(O.sam(pred, lab)), rtol=1e-3)
+    np.testing.assert_allclose(m.eval_metrics[3]["ssim"], float(O.ssim(pred, lab, gmax)), rtol=1e-3)
