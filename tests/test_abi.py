@@ -75,3 +75,22 @@ def test_cpu_tensors_fail_loudly():
         m.compute_loss(torch.rand(1, 64, 32, 32))
     with pytest.raises(S.lib.SshslieError):
         m.illum_adjust_net(torch.rand(1, 1, 8, 8), torch.rand(1, 64, 8, 8))
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU and prints ONE JSON line with the
+    contract keys; ours refuses to run without a CUDA device instead of falling back."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-1000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_patches_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    if not torch.cuda.is_available():
+        ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"],
+                              capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert ours.returncode != 0 and "CUDA" in (ours.stderr + ours.stdout)
