@@ -424,11 +424,15 @@ class LowLightEnhance(nn.Module):
                 flat[off:off + n].copy_(p.detach().reshape(-1).float())
                 p.data = flat[off:off + n].view(p.shape)
         self._flat = flat
-        self._flat_grad = torch.zeros_like(flat)
+        # gradients and the 8 loss scalars share one allocation: under data parallelism the losses ride in the same
+        # all-reduce as the illum_adjust_net bucket (the slice right before them) and one kernel turns sums into means
+        self._grad_store = torch.zeros(self._nparams + 8, dtype=torch.float32, device=p0.device)
+        self._flat_grad = self._grad_store[:self._nparams]
         self._grad_views = [self._flat_grad[off:off + n].view(p.shape) for p, (off, n) in
                             zip(self._plist, self._pranges)]
         self._anchor = torch.zeros((), device=p0.device, requires_grad=True)
-        self._losses_dev = torch.zeros(8, dtype=torch.float32, device=p0.device)
+        self._losses_dev = self._grad_store[self._nparams:]
+        self._dp_ranges = None
         self._engines = {}
 
     def _cfg(self):
@@ -542,9 +546,9 @@ class LowLightEnhance(nn.Module):
     def _dp_step(self, eng):
         import torch.distributed as dist
         from . import parallel as P
-        offs = [o for o, _ in self._pranges]
-        sizes = [n for _, n in self._pranges]
-        dec, ill = P.bucket_ranges(offs, sizes)
+        if self._dp_ranges is None:
+            self._dp_ranges = P.bucket_ranges([o for o, _ in self._pranges], [n for _, n in self._pranges])
+        dec, ill = self._dp_ranges
         cur = torch.cuda.current_stream(self._flat.device)
         eng.calls += 1
         if self.use_cuda_graph and eng.graph is None and eng.calls >= 3:
@@ -562,12 +566,12 @@ class LowLightEnhance(nn.Module):
         ev.record(cur)
         with torch.cuda.stream(self._dp_stream):
             self._dp_stream.wait_event(ev)
-            P.allreduce_bucket(self._flat_grad, ill, self.dp_group)           # overlaps the pass-1 backward below
-            dist.all_reduce(self._losses_dev, group=self.dp_group)
+            # illum_adjust_net bucket + the loss scalars behind it, one call; overlaps the pass-1 backward below
+            P.allreduce_bucket(self._grad_store, (ill[0], self._nparams + 8), self.dp_group)
         run(2)                                       # pass-1 decomposition backward
-        P.allreduce_bucket(self._flat_grad, dec, self.dp_group)
+        P.allreduce_bucket(self._grad_store, dec, self.dp_group)
         cur.wait_stream(self._dp_stream)
-        P.finish_mean(self._flat_grad, self._losses_dev, self._dp_world)      # p.grad = mean over ranks
+        P.finish_mean(self._grad_store, None, self._dp_world)                 # p.grad (and the losses) = mean over ranks
 
     # ------------------------------------------------------------------ loops (host glue, model.py:236-443)
     def train_model(self, train_data_path, eval_data_path, batch_size, patch_size, num_epochs, start_lr, ckpt_dir,
