@@ -22,14 +22,15 @@ def _worker(rank, world, port, out_dir):
     dec, ill = P.bucket_ranges(offs, sizes)
     assert dec == (0, 849121) and ill == (849121, 1141922)          # SURVEY.md §8e parameter split
     g = torch.Generator().manual_seed(100 + rank)
-    flat = torch.randn(total, generator=g)
-    losses = torch.full((8,), float(rank + 1))
+    # the layout LowLightEnhance._dp_step exchanges: gradients, then the 8 loss scalars in the same allocation, so that
+    # the losses ride in the illum bucket's all-reduce and ONE kernel turns sums into means
+    store = torch.cat([torch.randn(total, generator=g), torch.full((8,), float(rank + 1))])
+    flat, losses = store[:total], store[total:]
     mine = flat.clone()
-    P.allreduce_bucket(flat, ill)                                     # bucket 1 first (ready mid-backward)
+    P.allreduce_bucket(store, (ill[0], total + 8))                    # bucket 1 + losses first (ready mid-backward)
     assert torch.equal(flat[:dec[1]], mine[:dec[1]])                  # decomposition slice untouched so far
-    P.allreduce_bucket(flat, dec)
-    dist.all_reduce(losses)
-    P.finish_mean(flat, losses, world)
+    P.allreduce_bucket(store, dec)
+    P.finish_mean(store, None, world)
     others = [torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
     ref = sum(others) / world
     torch.testing.assert_close(flat, ref, rtol=1e-6, atol=1e-6)
