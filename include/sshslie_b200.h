@@ -145,8 +145,8 @@ SSHSLIE_API int sshslie_pixel_losses(const float* x, const float* R, const float
 
 /* One conv layer through the implicit-GEMM executors, for kernel parity tests: x (B,Cin,H,W) fp32,
  * w (Cout,Cin,k,k) [or (Cin,Cout,k,k) when transposed], y (B,Cout,OH,OW) fp32.  Internally converts to the
- * engine's bf16 NHWC layout, runs the per-tap tcgen05 (impl=1), halo-reuse tcgen05 (impl=2, stride-1 layers) or
- * CUDA-core (impl=0) kernel, converts back.
+ * engine's bf16 NHWC layout, runs the per-tap tcgen05 (impl=1), halo-reuse tcgen05 (impl=2, stride-1 layers), persistent
+ * pipelined tcgen05 (impl=3, stride-1 layers, forward / dgrad) or CUDA-core (impl=0) kernel, converts back.
  * kind: 0 = forward, 1 = dgrad (x is dY, y is dX), 2 = wgrad (x is the layer input, w receives dW, y is dY; a non-NULL
  * `bias` then receives db = sum of dY over pixels, as the fused bias row of the tcgen05 weight gradient produces it).
  * scratch must hold sshslie_conv2d_scratch_bytes(...) bytes. */

@@ -22,16 +22,11 @@
 #include "epilogue.cuh"
 #include "kernels.h"
 
-#define UM_STAGES 4
-#define UM_A_BYTES (128 * 128)            // 128 rows x 64 bf16
-#define UM_THREADS 192
-#define UM_WAIT_CYCLES (2000000000LL)     // ~1 s: a stuck barrier traps instead of hanging the GPU
+#include "umma_ptx.cuh"
 
-struct alignas(64) UmmaMaps {
-  CUtensorMap src[SS_MAX_SRC];
-  CUtensorMap w;
-  CUtensorMap halo[SS_MAX_SRC];   // same views, box = one halo window (HALO_TW+2p) x (HALO_TH+2p) x 64 ch
-};
+#define UM_STAGES 4
+#define UM_THREADS 192
+
 size_t ss_umma_maps_size() { return sizeof(UmmaMaps); }
 static int g_pdl = -1;
 int ss_pdl_enabled() {
@@ -42,144 +37,6 @@ int ss_pdl_enabled() {
   return g_pdl;
 }
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-SS_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-SS_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-SS_DEVINL void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-SS_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-SS_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-SS_DEVINL void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-SS_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-SS_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > UM_WAIT_CYCLES) {
-      printf("sshslie: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-// whole-warp wait with ONE polling lane: 128 epilogue threads hammering try_wait on the same barrier slow the
-// SM's barrier unit down for the MMA warp's commits and the producer's arrivals (measured: 0.4 us per K-slab)
-SS_DEVINL void mbar_wait_warp(uint32_t bar, uint32_t parity, unsigned sleep_ns) {
-  if ((threadIdx.x & 31) == 0) {
-    if (!mbar_try_wait(bar, parity)) {
-      const long long t0 = clock64();
-      while (!mbar_try_wait(bar, parity)) {
-        if (sleep_ns) __nanosleep(sleep_ns);
-        if (clock64() - t0 > UM_WAIT_CYCLES) {
-          printf("sshslie: mbarrier wait timed out (block %d warp %d bar %u parity %u)\n", (int)blockIdx.x,
-                 (int)(threadIdx.x >> 5), bar, parity);
-          __trap();
-        }
-      }
-    }
-  }
-  __syncwarp();
-}
-SS_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-SS_DEVINL void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-SS_DEVINL void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
-SS_DEVINL void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-SS_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// programmatic dependent launch: let the next kernel's prologue overlap this kernel / wait for the previous kernel's
-// results.  Both are no-ops when the kernel was launched without the PDL attribute.
-SS_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-SS_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-SS_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-SS_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-SS_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// one elected lane of a CONVERGED warp (the MMA warp runs its loop warp-uniformly so that descriptors stay in uniform
-// registers; issuing tcgen05.mma under `if (lane == 0)` makes ptxas wrap every MMA in an ELECT/R2UR waterfall loop)
-SS_DEVINL bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-SS_DEVINL uint32_t uniform32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
-SS_DEVINL void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-SS_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor, K-major or MN-major operand in SWIZZLE_128B atoms (8 rows x 128 B = 1024 B)
-//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-SS_DEVINL uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), majors (bit 15/16),
-// N>>3 at bit 17, M>>4 at bit 24
-SS_DEVINL uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // ---------------------------------------------------------------------------------------------
 // gather GEMM kernel
@@ -320,8 +177,6 @@ conv_gather_umma4_kernel(const __grid_constant__ ConvGeom4 g4, const __grid_cons
 // CTA share each weight slab.  L2->SM traffic per MMA drops from 6 KB (per-tap kernel) to 2 KB / T.
 // ---------------------------------------------------------------------------------------------
 __device__ long long g_dbg[16];   // timing breadcrumbs of block 0 (SSHSLIE_HALO_DEBUG=64), read by sshslie_debug_read
-#define HALO_TW 8
-#define HALO_TH 16
 #define HALO_MAX_T 4
 #define HALO_MAX_STAGES 8
 
@@ -342,20 +197,6 @@ struct HaloArgs {
                                      // Lives in the kernel's constant bank: the MMA loop reads it with uniform loads.
 };
 
-SS_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 template <int T>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -572,7 +413,7 @@ int ss_umma_supported(const ConvGeom& g) {
   return 1;
 }
 
-static int env_int(const char* name, int dflt) {
+int ss_env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && e[0]) ? atoi(e) : dflt;
 }
@@ -608,13 +449,13 @@ static int halo_args(const ConvGeom& g, HaloArgs* out) {
     const int rounds = (g.nslabs + G - 1) / G;
     G = (g.nslabs + rounds - 1) / rounds;
   }
-  G = std::max(1, std::min(16, env_int("SSHSLIE_HALO_G", G)));
+  G = std::max(1, std::min(16, ss_env_int("SSHSLIE_HALO_G", G)));
   ha.G = G;
   const int min_ring = 2 * G * b_bytes;
   // tiles per CTA: small problems keep T = 1 (two CTAs per SM overlap each other's prologue / epilogue); when there
   // are more than ~4 waves of tiles, T = 2 halves the weight traffic per MMA
   int T = 1;      // measured: two co-resident T = 1 CTAs per SM beat one T = 2 CTA at every size of this network
-  T = std::max(1, std::min(HALO_MAX_T, env_int("SSHSLIE_HALO_T", T)));
+  T = std::max(1, std::min(HALO_MAX_T, ss_env_int("SSHSLIE_HALO_T", T)));
   if (T > 2) T = 2;
   while (T > 1 && (T * ha.nh * ha.halo_bytes + min_ring > HALO_SMEM_BUDGET || T * g.Npad > 512 || (ha.n_tiles % T))) --T;
   if (T * ha.nh * ha.halo_bytes + min_ring > HALO_SMEM_BUDGET || T * g.Npad > 512) return 0;
@@ -624,14 +465,14 @@ static int halo_args(const ConvGeom& g, HaloArgs* out) {
   int budget = (T == 1) ? std::max(T * ha.nh * ha.halo_bytes + min_ring, 108 * 1024) : HALO_SMEM_BUDGET;
   // when halo + two stages fit a THIRD of an SM, stop there: the next kernel's CTAs (programmatic dependent launch) can
   // then become resident and finish their prologue while this kernel's last CTAs drain
-  if (T == 1 && env_int("SSHSLIE_HALO_OCC3", 1) && ha.nh * ha.halo_bytes + min_ring <= 73 * 1024)
+  if (T == 1 && ss_env_int("SSHSLIE_HALO_OCC3", 1) && ha.nh * ha.halo_bytes + min_ring <= 73 * 1024)
     budget = ha.nh * ha.halo_bytes + min_ring;
   int stages = (budget - T * ha.nh * ha.halo_bytes) / (G * b_bytes);
   stages = std::max(2, std::min(stages, std::min(HALO_MAX_STAGES, std::max(2, n_iter))));
-  stages = std::max(2, std::min(HALO_MAX_STAGES, env_int("SSHSLIE_HALO_STAGES", stages)));
+  stages = std::max(2, std::min(HALO_MAX_STAGES, ss_env_int("SSHSLIE_HALO_STAGES", stages)));
   if (T * ha.nh * ha.halo_bytes + stages * G * b_bytes > 220 * 1024 - 2048) return 0;
   ha.stages = stages;
-  ha.debug = env_int("SSHSLIE_HALO_DEBUG", 0);
+  ha.debug = ss_env_int("SSHSLIE_HALO_DEBUG", 0);
   ha.nslabs = g.nslabs; ha.Npad = g.Npad; ha.N = g.N; ha.OH = g.OH; ha.OW = g.OW;
   const int pitch = HALO_TW + 2 * pad;
   for (int i = 0; i < g.nslabs; ++i) {
@@ -652,7 +493,7 @@ int ss_umma_halo_supported(const ConvGeom& g) {
   return ss_umma_supported(g) && halo_args(g, &ha);
 }
 
-static int encode_src(const SrcView& v, int ld_extent, int tw, int th, int B, CUtensorMap* out) {
+int ss_umma_encode_view(const SrcView& v, int ld_extent, int tw, int th, int B, CUtensorMap* out) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return SSHSLIE_ERR_CUDA;
   cuuint64_t dims[4] = {(cuuint64_t)ld_extent, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)B};
@@ -676,11 +517,11 @@ int ss_umma_build_maps(const ConvGeom& g, UmmaMaps* maps) {
     int ext = 64;
     for (int i = 0; i < g.nslabs; ++i)
       if (g.slab[i].src == s && g.slab[i].c0 + 64 > ext) ext = g.slab[i].c0 + 64;
-    int rc = encode_src(g.src[s], ext, g.tw, g.th, g.B, &maps->src[s]);
+    int rc = ss_umma_encode_view(g.src[s], ext, g.tw, g.th, g.B, &maps->src[s]);
     if (rc) return rc;
     HaloArgs ha;
     if (halo_args(g, &ha)) {
-      rc = encode_src(g.src[s], ext, HALO_TW + 2 * ha.pad, HALO_TH + 2 * ha.pad, g.B, &maps->halo[s]);
+      rc = ss_umma_encode_view(g.src[s], ext, HALO_TW + 2 * ha.pad, HALO_TH + 2 * ha.pad, g.B, &maps->halo[s]);
       if (rc) return rc;
     }
   }
@@ -992,7 +833,7 @@ int ss_umma_build_gmap(const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld
                        void* out_map) {
   SrcView v;
   v.base = G; v.sB = gB; v.sH = gH; v.sW = gW; v.H = g.OH; v.W = g.OW;
-  return encode_src(v, ld_extent, g.tw, g.th, g.B, reinterpret_cast<CUtensorMap*>(out_map));
+  return ss_umma_encode_view(v, ld_extent, g.tw, g.th, g.B, reinterpret_cast<CUtensorMap*>(out_map));
 }
 
 // second stage: dW[n][slab, j] += sum over pixel splits of the partial accumulators (deterministic, no atomics)
@@ -1429,7 +1270,7 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   wa.N = (gN > 64) ? 128 : 64;
   wa.g_atoms = wa.N / 64;
   wa.OH = g.OH; wa.OW = g.OW;
-  wa.debug = env_int("SSHSLIE_HALO_DEBUG", 0);
+  wa.debug = ss_env_int("SSHSLIE_HALO_DEBUG", 0);
   // tap pairs over the slabs that carry weights of their own (residual "lo" slabs are skipped), lower window first
   int slabs[SS_MAX_SLABS], ns = 0;
   for (int i = 0; i < g.nslabs; ++i)
@@ -1448,7 +1289,7 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   // TMEM budget of a CTA: all 512 columns (7 pair blocks + the bias block at N = 64).  A smaller budget would let a
   // forward / dgrad CTA of the main stream allocate tensor memory on the same SM, but it doubles the groups (and the halo
   // loads) of every small layer: measured at the training batch, 256 columns cost 2.6 % of the step (SSHSLIE_WGH_TMEM).
-  int tmem_cap = env_int("SSHSLIE_WGH_TMEM", 512);
+  int tmem_cap = ss_env_int("SSHSLIE_WGH_TMEM", 512);
   if (tmem_cap != 128 && tmem_cap != 256 && tmem_cap != 512) tmem_cap = 512;
   if (tmem_cap / wa.N < 2) tmem_cap = 2 * wa.N;
   const int max_pairs = tmem_cap / wa.N - 1;            // one accumulator block is reserved for the bias row
@@ -1458,10 +1299,10 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   wa.blocks_per_cta = wa.pairs_per_group + 1;
   wa.n_tiles = ha.n_tiles;
   // split the pixel axis: every CTA should own >= 4 pixel tiles (the split-K partials cost 32 KB x blocks per CTA)
-  const int min_tiles = std::max(1, env_int("SSHSLIE_WGH_MIN_TILES", 8));
+  const int min_tiles = std::max(1, ss_env_int("SSHSLIE_WGH_MIN_TILES", 8));
   int splits = (wa.n_tiles + min_tiles - 1) / min_tiles;
   splits = std::min(splits, std::max(1, 148 / wa.groups));
-  splits = std::max(1, env_int("SSHSLIE_WGH_SPLITS", splits));
+  splits = std::max(1, ss_env_int("SSHSLIE_WGH_SPLITS", splits));
   wa.tiles_per_cta = (wa.n_tiles + splits - 1) / splits;
   wa.splits = (wa.n_tiles + wa.tiles_per_cta - 1) / wa.tiles_per_cta;
   int cols = 32;
@@ -1473,7 +1314,7 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   int stages = (int)((216 * 1024 - WGH_ONES_BYTES) / wa.stage_bytes);
   stages = std::min(3, stages);
   if (2 * wa.stage_bytes + WGH_ONES_BYTES <= 108 * 1024) stages = 2;
-  stages = std::min(4, std::max(1, env_int("SSHSLIE_WGH_STAGES", stages)));
+  stages = std::min(4, std::max(1, ss_env_int("SSHSLIE_WGH_STAGES", stages)));
   if (stages < 2 || stages * wa.stage_bytes + WGH_ONES_BYTES > 216 * 1024) return 0;
   wa.stages = stages;
   *out = wa;
@@ -1492,7 +1333,7 @@ int ss_umma_build_gmap_halo(const bf16* G, int64_t gB, int64_t gH, int64_t gW, i
                             void* out_map) {
   SrcView v;
   v.base = G; v.sB = gB; v.sH = gH; v.sW = gW; v.H = g.OH; v.W = g.OW;
-  return encode_src(v, ld_extent, HALO_TW, HALO_TH, g.B, reinterpret_cast<CUtensorMap*>(out_map));
+  return ss_umma_encode_view(v, ld_extent, HALO_TW, HALO_TH, g.B, reinterpret_cast<CUtensorMap*>(out_map));
 }
 int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const UmmaMaps& maps, const void* gmap, int gN,
                               long long bias_off, float* partial, float* grads, cudaStream_t st) {
@@ -1654,7 +1495,7 @@ extern "C" SSHSLIE_API int sshslie_umma_probe(int N, int n_mma, int n_acc, int c
   const char* ao = getenv("SSHSLIE_PROBE_AOFF");
   const char* sb = getenv("SSHSLIE_PROBE_SBO");
   const int a_off = ao ? atoi(ao) : 0, a_sbo = sb ? atoi(sb) : 1024;
-  const int mn_major = env_int("SSHSLIE_PROBE_MN", 0), distinct = env_int("SSHSLIE_PROBE_DISTINCT", 0);
+  const int mn_major = ss_env_int("SSHSLIE_PROBE_MN", 0), distinct = ss_env_int("SSHSLIE_PROBE_DISTINCT", 0);
   if (N < 16 || N > 256 || (N % 16) || n_acc < 1 || n_acc * N > 512 || !out_cycles) {
     ss_set_error("sshslie_umma_probe: bad argument");
     return SSHSLIE_ERR_ARG;

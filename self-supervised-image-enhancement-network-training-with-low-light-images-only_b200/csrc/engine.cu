@@ -161,6 +161,13 @@ struct sshslie_engine {
   std::vector<int> geom_role;            // 0 = forward-type addressing, 1 = dgrad-type addressing
   mutable int last_layer = -1, last_role = 0;
   std::vector<unsigned char> maps_blob;  // UmmaMaps per geom
+  // persistent pipelined gather kernel (conv_pipe.cu): per geom, decided and planned at its first launch
+  std::vector<unsigned char> pipe_blob;
+  std::vector<int> pipe_valid;
+  std::vector<char> pipe_use;            // 0 = undecided, 1 = pipelined kernel, 2 = halo kernel
+  bool pipe_on = true;
+  int pipe_min_tiles = 1024;             // below this the halo kernel (2-3 small co-resident CTAs per SM) has the lower latency
+  int pipe_max_slabs = 36;               // the 9x9 layer (81 streamed slabs) is 8 % faster on the halo kernel
   ConvGeom* geoms_dev = nullptr;
   int* pack_start_dev = nullptr;
   std::vector<int> pack_start;
@@ -405,13 +412,28 @@ static double geom_flops(const ConvGeom& g) {
 static std::string geom_label(const sshslie_engine* e, int gi, const char* kind) {
   const int l = gi < (int)e->geom_layer.size() ? e->geom_layer[gi] : -1;
   std::string s = std::string(kind) + ":" + (l >= 0 && l < L_COUNT ? kLayerNames[l] : "layer");
-  s += e->geom_umma[gi] == 2 ? "[tcgen05-halo]" : (e->geom_umma[gi] ? "[tcgen05]" : "[simt]");
+  const bool pipe = kind[0] != 'w' && e->geom_umma[gi] == 2 && gi < (int)e->pipe_use.size() && e->pipe_use[gi] == 1;
+  s += pipe ? "[tcgen05-pipe]" : (e->geom_umma[gi] == 2 ? "[tcgen05-halo]" : (e->geom_umma[gi] ? "[tcgen05]" : "[simt]"));
   return s;
 }
 static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaStream_t st) {
   if (bias_layer >= 0) epi.bias = e->params + e->poff[2 * bias_layer + 1];
   const ConvGeom& g = e->geoms[gi];
+  if (e->geom_umma[gi] == 2 && e->pipe_on) {
+    if (e->pipe_use.size() < e->geoms.size()) {
+      e->pipe_use.resize(e->geoms.size(), 0);
+      e->pipe_valid.resize(e->geoms.size(), 0);
+      e->pipe_blob.resize(e->geoms.size() * ss_pipe_plan_size(), 0);
+    }
+    if (e->pipe_use[gi] == 0) {
+      const int n_tiles = g.B * ((g.OH + 15) / 16) * (g.OW / 8);
+      e->pipe_use[gi] = (n_tiles >= e->pipe_min_tiles && g.nslabs <= e->pipe_max_slabs && ss_umma_pipe_supported(g, epi)) ? 1 : 2;
+    }
+  }
   prof_note(geom_label(e, gi, e->geom_role[gi] ? "dgrad" : "fwd"), geom_flops(g), 0);
+  if (e->geom_umma[gi] == 2 && e->pipe_on && e->pipe_use[gi] == 1)
+    return ss_launch_conv_gather_pipe(g, *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
+                                      epi, e->pipe_blob.data() + gi * ss_pipe_plan_size(), &e->pipe_valid[gi], st);
   if (e->geom_umma[gi] == 2)
     return ss_launch_conv_gather_halo(e->geoms_dev + gi, g,
                                       *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
@@ -1141,6 +1163,12 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
     if (gs && atoi(gs) >= 1 && atoi(gs) <= 12) e->group_size = atoi(gs);
     const char* he0 = getenv("SSHSLIE_HALO");
     e->halo_on = !(he0 && he0[0] == '0');
+    const char* pe = getenv("SSHSLIE_PIPE");
+    e->pipe_on = !(pe && pe[0] == '0');
+    const char* pm = getenv("SSHSLIE_PIPE_MIN_TILES");
+    if (pm && pm[0]) e->pipe_min_tiles = atoi(pm);
+    const char* px = getenv("SSHSLIE_PIPE_MAX_SLABS");
+    if (px && px[0]) e->pipe_max_slabs = atoi(px);
     const char* sk = getenv("SSHSLIE_SKIP_WGRAD");
     e->skip_wgrad = (sk && sk[0] == '1');
     const char* ns = getenv("SSHSLIE_NO_SIDE");
@@ -1176,6 +1204,7 @@ extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t w
   cudaStream_t st = (cudaStream_t)stream;
   e->bound = false;
   e->gmaps.clear();
+  e->pipe_use.clear(); e->pipe_valid.clear(); e->pipe_blob.clear();
   if (!e->side[0]) {
     bool ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < SS_MAX_SIDE && ok; ++i)
@@ -1335,6 +1364,8 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
   sshslie_engine E;
   sshslie_engine* e = &E;
   e->B = B; e->C = 64; e->H = H; e->W = W; e->flags = 0; e->train = false; e->force_simt = (impl == 0);
+  e->pipe_on = (impl == 3);               // impl 3 = the persistent pipelined gather kernel (stride-1 layers)
+  e->pipe_min_tiles = 0; e->pipe_max_slabs = SS_MAX_SLABS;
   e->base = (unsigned char*)scratch; e->cursor = 0;
   memset(e->poff, 0, sizeof(e->poff));
   e->shapes[0] = {transposed ? Cin : Cout, transposed ? Cout : Cin, k, transposed != 0};
@@ -1427,10 +1458,10 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
   e->maps_blob.assign(e->geoms.size() * msz, 0);
   for (size_t i = 0; i < e->geoms.size(); ++i) {
     if (impl >= 1) {
-      if (!ss_umma_supported(e->geoms[i]) || (impl == 2 && !ss_umma_halo_supported(e->geoms[i]))) { ss_set_error("sshslie_conv2d: shape not taken by the tcgen05 kernel"); return SSHSLIE_ERR_ARG; }
+      if (!ss_umma_supported(e->geoms[i]) || (impl >= 2 && !ss_umma_halo_supported(e->geoms[i]))) { ss_set_error("sshslie_conv2d: shape not taken by the tcgen05 kernel"); return SSHSLIE_ERR_ARG; }
       int rc = ss_umma_build_maps(e->geoms[i], reinterpret_cast<UmmaMaps*>(e->maps_blob.data() + i * msz));
       if (rc) return rc;
-      e->geom_umma[i] = (char)impl;
+      e->geom_umma[i] = (char)(impl == 3 ? 2 : impl);
     }
   }
   cudaMemcpyAsync(e->geoms_dev, e->geoms.data(), e->geoms.size() * sizeof(ConvGeom), cudaMemcpyHostToDevice, st);

@@ -47,6 +47,12 @@ int ss_umma_build_gmap_halo(const bf16* G, int64_t gB, int64_t gH, int64_t gW, i
 int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g_host, const UmmaMaps& maps, const void* gmap,
                               int gN, long long bias_off, float* partial, float* grads, cudaStream_t st);
 
+// conv_pipe.cu: persistent pipelined gather (stride-1 layers), see the file header
+size_t ss_pipe_plan_size();
+int ss_umma_pipe_supported(const ConvGeom& g, const Epi& epi);
+int ss_launch_conv_gather_pipe(const ConvGeom& g, const UmmaMaps& maps, const Epi& epi, void* plan_cache,
+                               int* cache_valid, cudaStream_t st);
+
 // elementwise.cu
 int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st);
 int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, int W, int ldi, cudaStream_t st);

@@ -135,11 +135,16 @@ class FusedAdam(torch.optim.Optimizer):
         self._state_flat = own._flat_m
 
     def zero_grad(self, set_to_none=True):
+        own = self._owner[0]
         if set_to_none:
-            for p in self._owner[0]._plist:
+            for p in own._plist:
                 p.grad = None
+            own._grads_live = False
         else:
             super().zero_grad(set_to_none=False)
+            # parameters that still hold the views of the flat gradient buffer now hold zeros: the next compute_loss may
+            # overwrite the buffer and backward() leaves those views in place (0 + g = g)
+            own._grads_live = False
 
     def _launch(self, lo, hi):
         own = self._owner[0]
@@ -194,34 +199,43 @@ class FusedAdam(torch.optim.Optimizer):
 
 
 class _LossFn(torch.autograd.Function):
-    """compute_loss already ran forward AND backward on the GPU.  `loss.backward()` lands here once and hands the
-    finished gradient views to the parameters (p.grad = view, or += when a gradient is already there), instead of
-    routing 46 tensors through autograd's AccumulateGrad nodes."""
+    """compute_loss already ran forward AND backward on the GPU.  The returned loss is wired to all 46 parameters, so
+    the general autograd entry points work as on the reference's loss tensor - `torch.autograd.grad(loss, params)`,
+    `(2 * loss).backward()`, accumulation through AccumulateGrad - with the finished gradient (times the incoming
+    scalar, scaled on the device) as the result.  The plain `loss.backward()` of model.py:315 takes the shortcut in
+    `_fast_backward` instead and never reaches this node."""
 
     @staticmethod
-    def forward(ctx, anchor, owner_box):
+    def forward(ctx, owner_box, *params):
         ctx.owner_box = owner_box
         return owner_box[0]._losses_dev[0].clone()
 
     @staticmethod
     def backward(ctx, gout):
-        # general autograd path, e.g. (2 * loss).backward(): scale on the device - reading `gout` on the host would
-        # synchronise the stream every step
         own = ctx.owner_box[0]
-        scaled = own._flat_grad * gout.reshape(())
-        views = [scaled[off:off + n].view(p.shape) for p, (off, n) in zip(own._plist, own._pranges)]
-        _hand_over(own, views)
-        return None, None
+        scaled = own._flat_grad * gout.reshape(())      # a fresh tensor: later steps do not overwrite what autograd holds
+        grads = tuple(scaled[off:off + n].view(p.shape) if need else None
+                      for p, (off, n), need in zip(own._plist, own._pranges, ctx.needs_input_grad[1:]))
+        return (None,) + grads
 
 
 def _hand_over(own, views):
+    """p.grad <- finished gradient.  `views` alias the flat gradient buffer that every compute_loss overwrites, so:
+      * no gradient yet                      -> p.grad = view (no copy; FusedAdam.step sees `p.grad is view`);
+      * p.grad already IS that view           -> nothing to do: zero_grad(set_to_none=False) kept the view and the step
+                                                 that just ran refilled it (adding the buffer to itself would give 2 g);
+      * any other tensor (accumulated grads) -> a fresh tensor p.grad + view, as autograd's AccumulateGrad would."""
     for p, v in zip(own._plist, views):
         if not p.requires_grad:
             continue
-        if p.grad is None:
+        g = p.grad
+        if g is None:
             p.grad = v
+        elif g is v or (g.data_ptr() == v.data_ptr() and g.shape == v.shape):
+            pass
         else:
-            p.grad = p.grad + v
+            p.grad = g + v
+    own._grads_live = True
 
 
 def _fast_backward(own, total):
@@ -275,6 +289,31 @@ class LazyLosses(dict):
     def __repr__(self):
         self._sync()
         return dict.__repr__(self)
+
+    def __contains__(self, k):
+        return k in LOSS_KEYS
+
+    def get(self, k, default=None):
+        self._sync()
+        return dict.get(self, k, default)
+
+    def copy(self):
+        self._sync()
+        return dict(self)
+
+    def __eq__(self, other):
+        self._sync()
+        return dict.__eq__(self, other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __bool__(self):
+        return True
+
+    def __reduce__(self):          # pickle / copy.deepcopy see the plain dict of floats the reference returns
+        self._sync()
+        return (dict, (dict(self),))
 
 
 class DevicePatchSampler:
@@ -335,11 +374,13 @@ class _Engine:
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         L.check(lib.sshslie_engine_bind(self.handle, ctypes.c_void_p(base), nbytes, stream), "sshslie_engine_bind")
         self.x = torch.empty(B, C, H, W, device=device)
-        self.R = torch.empty(B, C, H, W, device=device)
-        self.I = torch.empty(B, 1, H, W, device=device)
-        self.Id = torch.empty(B, 1, H, W, device=device)
-        self.S = torch.empty(B, C, H, W, device=device)
+        if train:          # static output buffers of the (graph-captured) training step; forward() returns fresh tensors
+            self.R = torch.empty(B, C, H, W, device=device)
+            self.I = torch.empty(B, 1, H, W, device=device)
+            self.Id = torch.empty(B, 1, H, W, device=device)
+            self.S = torch.empty(B, C, H, W, device=device)
         self.graph = None
+        self.graph_cfg = None                  # loss weights baked into the captured kernel arguments
         self.calls = 0
 
     def __del__(self):
@@ -430,16 +471,37 @@ class LowLightEnhance(nn.Module):
         self._flat_grad = self._grad_store[:self._nparams]
         self._grad_views = [self._flat_grad[off:off + n].view(p.shape) for p, (off, n) in
                             zip(self._plist, self._pranges)]
-        self._anchor = torch.zeros((), device=p0.device, requires_grad=True)
         self._losses_dev = self._grad_store[self._nparams:]
         self._dp_ranges = None
         self._engines = {}
 
+    def _cfg_tuple(self):
+        return (float(self.c_loss_reconstruction), float(self.c_loss_r_fidelity),
+                float(self.c_loss_i_smooth_low), float(self.c_loss_i_smooth_delta),
+                float(self.c_loss_fourier), float(self.c_loss_spectral_cons),
+                float(self.alpha_i_smooth_low), float(self.alpha_i_smooth_delta))
+
     def _cfg(self):
-        return L.LossCfg(float(self.c_loss_reconstruction), float(self.c_loss_r_fidelity),
-                         float(self.c_loss_i_smooth_low), float(self.c_loss_i_smooth_delta),
-                         float(self.c_loss_fourier), float(self.c_loss_spectral_cons),
-                         float(self.alpha_i_smooth_low), float(self.alpha_i_smooth_delta))
+        return L.LossCfg(*self._cfg_tuple())
+
+    def _graph_current(self, eng):
+        """The captured graph(s) carry the loss weights as kernel arguments: a change of model.c_loss_* / alpha_* after
+        capture (loss-weight schedules, sweeps on one model object) drops them, and the step is captured again."""
+        if eng.graph is not None and eng.graph_cfg != self._cfg_tuple():
+            eng.graph = None
+            eng.calls = max(eng.calls, 3)      # already warm: capture again on this very call
+        return eng.graph is not None
+
+    def _keep_accumulated_grads(self):
+        """compute_loss overwrites the flat gradient buffer.  Gradients a previous backward() handed out as views of it
+        and that were not cleared since (micro-batch accumulation: backward; compute_loss(x2); backward) are detached
+        into tensors of their own first, so that the next backward() adds g2 to g1 instead of to itself."""
+        if not getattr(self, "_grads_live", False) or self._grad_views is None:
+            return
+        for p, v in zip(self._plist, self._grad_views):
+            if p.grad is v:
+                p.grad = v.clone()
+        self._grads_live = False
 
     def _engine(self, x, train):
         B, C, H, W = x.shape
@@ -467,9 +529,14 @@ class LowLightEnhance(nn.Module):
         self._stage_input(eng, input_low)
         lib = L.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)
-        L.check(lib.sshslie_forward(eng.handle, L.ptr(eng.x), L.ptr(self._flat), L.ptr(eng.R), L.ptr(eng.I),
-                                    L.ptr(eng.Id), L.ptr(eng.S), stream), "sshslie_forward")
-        return eng.R, eng.I, eng.Id, eng.S
+        # fresh result tensors per call, like the reference: a caller may hold R across two forward() calls
+        B, C, H, W = eng.x.shape
+        dev = eng.x.device
+        R, S = torch.empty(B, C, H, W, device=dev), torch.empty(B, C, H, W, device=dev)
+        I, Id = torch.empty(B, 1, H, W, device=dev), torch.empty(B, 1, H, W, device=dev)
+        L.check(lib.sshslie_forward(eng.handle, L.ptr(eng.x), L.ptr(self._flat), L.ptr(R), L.ptr(I),
+                                    L.ptr(Id), L.ptr(S), stream), "sshslie_forward")
+        return R, I, Id, S
 
     def _launch_loss_and_grad(self, eng, phase_mask=3):
         lib = L.load()
@@ -484,18 +551,20 @@ class LowLightEnhance(nn.Module):
         """model.py:544-575 -> (total_loss 0-dim tensor supporting .backward(), dict of 7 floats)."""
         self._ensure_flat()
         eng = self._engine(input_low, train=True)
+        self._keep_accumulated_grads()
         self._stage_input(eng, input_low)
         dp = self.dp_group is not None
         if dp:
             self._dp_step(eng)
         elif self.use_cuda_graph:
             eng.calls += 1
-            if eng.graph is None and eng.calls >= 3:       # two eager warm-up steps, then capture
+            if not self._graph_current(eng) and eng.calls >= 3:       # two eager warm-up steps, then capture
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._launch_loss_and_grad(eng)
                 eng.graph = g
+                eng.graph_cfg = self._cfg_tuple()
             if eng.graph is not None:
                 eng.graph.replay()
             else:
@@ -504,7 +573,7 @@ class LowLightEnhance(nn.Module):
             self._launch_loss_and_grad(eng)
         self.last_outputs = (eng.R, eng.I, eng.Id, eng.S)
         if torch.is_grad_enabled():
-            total = _LossFn.apply(self._anchor, self._box)
+            total = _LossFn.apply(self._box, *self._plist)
             total.backward = _fast_backward(self, total)       # instance attribute shadows Tensor.backward
         else:
             total = self._losses_dev[0].clone()
@@ -551,7 +620,7 @@ class LowLightEnhance(nn.Module):
         dec, ill = self._dp_ranges
         cur = torch.cuda.current_stream(self._flat.device)
         eng.calls += 1
-        if self.use_cuda_graph and eng.graph is None and eng.calls >= 3:
+        if self.use_cuda_graph and not self._graph_current(eng) and eng.calls >= 3:
             torch.cuda.synchronize()
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
@@ -559,6 +628,7 @@ class LowLightEnhance(nn.Module):
             with torch.cuda.graph(gb, pool=ga.pool()):
                 self._launch_loss_and_grad(eng, phase_mask=2)
             eng.graph = (ga, gb)
+            eng.graph_cfg = self._cfg_tuple()
         run = (lambda ph: eng.graph[ph - 1].replay()) if eng.graph is not None else \
               (lambda ph: self._launch_loss_and_grad(eng, phase_mask=ph))
         run(1)                                       # fwd + loss + pass-2 bwd + illum bwd

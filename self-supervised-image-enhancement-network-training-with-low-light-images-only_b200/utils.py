@@ -1,4 +1,4 @@
-"""Host-side I/O glue the training / test loops need (restates /root/reference/utils.py:7-57,171-178).
+"""Host-side I/O glue the training / test loops need (restates /root/reference/utils.py:7-57,59-101,171-178).
 Not on the accelerated path: numpy + scipy on the CPU, exactly where the reference does this work."""
 import numpy as np
 
@@ -10,13 +10,46 @@ def data_augmentation(image, mode):
     return np.flipud(out) if flip else out
 
 
-def global_normalization(x, max_val, min_val):
+def self_normalization(x):
+    """utils.py:90-94: the cube's maximum maps to 1 (no offset)."""
+    return x / np.max(x)
+
+
+def global_normalization(x, max_val=None, min_val=None):
+    """utils.py:76-88: (x - min) / (max - min) with data-set wide bounds; a missing minimum means 0."""
+    if max_val is None:
+        raise ValueError("max value is not provided for normalization")
+    if min_val is None:
+        min_val = 0.
+    if min_val > max_val:
+        raise ValueError("min value cannot be larger than the max value for normalization")
     return (x - min_val) / (max_val - min_val)
 
 
+def per_channel_normalization(x):
+    """utils.py:59-74: per-band min-max; a constant band keeps range 1 (no division by zero)."""
+    lo = np.min(x, axis=(0, 1), keepdims=True)
+    hi = np.max(x, axis=(0, 1), keepdims=True)
+    return (x - lo) / np.where(hi > lo, hi - lo, 1)
+
+
+def per_channel_standardization(x):
+    """utils.py:96-111: per-band zero mean / unit deviation; a constant band keeps deviation 1."""
+    mean = np.mean(x, axis=(0, 1), keepdims=True)
+    std = np.std(x, axis=(0, 1), keepdims=True)
+    return (x - mean) / np.where(std > 0, std, 1)
+
+
+_NORMALIZERS = {
+    'self': lambda x, hi, lo: self_normalization(x),
+    'per_channel_normalization': lambda x, hi, lo: per_channel_normalization(x),
+    'per_channel_standardization': lambda x, hi, lo: per_channel_standardization(x),
+}
+
+
 def load_hsi(file, matContentHeader='data', normalization=None, max_val=None, min_val=None):
-    """.mat -> float32 HWC cube.  'global_normalization' clamps negatives to 0 and then divides by the cube's
-    own max once more (utils.py:45-47,57), so every loaded cube peaks at exactly 1."""
+    """.mat -> float32 HWC cube (utils.py:36-57).  'global_normalization' clamps negatives to 0; every normalised cube is
+    then divided by its own maximum once more (utils.py:57), so it peaks at exactly 1."""
     import scipy.io as sio
     x = np.array(sio.loadmat(file)[matContentHeader], dtype='float32')
     if normalization is None:
@@ -24,14 +57,8 @@ def load_hsi(file, matContentHeader='data', normalization=None, max_val=None, mi
     if normalization == 'global_normalization':
         x = global_normalization(x, max_val, min_val)
         x[x < 0] = 0.
-    elif normalization == 'self':
-        x = (x - x.min()) / (x.max() - x.min())
-    elif normalization == 'per_channel_normalization':
-        mn = x.min(axis=(0, 1), keepdims=True)
-        mx = x.max(axis=(0, 1), keepdims=True)
-        x = (x - mn) / (mx - mn)
-    elif normalization == 'per_channel_standardization':
-        x = (x - x.mean(axis=(0, 1), keepdims=True)) / x.std(axis=(0, 1), keepdims=True)
+    elif normalization in _NORMALIZERS:
+        x = _NORMALIZERS[normalization](x, max_val, min_val)
     else:
         raise NotImplementedError(str(normalization) + ' is not implemented')
     return x.astype('float32') / np.max(x)

@@ -123,6 +123,43 @@ def test_conv_forward_halo(case):
     torch.testing.assert_close(y, ref, rtol=2 ** -7, atol=2e-3)
 
 
+PIPE_CASES = HALO_CASES + [
+    ("c3_64_64_b3", 64, 64, 3, 1, False, 128, 128, 3),      # 768 tiles: several tiles per CTA, both TMEM / halo buffers
+    ("c9_64_64_b2", 64, 64, 9, 1, False, 128, 128, 2),      # streamed weights across tile borders
+    ("c3_128_128_b8", 128, 128, 3, 1, False, 64, 64, 8),    # streamed weights, two staging tiles
+    ("c3_64_64_h24", 64, 64, 3, 1, False, 24, 40, 2),       # ragged rows: the TMA store clips rows beyond the image
+]
+
+
+@pytest.mark.parametrize("staged", ["1", "0"], ids=["tma_store", "direct_store"])
+@pytest.mark.parametrize("case", PIPE_CASES, ids=[c[0] for c in PIPE_CASES])
+def test_conv_forward_pipe(case, staged, monkeypatch):
+    """Persistent pipelined tcgen05 kernel (conv_pipe.cu): double-buffered halo windows and TMEM accumulators, resident
+    or streamed weights, epilogue through shared memory + TMA tensor stores (or direct stores)."""
+    from gpu_util import conv2d
+    monkeypatch.setenv("SSHSLIE_PIPE_STAGED", staged)
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    x, w, b = _mk(case)
+    ref = _ref_conv(x, w, b, k, stride, tr, relu=True)
+    y = torch.empty_like(ref)
+    conv2d(0, 3, tr, x, w, b, y, B, Cin, Cout, H, W, k, stride, relu=True)
+    torch.testing.assert_close(y, ref, rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("case", PIPE_CASES[:8] + PIPE_CASES[-4:], ids=[c[0] for c in PIPE_CASES[:8] + PIPE_CASES[-4:]])
+def test_conv_dgrad_pipe(case):
+    from gpu_util import conv2d, bf16_round
+    name, Cin, Cout, k, stride, tr, H, W, B = case
+    x, w, b = _mk(case)
+    x.requires_grad_(True)
+    yref = _ref_conv(x, w, None, k, stride, tr, relu=False)
+    dy = bf16_round(torch.randn(yref.shape, generator=torch.Generator().manual_seed(3))).cuda()
+    (dx_ref,) = torch.autograd.grad(yref, x, dy)
+    dx = torch.empty_like(dx_ref)
+    conv2d(1, 3, tr, dy, w, None, dx, B, Cin, Cout, H, W, k, stride, relu=False)
+    torch.testing.assert_close(dx, dx_ref, rtol=2 ** -7, atol=2e-3 * float(dx_ref.abs().max()))
+
+
 def _loss_inputs(B, C, H, W, seed=0):
     g = torch.Generator().manual_seed(seed)
     x = torch.rand(B, C, H, W, generator=g) * 0.3

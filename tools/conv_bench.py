@@ -1,6 +1,6 @@
 """GPU box: device time of ONE conv layer's own launches (forward / dgrad / wgrad) per implementation, through
 sshslie_conv2d with SSHSLIE_CONV2D_TIMING.  Usage: conv_bench.py [B] [reps]; env SSHSLIE_HALO_* tune the halo kernel.
-impl: 1 = per-tap tcgen05 kernel, 2 = halo-reuse tcgen05 kernel."""
+impl: 1 = per-tap tcgen05 kernel, 2 = halo-reuse tcgen05 kernel, 3 = persistent pipelined kernel (forward only)."""
 import os
 import sys
 
@@ -24,7 +24,7 @@ for name, cin, cout, k, hw in LAYERS:
     fl = 2.0 * B * hw * hw * cin * cout * k * k
     row = [f"{name:24s} B={B}"]
     for kind, kname in [(0, "fwd"), (2, "wgrad")]:
-        for impl in (1, 2):
+        for impl in ((1, 2, 3) if kind == 0 else (1, 2)):
             try:
                 if kind == 0:
                     conv2d(0, impl, False, x, w, None, y, B, cin, cout, hw, hw, k, 1, False)
