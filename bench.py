@@ -1,25 +1,35 @@
 #!/usr/bin/env python
 """Benchmark of the SS-HSLIE hot path (BASELINE.json metric: training HSI patches/sec, fwd + loss + bwd + Adam).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config jyu|cv1] [--no-sweep]
 
-Workload = BASELINE.json configs[1]: config_outdoor_jyu.yml train step, batch 2 x 64 bands x 128 x 128 per GPU,
-loss weights 10/1/1/2000/20/1, Adam lr 1e-3, synthetic low-light patches, seed-41 default-init weights.
+Workloads (BASELINE.json configs):
+  jyu  = configs[1]: config_outdoor_jyu.yml train step, batch 2 x 64 bands x 128 x 128 per GPU, loss weights
+         10/1/1/2000/20/1 - the headline configuration (default, every N: the driver derives scaling efficiency from the
+         per-N values of ONE workload)
+  cv1  = configs[2]: config_indoor_li_et_al_cv1.yml, batch 1 per GPU, loss weights 10/1/1/20/0.2/1.  For N > 1 the line
+         always carries a `cv1` block (data-parallel throughput + its own single-GPU reference measured in the same run +
+         dp_parity), `--config cv1` makes it the primary workload.
 A "step" is the reference's `optimizer.zero_grad(); loss,_ = compute_loss(x); loss.backward(); optimizer.step()`
-(model.py:313-316) on one batch.
+(model.py:313-316) on one batch of synthetic low-light patches, Adam lr 1e-3, seed-41 default-init weights.
 
 `--impl ours`: one process per GPU (torchrun for N > 1, NCCL gradient all-reduce), prints ONE JSON line:
-  value      whole-job patches/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        same metric through the public API with the batch coming from pinned host memory every step
-             (H2D copy and the 7-float loss read-back inside the timed region)
-  roofline   the kernel that takes the largest share of the step, timed with cudaEvent pairs inside this process
-  cpu_baseline  the CPU oracle (restatement of the reference, oracle/) timed on this box's host cores
-`--impl reference`: the reference's CPU path for the same step.  /root/reference does not exist on the GPU box and the
-reference is not pip-installable, so this arm times oracle/sshslie_oracle.py (kind "port"), all host threads.
+  value      whole-job patches/s, inputs resident in HBM, CUDA-event timed, max over ranks; the MEDIAN of `--regions`
+             (default 5) timed regions of exactly K steps each
+  e2e        same metric through the public API with the batch coming from pinned host memory every step: the H2D copy
+             of batch i+1 (LowLightEnhance.prefetch, copy stream, two staging buffers) overlaps step i, the 7-float loss
+             read-back synchronises every step
+  roofline   the kernel function with the largest share of the step, timed with cudaEvent pairs inside this process
+  dp_parity  (N > 1, outside the timed region) averaged gradient vs the CPU oracle on the concatenated global batch
+  cpu_baseline  the reference's CPU path timed on this box's host cores (N = 1)
+`--impl reference`: the reference's CPU implementation of the same step, all host threads, honouring --steps/--warmup:
+  the UNMODIFIED reference modules from oracle/_ref (copied there at build time by oracle/make_ref.py, kind "reference")
+  when present, else the pinned restatement oracle/sshslie_oracle.py (kind "port").
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -28,10 +38,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH_PER_GPU = 2
 CHANNELS, SIZE = 64, 128
 FLOPS_PER_PATCH_FWD_BWD = 122.8e9       # SURVEY.md §8d (2 FLOP/MAC on conv/linear/attention only)
-WORKLOAD = "config_outdoor_jyu.yml train step: B=2/GPU x 64 bands x 128x128, fwd+6-term loss+bwd+Adam"
+
+
+def workloads():
+    from oracle import sshslie_oracle as O
+    return {
+        "jyu": dict(batch=2, coef=O.JYU_COEF,
+                    name="config_outdoor_jyu.yml train step: B=2/GPU x 64 bands x 128x128, fwd+6-term loss+bwd+Adam"),
+        "cv1": dict(batch=1, coef=O.DEFAULT_COEF,
+                    name="config_indoor_li_et_al_cv1.yml train step: B=1/GPU x 64 bands x 128x128, fwd+6-term loss+bwd+Adam"),
+    }
 
 
 def peaks():
@@ -79,51 +97,91 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def oracle_cpu_steps(steps, warmup, threads):
-    """The reference's train step restated in oracle/ (torch CPU fp32).  Returns seconds per step (best)."""
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's CPU path
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, threads, wl):
+    """Seconds of each of `steps` train steps on the host (after `warmup` untimed ones) + (kind, description).
+    Runs the unmodified reference from oracle/_ref when the build placed it there, else the oracle restatement."""
     import torch
-    from oracle import sshslie_oracle as O
+    from oracle import make_ref, sshslie_oracle as O
     torch.set_num_threads(threads)
+    x = O.synthetic_patches(wl["batch"], CHANNELS, SIZE, seed=41)
+    ts = []
+    ref = make_ref.ref_dir()
+    if ref is not None:
+        from oracle import ref_shims
+        M = ref_shims.import_reference_model(ref)
+        torch.manual_seed(41)
+        m = M.LowLightEnhance(input_channels=CHANNELS, lr=1e-3, **wl["coef"])
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            m.optimizer.zero_grad()
+            loss, _ = m.compute_loss(x)
+            loss.backward()
+            m.optimizer.step()
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+        return ts, "reference", "unmodified reference LowLightEnhance (oracle/_ref/model.py), torch CPU fp32"
     p = O.init_params(41)
     state = {}
-    x = O.synthetic_patches(BATCH_PER_GPU, CHANNELS, SIZE, seed=41)
-    ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        _, grads, _ = O.loss_and_grads(p, x, O.JYU_COEF)
+        _, grads, _ = O.loss_and_grads(p, x, wl["coef"])
         p = O.adam_step(p, grads, state, lr=1e-3)
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
-    return ts
+    return ts, "port", "oracle/sshslie_oracle.py (pinned restatement of the reference), torch CPU fp32"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = workloads()[args.config]
     cores = os.cpu_count() or 1
-    ts = oracle_cpu_steps(args.steps, min(args.warmup, 2), cores)
+    ts, kind, what = cpu_reference_steps(args.steps, args.warmup, cores, wl)
     total = sum(ts)
-    value = BATCH_PER_GPU * len(ts) / total
+    value = wl["batch"] * len(ts) / total
     line = {
         "impl": "reference", "metric": "train_patches_per_sec", "value": value, "unit": "patches/s",
-        "n_gpus": args.gpus, "steps": len(ts), "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * total / len(ts),
+        "n_gpus": args.gpus, "steps": len(ts), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": BATCH_PER_GPU, "note": "CPU only: the reference has no "
-                   "multi-GPU path; rank 0 runs one replica of the step on all host cores"},
-        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(ts)} full train steps of B={BATCH_PER_GPU} (oracle/sshslie_oracle.py, torch CPU fp32)"},
+        "config": {"workload": wl["name"], "global_batch": wl["batch"],
+                   "note": "CPU only: the reference has no multi-GPU path; rank 0 runs one replica of the step on all "
+                           "host cores"},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": kind,
+                         "sample": f"{len(ts)} full train steps of B={wl['batch']} ({what}, {cores} threads)"},
         "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------------------------
+def kernel_of(name):
+    """profile row ("phase/kind:layer[impl]") -> the CUDA kernel function that executes it"""
+    op = name.split("/", 1)[1]
+    if op.startswith("splitk_reduce"):
+        return "conv_wgrad_*_reduce_kernel"
+    if op.startswith("wgrad:"):
+        return "conv_wgrad_halo_kernel" if "halo" in op else ("conv_wgrad_umma_kernel" if "tcgen05" in op else "conv_wgrad_simt_kernel")
+    if op.startswith(("fwd:", "dgrad:")):
+        if "pipe" in op:
+            return "conv_gather_pipe_kernel"
+        if "halo" in op:
+            return "conv_gather_halo_kernel"
+        return "conv_gather_umma_kernel" if "tcgen05" in op else "conv_gather_simt_kernel"
+    return {"loss:fourier_fft+grad": "fourier_loss_kernel", "loss:pixel_terms+grads": "pixel_losses_kernel"}.get(op, op)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import sshslie_b200 as S
-    from oracle import sshslie_oracle as O      # only for synthetic inputs + the cpu_baseline leg
+    from oracle import sshslie_oracle as O      # only for synthetic inputs + the checker / cpu_baseline legs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -134,55 +192,113 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    K, W = args.steps, max(args.warmup, 3)
-
-    torch.manual_seed(41)
-    m = S.LowLightEnhance(input_channels=CHANNELS, lr=1e-3, **O.JYU_COEF).to(dev)
-    if world > 1:
-        m.enable_data_parallel()
+    K, W, R = args.steps, max(args.warmup, 3), max(1, args.regions)
+    WL = workloads()
     lib = S.lib.load()
-    pool = [O.synthetic_patches(BATCH_PER_GPU, CHANNELS, SIZE, seed=41 + rank * 1000 + i) for i in range(8)]
-    pool_dev = [t.to(dev) for t in pool]
-    pool_pin = [t.pin_memory() for t in pool]
-
-    def step(x):
-        m.optimizer.zero_grad()
-        loss, losses = m.compute_loss(x)
-        loss.backward()
-        m.optimizer.step()
-        return losses
+    pk = peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(inputs, read_losses):
-        for i in range(W):
-            losses = step(inputs[i % len(inputs)])
-            if read_losses:
-                _ = losses["total_loss"]
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = lib.sshslie_launch_count()
-        e0.record()
-        for i in range(K):
-            losses = step(inputs[i % len(inputs)])
-            if read_losses:
-                _ = losses["total_loss"]            # D2H of the 7 loss floats + sync, as model.py:566-574 / 319
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+    def max_over_ranks(ms):
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms, lib.sshslie_launch_count() - launches0
+            return float(t)
+        return ms
 
+    def make_model(wl, dp):
+        torch.manual_seed(41)
+        m = S.LowLightEnhance(input_channels=CHANNELS, lr=1e-3, **wl["coef"]).to(dev)
+        if dp and world > 1:
+            m.enable_data_parallel()
+        return m
+
+    def step(m, x):
+        m.optimizer.zero_grad()
+        loss, losses = m.compute_loss(x)
+        loss.backward()
+        m.optimizer.step()
+        return losses
+
+    def timed(m, pool, mode, k=None, regions=None, sync_ranks=True):
+        """Median over `regions` timed regions of exactly k steps (barrier + synchronize on both sides, max over ranks).
+        mode "device": inputs resident in HBM.  mode "e2e": pinned host batches through LowLightEnhance.prefetch (H2D of
+        batch i+1 overlaps step i) and the 7-float loss read-back after every step."""
+        k, regions = k or K, regions or R
+        n = len(pool)
+        out = []
+        for r in range(regions + 1):                 # region 0 = warm-up (W steps), not recorded
+            steps = W if r == 0 else k
+            if sync_ranks:
+                barrier()
+            else:
+                torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if mode == "e2e":
+                nxt = m.prefetch(pool[0])
+                for i in range(steps):
+                    cur, nxt = nxt, m.prefetch(pool[(i + 1) % n])
+                    _ = step(m, cur)["total_loss"]      # D2H of the 7 loss floats + sync, as model.py:566-574 / 319
+            else:
+                for i in range(steps):
+                    step(m, pool[i % n])
+            e1.record()
+            if sync_ranks:
+                barrier()
+            else:
+                torch.cuda.synchronize()
+            if r > 0:
+                ms = e0.elapsed_time(e1)
+                out.append(max_over_ranks(ms) if sync_ranks else ms)
+        return statistics.median(out), out
+
+    def pools(batch, seed0=41):
+        host = [O.synthetic_patches(batch, CHANNELS, SIZE, seed=seed0 + rank * 1000 + i) for i in range(8)]
+        return [t.to(dev) for t in host], [t.pin_memory() for t in host]
+
+    def dp_parity(wl):
+        """Outside any timed region: every rank runs 4 data-parallel steps WITHOUT optimizer.step on its own patches
+        (steps 3+ replay the captured graph incl. the NCCL calls); rank 0 compares the averaged gradient and loss with the
+        CPU oracle on the concatenated global batch; all ranks must hold bit-identical gradients."""
+        m = make_model(wl, dp=True)
+        xs = [O.synthetic_patches(wl["batch"], CHANNELS, SIZE, seed=41 + r) for r in range(world)]
+        for _ in range(4):
+            m.optimizer.zero_grad()
+            loss, losses = m.compute_loss(xs[rank].to(dev))
+            loss.backward()
+        torch.cuda.synchronize()
+        g = torch.cat([p.grad.detach().flatten() for p in m.parameters()])
+        lo, hi = g.clone(), g.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+        res = None
+        if rank == 0:
+            torch.set_num_threads(os.cpu_count() or 1)
+            ref_l, ref_g, _ = O.loss_and_grads(O.init_params(41), torch.cat(xs, 0), wl["coef"])
+            r = torch.cat([v.flatten() for v in ref_g.values()]).double()
+            gd = g.cpu().double()
+            res = {"grad_cos": float(gd @ r / (gd.norm() * r.norm())), "grad_norm_ratio": float(gd.norm() / r.norm()),
+                   "loss_rel": abs(losses["total_loss"] - ref_l["total_loss"]) / abs(ref_l["total_loss"]),
+                   "ranks_identical": same, "global_batch": world * wl["batch"],
+                   "checker": "oracle/sshslie_oracle.py fp32 autograd on the concatenated global batch (CPU)"}
+        del m
+        torch.cuda.empty_cache()
+        barrier()
+        return res
+
+    # ---------------------------------------------------------------- primary workload
+    wl = WL[args.config]
+    m = make_model(wl, dp=True)
+    pool_dev, pool_pin = pools(wl["batch"])
     # launches per step, counted on an eager step (graph replays do not pass through the launch counter)
     m.use_cuda_graph = False
     c0 = lib.sshslie_launch_count()
-    step(pool_dev[0])
+    step(m, pool_dev[0])
     torch.cuda.synchronize()
     launches_per_step = lib.sshslie_launch_count() - c0
     m.use_cuda_graph = True
@@ -190,41 +306,88 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, _ = timed(pool_dev, read_losses=False)
-    ms_e2e, _ = timed(pool_pin, read_losses=True)
+    ms_dev, regions_dev = timed(m, pool_dev, "device")
+    ms_e2e, regions_e2e = timed(m, pool_pin, "e2e")
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-kernel device time: K eager steps with a cudaEvent pair around every launch group (same inputs)
+    # ---------------------------------------------------------------- N > 1: parity + the cv1 workload + own N=1 reference
+    parity = cv1 = n1_ref = None
+    if world > 1:
+        parity = dp_parity(wl)
+        # single-GPU rate of the SAME workload in the same run (every rank alone, no communication): the reference point
+        # for the data-parallel efficiency of this line
+        m1 = make_model(wl, dp=False)
+        ms1, _ = timed(m1, pool_dev, "device", regions=3)
+        n1_ref = {"value": wl["batch"] * K / (ms1 * 1e-3), "ms_per_step": ms1 / K,
+                  "what": "one GPU alone, same workload, same run (max over ranks of K-step regions, median of 3)"}
+        del m1
+        torch.cuda.empty_cache()
+        if args.config != "cv1":
+            wc = WL["cv1"]
+            pc_dev, pc_pin = pools(wc["batch"], seed0=141)
+            mc1 = make_model(wc, dp=False)
+            msc1, _ = timed(mc1, pc_dev, "device", regions=3)
+            del mc1
+            torch.cuda.empty_cache()
+            mc = make_model(wc, dp=True)
+            msc, _ = timed(mc, pc_dev, "device", regions=3)
+            msc_e2e, _ = timed(mc, pc_pin, "e2e", regions=3)
+            del mc
+            torch.cuda.empty_cache()
+            par_c = dp_parity(wc)
+            v1, vn = wc["batch"] * K / (msc1 * 1e-3), world * wc["batch"] * K / (msc * 1e-3)
+            cv1 = {"workload": wc["name"], "global_batch": world * wc["batch"], "value": vn, "unit": "patches/s",
+                   "ms_per_step": msc / K, "e2e_value": world * wc["batch"] * K / (msc_e2e * 1e-3),
+                   "single_gpu_value_same_run": v1, "efficiency_vs_single_gpu": vn / (world * v1), "dp_parity": par_c}
+
+    # ---------------------------------------------------------------- per-kernel device time (rank 0)
     prof = {}
     if rank == 0:
-        for i in range(max(3, min(K, 10))):
-            for name, ms, fl, by in m.profile_step(pool_dev[i % 8]):
+        mp_ = make_model(wl, dp=False)
+        for i in range(5 if world == 1 else 3):
+            for name, ms, fl, by in mp_.profile_step(pool_dev[i % 8]):
                 a = prof.setdefault(name, [0.0, 0, fl, by])
                 a[0] += ms
                 a[1] += 1
-    # BASELINE.json's second metric (configs[3]): full-image inference, 1 x 64 x 512 x 512 cube, forward only
+        del mp_
+        torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- configs[3]: full-image inference (N = 1)
     infer = None
     if rank == 0 and world == 1:
+        mi = make_model(wl, dp=False)
         xi = O.synthetic_patches(1, CHANNELS, 512, seed=41)
-        xi_dev, xi_pin = xi.to(dev), xi.pin_memory()
+        xi_dev, xi_pin = xi.to(dev), [xi.pin_memory(), xi.clone().pin_memory()]
         vox = float(xi.numel()) / 1e6
 
-        def fwd_timed(inp, reps):
+        def fwd_timed(e2e, reps):
             with torch.no_grad():
                 for _ in range(3):
-                    m.forward(inp)
+                    mi.forward(xi_dev)
                 torch.cuda.synchronize()
                 a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                for _ in range(reps):
-                    R_, I_, Id_, S_ = m.forward(inp)
-                    if inp.device.type == "cpu":
-                        _ = float(S_[0, 0, 0, 0])      # read-back so that the H2D + compute of this image is complete
+                if e2e:       # H2D of image i+1 overlaps the forward of image i; one output element read back per image
+                    nxt = mi.prefetch(xi_pin[0])
+                    for i in range(reps):
+                        cur, nxt = nxt, mi.prefetch(xi_pin[(i + 1) & 1])
+                        S_ = mi.forward(cur)[3]
+                        _ = float(S_[0, 0, 0, 0])
+                else:
+                    for _ in range(reps):
+                        mi.forward(xi_dev)
                 b_.record()
                 torch.cuda.synchronize()
             return a.elapsed_time(b_) / reps
-        ms_i = fwd_timed(xi_dev, 10)
-        ms_i_e2e = fwd_timed(xi_pin, 10)
+        ms_i = statistics.median(fwd_timed(False, 10) for _ in range(3))
+        ms_i_e2e = statistics.median(fwd_timed(True, 10) for _ in range(3))
+        fwd_prof = {}
+        for name, ms, fl, by in mi.profile_step(xi_dev, train=False):
+            a = fwd_prof.setdefault(kernel_of(name), [0.0, 0.0])
+            a[0] += ms
+            a[1] += fl
+        del mi
+        torch.cuda.empty_cache()
         torch.set_num_threads(os.cpu_count() or 1)
         p_cpu = O.init_params(41)
         with torch.no_grad():
@@ -235,83 +398,66 @@ def run_ours(args):
         infer = {"metric": "inference_mvoxel_per_sec", "workload": "forward on a 1x64x512x512 cube (phase=test, model.py:418)",
                  "value": vox / (ms_i * 1e-3), "ms_per_image": ms_i, "e2e_value": vox / (ms_i_e2e * 1e-3),
                  "e2e_ms_per_image": ms_i_e2e, "h2d_bytes_per_image": int(xi.numel() * 4), "unit": "Mvoxel/s",
+                 "e2e_note": "pinned host cube -> prefetch (copy stream, overlaps the previous image) -> forward -> read-back",
                  "tflops_model": 391.4e9 / (ms_i * 1e-3) / 1e12,
+                 "kernels_ms": {k: round(v[0], 4) for k, v in sorted(fwd_prof.items(), key=lambda kv: -kv[1][0])[:8]},
                  "cpu_baseline": {"value": vox / cpu_s, "unit": "Mvoxel/s", "cores": os.cpu_count() or 1, "kind": "port",
                                   "sample": "1 forward of the same cube (oracle, torch CPU fp32)"}}
-    # BASELINE.json configs[4]: batch sweep (per-GPU batch 8 / 32, same loss weights), CUDA-graph replays, device timed;
-    # plus the per-launch roofline of the 9x9 layer at the largest batch (the kernels leave the launch-latency regime there)
-    sweep = None
-    if rank == 0 and world == 1 and not args.no_sweep:
-        sweep = []
-        for bsz in (8, 32):
-            mb = S.LowLightEnhance(input_channels=CHANNELS, lr=1e-3, **O.JYU_COEF).to(dev)
-            xb = O.synthetic_patches(bsz, CHANNELS, SIZE, seed=7).to(dev)
 
-            def stepb():
-                mb.optimizer.zero_grad()
-                loss, _ = mb.compute_loss(xb)
-                loss.backward()
-                mb.optimizer.step()
-            for _ in range(5):
-                stepb()
-            torch.cuda.synchronize()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 10
-            a.record()
-            for _ in range(reps):
-                stepb()
-            b_.record()
-            torch.cuda.synchronize()
-            msb = a.elapsed_time(b_) / reps
-            row = {"batch_per_gpu": bsz, "ms_per_step": msb, "patches_per_sec": bsz / (msb * 1e-3),
-                   "tflops_model": bsz * FLOPS_PER_PATCH_FWD_BWD / (msb * 1e-3) / 1e12}
-            if bsz == 32:
+    # ---------------------------------------------------------------- configs[4]: batch sweep with the cv weights
+    sweep = None
+    if not args.no_sweep:
+        sweep = []
+        batches = (1, 8, 32, 128) if world == 1 else (8, 32)
+        wc = WL["cv1"]
+        for bsz in batches:
+            mb = make_model(wc, dp=True)
+            xb = [O.synthetic_patches(bsz, CHANNELS, SIZE, seed=7 + rank).to(dev)]
+            kb = 10 if bsz <= 32 else 5
+            msb, _ = timed(mb, xb, "device", k=kb, regions=3)
+            row = None
+            if rank == 0:
+                row = {"batch_per_gpu": bsz, "global_batch": world * bsz, "ms_per_step": msb / kb,
+                       "patches_per_sec": world * bsz * kb / (msb * 1e-3),
+                       "tflops_model_per_gpu": bsz * kb * FLOPS_PER_PATCH_FWD_BWD / (msb * 1e-3) / 1e12}
+                row["frac_of_sustained_bf16_peak"] = row["tflops_model_per_gpu"] / pk["sustained"]
+            if bsz == 32 and rank == 0:       # roofline row per kernel class where the kernels leave the launch-latency regime
+                mq = make_model(wc, dp=False)
                 pr = {}
                 for _ in range(2):
-                    for name, ms, fl, by in mb.profile_step(xb):
-                        if "shallow9x9" in name or "loss:" in name:
-                            a_ = pr.setdefault(name, [0.0, 0, fl, by])
-                            a_[0] += ms
-                            a_[1] += 1
-                pk_ = peaks()
-                row["kernels"] = [
-                    {"kernel": k, "ms_per_launch": v[0] / v[1],
-                     **({"tflops": v[2] / (v[0] / v[1] * 1e-3) / 1e12, "frac_of_bf16_peak": v[2] / (v[0] / v[1] * 1e-3) / 1e12 / pk_["burst"]}
-                        if v[2] > 0 else
-                        {"gbs": v[3] / (v[0] / v[1] * 1e-3) / 1e9, "frac_of_hbm_peak": v[3] / (v[0] / v[1] * 1e-3) / 1e9 / pk_["hbm"]})}
-                    for k, v in sorted(pr.items())]
-            sweep.append(row)
+                    for name, ms, fl, by in mq.profile_step(xb[0]):
+                        a_ = pr.setdefault(kernel_of(name), [0.0, 0.0, 0.0])
+                        a_[0] += ms / 2
+                        a_[1] += fl / 2
+                        a_[2] += by / 2
+                del mq
+                rows = []
+                for kname, v in sorted(pr.items(), key=lambda kv: -kv[1][0]):
+                    r_ = {"kernel": kname, "ms_per_step": v[0]}
+                    if v[1] > 0:
+                        r_.update(tflops=v[1] / (v[0] * 1e-3) / 1e12, frac_of_bf16_peak=v[1] / (v[0] * 1e-3) / 1e12 / pk["burst"])
+                    elif v[2] > 0:
+                        r_.update(gbs=v[2] / (v[0] * 1e-3) / 1e9, frac_of_hbm_peak=v[2] / (v[0] * 1e-3) / 1e9 / pk["hbm"])
+                    rows.append(r_)
+                row["kernels"] = rows
+            if row:
+                sweep.append(row)
             del mb, xb
             torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1:
         cores = os.cpu_count() or 1
-        ts = oracle_cpu_steps(3, 1, cores)
-        cpu = {"value": BATCH_PER_GPU * len(ts) / sum(ts), "unit": "patches/s", "cores": cores, "kind": "port",
-               "sample": f"{len(ts)} full train steps of B={BATCH_PER_GPU} on the host (oracle/sshslie_oracle.py, torch CPU fp32, "
-                         f"{cores} threads)"}
+        ts, kind, what = cpu_reference_steps(3, 1, cores, wl)
+        cpu = {"value": wl["batch"] * len(ts) / sum(ts), "unit": "patches/s", "cores": cores, "kind": kind,
+               "sample": f"{len(ts)} full train steps of B={wl['batch']} on the host ({what}, {cores} threads)"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    pk = peaks()
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
     total_prof = sum(v[0] / v[1] for v in prof.values())
-
-    def kernel_of(name):
-        """profile row -> the CUDA kernel (function) that executes it"""
-        op = name.split("/", 1)[1]
-        if op.startswith("splitk_reduce"):
-            return "conv_wgrad_*_reduce_kernel"
-        if op.startswith("wgrad:"):
-            return "conv_wgrad_halo_kernel" if "halo" in op else ("conv_wgrad_umma_kernel" if "tcgen05" in op else "conv_wgrad_simt_kernel")
-        if op.startswith(("fwd:", "dgrad:")):
-            if "halo" in op:
-                return "conv_gather_halo_kernel"
-            return "conv_gather_umma_kernel" if "tcgen05" in op else "conv_gather_simt_kernel"
-        return {"loss:fourier_fft+grad": "fourier_loss_kernel", "loss:pixel_terms+grads": "pixel_losses_kernel"}.get(op, op)
-
-    # dominant kernel = the kernel function with the largest share of the step's device time (all its launches);
-    # achieved = its algorithmic FLOPs (bytes) over all launches / their total duration
     byk = {}
     for name, v in prof.items():
         a = byk.setdefault(kernel_of(name), [0.0, 0.0, 0.0, 0, None])
@@ -334,55 +480,60 @@ def run_ours(args):
     top_name, top = max(cand.items(), key=lambda kv: kv[1][0])
     roof = roof_of(top[0], top[1], top[2])
     big = top[4]
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        traffic = tj.get(big[0].split("/", 1)[1].split("[")[0])
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    for tf in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            traffic = tj.get(big[0].split("/", 1)[1].split("[")[0])
+            if traffic is not None:
+                traffic_src = "profiles/" + tf + " (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)"
+                break
+        except Exception:
+            pass
     roof.update({"kernel": top_name, "launches_per_step": top[3], "ms_per_step": top[0], "ms_per_launch": top[0] / top[3],
                  "share_of_step": top[0] / total_prof, "algorithmic_flops_per_step": top[1],
                  "algorithmic_bytes_per_step": top[2],
                  "largest_launch": dict(roof_of(big[1], big[2], big[3]), kernel=big[0], ms_per_launch=big[1],
                                         algorithmic_flops_per_launch=big[2], traffic=traffic),
-                 "traffic": traffic, "peak_source": pk["source"],
+                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"],
                  "timing": "cudaEvent pair around 4 back-to-back enqueues of each launch group (time / 4), eager steps after "
-                           "the timed region, on the stream the kernels run on (sshslie_profile_step); traffic = DRAM bytes of "
-                           "the largest launch from the ncu --set full capture in profiles/"})
+                           "the timed region, on the stream the kernels run on (sshslie_profile_step)"})
     roof["by_kernel"] = [dict(roof_of(v[0], v[1], v[2]) if (v[1] > 0 or v[2] > 0) else {}, kernel=k, launches_per_step=v[3],
                               ms_per_step=v[0], share_of_step=v[0] / total_prof)
-                         for k, v in sorted(byk.items(), key=lambda kv: -kv[1][0])[:8]]
-    patches = world * BATCH_PER_GPU * K
+                         for k, v in sorted(byk.items(), key=lambda kv: -kv[1][0])[:10]]
+    patches = world * wl["batch"] * K
     value = patches / (ms_dev * 1e-3)
     e2e = patches / (ms_e2e * 1e-3)
-    h2d = world * BATCH_PER_GPU * CHANNELS * SIZE * SIZE * 4
-    top5 = sorted(((k, v[0] / v[1]) for k, v in prof.items()), key=lambda kv: -kv[1])[:8]
-    classes = {}
-    for k, v in prof.items():
-        kind = k.split("/")[1].split(":")[0]
-        if "tcgen05" in k:
-            kind += "[tcgen05]"
-        classes[kind] = classes.get(kind, 0.0) + v[0] / v[1]
-    classes = {k: round(v, 4) for k, v in sorted(classes.items(), key=lambda kv: -kv[1])[:8]}
+    h2d = world * wl["batch"] * CHANNELS * SIZE * SIZE * 4
+    top8 = sorted(((k, v[0] / v[1]) for k, v in prof.items()), key=lambda kv: -kv[1])[:8]
     line = {
         "metric": "train_patches_per_sec", "value": value, "unit": "patches/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * BATCH_PER_GPU, "parallelism": f"dp{world}",
+        "config": {"workload": wl["name"], "global_batch": world * wl["batch"], "parallelism": f"dp{world}",
                    "l2": "no explicit flush: each step streams a >250 MB activation workspace (2x the 126 MB L2) and "
                          "inputs rotate over a pool of 8 resident batches",
-                   "cuda_graph": True},
+                   "cuda_graph": True, "timed_regions": R,
+                   "region_ms": [round(x, 4) for x in regions_dev]},
         "tflops_model": value * FLOPS_PER_PATCH_FWD_BWD / 1e12,
         "frac_of_sustained_bf16_peak": value * FLOPS_PER_PATCH_FWD_BWD / 1e12 / (world * pk["sustained"]),
         "roofline": roof,
         "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": world * 7 * 4},
+                "d2h_bytes_per_step": world * 7 * 4, "region_ms": [round(x, 4) for x in regions_e2e],
+                "how": "pinned host batch -> LowLightEnhance.prefetch (copy stream, two staging buffers: the H2D of batch "
+                       "i+1 overlaps step i) -> compute_loss/backward/step -> losses['total_loss'] read back every step"},
         "gpu_launches": launches_per_step * K,
         "launches_per_step": launches_per_step,
         "clocks": clocks,
-        "top_kernels_ms": top5,
-        "kernel_class_ms_per_step": classes,
+        "top_kernels_ms": top8,
     }
+    if parity:
+        line["dp_parity"] = parity
+    if n1_ref:
+        line["single_gpu_same_run"] = n1_ref
+        line["efficiency_vs_single_gpu_same_run"] = value / (world * n1_ref["value"])
+    if cv1:
+        line["cv1"] = cv1
     if sweep:
         line["batch_sweep"] = sweep
     if cpu:
@@ -400,11 +551,12 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-sweep", dest="no_sweep", action="store_true", help="skip the batch-8/32 sweep (configs[4])")
+    ap.add_argument("--config", default="jyu", choices=["jyu", "cv1"],
+                    help="primary workload: jyu = configs[1] (B=2/GPU), cv1 = configs[2] (B=1/GPU)")
+    ap.add_argument("--regions", type=int, default=5, help="timed regions of --steps steps each; the median is reported")
+    ap.add_argument("--no-sweep", dest="no_sweep", action="store_true", help="skip the batch sweep (configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps > 10:
-            args.steps = 10          # bounded sample: ~1 s per CPU step
         run_reference(args)
     else:
         run_ours(args)

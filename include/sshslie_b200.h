@@ -130,18 +130,24 @@ SSHSLIE_API int sshslie_ssim_sum(const float* pred_hwc, const float* target_hwc,
 
 /* ---- single kernels, exported for kernel-level parity tests and profiling ---- */
 
+/* Scratch of the two loss entry points below for a (B,C,H,W) problem: they keep NO floating-point atomics - every block
+ * writes its partial sums to the scratch and a second launch adds them in a fixed order, so results are bit-repeatable
+ * (the reference trains with cudnn.deterministic = True, main.py:165). */
+SSHSLIE_API int64_t sshslie_loss_scratch_bytes(int B, int C, int H, int W);
+
 /* fourier_spectrum_loss (model.py:456-473) forward + d/dS.  x,S,dS: (n_img,H,W) fp32 planes, H and W
- * powers of two in [8,128]; mask (H,W) fp32; accumulates sum_k mask*| |X|-|S| | into *sum_out (not zeroed);
- * dS += grad_scale * d(sum)/dS when dS != NULL. */
+ * powers of two in [8,128]; mask (H,W) fp32; adds sum_k mask*| |X|-|S| | to *sum_out (not zeroed);
+ * dS += grad_scale * d(sum)/dS when dS != NULL.  scratch: >= n_img floats. */
 SSHSLIE_API int sshslie_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out,
-                         int n_img, int H, int W, float grad_scale, void* stream);
+                         int n_img, int H, int W, float grad_scale, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* The five pixel-space loss terms (model.py:450-454, 475-481, 491-542, 551) and their gradients.
- * sums[8] (device) receives the raw term sums; gradients are written (not accumulated) already scaled by
- * c_loss_x / count.  Any gradient pointer may be NULL (forward only). */
+ * sums[9] (device) receives the raw term sums; gradients are written (not accumulated) already scaled by
+ * c_loss_x / count.  Any gradient pointer may be NULL (forward only).  scratch: sshslie_loss_scratch_bytes(B,C,H,W). */
 SSHSLIE_API int sshslie_pixel_losses(const float* x, const float* R, const float* I, const float* Idelta, const float* S,
                          const float* R_enh, const sshslie_loss_cfg* cfg, int B, int C, int H, int W,
-                         float* sums, float* dR, float* dI, float* dIdelta, float* dS, float* dR_enh, void* stream);
+                         float* sums, float* dR, float* dI, float* dIdelta, float* dS, float* dR_enh,
+                         void* scratch, int64_t scratch_bytes, void* stream);
 
 /* One conv layer through the implicit-GEMM executors, for kernel parity tests: x (B,Cin,H,W) fp32,
  * w (Cout,Cin,k,k) [or (Cin,Cout,k,k) when transposed], y (B,Cout,OH,OW) fp32.  Internally converts to the

@@ -58,9 +58,11 @@ def install_stubs():
     sk.metrics = skm
 
 
-def import_reference_model():
+def import_reference_model(root=REFERENCE_ROOT):
+    """`root` = /root/reference in the build container, or oracle/_ref (the build-time copy made by oracle/make_ref.py,
+    git-ignored, shipped to the GPU box with the built libraries) for bench.py's reference arm."""
     install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import model  # noqa: the reference's model.py, unmodified
     return model

@@ -11,41 +11,6 @@
 #define AT_HEADS 4
 #define AT_HD 16
 
-// dW[o, i] += sum_t dY[t,o] * X[t,i] ;  db[o] += sum_t dY[t,o]   (dY optionally masked by hmask > 0)
-// grid.x = token chunks of 64; block 256 = 64 (i) x 4 (o phase); atomics into the flat gradient buffer
-__global__ void __launch_bounds__(256) linear_bwd_weight_kernel(const float* __restrict__ dY,
-                                                                const float* __restrict__ hmask,
-                                                                const float* __restrict__ X, float* __restrict__ dW,
-                                                                float* __restrict__ db, int T) {
-  __shared__ float Ys[64][AT_D + 1];
-  __shared__ float Xs[64][AT_D + 1];
-  const int t0 = blockIdx.x * 64;
-  for (int i = threadIdx.x; i < 64 * AT_D; i += 256) {
-    const int t = t0 + (i >> 6);
-    float y = 0.f, xv = 0.f;
-    if (t < T) {
-      y = dY[(int64_t)t * AT_D + (i & 63)];
-      if (hmask && !(hmask[(int64_t)t * AT_D + (i & 63)] > 0.f)) y = 0.f;
-      xv = X[(int64_t)t * AT_D + (i & 63)];
-    }
-    Ys[i >> 6][i & 63] = y;
-    Xs[i >> 6][i & 63] = xv;
-  }
-  __syncthreads();
-  const int ii = threadIdx.x & 63;
-  for (int o = threadIdx.x >> 6; o < AT_D; o += 4) {
-    float acc = 0.f;
-#pragma unroll 16
-    for (int t = 0; t < 64; ++t) acc = fmaf(Ys[t][o], Xs[t][ii], acc);
-    atomicAdd(dW + o * AT_D + ii, acc);
-  }
-  if (threadIdx.x < AT_D) {
-    float acc = 0.f;
-    for (int t = 0; t < 64; ++t) acc += Ys[t][threadIdx.x];
-    atomicAdd(db + threadIdx.x, acc);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // fused token kernels (16 tokens per block, 256 threads = 64 features x 4 token phases)
 // ---------------------------------------------------------------------------------------------
@@ -58,84 +23,6 @@ SS_DEVINL void stage_w(float (*Ws)[AT_D + 1], const float* __restrict__ Wt) {
   for (int k = 0; k < 16; ++k) {
     const int i = threadIdx.x + k * 256;
     Ws[i >> 6][i & 63] = r[k];
-  }
-}
-
-// x = fp32(a3);  q,k,v = x Wq^T + bq, ...                                   (model.py:103-106)
-__global__ void __launch_bounds__(256) attn_qkv_kernel(const bf16* __restrict__ a3, const float* __restrict__ P,
-                                                       const int64_t* __restrict__ poff_unused, int64_t oq, int64_t obq,
-                                                       int64_t ok, int64_t obk, int64_t ov, int64_t obv,
-                                                       float* __restrict__ X, float* __restrict__ Q,
-                                                       float* __restrict__ K, float* __restrict__ V, int T) {
-  extern __shared__ float smf[];
-  float (*Wq)[AT_D + 1] = reinterpret_cast<float (*)[AT_D + 1]>(smf);
-  float (*Wk)[AT_D + 1] = Wq + AT_D;
-  float (*Wv)[AT_D + 1] = Wk + AT_D;
-  float (*Xs)[AT_D] = reinterpret_cast<float (*)[AT_D]>(smf + 3 * AT_D * (AT_D + 1));
-  const int t0 = blockIdx.x * TK;
-  stage_w(Wq, P + oq); stage_w(Wk, P + ok); stage_w(Wv, P + ov);
-  for (int i = threadIdx.x; i < TK * AT_D; i += 256) {
-    const int t = t0 + (i >> 6);
-    float v = 0.f;
-    if (t < T) {
-      v = bf2f(a3[(int64_t)t * AT_D + (i & 63)]);
-      X[(int64_t)t * AT_D + (i & 63)] = v;
-    }
-    Xs[i >> 6][i & 63] = v;
-  }
-  __syncthreads();
-  const int o = threadIdx.x & 63;
-  for (int tt = threadIdx.x >> 6; tt < TK; tt += 4) {
-    const int t = t0 + tt;
-    if (t >= T) break;
-    float aq = P[obq + o], ak = P[obk + o], av = P[obv + o];
-#pragma unroll 16
-    for (int i = 0; i < AT_D; ++i) {
-      const float xv = Xs[tt][i];
-      aq = fmaf(xv, Wq[o][i], aq);
-      ak = fmaf(xv, Wk[o][i], ak);
-      av = fmaf(xv, Wv[o][i], av);
-    }
-    Q[(int64_t)t * AT_D + o] = aq;
-    K[(int64_t)t * AT_D + o] = ak;
-    V[(int64_t)t * AT_D + o] = av;
-  }
-}
-
-// h = relu(o W1^T + b1) ; t = x + h W2^T + b2  -> h (kept for backward), t as bf16     (model.py:115-118)
-__global__ void __launch_bounds__(256) attn_ffn_kernel(const float* __restrict__ O, const float* __restrict__ X,
-                                                       const float* __restrict__ P, int64_t o1, int64_t ob1, int64_t o2,
-                                                       int64_t ob2, float* __restrict__ Hh, bf16* __restrict__ Tout,
-                                                       int T) {
-  extern __shared__ float smf[];
-  float (*W1)[AT_D + 1] = reinterpret_cast<float (*)[AT_D + 1]>(smf);
-  float (*W2)[AT_D + 1] = W1 + AT_D;
-  float (*Os)[AT_D] = reinterpret_cast<float (*)[AT_D]>(smf + 2 * AT_D * (AT_D + 1));
-  float (*Hs)[AT_D] = Os + TK;
-  const int t0 = blockIdx.x * TK;
-  stage_w(W1, P + o1); stage_w(W2, P + o2);
-  for (int i = threadIdx.x; i < TK * AT_D; i += 256) {
-    const int t = t0 + (i >> 6);
-    Os[i >> 6][i & 63] = (t < T) ? O[(int64_t)t * AT_D + (i & 63)] : 0.f;
-  }
-  __syncthreads();
-  const int o = threadIdx.x & 63;
-  for (int tt = threadIdx.x >> 6; tt < TK; tt += 4) {
-    float acc = P[ob1 + o];
-#pragma unroll 16
-    for (int i = 0; i < AT_D; ++i) acc = fmaf(Os[tt][i], W1[o][i], acc);
-    acc = fmaxf(acc, 0.f);
-    Hs[tt][o] = acc;
-    if (t0 + tt < T) Hh[(int64_t)(t0 + tt) * AT_D + o] = acc;
-  }
-  __syncthreads();
-  for (int tt = threadIdx.x >> 6; tt < TK; tt += 4) {
-    const int t = t0 + tt;
-    if (t >= T) break;
-    float acc = P[ob2 + o];
-#pragma unroll 16
-    for (int i = 0; i < AT_D; ++i) acc = fmaf(Hs[tt][i], W2[o][i], acc);
-    Tout[(int64_t)t * AT_D + o] = f2bf(acc + X[(int64_t)t * AT_D + o]);
   }
 }
 
@@ -225,83 +112,6 @@ __global__ void __launch_bounds__(256) attn_dx_kernel(const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 #define AT_KT 64
 #define AT_QB 32
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K,
-                                                       const float* __restrict__ V, float* __restrict__ O,
-                                                       float* __restrict__ LSE, int L) {
-  __shared__ float Ks[AT_KT][AT_HD + 1];
-  __shared__ float Vs[AT_KT][AT_HD + 1];
-  const int head = blockIdx.y, b = blockIdx.z;
-  const int part = threadIdx.x & 3;
-  const int qi = blockIdx.x * AT_QB + (threadIdx.x >> 2);
-  const bool ok = qi < L;
-  const int64_t rowbase = (int64_t)b * L;
-  float q[AT_HD], o[AT_HD];
-#pragma unroll
-  for (int d = 0; d < AT_HD; ++d) {
-    q[d] = ok ? Q[(rowbase + qi) * AT_D + head * AT_HD + d] * 0.25f : 0.f;   // 1/sqrt(16), model.py:110-111
-    o[d] = 0.f;
-  }
-  float mx = -INFINITY, l = 0.f;
-  for (int k0 = 0; k0 < L; k0 += AT_KT) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < AT_KT * AT_HD; i += 128) {
-      const int kk = k0 + (i >> 4);
-      const int64_t a = (rowbase + kk) * AT_D + head * AT_HD + (i & 15);
-      Ks[i >> 4][i & 15] = (kk < L) ? K[a] : 0.f;
-      Vs[i >> 4][i & 15] = (kk < L) ? V[a] : 0.f;
-    }
-    __syncthreads();
-    const int kn = min(AT_KT, L - k0);
-    float sc[AT_KT / 4];
-    float tmax = mx;
-#pragma unroll
-    for (int jj = 0; jj < AT_KT / 4; ++jj) {
-      const int j = jj * 4 + part;
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < AT_HD; ++d) a = fmaf(q[d], Ks[j][d], a);
-      sc[jj] = (j < kn) ? a : -INFINITY;
-      tmax = fmaxf(tmax, sc[jj]);
-    }
-    if (tmax > -INFINITY) {
-      const float corr = __expf(mx - tmax);
-      l *= corr;
-#pragma unroll
-      for (int d = 0; d < AT_HD; ++d) o[d] *= corr;
-#pragma unroll
-      for (int jj = 0; jj < AT_KT / 4; ++jj) {
-        const int j = jj * 4 + part;
-        const float pj = __expf(sc[jj] - tmax);
-        l += pj;
-#pragma unroll
-        for (int d = 0; d < AT_HD; ++d) o[d] = fmaf(pj, Vs[j][d], o[d]);
-      }
-      mx = tmax;
-    }
-  }
-  // merge the four partial states of the query
-#pragma unroll
-  for (int sh = 1; sh <= 2; sh <<= 1) {
-    const float mo = __shfl_xor_sync(0xffffffffu, mx, sh);
-    const float lo = __shfl_xor_sync(0xffffffffu, l, sh);
-    const float mn = fmaxf(mx, mo);
-    const float ca = (mx > -INFINITY) ? __expf(mx - mn) : 0.f, cb = (mo > -INFINITY) ? __expf(mo - mn) : 0.f;
-    l = l * ca + lo * cb;
-#pragma unroll
-    for (int d = 0; d < AT_HD; ++d) {
-      const float oo = __shfl_xor_sync(0xffffffffu, o[d], sh);
-      o[d] = o[d] * ca + oo * cb;
-    }
-    mx = mn;
-  }
-  if (ok && part == 0) {
-    const float inv = 1.f / l;
-#pragma unroll
-    for (int d = 0; d < AT_HD; ++d) O[(rowbase + qi) * AT_D + head * AT_HD + d] = o[d] * inv;
-    if (LSE) LSE[((int64_t)b * AT_HEADS + head) * L + qi] = mx + __logf(l);
-  }
-}
-
 // attention backward, query side: dQ_i = 0.25 * sum_j dS_ij K_j ;  also Dv_i = dO_i . O_i
 __global__ void __launch_bounds__(128) attn_bwd_q_kernel(const float* __restrict__ Q, const float* __restrict__ K,
                                                          const float* __restrict__ V, const float* __restrict__ O,
@@ -827,51 +637,59 @@ struct LinW5 {
   float* dW[5];
   float* db[5];
 };
-__global__ void __launch_bounds__(256) linear_bwd_weight5_kernel(const __grid_constant__ LinW5 a, int T) {
+__global__ void __launch_bounds__(256) linear_bwd_weight5_kernel(const __grid_constant__ LinW5 a, int T, int nchunks,
+                                                                 float* __restrict__ partials) {
+  // block (bx, l) walks the 32-token chunks bx, bx + gridDim.x, ... of layer l and leaves its sums in row bx of
+  // `partials` ([gridDim.x][5][64*64 + 64]); ss_launch_reduce_rows adds the rows in a fixed order (no atomics)
   __shared__ __align__(16) float Ys[32][AT_D + 4];
   __shared__ float Xs[32][AT_D + 1];
-  const int l = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x;
+  const int l = blockIdx.y, tid = threadIdx.x;
   const float* __restrict__ dY = a.dY[l];
   const float* __restrict__ hm = a.hmask[l];
   const float* __restrict__ X = a.X[l];
-  float y[8], xv[8], m[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {                 // all loads in flight before the first store
-    const int i = tid + k * 256, t = t0 + (i >> 6);
-    const int64_t g = (int64_t)t * AT_D + (i & 63);
-    y[k] = (t < T) ? dY[g] : 0.f;
-    xv[k] = (t < T) ? X[g] : 0.f;
-    m[k] = (hm && t < T) ? hm[g] : 1.f;
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int i = tid + k * 256;
-    Ys[i >> 6][i & 63] = (m[k] > 0.f) ? y[k] : 0.f;
-    Xs[i >> 6][i & 63] = xv[k];
-  }
-  __syncthreads();
   const int ii = tid & 63, o0 = (tid >> 6) * 16;
   float acc[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-#pragma unroll 4
-  for (int t = 0; t < 32; ++t) {
-    const float xi = Xs[t][ii];
+  float sb = 0.f;
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int t0 = ch * 32;
+    float y[8], xv[8], m[8];
 #pragma unroll
-    for (int c4 = 0; c4 < 16; c4 += 4) {
-      const float4 yv = *reinterpret_cast<const float4*>(&Ys[t][o0 + c4]);
-      acc[c4] = fmaf(yv.x, xi, acc[c4]); acc[c4 + 1] = fmaf(yv.y, xi, acc[c4 + 1]);
-      acc[c4 + 2] = fmaf(yv.z, xi, acc[c4 + 2]); acc[c4 + 3] = fmaf(yv.w, xi, acc[c4 + 3]);
+    for (int k = 0; k < 8; ++k) {                 // all loads in flight before the first store
+      const int i = tid + k * 256, t = t0 + (i >> 6);
+      const int64_t g = (int64_t)t * AT_D + (i & 63);
+      y[k] = (t < T) ? dY[g] : 0.f;
+      xv[k] = (t < T) ? X[g] : 0.f;
+      m[k] = (hm && t < T) ? hm[g] : 1.f;
+    }
+    __syncthreads();                              // the previous chunk's tiles have been consumed
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = tid + k * 256;
+      Ys[i >> 6][i & 63] = (m[k] > 0.f) ? y[k] : 0.f;
+      Xs[i >> 6][i & 63] = xv[k];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int t = 0; t < 32; ++t) {
+      const float xi = Xs[t][ii];
+#pragma unroll
+      for (int c4 = 0; c4 < 16; c4 += 4) {
+        const float4 yv = *reinterpret_cast<const float4*>(&Ys[t][o0 + c4]);
+        acc[c4] = fmaf(yv.x, xi, acc[c4]); acc[c4 + 1] = fmaf(yv.y, xi, acc[c4 + 1]);
+        acc[c4 + 2] = fmaf(yv.z, xi, acc[c4 + 2]); acc[c4 + 3] = fmaf(yv.w, xi, acc[c4 + 3]);
+      }
+    }
+    if (tid < AT_D) {
+#pragma unroll 8
+      for (int t = 0; t < 32; ++t) sb += Ys[t][tid];
     }
   }
+  float* out = partials + ((size_t)blockIdx.x * 5 + l) * (AT_D * AT_D + AT_D);
 #pragma unroll
-  for (int c = 0; c < 16; ++c) atomicAdd(a.dW[l] + (o0 + c) * AT_D + ii, acc[c]);
-  if (tid < AT_D) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int t = 0; t < 32; ++t) s += Ys[t][tid];
-    atomicAdd(a.db[l] + tid, s);
-  }
+  for (int c = 0; c < 16; ++c) out[(o0 + c) * AT_D + ii] = acc[c];
+  if (tid < AT_D) out[AT_D * AT_D + tid] = sb;
 }
 
 static const size_t kSmemQkv4 = (AT_D * AF_W3P + AT_D * AF_TP) * sizeof(float);
@@ -882,9 +700,7 @@ static const size_t kSmem2 = (2 * AT_D * (AT_D + 1) + 2 * TK * AT_D) * sizeof(fl
 static int attn_attrs() {
   static bool done = false;
   if (done) return 0;
-  cudaError_t e = cudaFuncSetAttribute(attn_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
+  cudaError_t e = cudaFuncSetAttribute(attn_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_ffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_qkv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemQkv4);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCore);
@@ -901,24 +717,14 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* P, const int6
                          cudaStream_t st) {
   if (attn_attrs()) return SSHSLIE_ERR_CUDA;
   const int T = B * L;
-  static const bool fused_ok = !(getenv("SSHSLIE_ATTN_FUSED") && getenv("SSHSLIE_ATTN_FUSED")[0] == '0');
-  if (fused_ok) {      // register-tiled kernels; keys stream through 256-row tiles (one tile at the training size)
-    ss_launch_pdl(attn_qkv4_kernel, dim3((T + AF_QB - 1) / AF_QB), dim3(192), (size_t)(kSmemQkv4), st, a3, P, poff[0], poff[1], poff[2], poff[3], poff[4],
-                                                                     poff[5], bf.x, bf.q, bf.k, bf.v, T);
-    dim3 g((L + AF_QB - 1) / AF_QB, B);
-    ss_launch_pdl(attn_core_ffn_kernel, dim3(g), dim3(256), (size_t)(kSmemCore), st, bf.x, bf.q, bf.k, bf.v, P, poff[6], poff[7], poff[8], poff[9], bf.o,
-                                                     bf.lse, bf.h, t_out, L);
-    ss_count_launches(1);
-    return ss_check_launch("attention_forward_fused");
-  }
-  const int gl = (T + TK - 1) / TK;
-  attn_qkv_kernel<<<gl, 256, kSmem3, st>>>(a3, P, nullptr, poff[0], poff[1], poff[2], poff[3], poff[4], poff[5], bf.x, bf.q,
-                                            bf.k, bf.v, T);
-  dim3 ga((L + AT_QB - 1) / AT_QB, AT_HEADS, B);
-  attn_fwd_kernel<<<ga, 128, 0, st>>>(bf.q, bf.k, bf.v, bf.o, bf.lse, L);
-  attn_ffn_kernel<<<gl, 256, kSmem2, st>>>(bf.o, bf.x, P, poff[6], poff[7], poff[8], poff[9], bf.h, t_out, T);
-  ss_count_launches(2);
-  return ss_check_launch("attention_forward");
+  // register-tiled kernels; keys stream through 256-row tiles (one tile at the training size)
+  ss_launch_pdl(attn_qkv4_kernel, dim3((T + AF_QB - 1) / AF_QB), dim3(192), (size_t)(kSmemQkv4), st, a3, P, poff[0], poff[1], poff[2], poff[3], poff[4],
+                                                                   poff[5], bf.x, bf.q, bf.k, bf.v, T);
+  dim3 g((L + AF_QB - 1) / AF_QB, B);
+  ss_launch_pdl(attn_core_ffn_kernel, dim3(g), dim3(256), (size_t)(kSmemCore), st, bf.x, bf.q, bf.k, bf.v, P, poff[6], poff[7], poff[8], poff[9], bf.o,
+                                                   bf.lse, bf.h, t_out, L);
+  ss_count_launches(1);
+  return ss_check_launch("attention_forward_fused");
 }
 
 int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const float* P, float* G, const int64_t* poff,
@@ -929,8 +735,7 @@ int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const floa
   const int gl = (T + TK - 1) / TK;
   // data-gradient chain only; the five weight gradients run in ss_attention_backward_weights (side stream)
   ss_launch_pdl(attn_ffn_bwd_kernel, dim3(gl), dim3(256), (size_t)(kSmem2), st, dt, bf.h, P, poff[6], poff[8], bf.dh, bf.d_o, T);
-  static const bool fused_ok = !(getenv("SSHSLIE_ATTN_FUSED") && getenv("SSHSLIE_ATTN_FUSED")[0] == '0');
-  if (L <= AF_LMAX && fused_ok) {
+  if (L <= AF_LMAX) {
     dim3 g16((L + 15) / 16, AT_HEADS, B);
     ss_launch_pdl(attn_bwd_q16_kernel, dim3(g16), dim3(256), (size_t)(0), st, bf.q, bf.k, bf.v, bf.o, bf.d_o, bf.lse, bf.dq, bf.Dv, L);
     ss_launch_pdl(attn_bwd_kv16_kernel, dim3(g16), dim3(256), (size_t)(0), st, bf.q, bf.k, bf.v, bf.d_o, bf.lse, bf.Dv, bf.dk, bf.dv, L);
@@ -946,7 +751,8 @@ int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const floa
 
 // dW, db of the five Linear layers (reads dt, dh, dq, dk, dv produced by ss_attention_backward)
 int ss_attention_backward_weights(const float* dt, float* G, const int64_t* poff, AttnBuffers bf, int B, int L,
-                                  cudaStream_t st) {
+                                  float* scratch, cudaStream_t st) {
+  if (!scratch) { ss_set_error("attention_backward_weights: scratch missing"); return SSHSLIE_ERR_WORKSPACE; }
   const int T = B * L;
   LinW5 a;
   const float* dys[5] = {dt, bf.dh, bf.dq, bf.dk, bf.dv};
@@ -957,6 +763,17 @@ int ss_attention_backward_weights(const float* dt, float* G, const int64_t* poff
     a.dY[i] = dys[i]; a.hmask[i] = hms[i]; a.X[i] = xs[i];
     a.dW[i] = G + poff[wi[i]]; a.db[i] = G + poff[wi[i] + 1];
   }
-  linear_bwd_weight5_kernel<<<dim3((T + 31) / 32, 5), 256, 0, st>>>(a, T);
-  return ss_check_launch("attention_backward_weights");
+  const int nchunks = (T + 31) / 32;
+  const int nb = nchunks < SS_ATTN_WGRAD_MAX_BLOCKS ? nchunks : SS_ATTN_WGRAD_MAX_BLOCKS;
+  linear_bwd_weight5_kernel<<<dim3(nb, 5), 256, 0, st>>>(a, T, nchunks, scratch);
+  int rc = ss_check_launch("attention_backward_weights");
+  if (rc) return rc;
+  RedSegs segs;
+  memset(&segs, 0, sizeof(segs));
+  segs.n = 10;
+  for (int i = 0; i < 5; ++i) {                   // column layout of a partial row: [layer][dW (64*64) | db (64)]
+    segs.dst[2 * i] = a.dW[i]; segs.len[2 * i] = AT_D * AT_D;
+    segs.dst[2 * i + 1] = a.db[i]; segs.len[2 * i + 1] = AT_D;
+  }
+  return ss_launch_reduce_rows(scratch, nb, SS_ATTN_WGRAD_COLS, segs, st);
 }

@@ -70,7 +70,8 @@ int ss_launch_conv_gather_simt(const ConvGeom* g_dev, const ConvGeom& g_host, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight-gradient GEMM:  dW[n][s*64+j] += sum_m G[m, n] * A_s[m, j]      (fp32 atomics into the flat grads)
+// weight-gradient GEMM:  dW[n][s*64+j] += sum_m G[m, n] * A_s[m, j]      (fp32 atomics into the flat grads: this is the
+// CUDA-core CROSS-CHECK kernel, run only under SSHSLIE_FLAG_FORCE_SIMT in tests - the product path never launches it)
 // grid = (nslabs, ceil(Npad/32), splitM); block = 256 threads: thread -> (n = t/8, 8 channels j = (t%8)*8..)
 // ---------------------------------------------------------------------------------------------
 #define WG_ROWS 32
@@ -155,9 +156,10 @@ int ss_launch_conv_wgrad_simt(const ConvGeom* g_dev, const ConvGeom& g_host, con
 
 // ---------------------------------------------------------------------------------------------
 // bias gradient: db[n] += sum over pixels of G[pixel, n]   (G: bf16, pixel stride `ld`, N <= 256 columns)
+// Every block sums a contiguous pixel range into its row of `partials`; a second launch adds the rows in a fixed order.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__ G, int64_t npix, int ld, int N,
-                                                        float* __restrict__ db, int pix_per_block) {
+                                                        float* __restrict__ partials, int pix_per_block) {
   // thread -> column n = t % 64 (+64 ...), row phase = t / 64
   __shared__ float red[256];
   const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
@@ -170,15 +172,24 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const bf16* __restrict__
     red[threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.x < 64 && n < N)
-      atomicAdd(db + n, red[threadIdx.x] + red[threadIdx.x + 64] + red[threadIdx.x + 128] + red[threadIdx.x + 192]);
+      partials[(size_t)blockIdx.x * N + n] =
+          red[threadIdx.x] + red[threadIdx.x + 64] + red[threadIdx.x + 128] + red[threadIdx.x + 192];
     __syncthreads();
   }
 }
 
-int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, cudaStream_t st) {
-  const int ppb = 64;
-  bias_grad_kernel<<<(unsigned)((npix + ppb - 1) / ppb), 256, 0, st>>>(G, npix, ld, N, db, ppb);
-  return ss_check_launch("bias_grad");
+int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, float* scratch, cudaStream_t st) {
+  if (!scratch) { ss_set_error("bias_grad: scratch missing"); return SSHSLIE_ERR_WORKSPACE; }
+  int64_t ppb = 64;
+  while ((npix + ppb - 1) / ppb > SS_BIAS_GRAD_MAX_BLOCKS) ppb *= 2;
+  const int nblk = (int)((npix + ppb - 1) / ppb);
+  bias_grad_kernel<<<nblk, 256, 0, st>>>(G, npix, ld, N, scratch, (int)ppb);
+  int rc = ss_check_launch("bias_grad");
+  if (rc) return rc;
+  RedSegs segs;
+  memset(&segs, 0, sizeof(segs));
+  segs.n = 1; segs.dst[0] = db; segs.len[0] = N;
+  return ss_launch_reduce_rows(scratch, nblk, N, segs, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -435,13 +435,48 @@ int ss_launch_pool2(const bf16* du, const bf16* addp, const bf16* maskr, bf16* o
 }
 
 // ---------------------------------------------------------------------------------------------
+// fixed-order reduction of per-block partials into the flat gradient buffer (deterministic replacement of fp32 atomics)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partials, int nrows, int ncols,
+                                                          const __grid_constant__ RedSegs segs) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ncols) return;
+  float t = 0.f;
+  for (int r = 0; r < nrows; ++r) t += partials[(size_t)r * ncols + j];
+  int o = j;
+  for (int s = 0; s < segs.n; ++s) {
+    if (o < segs.len[s]) { segs.dst[s][o] += t; return; }
+    o -= segs.len[s];
+  }
+}
+int ss_launch_reduce_rows(const float* partials, int nrows, int ncols, const RedSegs& segs, cudaStream_t st) {
+  reduce_rows_kernel<<<(ncols + 255) / 256, 256, 0, st>>>(partials, nrows, ncols, segs);
+  EW_CHECK("reduce_rows");
+}
+
+// ---------------------------------------------------------------------------------------------
 // raw term sums -> the seven loss values of model.py:557-574
 //   sums: 0 rec | 1,2 I_smooth_low x,y | 3 |R-Re| | 4,5 grad fidelity x,y | 6,7 I_smooth_delta x,y | 8 spectral | 9 fourier
 // ---------------------------------------------------------------------------------------------
-__global__ void finalize_losses_kernel(const float* __restrict__ sums, sshslie_loss_cfg cfg, float* __restrict__ losses,
-                                       int B, int C, int H, int W) {
+// one warp per term sum: lanes stride the per-block partial sums of the loss kernels in a fixed order, fixed shuffle tree ->
+// the seven loss values are bit-repeatable (the reference runs with cudnn.deterministic, main.py:165)
+__global__ void __launch_bounds__(320) finalize_losses_kernel(const float* __restrict__ pix, int pix_rows,
+                                                              const float* __restrict__ four, int four_rows,
+                                                              sshslie_loss_cfg cfg, float* __restrict__ losses, int B, int C,
+                                                              int H, int W) {
   SS_PDL_ENTRY();
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ float sums[10];
+  const int term = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float t = 0.f;
+  if (term < 9) {
+    for (int r = lane; r < pix_rows; r += 32) t += pix[(size_t)r * 9 + term];
+  } else {
+    for (int r = lane; r < four_rows; r += 32) t += four[r];
+  }
+  t = warp_sum(t);
+  if (lane == 0) sums[term] = t;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   const double n0 = (double)B * C * H * W;
   const double nx1 = (double)B * H * (W - 1), ny1 = (double)B * (H - 1) * W;
   const double nxc = nx1 * C, nyc = ny1 * C;
@@ -463,9 +498,10 @@ __global__ void finalize_losses_kernel(const float* __restrict__ sums, sshslie_l
   losses[5] = (float)l_four;
   losses[6] = (float)l_spec;
 }
-int ss_launch_finalize_losses(const float* sums, const sshslie_loss_cfg* cfg, float* losses, int B, int C, int H, int W,
-                              cudaStream_t st) {
-  ss_launch_pdl(finalize_losses_kernel, dim3(1), dim3(32), (size_t)(0), st, sums, *cfg, losses, B, C, H, W);
+int ss_launch_finalize_losses(const float* pix_partials, int pix_rows, const float* four_partials, int four_rows,
+                              const sshslie_loss_cfg* cfg, float* losses, int B, int C, int H, int W, cudaStream_t st) {
+  ss_launch_pdl(finalize_losses_kernel, dim3(1), dim3(320), (size_t)(0), st, pix_partials, pix_rows, four_partials,
+                four_rows, *cfg, losses, B, C, H, W);
   EW_CHECK("finalize_losses");
 }
 

@@ -173,7 +173,11 @@ struct sshslie_engine {
   std::vector<int> pack_start;
   int pack_blocks = 0, pack_split = 0;
   float* mask_dev = nullptr;
-  float* sums_dev = nullptr;
+  // per-block partial sums of the loss kernels, of the thin weight-gradient kernels and of the bias gradient: everything
+  // that used to be an fp32 atomicAdd is a fixed-order reduction over these (deterministic step, main.py:165)
+  float *pix_partials = nullptr, *four_partials = nullptr, *final_partials = nullptr, *attn_partials = nullptr;
+  float* bias_partials[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};   // one per side stream
+  int pix_rows = 0;
   // split-K partial accumulators of the tcgen05 wgrad (sized for the largest op), one buffer per side stream
   float* wg_partial[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};
   size_t wg_partial_floats = 0;
@@ -209,6 +213,11 @@ struct sshslie_engine {
     for (int i = 1; i < n_side; ++i)
       if (side[i] && st == side[i]) return wg_partial[i];
     return wg_partial[0];
+  }
+  float* bias_partial_for(cudaStream_t st) const {
+    for (int i = 1; i < n_side; ++i)
+      if (side[i] && st == side[i]) return bias_partials[i];
+    return bias_partials[0];
   }
 
   // per-call state read by the recorded launches
@@ -375,15 +384,16 @@ __global__ void __launch_bounds__(256) final_dgrad_kernel(const float* __restric
   o.x = pack2(acc[0], acc[1]); o.y = pack2(acc[2], acc[3]); o.z = pack2(acc[4], acc[5]); o.w = pack2(acc[6], acc[7]);
   reinterpret_cast<uint4*>(dff)[i] = o;
 }
-// dw[c][tap] += sum_pix dId[pix] * ff[pix + tap, c] ; db += sum dId.   block = 576 threads (c = t%64, tap = t/64)
+// dw[c][tap] += sum_pix dId[pix] * ff[pix + tap, c] ; db += sum dId.   block = 576 threads (c = t%64, tap = t/64).
+// Block blk sums the image rows blk, blk + gridDim.x, ... into row blk of `partials` ([gridDim.x][577]: 576 weights, then
+// the bias); ss_launch_reduce_rows adds the rows in a fixed order (deterministic, no atomics).
+#define FINAL_WGRAD_MAX_BLOCKS 296
 __global__ void __launch_bounds__(576) final_wgrad_kernel(const float* __restrict__ dId, const bf16* __restrict__ ff,
-                                                          float* __restrict__ dw, float* __restrict__ db, int B, int H,
-                                                          int W, int rows_per_block) {
+                                                          float* __restrict__ partials, int B, int H, int W) {
   const int c = threadIdx.x & 63, tap = threadIdx.x >> 6;
   const int kh = tap / 3, kw = tap - kh * 3;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;      // image rows over B*H
   float acc = 0.f, accb = 0.f;
-  for (int64_t r = r0; r < r0 + rows_per_block && r < (int64_t)B * H; ++r) {
+  for (int64_t r = blockIdx.x; r < (int64_t)B * H; r += gridDim.x) {      // image rows over B*H
     const int y = (int)(r % H);
     const int64_t b = r / H;
     const int iy = y + kh - 1;
@@ -395,8 +405,8 @@ __global__ void __launch_bounds__(576) final_wgrad_kernel(const float* __restric
       acc = fmaf(g, bf2f(ff[((b * H + iy) * W + ix) * 64 + c]), acc);
     }
   }
-  atomicAdd(dw + c * 9 + tap, acc);
-  if (threadIdx.x == 0) atomicAdd(db, accb);
+  partials[(size_t)blockIdx.x * 577 + c * 9 + tap] = acc;
+  if (threadIdx.x == 0) partials[(size_t)blockIdx.x * 577 + 576] = accb;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -509,7 +519,8 @@ static int run_wgrad(sshslie_engine* e, int gi, const Tens& G, int gN, int qh, i
                                      e->partial_for(st), e->grads, st);
   }
   if (bias_layer >= 0) {
-    const int rc = ss_launch_bias_grad(G.p, G.pix(), G.ld, gN, e->grads + e->poff[2 * bias_layer + 1], st);
+    const int rc = ss_launch_bias_grad(G.p, G.pix(), G.ld, gN, e->grads + e->poff[2 * bias_layer + 1],
+                                       e->bias_partial_for(st), st);
     if (rc) return rc;
   }
   return ss_launch_conv_wgrad_simt(e->geoms_dev + gi, g, gp, gB, gH, gW, gN, e->grads, st);
@@ -688,7 +699,7 @@ static void plan_decomp_bwd(sshslie_engine* e, std::vector<sshslie_engine::OpFn>
   float** grads = &e->grads;
   const int64_t* poff = e->poff;
   auto bias_grad = [&](const Tens& t, int n, int layer) {
-    PUSH_SIDE(ops, return ss_launch_bias_grad(t.p, t.pix(), t.ld, n, *grads + poff[2 * layer + 1], st););
+    PUSH_SIDE(ops, return ss_launch_bias_grad(t.p, t.pix(), t.ld, n, *grads + poff[2 * layer + 1], e->bias_partial_for(st), st););
   };
   // recon
   queue_wgrad(e, ops, G.recon, dc8, dc8_n, L_D_RECON);
@@ -802,7 +813,14 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   e->pack_start_dev = (int*)e->alloc(sizeof(int) * 130);
   e->mask_dev = e->falloc((int64_t)H * W);
   e->wg_jobs_dev = e->alloc((int64_t)ss_wgjob_size() * WG_MAX_JOBS);
-  e->sums_dev = e->falloc(16);
+  if (train) {
+    e->pix_rows = ss_pixel_losses_blocks(B, C, H, W);
+    e->pix_partials = e->falloc((int64_t)e->pix_rows * 9);
+    e->four_partials = e->falloc((int64_t)B * C);
+    e->final_partials = e->falloc((int64_t)FINAL_WGRAD_MAX_BLOCKS * 577);
+    e->attn_partials = e->falloc((int64_t)SS_ATTN_WGRAD_MAX_BLOCKS * SS_ATTN_WGRAD_COLS);
+    for (int i = 0; i < SS_MAX_SIDE; ++i) e->bias_partials[i] = e->falloc((int64_t)SS_BIAS_GRAD_MAX_BLOCKS * 256);
+  }
 
   // ---- tensors -----------------------------------------------------------------------------
   Tens X = e->talloc(B, H, W, 64);
@@ -839,7 +857,6 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   auto& F = e->ops_fwd;
   if (train) {
     // per-step zeroing first: a memset node between two kernels would break their programmatic-dependent-launch edge
-    PUSH(F, return cudaMemsetAsync(e->sums_dev, 0, 16 * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
     PUSH(F, if (!e->grads) return SSHSLIE_OK;
             return cudaMemsetAsync(e->grads, 0, e->nparams * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
   }
@@ -946,16 +963,17 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     // gradient into a plane of its own (dSf32, summed in s_bwd) and is joined before the loss values are finalised.
     float* dSf32 = e->falloc(n * C);
     PUSH_SIDE(Lq, prof_note("loss:fourier_fft+grad", 0, 12.0 * 1048576.0 * B);
-                  return ss_fourier_loss(e->x, e->S32, e->mask_dev, dSf32, e->sums_dev + 9, B * C, H, W,
+                  return ss_fourier_loss(e->x, e->S32, e->mask_dev, dSf32, e->four_partials, B * C, H, W,
                                          (float)(e->cfg.c_loss_fourier / ((double)B * C * H * W)), 0, st););
     DecompGeoms G2 = plan_decomp_fwd(e, Lq, Sb, d2, head2);          // model.py:546
 
     // algorithmic HBM bytes: 24.25 MiB per patch for the 5-term loss + gradients, 12 MiB for the Fourier term
     PUSH(Lq, prof_note("loss:pixel_terms+grads", 0, 24.25 * 1048576.0 * B);
-             return ss_pixel_losses(e->x, e->R32, e->I32, e->Id32, Re32, e->cfg, B, C, H, W, e->sums_dev, dR32, dI32,
+             return ss_pixel_losses(e->x, e->R32, e->I32, e->Id32, Re32, e->cfg, B, C, H, W, e->pix_partials, dR32, dI32,
                                     dId32, dS32, dRe32, st););
     PUSH_JOIN(Lq);
-    PUSH(Lq, return ss_launch_finalize_losses(e->sums_dev, &e->cfg, e->losses, B, C, H, W, st););
+    PUSH(Lq, return ss_launch_finalize_losses(e->pix_partials, e->pix_rows, e->four_partials, B * C, &e->cfg, e->losses, B,
+                                              C, H, W, st););
 
     // backward, pass 2 (R_enh branch).  I_enh is unused (model.py:546) -> only C gradient columns.
     DecompGrads gr;
@@ -981,11 +999,16 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     float* dt32 = e->falloc(T64);
     {
       const int64_t total = n * 8;
-      const int rows_pb = 2;
-      PUSH_SIDE(Lq, final_wgrad_kernel<<<(unsigned)(((int64_t)B * H + rows_pb - 1) / rows_pb), 576, 0, st>>>(
-                   dId32, ff.p, e->grads + e->poff[2 * L_I_FINAL], e->grads + e->poff[2 * L_I_FINAL + 1], B, H, W,
-                   rows_pb);
-               return ss_check_launch("final_wgrad"););
+      const int fw_blocks = (int)std::min<int64_t>(FINAL_WGRAD_MAX_BLOCKS, (int64_t)B * H);
+      PUSH_SIDE(Lq, final_wgrad_kernel<<<fw_blocks, 576, 0, st>>>(dId32, ff.p, e->final_partials, B, H, W);
+               int rc = ss_check_launch("final_wgrad");
+               if (rc) return rc;
+               RedSegs segs;
+               memset(&segs, 0, sizeof(segs));
+               segs.n = 2;
+               segs.dst[0] = e->grads + e->poff[2 * L_I_FINAL]; segs.len[0] = 576;
+               segs.dst[1] = e->grads + e->poff[2 * L_I_FINAL + 1]; segs.len[1] = 1;
+               return ss_launch_reduce_rows(e->final_partials, fw_blocks, 577, segs, st););
       PUSH(Lq, ss_launch_pdl(final_dgrad_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, 
                    dId32, e->params + e->poff[2 * L_I_FINAL], dff.p, H, W, total);
                return ss_check_launch("final_dgrad"););
@@ -1026,7 +1049,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     }
     PUSH(Lq, return ss_launch_pool2(du1.p, nullptr, nullptr, nullptr, nullptr, dt32, B, H / 8, W / 8, st););
     PUSH(Lq, return ss_attention_backward(dt32, a3.p, da3.p, e->params, e->grads, apoff, ab, B, L, st););
-    PUSH_SIDE(Lq, return ss_attention_backward_weights(dt32, e->grads, apoff, ab, B, L, st););
+    PUSH_SIDE(Lq, return ss_attention_backward_weights(dt32, e->grads, apoff, ab, B, L, e->attn_partials, st););
     // conv3 / conv2 / conv1 (stride 2): wgrad on the forward geom, dgrad per input parity class (+ skip gradient)
     struct S2 { int layer, gfwd; Tens dy, x_in, dx, addp; bool mask; };
     const S2 s2[3] = {{L_I_CONV3, g_i3, da3, a2, da2, da2p, true},

@@ -121,7 +121,7 @@ SS_DEVINL void fft_axis(float2* z, const float2* tw, int H, int W, int lgW, int 
 
 __global__ void __launch_bounds__(FFT_THREADS, 1)
 fourier_loss_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ mask,
-                    float* __restrict__ dS, float* __restrict__ sum_out, int H, int W, int lgH, int lgW,
+                    float* __restrict__ dS, float* __restrict__ partial_out, int H, int W, int lgH, int lgW,
                     float grad_scale, int accumulate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* z = reinterpret_cast<float2*>(smem_raw);                    // H*W
@@ -198,7 +198,7 @@ fourier_loss_kernel(const float* __restrict__ x, const float* __restrict__ s, co
   __syncthreads();
   {
     const float t = block_sum(lsum, red);
-    if (threadIdx.x == 0) atomicAdd(sum_out, t);
+    if (threadIdx.x == 0) partial_out[blockIdx.x] = t;        // one partial per plane, reduced in a fixed order later
   }
   if (dS == nullptr) return;
 
@@ -304,7 +304,7 @@ SS_DEVINL void fft128_lines(float2* __restrict__ z, const float2* __restrict__ t
 
 __global__ void __launch_bounds__(F128_THREADS, 1)
 fourier_loss128_kernel(const float* __restrict__ x, const float* __restrict__ s, const float* __restrict__ mask,
-                       float* __restrict__ dS, float* __restrict__ sum_out, float grad_scale, int accumulate) {
+                       float* __restrict__ dS, float* __restrict__ partial_out, float grad_scale, int accumulate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* z = reinterpret_cast<float2*>(smem_raw);                    // [128][F128_PITCH]
   float2* tw128 = z + F128_N * F128_PITCH;                            // (cos, sin)(2 pi i / 128)
@@ -362,7 +362,7 @@ fourier_loss128_kernel(const float* __restrict__ x, const float* __restrict__ s,
   __syncthreads();
   {
     const float t = block_sum(lsum, red);
-    if (threadIdx.x == 0) atomicAdd(sum_out, t);
+    if (threadIdx.x == 0) partial_out[blockIdx.x] = t;        // one partial per plane, reduced in a fixed order later
   }
   if (dS == nullptr) return;
   fft128_lines<true>(z, tw128, F128_PITCH, 1);         // inverse (unnormalised): columns, then rows
@@ -390,10 +390,11 @@ static int ilog2_exact(int v) {
 
 // accumulate = 1: dS += gradient (the exported entry point); 0: dS = gradient (the engine gives the term its own plane so
 // that it can run beside the second decomposition pass instead of after the pixel-space terms)
-int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out, int n_img, int H,
+// partial_out[n_img]: the masked-magnitude L1 sum of every plane (the caller adds them up in a fixed order)
+int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* partial_out, int n_img, int H,
                     int W, float grad_scale, int accumulate, cudaStream_t stream) {
   const int lgH = ilog2_exact(H), lgW = ilog2_exact(W);
-  if (!x || !S || !mask || !sum_out || n_img < 1 || lgH < 3 || lgW < 3 || H > 128 || W > 128) {
+  if (!x || !S || !mask || !partial_out || n_img < 1 || lgH < 3 || lgW < 3 || H > 128 || W > 128) {
     ss_set_error("sshslie_fourier_loss: H and W must be powers of two in [8,128] (got %dx%d)", H, W);
     return SSHSLIE_ERR_ARG;
   }
@@ -410,7 +411,7 @@ int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS
       }
       attr128 = true;
     }
-    fourier_loss128_kernel<<<n_img, F128_THREADS, smem128, stream>>>(x, S, mask, dS, sum_out, grad_scale, accumulate);
+    fourier_loss128_kernel<<<n_img, F128_THREADS, smem128, stream>>>(x, S, mask, dS, partial_out, grad_scale, accumulate);
     return ss_check_launch("fourier_loss128");
   }
   const size_t smem = (size_t)H * W * sizeof(float2) + 128 * sizeof(float2);
@@ -424,11 +425,18 @@ int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS
     }
     attr_set = true;
   }
-  fourier_loss_kernel<<<n_img, FFT_THREADS, smem, stream>>>(x, S, mask, dS, sum_out, H, W, lgH, lgW, grad_scale,
+  fourier_loss_kernel<<<n_img, FFT_THREADS, smem, stream>>>(x, S, mask, dS, partial_out, H, W, lgH, lgW, grad_scale,
                                                             accumulate);
   return ss_check_launch("fourier_loss");
 }
 extern "C" int sshslie_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out,
-                                    int n_img, int H, int W, float grad_scale, void* stream) {
-  return ss_fourier_loss(x, S, mask, dS, sum_out, n_img, H, W, grad_scale, 1, (cudaStream_t)stream);
+                                    int n_img, int H, int W, float grad_scale, void* scratch, int64_t scratch_bytes,
+                                    void* stream) {
+  if (!sum_out || !scratch || scratch_bytes < (int64_t)n_img * (int64_t)sizeof(float)) {
+    ss_set_error("sshslie_fourier_loss: need sum_out and n_img floats of scratch");
+    return SSHSLIE_ERR_WORKSPACE;
+  }
+  const int rc = ss_fourier_loss(x, S, mask, dS, (float*)scratch, n_img, H, W, grad_scale, 1, (cudaStream_t)stream);
+  if (rc) return rc;
+  return ss_reduce_partials((const float*)scratch, n_img, 1, sum_out, 1, (cudaStream_t)stream);
 }

@@ -8,7 +8,8 @@
 int ss_launch_conv_gather_simt(const ConvGeom* g_dev, const ConvGeom& g_host, const Epi& epi, cudaStream_t st);
 int ss_launch_conv_wgrad_simt(const ConvGeom* g_dev, const ConvGeom& g_host, const bf16* G, int64_t gB, int64_t gH,
                               int64_t gW, int gN, float* grads, cudaStream_t st);
-int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, cudaStream_t st);
+// db[n] += sum over pixels of G[pixel, n]; scratch: SS_BIAS_GRAD_MAX_BLOCKS x N floats (per-block partials, fixed-order sum)
+int ss_launch_bias_grad(const bf16* G, int64_t npix, int ld, int N, float* db, float* scratch, cudaStream_t st);
 int ss_launch_pack_weights(const ConvGeom* geoms_dev, const int* block_start_dev, int njobs, int total_blocks,
                            const float* params, cudaStream_t st, int first_block = 0, int n_blocks = -1);
 
@@ -64,7 +65,7 @@ int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32
                      cudaStream_t st);
 int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, const float* R, const float* I,
                     const float* Id, float* dR32, float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st);
-int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out, int n_img, int H,
+int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* partial_out, int n_img, int H,
                     int W, float grad_scale, int accumulate, cudaStream_t stream);
 int ss_launch_head_bwd(const float* dR32, const float* R32, const bf16* dRI, int ld_dri, const float* dI32,
                        const float* I32, bf16* dc8, int ld_out, int B, int C, int H, int W, cudaStream_t st);
@@ -72,8 +73,16 @@ int ss_launch_concat_bwd(const bf16* dfg, const bf16* r3, bf16* dr3, bf16* p2, b
                          cudaStream_t st);
 int ss_launch_pool2(const bf16* du, const bf16* addp, const bf16* maskr, bf16* out_sum, bf16* out_masked, float* out32,
                     int B, int h, int w, cudaStream_t st);
-int ss_launch_finalize_losses(const float* sums, const sshslie_loss_cfg* cfg_dev, float* losses, int B, int C, int H,
-                              int W, cudaStream_t st);
+int ss_launch_finalize_losses(const float* pix_partials, int pix_rows, const float* four_partials, int four_rows,
+                              const sshslie_loss_cfg* cfg, float* losses, int B, int C, int H, int W, cudaStream_t st);
+
+// fixed-order reduction of per-block partial results into (segments of) the flat gradient buffer: column j of the
+// partial rows belongs to the segment that contains it; dst[j] += sum over rows (row order fixed -> deterministic)
+struct RedSegs { float* dst[10]; int len[10]; int n; };
+int ss_launch_reduce_rows(const float* partials, int nrows, int ncols, const RedSegs& segs, cudaStream_t st);
+#define SS_BIAS_GRAD_MAX_BLOCKS 512
+#define SS_ATTN_WGRAD_MAX_BLOCKS 16
+#define SS_ATTN_WGRAD_COLS (5 * (64 * 64 + 64))
 
 // attention.cu   (tokens: T = B*L rows of 64 fp32)
 struct AttnBuffers {
@@ -85,10 +94,13 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* params, const
 int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const float* params, float* grads,
                           const int64_t* poff, AttnBuffers bufs, int B, int L, cudaStream_t st);
 
+// scratch: SS_ATTN_WGRAD_MAX_BLOCKS x SS_ATTN_WGRAD_COLS floats
 int ss_attention_backward_weights(const float* dt, float* grads, const int64_t* poff, AttnBuffers bufs, int B, int L,
-                                  cudaStream_t st);
+                                  float* scratch, cudaStream_t st);
 
 // loss.cu / fft_loss.cu / adam.cu : see include/sshslie_b200.h (exported directly)
 int ss_pixel_losses(const float* x, const float* R, const float* I, const float* Id, const float* Re,
-                    const sshslie_loss_cfg& cfg, int B, int C, int H, int W, float* sums, float* dR, float* dI,
+                    const sshslie_loss_cfg& cfg, int B, int C, int H, int W, float* partials, float* dR, float* dI,
                     float* dId, float* dS, float* dRe, cudaStream_t st);
+int ss_pixel_losses_blocks(int B, int C, int H, int W);       // rows of 9 partial sums ss_pixel_losses writes
+int ss_reduce_partials(const float* partials, int nrows, int ncols, float* out, int accumulate, cudaStream_t st);

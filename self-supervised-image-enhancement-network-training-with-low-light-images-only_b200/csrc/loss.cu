@@ -1,5 +1,6 @@
 // Fused forward + gradient of the five pixel-space loss terms of LowLightEnhance.compute_loss
-// (model.py:551-555 with helpers 445-454, 475-542), fp32, NCHW planes, one pass, no atomics on tensors.
+// (model.py:551-555 with helpers 445-454, 475-542), fp32, NCHW planes, one pass, no atomics anywhere: every block writes its
+// nine term sums to a row of `partials`, which one warp per term adds up in a fixed order (deterministic, main.py:165).
 //
 //   0 L_reconstruction   mean |R*I - x|                                                  model.py:551
 //   1,2 L_I_smooth_low   mean(wx |dx I|) + mean(wy |dy I|),  w = exp(-a1 * mean_c |d R|)   model.py:505-515
@@ -18,7 +19,7 @@
 
 struct PixLossArgs {
   const float *x, *R, *I, *Id, *Re;
-  float *sums, *dR, *dI, *dId, *dS, *dRe;
+  float *partials, *dR, *dI, *dId, *dS, *dRe;      // partials[block][9]
   int B, C, H, W;
   float a1, a2;
   float k_rec, k_ilx, k_ily, k_rf, k_rfx, k_rfy, k_idx, k_idy, k_sp;   // c_loss / count per term
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(PL_WX* PL_CHUNKS) pixel_losses_kernel(PixLossA
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
     const float t = block_sum_2d(s[i], red, tid, nthreads);
-    if (tid == 0) atomicAdd(p.sums + i, t);
+    if (tid == 0) p.partials[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 9 + i] = t;
   }
 }
 
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(PT_PIX* PL_CHUNKS) pixel_losses_tiled_kernel(P
     if (p.dI) p.dI[pix] = a;
     if (p.dId) p.dId[pix] = d;
   }
-  // the nine term sums of the block: warp sums -> one shared-memory exchange -> nine atomics (one barrier instead of 18)
+  // the nine term sums of the block: warp sums -> one shared-memory exchange -> this block's row of `partials`
   __shared__ float wred[PT_PIX * PL_CHUNKS / 32][9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
@@ -390,17 +391,42 @@ __global__ void __launch_bounds__(PT_PIX* PL_CHUNKS) pixel_losses_tiled_kernel(P
     float t = 0.f;
 #pragma unroll
     for (int wv = 0; wv < PT_PIX * PL_CHUNKS / 32; ++wv) t += wred[wv][tid];
-    atomicAdd(p.sums + tid, t);
+    p.partials[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 9 + tid] = t;
   }
   (void)nthreads;
 }
 
+static bool pixel_tiled(int C, int H, int W) {
+  static const bool tiled_ok = !(getenv("SSHSLIE_LOSS_TILED") && getenv("SSHSLIE_LOSS_TILED")[0] == '0');
+  return tiled_ok && C == PT_C && (W % PT_TW) == 0 && (H % PT_TH) == 0;
+}
+// rows of 9 partial sums the kernel writes for this shape (= its grid size)
+int ss_pixel_losses_blocks(int B, int C, int H, int W) {
+  if (pixel_tiled(C, H, W)) return (W / PT_TW) * (H / PT_TH) * B;
+  const int wx = W < PL_WX ? W : PL_WX;
+  return ((W + wx - 1) / wx) * H * B;
+}
+
+// out[i] (+)= sum over rows of partials[row][i]: one warp per column, lanes stride the rows, fixed shuffle tree
+__global__ void __launch_bounds__(32) reduce_partials_kernel(const float* __restrict__ partials, int nrows, int ncols,
+                                                             float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x;
+  float t = 0.f;
+  for (int r = threadIdx.x; r < nrows; r += 32) t += partials[(size_t)r * ncols + c];
+  t = warp_sum(t);
+  if (threadIdx.x == 0) out[c] = accumulate ? out[c] + t : t;
+}
+int ss_reduce_partials(const float* partials, int nrows, int ncols, float* out, int accumulate, cudaStream_t st) {
+  reduce_partials_kernel<<<ncols, 32, 0, st>>>(partials, nrows, ncols, out, accumulate);
+  return ss_check_launch("reduce_partials");
+}
+
 int ss_pixel_losses(const float* x, const float* R, const float* I, const float* Id, const float* Re,
-                    const sshslie_loss_cfg& cfg, int B, int C, int H, int W, float* sums, float* dR, float* dI,
+                    const sshslie_loss_cfg& cfg, int B, int C, int H, int W, float* partials, float* dR, float* dI,
                     float* dId, float* dS, float* dRe, cudaStream_t st) {
   PixLossArgs p;
   p.x = x; p.R = R; p.I = I; p.Id = Id; p.Re = Re;
-  p.sums = sums; p.dR = dR; p.dI = dI; p.dId = dId; p.dS = dS; p.dRe = dRe;
+  p.partials = partials; p.dR = dR; p.dI = dI; p.dId = dId; p.dS = dS; p.dRe = dRe;
   p.B = B; p.C = C; p.H = H; p.W = W;
   p.a1 = cfg.alpha_i_smooth_low;
   p.a2 = cfg.alpha_i_smooth_delta;
@@ -415,8 +441,7 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
   p.k_idx = (float)(cfg.c_loss_i_smooth_delta / (nx1 * C));
   p.k_idy = (float)(cfg.c_loss_i_smooth_delta / (ny1 * C));
   p.k_sp = (float)(cfg.c_loss_spectral_cons / ((double)B * (C - 1) * H * W));
-  static const bool tiled_ok = !(getenv("SSHSLIE_LOSS_TILED") && getenv("SSHSLIE_LOSS_TILED")[0] == '0');
-  if (tiled_ok && C == PT_C && (W % PT_TW) == 0 && (H % PT_TH) == 0) {
+  if (pixel_tiled(C, H, W)) {
     const size_t smem = (size_t)2 * PT_C * PT_PLANE * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -437,15 +462,27 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
   return ss_check_launch("pixel_losses");
 }
 
+extern "C" int64_t sshslie_loss_scratch_bytes(int B, int C, int H, int W) {
+  const int64_t rows = ss_pixel_losses_blocks(B, C, H, W);
+  const int64_t planes = (int64_t)B * C;                      // the Fourier kernels write one partial per (b, band) plane
+  return (rows * 9 > planes ? rows * 9 : planes) * (int64_t)sizeof(float);
+}
+
 extern "C" int sshslie_pixel_losses(const float* x, const float* R, const float* I, const float* Idelta,
                                     const float* S, const float* R_enh, const sshslie_loss_cfg* cfg, int B, int C,
                                     int H, int W, float* sums, float* dR, float* dI, float* dIdelta, float* dS,
-                                    float* dR_enh, void* stream) {
+                                    float* dR_enh, void* scratch, int64_t scratch_bytes, void* stream) {
   (void)S;  // S = R*(Idelta + I) is recomputed in-kernel (model.py:233), the argument documents the dependency
-  if (!x || !R || !I || !Idelta || !R_enh || !cfg || !sums || B < 1 || C < 2 || H < 2 || W < 2) {
+  if (!x || !R || !I || !Idelta || !R_enh || !cfg || !sums || !scratch || B < 1 || C < 2 || H < 2 || W < 2) {
     ss_set_error("sshslie_pixel_losses: bad argument");
     return SSHSLIE_ERR_ARG;
   }
-  return ss_pixel_losses(x, R, I, Idelta, R_enh, *cfg, B, C, H, W, sums, dR, dI, dIdelta, dS, dR_enh,
-                         (cudaStream_t)stream);
+  if (scratch_bytes < sshslie_loss_scratch_bytes(B, C, H, W)) {
+    ss_set_error("sshslie_pixel_losses: scratch too small (need sshslie_loss_scratch_bytes)");
+    return SSHSLIE_ERR_WORKSPACE;
+  }
+  const int rc = ss_pixel_losses(x, R, I, Idelta, R_enh, *cfg, B, C, H, W, (float*)scratch, dR, dI, dIdelta, dS, dR_enh,
+                                 (cudaStream_t)stream);
+  if (rc) return rc;
+  return ss_reduce_partials((const float*)scratch, ss_pixel_losses_blocks(B, C, H, W), 9, sums, 0, (cudaStream_t)stream);
 }

@@ -251,16 +251,17 @@ def _fast_backward(own, total):
 class LazyLosses(dict):
     """dict[str, float] whose values are read back from the device (one sync) on first access."""
 
-    def __init__(self, dev_tensor):
+    def __init__(self, dev_tensor, term_scale=1.0):
         super().__init__()
         self._dev = dev_tensor
         self._ready = False
+        self._term_scale = term_scale          # data parallel: the six term values arrive as sums over the ranks
 
     def _sync(self):
         if not self._ready:
             vals = self._dev.detach().cpu().tolist()
-            for k, v in zip(LOSS_KEYS, vals):
-                dict.__setitem__(self, k, v)
+            for i, (k, v) in enumerate(zip(LOSS_KEYS, vals)):
+                dict.__setitem__(self, k, v if i == 0 else v * self._term_scale)
             self._ready = True
 
     def __getitem__(self, k):
@@ -519,7 +520,47 @@ class LowLightEnhance(nn.Module):
     def _stage_input(self, eng, x):
         if x.dtype != torch.float32:
             x = x.float()
+        ev = getattr(x, "_sshslie_ready", None)
+        if ev is not None:                     # a batch from prefetch(): its H2D copy ran on the copy stream
+            torch.cuda.current_stream(self._flat.device).wait_event(ev)
         eng.x.copy_(x, non_blocking=True)      # H2D (or D2D) into the engine's static input buffer
+
+    def prefetch(self, x_host):
+        """Start the host->device copy of a (pinned) batch on a copy stream and return the device tensor; pass it to
+        compute_loss / forward later.  Two staging buffers per shape alternate, so the copy of batch i+1 overlaps the
+        step on batch i (the reference's loop pays torch.from_numpy(...).to(device) serially, model.py:312).  At most
+        one prefetched batch per shape may be outstanding besides the one being consumed."""
+        self._ensure_flat()
+        dev = self._flat.device
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_bufs = {}
+        key = (tuple(x_host.shape), x_host.dtype)
+        slot = self._stage_bufs.get(key)
+        if slot is None:
+            slot = self._stage_bufs[key] = {"bufs": [torch.empty(x_host.shape, dtype=x_host.dtype, device=dev)
+                                                     for _ in range(2)], "used": [None, None], "i": 0}
+        k = slot["i"]
+        slot["i"] = k ^ 1
+        buf = slot["bufs"][k]
+        with torch.cuda.stream(self._copy_stream):
+            if slot["used"][k] is not None:    # the step that last consumed this buffer has read it
+                self._copy_stream.wait_event(slot["used"][k])
+            buf.copy_(x_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        out = buf.view(buf.shape)              # a fresh tensor object carrying this copy's event
+        out._sshslie_ready = ev
+        out._sshslie_slot = (slot, k)
+        return out
+
+    def _release_staged(self, x):
+        ref = getattr(x, "_sshslie_slot", None)
+        if ref is not None:                    # the consumer's copy out of the staging buffer is enqueued: mark it reusable
+            slot, k = ref
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self._flat.device))
+            slot["used"][k] = ev
 
     # ------------------------------------------------------------------ hot path
     def forward(self, input_low):
@@ -527,6 +568,7 @@ class LowLightEnhance(nn.Module):
         self._ensure_flat()
         eng = self._engine(input_low, train=False)
         self._stage_input(eng, input_low)
+        self._release_staged(input_low)
         lib = L.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)
         # fresh result tensors per call, like the reference: a caller may hold R across two forward() calls
@@ -553,6 +595,7 @@ class LowLightEnhance(nn.Module):
         eng = self._engine(input_low, train=True)
         self._keep_accumulated_grads()
         self._stage_input(eng, input_low)
+        self._release_staged(input_low)
         dp = self.dp_group is not None
         if dp:
             self._dp_step(eng)
@@ -577,7 +620,7 @@ class LowLightEnhance(nn.Module):
             total.backward = _fast_backward(self, total)       # instance attribute shadows Tensor.backward
         else:
             total = self._losses_dev[0].clone()
-        return total, LazyLosses(self._losses_dev[:7].clone())
+        return total, LazyLosses(self._losses_dev[:7].clone(), 1.0 / self._dp_world if dp else 1.0)
 
     def profile_step(self, input_low, train=True):
         """One eager training step (train=False: forward only) with device timing per launch group: list of
@@ -612,36 +655,61 @@ class LowLightEnhance(nn.Module):
         self._ensure_flat()
         dist.broadcast(self._flat, src=dist.get_global_rank(self.dp_group, 0), group=self.dp_group)
 
+    def _dp_cfg(self):
+        """Loss weights of one rank's step under data parallelism: c_loss_* / world, so that the all-reduce(SUM) of the
+        per-rank gradients IS the gradient of the global-batch loss (every term is a mean over equal shards) and no
+        kernel has to rescale 1.14 M floats afterwards.  The alphas are not weights and stay as they are."""
+        c = list(self._cfg_tuple())
+        for k in range(6):
+            c[k] = c[k] / self._dp_world
+        return L.LossCfg(*c)
+
+    def _dp_body(self, eng, cur):
+        """One data-parallel step on stream `cur` (eager or under CUDA-graph capture): phase 1 -> all-reduce of the
+        illum_adjust_net bucket + loss scalars on a side stream, overlapping phase 2 -> all-reduce of the decomposition
+        bucket -> join."""
+        from . import parallel as P
+        dec, ill = self._dp_ranges
+        lib = L.load()
+        cfg = self._dp_cfg()
+
+        def phase(mask):
+            L.check(lib.sshslie_loss_and_grad(eng.handle, L.ptr(eng.x), L.ptr(self._flat), ctypes.byref(cfg),
+                                              L.ptr(self._flat_grad), L.ptr(self._losses_dev), L.ptr(eng.R),
+                                              L.ptr(eng.I), L.ptr(eng.Id), L.ptr(eng.S), mask,
+                                              ctypes.c_void_p(cur.cuda_stream)), "sshslie_loss_and_grad")
+        phase(1)                                     # fwd + loss + pass-2 bwd + illum bwd
+        self._dp_stream.wait_stream(cur)
+        with torch.cuda.stream(self._dp_stream):
+            # illum_adjust_net bucket + the loss scalars behind it, one call; overlaps the pass-1 backward below
+            P.allreduce_bucket(self._grad_store, (ill[0], self._nparams + 8), self.dp_group)
+        phase(2)                                     # pass-1 decomposition backward
+        P.allreduce_bucket(self._grad_store, dec, self.dp_group)
+        cur.wait_stream(self._dp_stream)
+
     def _dp_step(self, eng):
-        import torch.distributed as dist
         from . import parallel as P
         if self._dp_ranges is None:
             self._dp_ranges = P.bucket_ranges([o for o, _ in self._pranges], [n for _, n in self._pranges])
-        dec, ill = self._dp_ranges
         cur = torch.cuda.current_stream(self._flat.device)
         eng.calls += 1
-        if self.use_cuda_graph and not self._graph_current(eng) and eng.calls >= 3:
-            torch.cuda.synchronize()
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga):
-                self._launch_loss_and_grad(eng, phase_mask=1)
-            with torch.cuda.graph(gb, pool=ga.pool()):
-                self._launch_loss_and_grad(eng, phase_mask=2)
-            eng.graph = (ga, gb)
-            eng.graph_cfg = self._cfg_tuple()
-        run = (lambda ph: eng.graph[ph - 1].replay()) if eng.graph is not None else \
-              (lambda ph: self._launch_loss_and_grad(eng, phase_mask=ph))
-        run(1)                                       # fwd + loss + pass-2 bwd + illum bwd
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        with torch.cuda.stream(self._dp_stream):
-            self._dp_stream.wait_event(ev)
-            # illum_adjust_net bucket + the loss scalars behind it, one call; overlaps the pass-1 backward below
-            P.allreduce_bucket(self._grad_store, (ill[0], self._nparams + 8), self.dp_group)
-        run(2)                                       # pass-1 decomposition backward
-        P.allreduce_bucket(self._grad_store, dec, self.dp_group)
-        cur.wait_stream(self._dp_stream)
-        P.finish_mean(self._grad_store, None, self._dp_world)                 # p.grad (and the losses) = mean over ranks
+        one_graph = os.environ.get("SSHSLIE_DP_GRAPH", "1") != "0"
+        if self.use_cuda_graph and one_graph:
+            # the whole step - both phases AND the two NCCL all-reduces - is ONE graph: no host launch gaps between the
+            # phase graphs and the collectives (those gaps were the scaling tail at 8 GPUs)
+            if not self._graph_current(eng) and eng.calls >= 3:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._dp_body(eng, torch.cuda.current_stream(self._flat.device))
+                eng.graph = g
+                eng.graph_cfg = self._cfg_tuple()
+            if eng.graph is not None:
+                eng.graph.replay()
+            else:
+                self._dp_body(eng, cur)
+            return
+        self._dp_body(eng, cur)
 
     # ------------------------------------------------------------------ loops (host glue, model.py:236-443)
     def train_model(self, train_data_path, eval_data_path, batch_size, patch_size, num_epochs, start_lr, ckpt_dir,

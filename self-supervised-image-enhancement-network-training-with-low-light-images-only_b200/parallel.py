@@ -23,8 +23,15 @@ def allreduce_bucket(flat, rng, group=None):
     dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
 
 
+def dp_loss_weights(weights, world):
+    """Per-rank loss weights c_loss_* / world: the all-reduce(SUM) of the per-rank gradients is then the gradient of the
+    global-batch loss directly (every loss term is a mean over equal shards), with no rescaling pass afterwards."""
+    return [w / world for w in weights]
+
+
 def finish_mean(flat, losses, world):
-    """sum -> mean for gradients and the 7 logged loss values (every loss term is a mean over equal shards)."""
+    """sum -> mean for a buffer that was reduced WITHOUT pre-scaled loss weights (kept for callers that exchange raw
+    per-rank gradients; LowLightEnhance._dp_step uses dp_loss_weights instead)."""
     flat.mul_(1.0 / world)
     if losses is not None:
         losses.mul_(1.0 / world)

@@ -35,6 +35,26 @@ def _worker(rank, world, port, out_dir):
     ref = sum(others) / world
     torch.testing.assert_close(flat, ref, rtol=1e-6, atol=1e-6)
     assert abs(float(losses[0]) - 1.5) < 1e-6
+    # what LowLightEnhance._dp_step does instead of the rescaling pass: every rank differentiates loss / world (loss weights
+    # c_loss_* / world, parallel.dp_loss_weights), so the all-reduce(SUM) is the mean already.  The gradient is linear in
+    # the weights; the logged total rides along pre-scaled, the six raw term values arrive as sums and are divided when
+    # the host reads them (LazyLosses term_scale)
+    from sshslie_b200.model import LazyLosses, LOSS_KEYS
+    w = [10.0, 1.0, 1.0, 2000.0, 20.0, 1.0]
+    ws = P.dp_loss_weights(w, world)
+    terms = torch.tensor([0.1 * (rank + 1) * (k + 1) for k in range(6)])         # this rank's raw term values
+    grad_k = [torch.randn(16, generator=torch.Generator().manual_seed(7 * r + k)) for r in range(world) for k in range(6)]
+    my = sum(ws[k] * grad_k[rank * 6 + k] for k in range(6))                     # d(loss_r / world)
+    store2 = torch.cat([my, torch.tensor([float(sum(ws[k] * terms[k] for k in range(6)))]), terms, torch.zeros(1)])
+    dist.all_reduce(store2, op=dist.ReduceOp.SUM)
+    want = sum(w[k] * grad_k[r * 6 + k] for r in range(world) for k in range(6)) / world
+    torch.testing.assert_close(store2[:16], want, rtol=1e-5, atol=1e-5)
+    ll = LazyLosses(store2[16:23].clone(), 1.0 / world)
+    mean_terms = [sum(0.1 * (r + 1) * (k + 1) for r in range(world)) / world for k in range(6)]
+    assert abs(ll["total_loss"] - sum(w[k] * mean_terms[k] for k in range(6))) < 1e-3
+    for k in range(6):
+        assert abs(ll[LOSS_KEYS[k + 1]] - mean_terms[k]) < 1e-6
+    assert "total_loss" in ll and ll.get("L_fourier") is not None and len(ll.copy()) == 7
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
@@ -55,4 +75,5 @@ def test_bench_reference_arm_two_ranks():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "patches/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["steps"] == 1 and d["warmup"] == 0                      # the arm honours --steps / --warmup

@@ -318,3 +318,121 @@ def test_engine_cache_is_bounded():
                     assert torch.equal(first, S)          # rebuilt engine, same deterministic forward
             assert len(m._engines) <= m.max_cached_engines
     assert len(m._engines) == m.max_cached_engines
+
+
+def _flat_grads(m):
+    return torch.cat([p.grad.detach().flatten() for p in m.parameters()]).clone()
+
+
+def test_gradient_accumulation_over_two_batches():
+    """Micro-batch accumulation exactly as autograd does it (backward; compute_loss(x2); backward -> g1 + g2): the views
+    of the flat gradient buffer handed out by the first backward must survive the second compute_loss overwriting it."""
+    from oracle import sshslie_oracle as O
+    m = _model(O.JYU_COEF)
+    x1 = O.synthetic_patches(1, 64, 64, seed=5).cuda()
+    x2 = O.synthetic_patches(1, 64, 64, seed=6).cuda()
+    m.optimizer.zero_grad()
+    l1, _ = m.compute_loss(x1)
+    l1.backward()
+    g1 = _flat_grads(m)
+    m.optimizer.zero_grad()
+    l2, _ = m.compute_loss(x2)
+    l2.backward()
+    g2 = _flat_grads(m)
+    assert float((g1 - g2).abs().max()) > 1e-3 * float(g1.abs().max())           # the batches really differ
+    m.optimizer.zero_grad()
+    la, _ = m.compute_loss(x1)
+    la.backward()
+    lb, _ = m.compute_loss(x2)            # overwrites the flat buffer the first gradients were views of
+    lb.backward()
+    torch.testing.assert_close(_flat_grads(m), g1 + g2, rtol=1e-5, atol=1e-6 * float(g1.abs().max()))
+
+
+def test_zero_grad_set_to_none_false_does_not_double():
+    """optimizer.zero_grad(set_to_none=False) keeps p.grad = view of the flat buffer; the next step must give g, not 2 g."""
+    from oracle import sshslie_oracle as O
+    m = _model(O.JYU_COEF)
+    x = O.synthetic_patches(1, 64, 64, seed=5).cuda()
+    m.optimizer.zero_grad()
+    l, _ = m.compute_loss(x)
+    l.backward()
+    g = _flat_grads(m)
+    for _ in range(3):
+        m.optimizer.zero_grad(set_to_none=False)
+        l, _ = m.compute_loss(x)
+        l.backward()
+        torch.testing.assert_close(_flat_grads(m), g, rtol=0, atol=0)               # bit-repeatable as well
+
+
+def test_autograd_grad_on_the_loss():
+    """torch.autograd.grad(loss, params) works as on the reference's loss tensor (the loss node is wired to all 46
+    parameters) and leaves .grad alone."""
+    from oracle import sshslie_oracle as O
+    m = _model(O.JYU_COEF)
+    x = O.synthetic_patches(1, 64, 64, seed=5).cuda()
+    m.optimizer.zero_grad()
+    l, _ = m.compute_loss(x)
+    l.backward()
+    g = _flat_grads(m)
+    m.optimizer.zero_grad()
+    l, _ = m.compute_loss(x)
+    gs = torch.autograd.grad(l, list(m.parameters()))
+    assert all(p.grad is None for p in m.parameters())
+    torch.testing.assert_close(torch.cat([t.flatten() for t in gs]), g, rtol=0, atol=0)
+
+
+def test_loss_weights_changed_after_graph_capture():
+    """The captured CUDA graph bakes the loss weights into kernel arguments; changing model.c_loss_* afterwards must take
+    effect on the next step (the graph is re-captured), not be silently ignored."""
+    from oracle import sshslie_oracle as O
+    m = _model(O.JYU_COEF, graph=True)
+    x = O.synthetic_patches(1, 64, 64, seed=5).cuda()
+    for _ in range(4):                                    # steps 3+ replay the graph
+        m.optimizer.zero_grad()
+        l, losses = m.compute_loss(x)
+        l.backward()
+    t_jyu = losses["total_loss"]
+    m.c_loss_i_smooth_delta, m.c_loss_fourier = 20.0, 0.2     # the cv1 weights
+    m.optimizer.zero_grad()
+    l, losses = m.compute_loss(x)
+    l.backward()
+    t_cv = losses["total_loss"]
+    want = (10 * losses["L_reconstruction"] + losses["L_R_fidelity"] + losses["L_I_smooth_low"]
+            + 20 * losses["L_I_smooth_delta"] + 0.2 * losses["L_fourier"] + losses["L_spectral_cons"])
+    assert abs(t_cv - want) <= 1e-4 * abs(want) and abs(t_cv - t_jyu) > 1e-2 * abs(t_jyu)
+    m2 = _model(O.DEFAULT_COEF)
+    m2.optimizer.zero_grad()
+    l2, _ = m2.compute_loss(x)
+    l2.backward()
+    torch.testing.assert_close(_flat_grads(m), _flat_grads(m2), rtol=0, atol=0)
+
+
+def test_forward_returns_fresh_tensors():
+    """The reference returns new tensors from every forward(); a caller holding R across two calls must not see it
+    overwritten."""
+    from oracle import sshslie_oracle as O
+    m = _model(O.JYU_COEF)
+    xa = O.synthetic_patches(1, 64, 64, seed=1).cuda()
+    xb = O.synthetic_patches(1, 64, 64, seed=2).cuda()
+    with torch.no_grad():
+        Ra, _, _, Sa = m.forward(xa)
+        keep = Ra.clone()
+        Rb, _, _, Sb = m.forward(xb)
+    torch.cuda.synchronize()
+    assert Ra.data_ptr() != Rb.data_ptr() and torch.equal(Ra, keep) and not torch.equal(Ra, Rb)
+
+
+def test_step_is_bit_repeatable():
+    """The reference runs with cudnn.deterministic=True (main.py:165): two runs of the same step give bit-identical
+    losses and gradients (no floating-point atomics anywhere on the training path)."""
+    from oracle import sshslie_oracle as O
+    outs = []
+    for _ in range(2):
+        m = _model(O.JYU_COEF)
+        x = O.synthetic_patches(2, 64, 128, seed=41).cuda()
+        m.optimizer.zero_grad()
+        l, losses = m.compute_loss(x)
+        l.backward()
+        outs.append((_flat_grads(m), [losses[k] for k in O.LOSS_KEYS]))
+    assert outs[0][1] == outs[1][1]
+    assert torch.equal(outs[0][0], outs[1][0])
