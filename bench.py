@@ -177,6 +177,20 @@ def kernel_of(name):
     return {"loss:fourier_fft+grad": "fourier_loss_kernel", "loss:pixel_terms+grads": "pixel_losses_kernel"}.get(op, op)
 
 
+def finish(world):
+    """End of a rank's work.  Under torchrun every rank leaves through os._exit after its last collective: tearing the
+    NCCL communicator down while captured CUDA graphs still hold its kernels (the data-parallel step is ONE graph incl.
+    both all-reduces) can block forever in destroy_process_group / interpreter shutdown."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        dist.barrier()            # the other ranks stay alive (blocked here) until rank 0 has printed its line
+        torch.cuda.synchronize()
+        os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -452,8 +466,7 @@ def run_ours(args):
         cpu = {"value": wl["batch"] * len(ts) / sum(ts), "unit": "patches/s", "cores": cores, "kind": kind,
                "sample": f"{len(ts)} full train steps of B={wl['batch']} on the host ({what}, {cores} threads)"}
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
@@ -541,8 +554,7 @@ def run_ours(args):
     if infer:
         line["inference"] = infer
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 def main():

@@ -21,6 +21,6 @@ def test_data_parallel_gradient_matches_oracle(graph):
     env = dict(os.environ, SSHSLIE_DP_GRAPH=graph)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "dp_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT, env=env)
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
     assert "DP_CHECK ok" in out.stdout
