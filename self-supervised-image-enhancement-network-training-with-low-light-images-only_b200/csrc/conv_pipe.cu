@@ -60,6 +60,8 @@ struct PipeArgs {
   int debug;                   // timing experiments only (SSHSLIE_PIPE_DEBUG): 1 no halo reloads, 2 no epilogue work, 4 no MMAs
   int G, n_iter, slots, resident;   // weight chunks of G slabs; `slots` chunk buffers; resident: slots == n_iter, loaded once
   int staged, n_ent, nsb;      // staged epilogue: nsb (1 or 2) staging buffers of n_ent tiles per lane
+  int head;                    // EPI_HEAD: the fp32 (b, c, h, w) reflectance tile is staged as [c][16][8] (2 tiles = 32 KB) and
+                               // leaves with ONE TMA store; the bf16 copies for the illumination net are written directly
   int ent_map[PIPE_MAX_ENT];   // which output map (0 = out, 1 = out_lo, 2 = out2) and channel offset of each staging tile
   int ent_c0[PIPE_MAX_ENT];
   int n_main, has_lo, n_split, n_store2, t_lo0, t_20;   // accumulator column -> staging tile (see epi_stage16)
@@ -192,6 +194,46 @@ SS_DEVINL void epi_stage16(const Epi& e, const PipeArgs& pa, int c, bool ok, int
     unsigned char* rl = stg + (pa.t_lo0 + (cc >> 6)) * PIPE_STG_TILE + row * 128;
     *reinterpret_cast<uint4*>(rl + ((j ^ sw) << 4)) = lo;
     *reinterpret_cast<uint4*>(rl + (((j + 1) ^ sw) << 4)) = hi;
+  }
+}
+
+// sigmoid head (model.py:65-70), 16 accumulator columns [c, c + 16) of one pixel: R -> fp32 staging tile [band][h][w]
+// (a warp's 32 pixels are 4 image rows x 8 columns = 128 contiguous bytes per band: conflict-free), I -> its fp32 plane,
+// and the bf16 cat[R, I] (+ residual) the illumination net reads, exactly as epi_apply16 / EPI_HEAD writes them
+SS_DEVINL void epi_head16_staged(const Epi& e, int c, bool ok, int b, int oh, int ow, float* v, const float* bias_s,
+                                 float* stg32, int row) {
+  {
+    const float4* bp = reinterpret_cast<const float4*>(bias_s + c);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bv = bp[q];
+      v[4 * q] += bv.x; v[4 * q + 1] += bv.y; v[4 * q + 2] += bv.z; v[4 * q + 3] += bv.w;
+    }
+  }
+  const int64_t pix = ((int64_t)b * e.H + oh) * e.W + ow;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int n = c + i;
+    const float s = sigmoidf_(v[i]);
+    if (n < e.C) stg32[n * 128 + row] = s;
+    else if (n == e.C && e.I32 && ok) e.I32[pix] = s;
+    v[i] = (n <= e.C) ? s : 0.f;
+  }
+  if (e.RI && ok) {
+    bf16* p = e.RI + pix * e.ri_c + c;
+    uint4 lo, hi;
+    pack16(v, lo, hi);
+    *reinterpret_cast<uint4*>(p) = lo;
+    *reinterpret_cast<uint4*>(p + 8) = hi;
+    if (e.ri_lo_off > 0 && c < e.C) {
+      float r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = (c + i < e.C) ? v[i] - bf2f(f2bf(v[i])) : 0.f;
+      pack16(r, lo, hi);
+      bf16* q = p + e.ri_lo_off;
+      *reinterpret_cast<uint4*>(q) = lo;
+      *reinterpret_cast<uint4*>(q + 8) = hi;
+    }
   }
 }
 
@@ -444,14 +486,20 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
             if (__float_as_uint(v[31]) == 0x7fc12345u) g_pipe_dbg[127] = 1;     // forces the scoreboard wait on the TMEM load
 #endif
             if (m < 8) PDBG(crumb, 32 + m * 8 + (n0 == 0 ? 3 : 5));
-            epi_stage16(epi, pa, n0, ok, b, oh, ow, v, bias_s, stg, row);
-            epi_stage16(epi, pa, n0 + 16, ok, b, oh, ow, v + 16, bias_s, stg, row);
+            if (pa.head) {
+              epi_head16_staged(epi, n0, ok, b, oh, ow, v, bias_s, reinterpret_cast<float*>(stg), row);
+              epi_head16_staged(epi, n0 + 16, ok, b, oh, ow, v + 16, bias_s, reinterpret_cast<float*>(stg), row);
+            } else {
+              epi_stage16(epi, pa, n0, ok, b, oh, ow, v, bias_s, stg, row);
+              epi_stage16(epi, pa, n0 + 16, ok, b, oh, ow, v + 16, bias_s, stg, row);
+            }
             if (m < 8 && n0 == 0) PDBG(crumb, 32 + m * 8 + 4);
           }
           if (n0 < Npad) {
             float v[16];
             tmem_ld16(trow + (uint32_t)n0, v);
-            epi_stage16(epi, pa, n0, ok, b, oh, ow, v, bias_s, stg, row);
+            if (pa.head) epi_head16_staged(epi, n0, ok, b, oh, ow, v, bias_s, reinterpret_cast<float*>(stg), row);
+            else epi_stage16(epi, pa, n0, ok, b, oh, ow, v, bias_s, stg, row);
           }
           if (m < 8) PDBG(crumb, 32 + m * 8 + 6);
           tc_fence_before();
@@ -500,9 +548,13 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
         if (i < 8) PDBG(true, 96 + i * 4 + 0);
         if (!(pa.debug & 2)) {
           const uint32_t s_u32 = dyn_base + stg_off + (uint32_t)g * stg_lane + sb * stg_buf;
-          for (int q = 0; q < pa.n_ent; ++q)
-            tma_store_4d(&omaps.m[pa.ent_map[q]], s_u32 + (uint32_t)q * PIPE_STG_TILE, pa.ent_c0[q], t.twi * HALO_TW,
-                         t.thi * HALO_TH, t.b);
+          if (pa.head) {      // fp32 (b, band, h, w) planes: box {8 w, 16 h, 64 bands}
+            tma_store_4d(&omaps.m[0], s_u32, t.twi * HALO_TW, t.thi * HALO_TH, 0, t.b);
+          } else {
+            for (int q = 0; q < pa.n_ent; ++q)
+              tma_store_4d(&omaps.m[pa.ent_map[q]], s_u32 + (uint32_t)q * PIPE_STG_TILE, pa.ent_c0[q], t.twi * HALO_TW,
+                           t.thi * HALO_TH, t.b);
+          }
           bulk_commit();
           if (i < 8) PDBG(true, 96 + i * 4 + 1);
           bulk_wait_read0();                                  // the staging buffer has been read: the lane may refill it
@@ -588,7 +640,11 @@ static int pipe_plan(const ConvGeom& g, const Epi& epi, PipePlan* out) {
   bool staged = epi.mode == EPI_BF16 && ss_env_int("SSHSLIE_PIPE_STAGED", 1) != 0 && epi.oW >= 64 && (epi.oW % 8) == 0 &&
                 (epi.n_store % 16) == 0 && (epi.n_split % 64) == 0 && (epi.n_store2 % 16) == 0;
   if (staged && epi.n_split && (epi.o2W < 64 || (epi.o2W % 8))) staged = false;
-  if (staged) {
+  if (epi.mode == EPI_HEAD && ss_env_int("SSHSLIE_PIPE_STAGED", 1) != 0 && epi.C == 64 && epi.R32 && (g.OW % 4) == 0) {
+    staged = true;
+    pa.head = 1;
+    pa.n_ent = 2;             // 64 bands x 128 pixels x fp32 = two 16 KB staging tiles
+  } else if (staged) {
     const int n1 = epi.n_split ? std::min(epi.n_store, epi.n_split) : epi.n_store;
     const int n_main_t = (n1 + 63) / 64, n_2_t = epi.n_split ? (epi.n_store2 + 63) / 64 : 0;
     const int ne = n_main_t * (epi.out_lo ? 2 : 1) + n_2_t;
@@ -691,7 +747,13 @@ int ss_launch_conv_gather_pipe(const ConvGeom& g, const UmmaMaps& maps, const Ep
       return SSHSLIE_ERR_ARG;
     }
     memset(&p->om, 0, sizeof(p->om));
-    if (p->pa.staged) {
+    if (p->pa.head) {
+      const uint64_t dims[4] = {(uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)epi.C, (uint64_t)g.B};
+      const uint64_t str[3] = {(uint64_t)g.OW * 4, (uint64_t)g.OW * g.OH * 4, (uint64_t)g.OW * g.OH * epi.C * 4};
+      const uint32_t box[4] = {HALO_TW, HALO_TH, 64, 1};
+      const int rc = ss_tma_encode_4d(&p->om.m[0], 1, epi.R32, dims, str, box, 0);
+      if (rc) return rc;
+    } else if (p->pa.staged) {
       int rc = encode_out(epi.out, epi.oB, epi.oH, epi.oW, g.OH, g.OW, g.B, &p->om.m[0]);
       if (!rc && epi.out_lo) rc = encode_out(epi.out_lo, epi.oB, epi.oH, epi.oW, g.OH, g.OW, g.B, &p->om.m[1]);
       if (!rc && epi.n_split) rc = encode_out(epi.out2, epi.o2B, epi.o2H, epi.o2W, g.OH, g.OW, g.B, &p->om.m[2]);

@@ -402,6 +402,25 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// generic 4-D tiled map (used for the fp32 NCHW tile stores of the sigmoid head)
+int ss_tma_encode_4d(CUtensorMap* out, int fp32, void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle128) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return SSHSLIE_ERR_CUDA;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, d, s, b, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ss_set_error("cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
+    return SSHSLIE_ERR_CUDA;
+  }
+  return SSHSLIE_OK;
+}
+
 int ss_umma_supported(const ConvGeom& g) {
   if (g.Npad < 16 || g.Npad > 256 || (g.Npad % 16)) return 0;
   if (g.tw < 8 || g.tw * g.th != 128) return 0;
@@ -1342,7 +1361,12 @@ int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const Um
     ss_set_error("conv_wgrad_halo: geometry not eligible");
     return SSHSLIE_ERR_ARG;
   }
-  const size_t smem = (size_t)wa.stages * wa.stage_bytes + WGH_ONES_BYTES + 1024;
+  size_t smem = (size_t)wa.stages * wa.stage_bytes + WGH_ONES_BYTES + 1024;
+  // A weight-gradient CTA that owns all 512 TMEM columns must not share its SM with a forward / dgrad CTA of the main
+  // stream: the block scheduler does not know about tensor memory, the co-located CTA would sit in tcgen05.alloc until
+  // this one exits (up to 25 us added to a 7 us kernel of the critical path).  Asking for more shared memory than a
+  // gather CTA leaves free keeps them apart.
+  if (wa.tmem_cols > 256) smem = std::max(smem, (size_t)ss_env_int("SSHSLIE_WGH_SMEM_KB", 160) * 1024);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=

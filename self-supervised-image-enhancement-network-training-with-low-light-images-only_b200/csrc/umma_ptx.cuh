@@ -174,3 +174,5 @@ SS_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
 int ss_env_int(const char* name, int dflt);
 // 4-D tiled SWIZZLE_128B map over a bf16 NHWC view: dims {channels (ld_extent), W, H, B}, box {64, tw, th, 1}
 int ss_umma_encode_view(const SrcView& v, int ld_extent, int tw, int th, int B, CUtensorMap* out);
+int ss_tma_encode_4d(CUtensorMap* out, int fp32, void* base, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle128);

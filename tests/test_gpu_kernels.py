@@ -379,3 +379,47 @@ def test_ssim_vs_oracle():
     np.testing.assert_allclose(got, float(O.ssim(p, t, 4095.0)), rtol=1e-4)
     got2 = S.metrics.ssim(p, t, (238.0, 3000.0))
     np.testing.assert_allclose(got2, float(O.ssim(p, t, (238.0, 3000.0))), rtol=1e-4)
+
+
+def test_metrics_closed_form_known_answers():
+    """torchmetrics 1.6.2 (the arithmetic behind metrics.py:13-34) cannot be installed offline, so besides the oracle
+    restatement the metric kernels are pinned to closed-form answers of the published definitions:
+      PSNR   constant offset d everywhere -> MSE = d^2 -> 10 log10(range^2 / d^2);
+      SAM    target = k * pred (k > 0) -> every spectral angle is 0; orthogonal spectra -> pi / 2; 45 degrees -> pi / 4;
+      SSIM   identical cubes -> 1 exactly; the mean runs over the H x (W-10) x (C-10) positions the 11x11 window leaves
+             (metrics.py:16-19 feeds (1,H,W,C), so H is the channel axis) - checked through a cube that is constant per
+             H-slice with a constant offset, where every window gives the same closed-form value."""
+    import math
+    import sshslie_b200 as S
+    g = torch.Generator().manual_seed(21)
+    t = torch.rand(24, 32, 64, generator=g) * 3000 + 500
+    # PSNR of a constant offset
+    d = 37.5
+    ps, _ = S.metrics.psnr_sam(t + d, t, 4095.0)
+    np.testing.assert_allclose(ps, 10.0 * math.log10(4095.0 ** 2 / d ** 2), rtol=1e-6)
+    # SAM: scaled spectra -> 0 (clamped acos of 1 +- rounding: below 1e-3 rad), orthogonal -> pi/2, 45 degrees -> pi/4
+    _, sa = S.metrics.psnr_sam(1.7 * t, t, 4095.0)
+    assert 0.0 <= sa < 1e-3
+    a = torch.zeros(8, 8, 64)
+    b = torch.zeros(8, 8, 64)
+    a[..., 0] = 3.0
+    b[..., 1] = 5.0
+    _, sa = S.metrics.psnr_sam(a, b, 1.0)
+    np.testing.assert_allclose(sa, math.pi / 2, rtol=1e-6)
+    b[..., 0] = 5.0
+    _, sa = S.metrics.psnr_sam(a, b, 1.0)
+    np.testing.assert_allclose(sa, math.pi / 4, rtol=1e-6)
+    # SSIM of identical cubes is exactly 1 at every window position
+    np.testing.assert_allclose(S.metrics.ssim(t, t.clone(), 4095.0), 1.0, rtol=0, atol=1e-6)
+    # per-slice constant cube + constant offset: variances and covariance vanish in every window, so each position gives
+    # (2 mu_x mu_y + c1) / (mu_x^2 + mu_y^2 + c1); the mean over H x (W-10) x (C-10) positions is the mean over slices
+    H, W, C, off, rng = 12, 30, 40, 50.0, 4095.0
+    lev = torch.linspace(400.0, 3000.0, H)
+    x = lev[:, None, None].expand(H, W, C).contiguous()
+    y = x + off
+    c1 = (0.01 * rng) ** 2
+    want = float(((2 * lev * (lev + off) + c1) / (lev ** 2 + (lev + off) ** 2 + c1)).double().mean())
+    np.testing.assert_allclose(S.metrics.ssim(y, x, rng), want, rtol=1e-3)      # fp32 E[x^2] - mu^2 noise vs c2 = 1.5e4
+    # the crop count: a cube whose W (or C) equals the window size + 1 leaves exactly 1 position along that axis
+    xs, ys = x[:, :11, :11].contiguous(), y[:, :11, :11].contiguous()
+    np.testing.assert_allclose(S.metrics.ssim(ys, xs, rng), want, rtol=1e-3)
