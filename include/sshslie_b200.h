@@ -161,6 +161,18 @@ SSHSLIE_API int sshslie_conv2d(int kind, int impl, int transposed, float* x, flo
                    int B, int Cin, int Cout, int H, int W, int k, int stride, int relu,
                    void* scratch, int64_t scratch_bytes, void* stream);
 
+/* TransformerBlock alone (model.py:99-119), for kernel-level parity tests of the attention kernels (fp32 CUDA-core kernels
+ * up to 1023 tokens, tcgen05 core from 1024 tokens).  x, y, dy, dx: fp32 (B, 64, H, W) as the reference block sees them
+ * (tokens = the H*W grid; the kernels read / write them as bf16 like the engine does); params / dparams: the block's ten
+ * tensors flat in state_dict order (q.w q.b k.w k.b v.w v.b ff1.w ff1.b ff2.w ff2.b = 20800 floats).  with_backward != 0:
+ * also dparams = d/dparams of <y, dy> and dx = (d/dx of <y, dy>) masked by x > 0: in the network the block's input is the
+ * output of a ReLU layer (model.py:128, 150-153) and the engine folds that layer's backward mask into this kernel.
+ * Synchronises.  scratch: 1024-byte aligned. */
+SSHSLIE_API int64_t sshslie_transformer_block_scratch_bytes(int B, int H, int W);
+SSHSLIE_API int sshslie_transformer_block(int with_backward, const float* x, const float* params, float* y, const float* dy,
+                              float* dx, float* dparams, int B, int H, int W, void* scratch, int64_t scratch_bytes,
+                              void* stream);
+
 /* with SSHSLIE_CONV2D_TIMING=n in the environment, sshslie_conv2d repeats the layer's launches n times between two
  * CUDA events; this returns the mean device time (ms) of the last such call (tools/conv_bench.py) */
 SSHSLIE_API float sshslie_conv2d_last_ms(void);

@@ -26,6 +26,45 @@ SS_DEVINL void stage_w(float (*Ws)[AT_D + 1], const float* __restrict__ Wt) {
   }
 }
 
+// h = relu(o W1^T + b1) ; t = x + h W2^T + b2  -> h (kept for backward), t as bf16     (model.py:115-118).  Stand-alone FFN
+// behind the tensor-core attention core (attention_tc.cu); at the training size the FFN is fused into attn_core_ffn_kernel.
+__global__ void __launch_bounds__(256) attn_ffn_kernel(const float* __restrict__ O, const float* __restrict__ X,
+                                                       const float* __restrict__ P, int64_t o1, int64_t ob1, int64_t o2,
+                                                       int64_t ob2, float* __restrict__ Hh, bf16* __restrict__ Tout,
+                                                       int T) {
+  SS_PDL_ENTRY();
+  extern __shared__ float smf[];
+  float (*W1)[AT_D + 1] = reinterpret_cast<float (*)[AT_D + 1]>(smf);
+  float (*W2)[AT_D + 1] = W1 + AT_D;
+  float (*Os)[AT_D] = reinterpret_cast<float (*)[AT_D]>(smf + 2 * AT_D * (AT_D + 1));
+  float (*Hs)[AT_D] = Os + TK;
+  const int t0 = blockIdx.x * TK;
+  stage_w(W1, P + o1); stage_w(W2, P + o2);
+  for (int i = threadIdx.x; i < TK * AT_D; i += 256) {
+    const int t = t0 + (i >> 6);
+    Os[i >> 6][i & 63] = (t < T) ? O[(int64_t)t * AT_D + (i & 63)] : 0.f;
+  }
+  __syncthreads();
+  const int o = threadIdx.x & 63;
+  for (int tt = threadIdx.x >> 6; tt < TK; tt += 4) {
+    float acc = P[ob1 + o];
+#pragma unroll 16
+    for (int i = 0; i < AT_D; ++i) acc = fmaf(Os[tt][i], W1[o][i], acc);
+    acc = fmaxf(acc, 0.f);
+    Hs[tt][o] = acc;
+    if (t0 + tt < T) Hh[(int64_t)(t0 + tt) * AT_D + o] = acc;
+  }
+  __syncthreads();
+  for (int tt = threadIdx.x >> 6; tt < TK; tt += 4) {
+    const int t = t0 + tt;
+    if (t >= T) break;
+    float acc = P[ob2 + o];
+#pragma unroll 16
+    for (int i = 0; i < AT_D; ++i) acc = fmaf(Hs[tt][i], W2[o][i], acc);
+    Tout[(int64_t)t * AT_D + o] = f2bf(acc + X[(int64_t)t * AT_D + o]);
+  }
+}
+
 // backward of the FFN, data path only:  dh = dt W2 (kept pre-mask), dO = (dh * [h>0]) W1
 __global__ void __launch_bounds__(256) attn_ffn_bwd_kernel(const float* __restrict__ dT, const float* __restrict__ Hh,
                                                            const float* __restrict__ P, int64_t o1, int64_t o2,
@@ -701,6 +740,7 @@ static int attn_attrs() {
   static bool done = false;
   if (done) return 0;
   cudaError_t e = cudaFuncSetAttribute(attn_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_ffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_qkv4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemQkv4);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCore);
@@ -720,6 +760,16 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* P, const int6
   // register-tiled kernels; keys stream through 256-row tiles (one tile at the training size)
   ss_launch_pdl(attn_qkv4_kernel, dim3((T + AF_QB - 1) / AF_QB), dim3(192), (size_t)(kSmemQkv4), st, a3, P, poff[0], poff[1], poff[2], poff[3], poff[4],
                                                                    poff[5], bf.x, bf.q, bf.k, bf.v, T);
+  static const bool tc_ok = !(getenv("SSHSLIE_ATTN_TC") && getenv("SSHSLIE_ATTN_TC")[0] == '0');
+  if (tc_ok && bf.qp && bf.kvp && L >= SS_ATTN_TC_MIN_L) {
+    // large token grids (full-image inference): softmax(Q K^T) V on the tensor cores, then the FFN
+    int rc = ss_check_launch("attention_qkv");
+    if (!rc) rc = ss_attention_core_tc(bf.q, bf.k, bf.v, bf.qp, bf.kvp, bf.o, bf.lse, B, L, st);
+    if (rc) return rc;
+    ss_launch_pdl(attn_ffn_kernel, dim3((T + TK - 1) / TK), dim3(256), (size_t)(kSmem2), st, bf.o, bf.x, P, poff[6], poff[7], poff[8], poff[9],
+                  bf.h, t_out, T);
+    return ss_check_launch("attention_ffn");
+  }
   dim3 g((L + AF_QB - 1) / AF_QB, B);
   ss_launch_pdl(attn_core_ffn_kernel, dim3(g), dim3(256), (size_t)(kSmemCore), st, bf.x, bf.q, bf.k, bf.v, P, poff[6], poff[7], poff[8], poff[9], bf.o,
                                                    bf.lse, bf.h, t_out, L);

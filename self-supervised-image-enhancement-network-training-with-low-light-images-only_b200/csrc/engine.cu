@@ -848,6 +848,10 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   memset(&ab, 0, sizeof(ab));
   ab.x = e->falloc(T64); ab.q = e->falloc(T64); ab.k = e->falloc(T64); ab.v = e->falloc(T64); ab.o = e->falloc(T64);
   ab.lse = e->falloc((int64_t)B * 4 * L); ab.h = e->falloc(T64); ab.t32 = e->falloc(T64);
+  if (L >= SS_ATTN_TC_MIN_L) {       // per-head bf16 operands of the tensor-core attention core
+    ab.qp = (bf16*)e->alloc(T64 * 4 * (int64_t)sizeof(bf16));
+    ab.kvp = (bf16*)e->alloc(T64 * 4 * (int64_t)sizeof(bf16));
+  }
   if (train) {
     ab.dq = e->falloc(T64); ab.dk = e->falloc(T64); ab.dv = e->falloc(T64); ab.d_o = e->falloc(T64);
     ab.dh = e->falloc(T64); ab.dx = e->falloc(T64); ab.Dv = e->falloc((int64_t)B * 4 * L);
@@ -1528,6 +1532,107 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
   return rc;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TransformerBlock alone (model.py:99-119), for kernel-level parity tests of the attention kernels: x, y, dy, dx are
+// fp32 (B, 64, H, W) as the reference block sees them (tokens = the H*W grid); params / dparams are the block's ten tensors
+// flat in state_dict order (q.w q.b k.w k.b v.w v.b ff1.w ff1.b ff2.w ff2.b = 20800 floats).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw32_to_tokens32_kernel(const float* __restrict__ x, float* __restrict__ t, int C,
+                                                                 int L, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int64_t bl = i / C;
+  const int l = (int)(bl % L);
+  const int64_t b = bl / L;
+  t[i] = x[(b * C + c) * L + l];
+}
+// (B, 64, L) fp32 <-> (B, L, 64) bf16 for any L (the engine's layout converters assume its 8-pixel tiling)
+__global__ void __launch_bounds__(256) nchw32_to_tokens16_kernel(const float* __restrict__ x, bf16* __restrict__ t, int C,
+                                                                 int L, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int64_t bl = i / C;
+  t[i] = f2bf(x[((bl / L) * C + c) * L + (bl % L)]);
+}
+__global__ void __launch_bounds__(256) tokens16_to_nchw32_kernel(const bf16* __restrict__ t, float* __restrict__ y, int C,
+                                                                 int L, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const int64_t bl = i / C;
+  y[((bl / L) * C + c) * L + (bl % L)] = bf2f(t[i]);
+}
+extern "C" int64_t sshslie_transformer_block_scratch_bytes(int B, int H, int W) {
+  const int64_t T64 = (int64_t)B * H * W * 64;
+  int64_t bytes = 3 * (T64 * 2 + 1024);                                   // a3, t, da3 (bf16)
+  bytes += 16 * (T64 * 4 + 1024) + 2 * ((int64_t)B * 4 * H * W * 4 + 1024);   // fp32 token buffers, lse, Dv
+  bytes += 2 * (T64 * 4 * 2 + 1024);                                      // qp, kvp
+  bytes += (int64_t)SS_ATTN_WGRAD_MAX_BLOCKS * SS_ATTN_WGRAD_COLS * 4 + 1024;
+  return bytes + (1 << 16);
+}
+extern "C" int sshslie_transformer_block(int with_backward, const float* x, const float* params, float* y, const float* dy,
+                                         float* dx, float* dparams, int B, int H, int W, void* scratch,
+                                         int64_t scratch_bytes, void* stream) {
+  if (!x || !params || !y || !scratch || B < 1 || H < 1 || W < 1 || ((uintptr_t)scratch & 1023) ||
+      (with_backward && (!dy || !dx || !dparams))) {
+    ss_set_error("sshslie_transformer_block: bad argument");
+    return SSHSLIE_ERR_ARG;
+  }
+  if (scratch_bytes < sshslie_transformer_block_scratch_bytes(B, H, W)) {
+    ss_set_error("sshslie_transformer_block: scratch too small");
+    return SSHSLIE_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  sshslie_engine E;
+  sshslie_engine* e = &E;
+  e->base = (unsigned char*)scratch; e->cursor = 0;
+  const int L = H * W;
+  const int64_t T64 = (int64_t)B * L * 64;
+  bf16* a3 = (bf16*)e->alloc(T64 * 2);
+  bf16* tt = (bf16*)e->alloc(T64 * 2);
+  bf16* da3 = (bf16*)e->alloc(T64 * 2);
+  AttnBuffers ab;
+  memset(&ab, 0, sizeof(ab));
+  ab.x = e->falloc(T64); ab.q = e->falloc(T64); ab.k = e->falloc(T64); ab.v = e->falloc(T64); ab.o = e->falloc(T64);
+  ab.lse = e->falloc((int64_t)B * 4 * L); ab.h = e->falloc(T64); ab.t32 = e->falloc(T64);
+  ab.dq = e->falloc(T64); ab.dk = e->falloc(T64); ab.dv = e->falloc(T64); ab.d_o = e->falloc(T64);
+  ab.dh = e->falloc(T64); ab.dx = e->falloc(T64); ab.Dv = e->falloc((int64_t)B * 4 * L);
+  float* dt32 = e->falloc(T64);
+  if (L >= SS_ATTN_TC_MIN_L) {
+    ab.qp = (bf16*)e->alloc(T64 * 4 * 2);
+    ab.kvp = (bf16*)e->alloc(T64 * 4 * 2);
+  }
+  float* partials = e->falloc((int64_t)SS_ATTN_WGRAD_MAX_BLOCKS * SS_ATTN_WGRAD_COLS);
+  int64_t poff[10];
+  for (int i = 0; i < 5; ++i) { poff[2 * i] = (int64_t)i * 4160; poff[2 * i + 1] = (int64_t)i * 4160 + 4096; }
+  const unsigned cgrid = (unsigned)((T64 + 255) / 256);
+  nchw32_to_tokens16_kernel<<<cgrid, 256, 0, st>>>(x, a3, 64, L, T64);
+  int rc = ss_check_launch("nchw32_to_tokens16");
+  if (!rc) rc = ss_attention_forward(a3, tt, params, poff, ab, B, L, st);
+  if (!rc) {
+    tokens16_to_nchw32_kernel<<<cgrid, 256, 0, st>>>(tt, y, 64, L, T64);
+    rc = ss_check_launch("tokens16_to_nchw32");
+  }
+  if (!rc && with_backward) {
+    nchw32_to_tokens32_kernel<<<(unsigned)((T64 + 255) / 256), 256, 0, st>>>(dy, dt32, 64, L, T64);
+    rc = ss_check_launch("nchw32_to_tokens32");
+    if (!rc && cudaMemsetAsync(dparams, 0, 20800 * sizeof(float), st) != cudaSuccess) rc = SSHSLIE_ERR_CUDA;
+    if (!rc) rc = ss_attention_backward(dt32, a3, da3, params, dparams, poff, ab, B, L, st);
+    if (!rc) rc = ss_attention_backward_weights(dt32, dparams, poff, ab, B, L, partials, st);
+    if (!rc) {
+      tokens16_to_nchw32_kernel<<<cgrid, 256, 0, st>>>(da3, dx, 64, L, T64);
+      rc = ss_check_launch("tokens16_to_nchw32");
+    }
+  }
+  if (cudaStreamSynchronize(st) != cudaSuccess) {
+    ss_set_error("sshslie_transformer_block: %s", cudaGetErrorString(cudaGetLastError()));
+    return SSHSLIE_ERR_CUDA;
+  }
+  return rc;
+}
 
 // ---------------------------------------------------------------------------------------------
 // profiling entry point: one eager step with a cudaEvent pair around every recorded op (synchronises)

@@ -88,7 +88,12 @@ int ss_launch_reduce_rows(const float* partials, int nrows, int ncols, const Red
 struct AttnBuffers {
   float *x, *q, *k, *v, *o, *lse, *h, *t32;                  // forward (x = a3 as fp32)
   float *dq, *dk, *dv, *d_o, *dh, *dx, *Dv;                  // backward scratch
+  bf16 *qp, *kvp;                                            // per-head bf16 hi+lo operands of the tensor-core core (L >= SS_ATTN_TC_MIN_L)
 };
+#define SS_ATTN_TC_MIN_L 1024
+// attention_tc.cu: tcgen05 attention core (q, k, v fp32 [B*L][64] -> o fp32 [B*L][64], lse [B][4][L])
+int ss_attention_core_tc(const float* q, const float* k, const float* v, bf16* qp, bf16* kvp, float* o, float* lse, int B,
+                         int L, cudaStream_t st);
 int ss_attention_forward(const bf16* a3, bf16* t_out, const float* params, const int64_t* poff, AttnBuffers bufs,
                          int B, int L, cudaStream_t st);
 int ss_attention_backward(const float* dt, const bf16* a3, bf16* da3, const float* params, float* grads,

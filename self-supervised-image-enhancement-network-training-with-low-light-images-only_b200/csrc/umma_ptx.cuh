@@ -170,6 +170,38 @@ SS_DEVINL void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// single-thread wait that leaves the issue slots to the other warps: the hardware may suspend the thread up to the hinted
+// time, and the software loop sleeps between polls
+SS_DEVINL bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+SS_DEVINL void mbar_wait_polite(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+    __nanosleep(64);
+    if (clock64() - t0 > UM_WAIT_CYCLES) {
+      printf("sshslie: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+// whole-warp variant: lane 0 waits politely, the rest of the warp sleeps at the reconvergence point
+SS_DEVINL void mbar_wait_warp_polite(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_polite(bar, parity);
+  __syncwarp();
+}
+
+
 // host helpers shared by the tcgen05 launchers (defined in conv_umma.cu)
 int ss_env_int(const char* name, int dflt);
 // 4-D tiled SWIZZLE_128B map over a bf16 NHWC view: dims {channels (ld_extent), W, H, B}, box {64, tw, th, 1}

@@ -21,6 +21,7 @@ EXPORTS = [
     "sshslie_loss_and_grad", "sshslie_adam_step", "sshslie_loss_scratch_bytes", "sshslie_fourier_loss", "sshslie_pixel_losses",
     "sshslie_conv2d_scratch_bytes", "sshslie_conv2d", "sshslie_profile_step", "sshslie_profile_row",
     "sshslie_launch_count", "sshslie_umma_probe", "sshslie_debug_read", "sshslie_gather_patches", "sshslie_conv2d_last_ms", "sshslie_denorm_hwc", "sshslie_psnr_sam", "sshslie_ssim_sum",
+    "sshslie_transformer_block_scratch_bytes", "sshslie_transformer_block",
 ]
 
 
@@ -72,6 +73,9 @@ def load():
     lib.sshslie_denorm_hwc.argtypes = [vp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_float, i32, vp]
     lib.sshslie_psnr_sam.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.sshslie_ssim_sum.argtypes = [vp, vp, i32, i32, i32, ctypes.c_float, ctypes.c_float, vp, vp]
+    lib.sshslie_transformer_block_scratch_bytes.restype = i64
+    lib.sshslie_transformer_block_scratch_bytes.argtypes = [i32, i32, i32]
+    lib.sshslie_transformer_block.argtypes = [i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i64, vp]
     lib.sshslie_launch_count.restype = ctypes.c_longlong
     lib.sshslie_conv2d_last_ms.restype = ctypes.c_float
     lib.sshslie_umma_probe.argtypes = [i32, i32, i32, i32, vp, i32, vp]
