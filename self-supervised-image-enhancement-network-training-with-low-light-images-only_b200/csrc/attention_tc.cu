@@ -20,8 +20,10 @@
 // of 64 bf16 = 128 bytes, Qp row = [0.25 q_hi | 0.25 q_lo | 0 | 0], KVp row = [k_hi | k_lo | v_hi | v_lo], so that one
 // 16 KB TMA tile feeds both GEMMs of a key tile.
 //
-// Warp roles (320 threads), ordered by the SM's issue priority (highest warp id first): warps 0..3 / 4..7 = softmax group
-// 0 / 1 (TMEM lane quarter = warp & 3), warp 8 = TMA producer, warp 9 = TMEM owner + MMA issuer.  Group g takes the key tiles with c & 1 == g (S buffer g, P buffer g); one warp per
+// Warp roles (576 threads), ordered by the SM's issue priority (highest warp id first): warps 0..7 / 8..15 = softmax group
+// 0 / 1 (TMEM lane quarter = warp & 3; warps 4..7 of a group take keys 64..127 of the tile, warps 0..3 keys 0..63: four
+// softmax warps per scheduler hide the TMEM-load and exp2 latencies that two could not - ncu: 35 % issue-active, average
+// warp latency 7 clk per instruction), warp 16 = TMA producer, warp 17 = TMEM owner + MMA issuer.  Group g takes the key tiles with c & 1 == g (S buffer g, P buffer g); one warp per
 // scheduler could not hide the TMEM-load latency (99 us for the 512 x 512 cube).  Row maxima / sums of the two groups are
 // merged through shared memory in a fixed order.
 #include <cuda.h>
@@ -33,8 +35,8 @@
 #include "umma_ptx.cuh"
 
 #define TC_TILE 128
-#define TC_SLOTS 3
-#define TC_THREADS 320
+#define TC_SLOTS 4
+#define TC_THREADS 576
 #define TC_TILE_BYTES (TC_TILE * 128)
 #define TC_P_BYTES (4 * TC_TILE_BYTES)          // probabilities of one key tile: bf16 hi (2 sub-tiles of 64 keys) + bf16 lo (2)
 #define TC_SMEM (TC_TILE_BYTES + TC_SLOTS * TC_TILE_BYTES + 2 * TC_P_BYTES + 1024)
@@ -95,13 +97,13 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   __shared__ __align__(8) uint64_t q_full;
   __shared__ __align__(8) uint64_t kv_full[TC_SLOTS];
   __shared__ __align__(8) uint64_t kv_empty[TC_SLOTS];
-  __shared__ __align__(8) uint64_t s_full[2];
-  __shared__ __align__(8) uint64_t s_empty[2];
+  __shared__ __align__(8) uint64_t s_full[3];          // THREE logit tiles in TMEM (columns 0 / 128 / 256), O at 384
+  __shared__ __align__(8) uint64_t s_empty[3];
   __shared__ __align__(8) uint64_t p_full[2];
   __shared__ __align__(8) uint64_t p_empty[2];
   __shared__ __align__(8) uint64_t o_full;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float xch[2][TC_TILE];                  // row maxima, then row sums, of the two softmax groups
+  __shared__ float xch[4][TC_TILE];                  // row maxima, then row sums, of the 2 groups x 2 key halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -113,26 +115,28 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   const int row_base = (b * 4 + head) * L;           // first row of this (image, head) in Qp / KVp
   const int n_tiles = 2 * nk;                        // pass A (row maxima) + pass B (softmax . V)
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     mbar_init(smem_u32(&q_full), 1);
     for (int s = 0; s < TC_SLOTS; ++s) { mbar_init(smem_u32(&kv_full[s]), 1); mbar_init(smem_u32(&kv_empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(smem_u32(&s_full[s]), 1);
-      mbar_init(smem_u32(&s_empty[s]), 4);           // one arrival per softmax warp
-      mbar_init(smem_u32(&p_full[s]), 4);
+      mbar_init(smem_u32(&s_empty[s]), 8);           // one arrival per softmax warp of the group that read it
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&p_full[s]), 8);
       mbar_init(smem_u32(&p_empty[s]), 1);
     }
     mbar_init(smem_u32(&o_full), 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  if (warp == 17) tmem_alloc(smem_u32(&tmem_base_smem), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp == 8) {
-    // ===== TMA producer: the query tile once, then the key/value tiles of both passes through a ring of three =====
+  if (warp == 16) {
+    // ===== TMA producer: the query tile once, then the key/value tiles of both passes through a ring =====
     if (lane == 0) {
       pdl_wait();
       mbar_expect_tx(smem_u32(&q_full), TC_TILE_BYTES);
@@ -146,7 +150,7 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         if (++slot == TC_SLOTS) { slot = 0; ++use; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ===== MMA issuer =====
     const uint32_t idesc_qk = make_idesc(128, 128, 0, 0);          // A = Q (K-major), B = K rows (K-major), N = 128 keys
     const uint32_t idesc_pv = make_idesc(128, 64, 0, 1);           // A = P (K-major), B = the same tile MN-major, N = 64
@@ -160,7 +164,7 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     mbar_wait_warp(smem_u32(&q_full), 0, 0);
     auto issue_qk = [&](int c) {
       const uint32_t slot = (uint32_t)(c % TC_SLOTS), kph = (uint32_t)((c / TC_SLOTS) & 1);
-      const uint32_t sb = (uint32_t)(c & 1), sph = (uint32_t)((c >> 1) & 1);
+      const uint32_t sb = (uint32_t)(c % 3), sph = (uint32_t)((c / 3) & 1);
       mbar_wait_warp(smem_u32(&kv_full[slot]), kph, 0);
       mbar_wait_warp(smem_u32(&s_empty[sb]), sph ^ 1u, 0);
       tc_fence_after();
@@ -176,11 +180,15 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       }
       __syncwarp();
     };
+    // the logits run TWO tiles ahead of the softmax (three S buffers for two softmax groups): when a group has finished
+    // tile c, S of its next tile c + 2 is already in TMEM - with two buffers each group idled for QK + P V + barrier
+    // latency (~1500 clk) per tile
     issue_qk(0);
+    if (n_tiles > 1) issue_qk(1);
     uint32_t pcount[2] = {0u, 0u};                   // pass-B uses of each P buffer so far
 #pragma unroll 1
     for (int c = 0; c < n_tiles; ++c) {
-      if (c + 1 < n_tiles) issue_qk(c + 1);                        // S of the next tile while the softmax works on this one
+      if (c + 2 < n_tiles) issue_qk(c + 2);
       if (c >= nk) {
         const int j = c - nk;
         const uint32_t slot = (uint32_t)(c % TC_SLOTS), pb = (uint32_t)(c & 1), pph = pcount[c & 1] & 1u;
@@ -190,7 +198,7 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
         if (elect_one()) {
           const uint32_t a0 = p_lo0 + pb * (TC_P_BYTES >> 4);
           const uint32_t b0 = vb_lo0 + slot * (TC_TILE_BYTES >> 4);
-          const uint32_t td = tm + 256u;
+          const uint32_t td = tm + 384u;
 #pragma unroll
           for (int part = 0; part < 2; ++part)    // P_hi, then P_lo (sub-tiles 2, 3 of the buffer)
 #pragma unroll
@@ -206,24 +214,26 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
     }
   } else {
     // ===== softmax warps: thread = query row; group g = key tiles with c & 1 == g =====
-    const int g = warp >> 2;
+    const int g = warp >> 3, half = (warp >> 2) & 1;     // half: keys 0..63 / 64..127 of every tile
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const uint32_t sb = (uint32_t)g;
-    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * 128u;
-    unsigned char* prow = dyn_ptr + (p_addr - dyn_base) + sb * TC_P_BYTES + row * 128;
+    const int nlo = half * 64;
+    const uint32_t pbuf = (uint32_t)g;
+    const uint32_t trow0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    unsigned char* prow = dyn_ptr + (p_addr - dyn_base) + pbuf * TC_P_BYTES + half * TC_TILE_BYTES + row * 128;
     const int sw = row & 7;
     float m = -INFINITY, l = 0.f;
-    uint32_t su = 0, pu = 0;                         // uses of this group's S buffer / P buffer so far
+    uint32_t pu = 0;                                 // uses of this group's P buffer so far
     pdl_wait();
     // ---- pass A: row maxima
 #pragma unroll 1
-    for (int c = g; c < nk; c += 2, ++su) {
+    for (int c = g; c < nk; c += 2) {
       const int valid = min(TC_TILE, L - c * TC_TILE);
-      mbar_wait_warp_polite(smem_u32(&s_full[sb]), su & 1u);
+      const uint32_t sb = (uint32_t)(c % 3), trow = trow0 + sb * 128u;
+      mbar_wait_warp_polite(smem_u32(&s_full[sb]), (uint32_t)((c / 3) & 1));
       tc_fence_after();
 #pragma unroll 1
-      for (int n0 = 0; n0 < TC_TILE; n0 += 32) {
+      for (int n0 = nlo; n0 < nlo + 64; n0 += 32) {
         float v[32];
         tmem_ld32(trow + (uint32_t)n0, v);
         if (valid == TC_TILE) {
@@ -238,35 +248,39 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_empty[sb]));
     }
-    xch[g][row] = m;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    m = fmaxf(xch[0][row], xch[1][row]);
+    xch[2 * g + half][row] = m;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    m = fmaxf(fmaxf(xch[0][row], xch[1][row]), fmaxf(xch[2][row], xch[3][row]));
     const float ml2 = m * TC_LOG2E;
-    asm volatile("bar.sync 1, 256;" ::: "memory");      // both groups have read the maxima before the sums reuse xch
+    asm volatile("bar.sync 1, 512;" ::: "memory");      // everybody has read the maxima before the sums reuse xch
     // ---- pass B: p = exp(s - m) -> bf16 hi + lo tiles, l += p
     const int c0 = nk + ((nk + g) & 1);                  // first pass-B tile with c & 1 == g
 #pragma unroll 1
-    for (int c = c0; c < n_tiles; c += 2, ++su, ++pu) {
+    for (int c = c0; c < n_tiles; c += 2, ++pu) {
       const int kt = c - nk;
       const int valid = min(TC_TILE, L - kt * TC_TILE);
-      mbar_wait_warp_polite(smem_u32(&s_full[sb]), su & 1u);
-      mbar_wait_warp_polite(smem_u32(&p_empty[sb]), (pu & 1u) ^ 1u);  // the MMAs that read this P buffer have retired
+      const uint32_t sb = (uint32_t)(c % 3), trow = trow0 + sb * 128u;
+      mbar_wait_warp_polite(smem_u32(&s_full[sb]), (uint32_t)((c / 3) & 1));
+      mbar_wait_warp_polite(smem_u32(&p_empty[pbuf]), (pu & 1u) ^ 1u);  // the MMAs that read this P buffer have retired
       tc_fence_after();
 #pragma unroll 1
-      for (int n0 = 0; n0 < TC_TILE; n0 += 32) {
+      for (int n0 = nlo; n0 < nlo + 64; n0 += 32) {
         float v[32];
         tmem_ld32(trow + (uint32_t)n0, v);
         if (valid == TC_TILE) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { v[i] = ex2_approx(fmaf(v[i], TC_LOG2E, -ml2)); l += v[i]; }
+          for (int i = 0; i < 32; ++i) v[i] = ex2_approx(fmaf(v[i], TC_LOG2E, -ml2));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = (n0 + i < valid) ? ex2_approx(fmaf(v[i], TC_LOG2E, -ml2)) : 0.f;
-            l += v[i];
-          }
+          for (int i = 0; i < 32; ++i) v[i] = (n0 + i < valid) ? ex2_approx(fmaf(v[i], TC_LOG2E, -ml2)) : 0.f;
         }
-        unsigned char* sub = prow + (n0 >> 6) * TC_TILE_BYTES;   // keys 0..63 | 64..127: two K-major SWIZZLE_128B tiles
+        {      // four independent partial sums (a single chain of 32 dependent adds stalls the warp), fixed order
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) { a0 += v[i]; a1 += v[i + 1]; a2 += v[i + 2]; a3 += v[i + 3]; }
+          l += (a0 + a1) + (a2 + a3);
+        }
+        unsigned char* sub = prow;                                // this warp's 64-key K-major SWIZZLE_128B sub-tile
         const int j0 = (n0 & 63) >> 3;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -294,18 +308,18 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(smem_u32(&s_empty[sb]));
-        mbar_arrive(smem_u32(&p_full[sb]));
+        mbar_arrive(smem_u32(&p_full[pbuf]));
       }
     }
-    xch[g][row] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    l = xch[0][row] + xch[1][row];
-    // ---- O columns 32..47 = P v_hi, 48..63 = P v_lo   (group 0 writes the tile's output)
-    if (g == 0) {
+    xch[2 * g + half][row] = l;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    l = (xch[0][row] + xch[1][row]) + (xch[2][row] + xch[3][row]);
+    // ---- O columns 32..47 = P v_hi, 48..63 = P v_lo   (the first four warps write the tile's output)
+    if (g == 0 && half == 0) {
       mbar_wait_warp_polite(smem_u32(&o_full), 0);
       tc_fence_after();
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 256u + 32u, v);
+      tmem_ld32(trow0 + 384u + 32u, v);
       const int i = qt * TC_TILE + row;
       if (i < L) {
         const float inv = 1.f / l;
@@ -320,7 +334,7 @@ attn_core_tc_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == 17) tmem_dealloc(tmem_base, 512);
 }
 
 int ss_attention_core_tc(const float* q, const float* k, const float* v, bf16* qp, bf16* kvp, float* o, float* lse, int B,
