@@ -113,7 +113,7 @@ struct GeomOp {        // one lowered GEMM: geometry + (for gathers) epilogue te
 };
 
 struct alignas(64) GMapBox { unsigned char bytes[128]; };
-#define SS_MAX_SIDE 4
+#define SS_MAX_SIDE 8
 
 struct sshslie_engine {
   int B, C, H, W, flags;
@@ -176,20 +176,20 @@ struct sshslie_engine {
   // per-block partial sums of the loss kernels, of the thin weight-gradient kernels and of the bias gradient: everything
   // that used to be an fp32 atomicAdd is a fixed-order reduction over these (deterministic step, main.py:165)
   float *pix_partials = nullptr, *four_partials = nullptr, *final_partials = nullptr, *attn_partials = nullptr;
-  float* bias_partials[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};   // one per side stream
+  float* bias_partials[SS_MAX_SIDE] = {};   // one per side stream
   int pix_rows = 0;
   // split-K partial accumulators of the tcgen05 wgrad (sized for the largest op), one buffer per side stream
-  float* wg_partial[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};
+  float* wg_partial[SS_MAX_SIDE] = {};
   size_t wg_partial_floats = 0;
   int64_t* attn_poff_dummy = nullptr;
 
   // side streams for weight gradients (created at bind; host objects only): consecutive wgrad launches rotate over
   // them, each with its own split-K partial buffer.  In the backward phases the weight-gradient kernels add up to more
   // device time than the data-gradient chain they hide behind, so two streams were not enough to keep up with it.
-  int n_side = SS_MAX_SIDE;
-  cudaStream_t side[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[SS_MAX_SIDE] = {nullptr, nullptr, nullptr, nullptr};
-  bool side_dirty[SS_MAX_SIDE] = {false, false, false, false}, use_side = true;
+  int n_side = 4;
+  cudaStream_t side[SS_MAX_SIDE] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[SS_MAX_SIDE] = {};
+  bool side_dirty[SS_MAX_SIDE] = {}, use_side = true;
   int side_rr = 0;
   cudaStream_t fork(cudaStream_t main_st) {
     if (!use_side || !side[0]) return main_st;
