@@ -181,9 +181,6 @@ SSHSLIE_API float sshslie_conv2d_last_ms(void);
 SSHSLIE_API int sshslie_umma_probe(int N, int n_mma, int n_acc, int commit_every, long long* out_cycles,
                        int n_ctas, void* stream);
 
-/* debugging aid: 16 cycle counters written by block 0 of the last instrumented kernel (host pointer) */
-SSHSLIE_API int sshslie_debug_read(long long* out16);
-
 #ifdef __cplusplus
 }
 #endif

@@ -737,8 +737,8 @@ static const size_t kSmemCore = (2 * AF_LMAX * AF_KP + 2 * AT_D * AF_WP + 2 * AT
 static const size_t kSmem3 = (3 * AT_D * (AT_D + 1) + 3 * TK * AT_D) * sizeof(float);   // 3 weight matrices + 3 token tiles
 static const size_t kSmem2 = (2 * AT_D * (AT_D + 1) + 2 * TK * AT_D) * sizeof(float);
 static int attn_attrs() {
-  static bool done = false;
-  if (done) return 0;
+  static DeviceOnce done;
+  if (done.done()) return 0;
   cudaError_t e = cudaFuncSetAttribute(attn_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_ffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2);
@@ -748,7 +748,7 @@ static int attn_attrs() {
     ss_set_error("attention: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     return SSHSLIE_ERR_CUDA;
   }
-  done = true;
+  done.set();
   return 0;
 }
 

@@ -350,13 +350,13 @@ int ss_attention_core_tc(const float* q, const float* k, const float* v, bf16* q
   rc = ss_umma_encode_view(vq, 64, TC_TILE, 1, 1, &qmap);
   if (!rc) rc = ss_umma_encode_view(vk, 64, TC_TILE, 1, 1, &kvmap);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (!attr_once.done()) {
     if (cudaFuncSetAttribute(attn_core_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess) {
       ss_set_error("attn_core_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_once.set();
   }
   dim3 grid((L + TC_TILE - 1) / TC_TILE, 4, B);
   ss_launch_pdl(attn_core_tc_kernel, grid, dim3(TC_THREADS), (size_t)TC_SMEM, st, qmap, kvmap, o, lse, L);

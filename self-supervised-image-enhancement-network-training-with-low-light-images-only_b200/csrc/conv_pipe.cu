@@ -57,7 +57,6 @@ struct PipeArgs {
   int pad, halo_bytes, tmem_cols, n_tiles;
   int nhb;                     // halo buffers (2..4)
   int lanes;                   // 1 or 2 issuer + epilogue lanes (2 needs 4 accumulators: 4 * Npad <= 512 TMEM columns)
-  int debug;                   // timing experiments only (SSHSLIE_PIPE_DEBUG): 1 no halo reloads, 2 no epilogue work, 4 no MMAs
   int G, n_iter, slots, resident;   // weight chunks of G slabs; `slots` chunk buffers; resident: slots == n_iter, loaded once
   int staged, n_ent, nsb;      // staged epilogue: nsb (1 or 2) staging buffers of n_ent tiles per lane
   int head;                    // EPI_HEAD: the fp32 (b, c, h, w) reflectance tile is staged as [c][16][8] (2 tiles = 32 KB) and
@@ -206,12 +205,6 @@ SS_DEVINL void epi_head16_staged(const Epi& e, int c, bool ok, int b, int oh, in
   }
 }
 
-#ifdef SSHSLIE_PIPE_CRUMBS      // tuning builds only (EXTRA=-DSSHSLIE_PIPE_CRUMBS ./build.sh): cycle breadcrumbs of block 0
-__device__ long long g_pipe_dbg[128];
-#define PDBG(cond, idx) do { if ((cond) && blockIdx.x == 0 && (idx) < 128) g_pipe_dbg[(idx)] = clock64() - ts0; } while (0)
-#else
-#define PDBG(cond, idx) do { } while (0)
-#endif
 
 template <int GU>      // slabs per weight chunk: the MMA issue loop is unrolled over one chunk
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
@@ -230,9 +223,6 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
   __shared__ __align__(16) float bias_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#ifdef SSHSLIE_PIPE_CRUMBS
-  const long long ts0 = clock64();
-#endif
   pdl_launch_dependents();
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* dyn_ptr = smem_dyn + (dyn_base - smem_u32(smem_dyn));
@@ -321,7 +311,7 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
     // ===== halo producer =====
     if (lane == 0) {
       uint32_t hbuf = 0, k = 1;                         // tile i -> buffer i % nhb, use i / nhb
-      for (int i = nhb; i < n_my && !(pa.debug & 1); ++i) {
+      for (int i = nhb; i < n_my; ++i) {
         mbar_wait_polite(smem_u32(&halo_empty[hbuf]), (k & 1u) ^ 1u);
         const uint32_t hb = smem_u32(&halo_full[hbuf]);
         mbar_expect_tx(hb, halo_tx);
@@ -376,11 +366,8 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
         if (!real && resident) break;                     // (streaming: a lane without a tile still releases the chunks)
         const uint32_t ab = (uint32_t)(2 * g + (m & 1)), aph = (uint32_t)((m >> 1) & 1);
         if (real) {
-          if (g == 0 && m < 8) PDBG(lane == 0, m * 4 + 0);
           mbar_wait_warp(ae0 + 8u * ab, aph ^ 1u, 0);       // the epilogue has drained this accumulator
-          if (g == 0 && m < 8) PDBG(lane == 0, m * 4 + 1);
-          if (!(pa.debug & 1) || m * lanes + g < nhb) mbar_wait_warp(hf0 + 8u * hbuf, hph, 0);   // halo windows landed
-          if (g == 0 && m < 8) PDBG(lane == 0, m * 4 + 2);
+          mbar_wait_warp(hf0 + 8u * hbuf, hph, 0);             // halo windows landed
           tc_fence_after();
         }
         const uint32_t a_base = a_lo0 + hbuf * hstep;
@@ -395,7 +382,7 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
           const uint32_t b_c = b_lo0 + slot * cstep;
           const uint32_t acc0 = (it > 0) ? 1u : 0u;
           if (elect_one()) {
-            if (real && !(pa.debug & 4)) {
+            if (real) {
 #pragma unroll
               for (int j = 0; j < GU; ++j)
 #pragma unroll
@@ -412,7 +399,6 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
           __syncwarp();
           if (++slot == (uint32_t)slots) { slot = 0; if (!resident) wph ^= 1u; }
         }
-        if (g == 0 && m < 8) PDBG(lane == 0, m * 4 + 3);
         hbuf += (uint32_t)lanes;
         if (hbuf >= (uint32_t)nhb) { hbuf -= (uint32_t)nhb; hph ^= 1u; }
       }
@@ -423,7 +409,6 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
     if (g < lanes) {
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;
-      const bool crumb = (g == 0 && warp == 0 && lane == 0);
       const uint32_t af0 = smem_u32(&acc_full[0]), ae0 = smem_u32(&acc_empty[0]);
       const uint32_t sf0 = smem_u32(&stg_full[2 * g]), se0 = smem_u32(&stg_empty[2 * g]);
       unsigned char* stg0 = dyn_ptr + stg_off + (uint32_t)g * stg_lane;
@@ -436,25 +421,18 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
         const int oh = t.thi * HALO_TH + (row >> 3), ow = t.twi * HALO_TW + (row & 7);
         const bool ok = oh < pa.OH;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * (uint32_t)Npad;
-        if (m < 8) PDBG(crumb, 32 + m * 8 + 0);
         if (pa.staged) {
           // staging buffer sb of this lane, use u: the TMA stores that last read it have finished reading
           const uint32_t sb = (pa.nsb == 2) ? (uint32_t)(m & 1) : 0u, u = (pa.nsb == 2) ? (uint32_t)(m >> 1) : (uint32_t)m;
           const uint32_t sf = sf0 + 8u * sb, se = se0 + 8u * sb;
           unsigned char* stg = stg0 + sb * stg_buf;
           mbar_wait_warp_polite(se, (u & 1u) ^ 1u);
-          if (m < 8) PDBG(crumb, 32 + m * 8 + 1);
           mbar_wait_warp_polite(af0 + 8u * ab, aph);
-          if (m < 8) PDBG(crumb, 32 + m * 8 + 2);
           tc_fence_after();
-          int n0 = (pa.debug & 2) ? Npad : 0;
+          int n0 = 0;
           for (; n0 + 32 <= Npad; n0 += 32) {
             float v[32];
             tmem_ld32(trow + (uint32_t)n0, v);
-#ifdef SSHSLIE_PIPE_CRUMBS
-            if (__float_as_uint(v[31]) == 0x7fc12345u) g_pipe_dbg[127] = 1;     // forces the scoreboard wait on the TMEM load
-#endif
-            if (m < 8) PDBG(crumb, 32 + m * 8 + (n0 == 0 ? 3 : 5));
             if (pa.head) {
               epi_head16_staged(epi, n0, ok, b, oh, ow, v, bias_s, reinterpret_cast<float*>(stg), row);
               epi_head16_staged(epi, n0 + 16, ok, b, oh, ow, v + 16, bias_s, reinterpret_cast<float*>(stg), row);
@@ -462,7 +440,6 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
               epi_stage16(epi, pa, n0, ok, b, oh, ow, v, bias_s, stg, row);
               epi_stage16(epi, pa, n0 + 16, ok, b, oh, ow, v + 16, bias_s, stg, row);
             }
-            if (m < 8 && n0 == 0) PDBG(crumb, 32 + m * 8 + 4);
           }
           if (n0 < Npad) {
             float v[16];
@@ -470,7 +447,6 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
             if (pa.head) epi_head16_staged(epi, n0, ok, b, oh, ow, v, bias_s, reinterpret_cast<float*>(stg), row);
             else epi_stage16(epi, pa, n0, ok, b, oh, ow, v, bias_s, stg, row);
           }
-          if (m < 8) PDBG(crumb, 32 + m * 8 + 6);
           tc_fence_before();
           fence_proxy_async();                                // staging writes -> visible to the TMA unit
           __syncwarp();
@@ -478,12 +454,10 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
             mbar_arrive(ae0 + 8u * ab);                       // accumulator free: the MMAs of tile i + 2 * lanes may start
             mbar_arrive(sf);                                  // this warp's 32 rows are staged
           }
-          if (m < 8) PDBG(crumb, 32 + m * 8 + 7);
         } else {
           mbar_wait_warp_polite(af0 + 8u * ab, aph);
-          if (m < 8) PDBG(crumb, 32 + m * 8 + 2);
           tc_fence_after();
-          int n0 = (pa.debug & 2) ? Npad : 0;
+          int n0 = 0;
           for (; n0 + 32 <= Npad; n0 += 32) {
             float v[32];
             tmem_ld32(trow + (uint32_t)n0, v);
@@ -500,7 +474,6 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(ae0 + 8u * ab);
-          if (m < 8) PDBG(crumb, 32 + m * 8 + 4);
         }
         tile_next(t);
       }
@@ -514,8 +487,7 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
       for (int i = 0; i < n_my; ++i) {
         const uint32_t sb = (pa.nsb == 2) ? (uint32_t)(m & 1) : 0u, u = (pa.nsb == 2) ? (uint32_t)(m >> 1) : (uint32_t)m;
         mbar_wait_polite(smem_u32(&stg_full[2 * g + sb]), u & 1u);
-        if (i < 8) PDBG(true, 96 + i * 4 + 0);
-        if (!(pa.debug & 2)) {
+        {
           const uint32_t s_u32 = dyn_base + stg_off + (uint32_t)g * stg_lane + sb * stg_buf;
           if (pa.head) {      // fp32 (b, band, h, w) planes: box {8 w, 16 h, 64 bands}
             tma_store_4d(&omaps.m[0], s_u32, t.twi * HALO_TW, t.thi * HALO_TH, 0, t.b);
@@ -525,9 +497,7 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
                            t.thi * HALO_TH, t.b);
           }
           bulk_commit();
-          if (i < 8) PDBG(true, 96 + i * 4 + 1);
           bulk_wait_read0();                                  // the staging buffer has been read: the lane may refill it
-          if (i < 8) PDBG(true, 96 + i * 4 + 2);
         }
         mbar_arrive(smem_u32(&stg_empty[2 * g + sb]));
         tile_next(t);
@@ -553,13 +523,10 @@ struct PipePlan {
 size_t ss_pipe_plan_size() { return sizeof(PipePlan); }
 
 static int sm_count() {
-  static int n = 0;
-  if (n <= 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        n <= 0)
-      n = 148;
-  }
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      n <= 0)
+    n = 148;
   return n;
 }
 
@@ -602,7 +569,6 @@ static int pipe_plan(const ConvGeom& g, const Epi& epi, PipePlan* out) {
       if (pa.src[j] == sl.src && pa.c0[j] == sl.c0) h = j;
     pa.aoff[i] = (uint16_t)((h * pa.halo_bytes + ((sl.dh + pad) * pitch + (sl.dw + pad)) * 128) >> 4);
   }
-  pa.debug = ss_env_int("SSHSLIE_PIPE_DEBUG", 0);
 
   // ---- staged epilogue: staging tiles = 64-channel groups of the main output [, of its bf16 residual] [, of the second
   // output of a column split]
@@ -739,15 +705,15 @@ int ss_launch_conv_gather_pipe(const ConvGeom& g, const UmmaMaps& maps, const Ep
     ss_set_error("conv_gather_pipe: no kernel for %d slabs per chunk", p->pa.G);
     return SSHSLIE_ERR_ARG;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (!attr_once.done()) {
     for (int gi = 1; gi <= 9; ++gi)
       if (kernels[gi] &&
           cudaFuncSetAttribute(kernels[gi], cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BUDGET) != cudaSuccess) {
         ss_set_error("conv_gather_pipe: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
         return SSHSLIE_ERR_CUDA;
       }
-    attr_set = true;
+    attr_once.set();
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -764,8 +730,3 @@ int ss_launch_conv_gather_pipe(const ConvGeom& g, const UmmaMaps& maps, const Ep
   return ss_check_launch("conv_gather_pipe");
 }
 
-#ifdef SSHSLIE_PIPE_CRUMBS
-extern "C" __attribute__((visibility("default"))) int sshslie_pipe_debug_read(long long* out128) {
-  return cudaMemcpyFromSymbol(out128, g_pipe_dbg, sizeof(long long) * 128) == cudaSuccess ? 0 : -2;
-}
-#endif

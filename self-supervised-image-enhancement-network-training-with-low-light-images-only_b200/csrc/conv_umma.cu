@@ -28,13 +28,15 @@
 #define UM_THREADS 192
 
 size_t ss_umma_maps_size() { return sizeof(UmmaMaps); }
-static int g_pdl = -1;
+static std::atomic<int> g_pdl{-1};
 int ss_pdl_enabled() {
-  if (g_pdl < 0) {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = getenv("SSHSLIE_PDL");
-    g_pdl = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl.store(v, std::memory_order_relaxed);
   }
-  return g_pdl;
+  return v;
 }
 
 
@@ -176,7 +178,6 @@ conv_gather_umma4_kernel(const __grid_constant__ ConvGeom4 g4, const __grid_cons
 // 4*HG*T MMAs (the per-slab version of this kernel spent 3x the MMA time in that bookkeeping), and T pixel tiles per
 // CTA share each weight slab.  L2->SM traffic per MMA drops from 6 KB (per-tap kernel) to 2 KB / T.
 // ---------------------------------------------------------------------------------------------
-__device__ long long g_dbg[16];   // timing breadcrumbs of block 0 (SSHSLIE_HALO_DEBUG=64), read by sshslie_debug_read
 #define HALO_MAX_T 4
 #define HALO_MAX_STAGES 8
 
@@ -191,7 +192,6 @@ struct HaloArgs {
   int n_tiles;
   int stages;              // depth of the weight ring (the only operand that streams)
   int G;                   // weight slabs per ring stage
-  int debug;               // 64: block 0 leaves cycle breadcrumbs in g_dbg
   int nslabs, Npad, N, OH, OW;
   uint16_t aoff[SS_MAX_SLABS + 3];   // per slab: (byte offset of its A window inside tile 0's halo block) >> 4.
                                      // Lives in the kernel's constant bank: the MMA loop reads it with uniform loads.
@@ -211,7 +211,6 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
   __shared__ float bias_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ts0 = (ha.debug & 64) ? clock64() : 0;
   pdl_launch_dependents();
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int Npad = ha.Npad, nslabs = ha.nslabs;
@@ -262,7 +261,6 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const long long ts1 = (ha.debug & 64) ? clock64() : 0;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -291,16 +289,12 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
     const uint32_t full0 = uniform32(smem_u32(&full_bar[0])), empty0 = uniform32(smem_u32(&empty_bar[0]));
     const uint32_t accb = uniform32(smem_u32(&accum_bar));
     const uint32_t tstep = (uint32_t)((nh * halo_bytes) >> 4), bstep = b_bytes >> 4, sstep = stage_bytes >> 4;
-    long long c_wait = 0;
     mbar_wait_warp(uniform32(smem_u32(&halo_bar)), 0, 0);
-    if ((ha.debug & 64) && blockIdx.x == 0 && lane == 0) g_dbg[2] = clock64() - ts0;
     uint32_t st = 0, ph = 0;
     int s = 0;
 #pragma unroll 1
     for (int it = 0; it < n_iter; ++it) {
-      const long long q0 = (ha.debug & 64) ? clock64() : 0;
       mbar_wait_warp(full0 + 8u * st, ph, 0);
-      if (ha.debug & 64) c_wait += clock64() - q0;
       tc_fence_after();
       uint32_t b_lo = b_lo0 + st * sstep;
       const int s_end = min(s + G, nslabs);
@@ -321,10 +315,6 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
       }
       s = s_end;
       __syncwarp();
-      if ((ha.debug & 64) && blockIdx.x == 0 && lane == 0) {
-        if (it == 0) g_dbg[3] = clock64() - ts0;
-        if (it == n_iter - 1) { g_dbg[4] = clock64() - ts0; g_dbg[7] = c_wait; }
-      }
       if (++st == (uint32_t)stages) { st = 0; ph ^= 1u; }
     }
   } else {
@@ -349,9 +339,6 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
     asm volatile("bar.sync 1, 128;" ::: "memory");      // bias_s visible to the four epilogue warps
     mbar_wait_warp(smem_u32(&accum_bar), 0, 100u);
     tc_fence_after();
-    if ((ha.debug & 64) && blockIdx.x == 0 && threadIdx.x == 64) {
-      g_dbg[0] = nslabs; g_dbg[1] = ts1 - ts0; g_dbg[5] = clock64() - ts0;
-    }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       int ti = t_first + t;
@@ -377,7 +364,6 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
       }
     }
   }
-  if ((ha.debug & 64) && blockIdx.x == 0 && threadIdx.x == 64) g_dbg[6] = clock64() - ts0;
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)ha.tmem_cols);
@@ -491,7 +477,6 @@ static int halo_args(const ConvGeom& g, HaloArgs* out) {
   stages = std::max(2, std::min(HALO_MAX_STAGES, ss_env_int("SSHSLIE_HALO_STAGES", stages)));
   if (T * ha.nh * ha.halo_bytes + stages * G * b_bytes > 220 * 1024 - 2048) return 0;
   ha.stages = stages;
-  ha.debug = ss_env_int("SSHSLIE_HALO_DEBUG", 0);
   ha.nslabs = g.nslabs; ha.Npad = g.Npad; ha.N = g.N; ha.OH = g.OH; ha.OW = g.OW;
   const int pitch = HALO_TW + 2 * pad;
   for (int i = 0; i < g.nslabs; ++i) {
@@ -569,15 +554,15 @@ int ss_launch_conv_gather_umma(const ConvGeom* g_dev, const ConvGeom& g, const U
   int cols = 32;
   while (cols < g.Npad) cols <<= 1;
   const size_t smem = (size_t)UM_STAGES * (UM_A_BYTES + (size_t)g.Npad * 128) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (!attr_once.done()) {
     if (cudaFuncSetAttribute(conv_gather_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
         cudaSuccess) {
       ss_set_error("conv_gather_umma: cannot raise dynamic shared memory: %s",
                    cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_once.set();
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -777,14 +762,14 @@ int ss_launch_conv_gather_umma4(const ConvGeom* g_dev, const ConvGeom* g4, const
   int cols = 32;
   while (cols < g.Npad) cols <<= 1;
   const size_t smem = (size_t)UM_STAGES * (UM_A_BYTES + (size_t)g.Npad * 128) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (!attr_once.done()) {
     if (cudaFuncSetAttribute(conv_gather_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
         cudaSuccess) {
       ss_set_error("conv_gather_umma4: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_once.set();
   }
   UmmaMaps4 m4;
   ConvGeom4 gg;
@@ -815,8 +800,8 @@ int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g, const U
     return SSHSLIE_ERR_ARG;
   }
   const size_t smem = (size_t)ha.T * ha.nh * ha.halo_bytes + (size_t)ha.stages * ha.G * g.Npad * 128 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (!attr_once.done()) {
     if (cudaFuncSetAttribute(conv_gather_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
             cudaSuccess ||
         cudaFuncSetAttribute(conv_gather_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
@@ -824,7 +809,7 @@ int ss_launch_conv_gather_halo(const ConvGeom* g_dev, const ConvGeom& g, const U
       ss_set_error("conv_gather_halo: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_once.set();
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -945,14 +930,14 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
   WgradArgs wa;
   wgrad_plan(g, gN, bias_off, &wa);
   const size_t smem = (size_t)WG_STAGES * WG_STAGE_BYTES + 2 * WG_G_BYTES + WG_ONES_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (!attr_once.done()) {
     if (cudaFuncSetAttribute(conv_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
         cudaSuccess) {
       ss_set_error("conv_wgrad_umma: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_once.set();
   }
   dim3 grid(wa.splits, wa.groups);
   int rc = SSHSLIE_OK;
@@ -991,7 +976,6 @@ struct WgHaloArgs {
   int n_tiles, tiles_per_cta, splits, groups, pairs_per_group, npairs, blocks_per_cta;
   int stages, stage_bytes;
   int OH, OW;
-  int debug;                   // 64: block (0,0) leaves cycle breadcrumbs in g_dbg
   uint32_t pair_lo[WGH_MAX_PAIRS];   // (window offset of slab a) >> 4  |  ((offset of slab b - offset of slab a) >> 4) << 16
   uint8_t pair_a[WGH_MAX_PAIRS];     // slab indices of the two M halves (pair_b = 255: none)
   uint8_t pair_b[WGH_MAX_PAIRS];
@@ -1008,8 +992,6 @@ SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const 
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool dbg = (wa.debug & 64) && bx == 0 && by == 0;
-  const long long ts0 = dbg ? clock64() : 0;
   const uint32_t dyn_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int nh = wa.nh, pad = wa.pad, stages = wa.stages;
   const uint32_t halo_bytes = (uint32_t)wa.halo_bytes, stage_bytes = (uint32_t)wa.stage_bytes;
@@ -1100,13 +1082,9 @@ SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const 
 #pragma unroll
     for (int p = 0; p < WGH_MAX_GROUP_PAIRS; ++p) plo[p] = uniform32(wa.pair_lo[min(p_begin + p, WGH_MAX_PAIRS - 1)]);
     uint32_t st = 0, ph = 0;
-    long long c_wait = 0;
-    if (dbg && lane == 0 && issuer == 0) g_dbg[1] = clock64() - ts0;
 #pragma unroll 1
     for (int ti = 0; ti < n_t; ++ti) {
-      const long long q0 = dbg ? clock64() : 0;
       mbar_wait_warp(full0 + 8u * st, ph, 0);
-      if (dbg) c_wait += clock64() - q0;
       tc_fence_after();
       const uint32_t s_lo = base_lo + st * sstep;
       const uint32_t acc0 = (ti > 0) ? 1u : 0u;
@@ -1127,10 +1105,6 @@ SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const 
         if (ti == n_t - 1) umma_commit(accb);
       }
       __syncwarp();
-      if (dbg && lane == 0 && issuer == 0) {
-        if (ti == 0) g_dbg[3] = clock64() - ts0;
-        if (ti == ntiles - 1) { g_dbg[4] = clock64() - ts0; g_dbg[7] = c_wait; g_dbg[0] = ntiles; }
-      }
       if (++st == nstages) { st = 0; ph ^= 1u; }
     }
   }
@@ -1139,7 +1113,6 @@ SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const 
     const int row = quarter * 32 + lane;
     mbar_wait_warp(smem_u32(&accum_bar), 0, 200);
     tc_fence_after();
-    if (dbg && threadIdx.x == 96) g_dbg[5] = clock64() - ts0;
     // partial[split][group][block][n][row]: lanes = consecutive rows -> 128-byte coalesced stores, no atomics
     float* out = partial + ((size_t)(bx * wa.groups + group) * wa.blocks_per_cta) * (size_t)wa.N * 128;
     const int nblocks = (p_end - p_begin) + (do_bias ? 1 : 0);
@@ -1153,7 +1126,6 @@ SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const 
       }
     }
   }
-  if (dbg && threadIdx.x == 96) g_dbg[6] = clock64() - ts0;
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)wa.tmem_cols);
@@ -1165,40 +1137,6 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
   wgrad_halo_body(maps.halo, &gmap, wa, partial, (int)blockIdx.x, (int)blockIdx.y);
 }
 
-// ---- grouped launch: the weight gradients of SEVERAL layers in one grid.  At the training batch a single layer's
-// split-K grid (32-64 CTAs) cannot fill 148 SMs and pays its first-load latency, epilogue and launch alone; one grid over
-// the jobs of a backward segment lets the CTAs of different layers share the SMs.  Job descriptors (tensor maps, pair
-// tables, split-K buffer) live in global memory; a CTA finds its job through the small table in the kernel parameters.
-struct alignas(64) WgJob {
-  CUtensorMap halo[SS_MAX_SRC];
-  CUtensorMap gmap;
-  WgHaloArgs wa;
-  float* partial;
-  int geom;                        // index into the plan's geom table (weight addressing of the reduce)
-  int smem_bytes;
-};
-#define WG_GROUP_MAX 12
-struct WgGroupTable {
-  int njobs;
-  int job[WG_GROUP_MAX];
-  int cta_start[WG_GROUP_MAX + 1];
-  int red_start[WG_GROUP_MAX + 1];
-};
-__global__ void __launch_bounds__(UM_THREADS, 1)
-conv_wgrad_halo_group_kernel(const WgJob* __restrict__ jobs, const __grid_constant__ WgGroupTable tbl) {
-  __shared__ WgHaloArgs swa;
-  int j = 0;
-  while (j + 1 < tbl.njobs && (int)blockIdx.x >= tbl.cta_start[j + 1]) ++j;
-  const WgJob* job = jobs + tbl.job[j];
-  {
-    const int* src = reinterpret_cast<const int*>(&job->wa);
-    int* dst = reinterpret_cast<int*>(&swa);
-    for (int i = threadIdx.x; i < (int)(sizeof(WgHaloArgs) / 4); i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  const int local = (int)blockIdx.x - tbl.cta_start[j];
-  wgrad_halo_body(job->halo, &job->gmap, swa, job->partial, local % swa.splits, local / swa.splits);
-}
 // second stage for the halo kernel: same partial layout as conv_wgrad_reduce_kernel, slab mapping through the pair table.
 // One thread per output element (accumulator row, column): it adds the `splits` partials of its element in a fixed order,
 // eight independent loads in flight at a time (the previous version - 1024-thread blocks that met in shared memory - ran
@@ -1242,28 +1180,6 @@ __global__ void __launch_bounds__(256) conv_wgrad_halo_reduce_kernel(const ConvG
                                                                      float* __restrict__ grads) {
   wgrad_halo_reduce_body(gp, partial, wa, grads, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z * 2 + (int)threadIdx.y);
 }
-// grouped reduce: blockIdx.x runs over (job, blk, group, n0 / 8)
-__global__ void __launch_bounds__(256) conv_wgrad_halo_reduce_group_kernel(const ConvGeom* __restrict__ geoms,
-                                                                            const WgJob* __restrict__ jobs,
-                                                                            const __grid_constant__ WgGroupTable tbl,
-                                                                            float* __restrict__ grads) {
-  __shared__ WgHaloArgs swa;
-  int j = 0;
-  while (j + 1 < tbl.njobs && (int)blockIdx.x >= tbl.red_start[j + 1]) ++j;
-  const WgJob* job = jobs + tbl.job[j];
-  {
-    const int* src = reinterpret_cast<const int*>(&job->wa);
-    int* dst = reinterpret_cast<int*>(&swa);
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    for (int i = tid; i < (int)(sizeof(WgHaloArgs) / 4); i += blockDim.x * blockDim.y) dst[i] = src[i];
-  }
-  __syncthreads();
-  int local = (int)blockIdx.x - tbl.red_start[j];
-  const int blk = local % swa.blocks_per_cta; local /= swa.blocks_per_cta;
-  const int group = local % swa.groups;
-  const int n = (local / swa.groups) * 2 + (int)threadIdx.y;
-  wgrad_halo_reduce_body(geoms + job->geom, job->partial, swa, grads, blk, group, n);
-}
 
 static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHaloArgs* out) {
   HaloArgs ha;
@@ -1277,7 +1193,6 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   wa.N = (gN > 64) ? 128 : 64;
   wa.g_atoms = wa.N / 64;
   wa.OH = g.OH; wa.OW = g.OW;
-  wa.debug = ss_env_int("SSHSLIE_HALO_DEBUG", 0);
   // tap pairs over the slabs that carry weights of their own (residual "lo" slabs are skipped), lower window first
   int slabs[SS_MAX_SLABS], ns = 0;
   for (int i = 0; i < g.nslabs; ++i)
@@ -1355,14 +1270,14 @@ int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const Um
   // this one exits (up to 25 us added to a 7 us kernel of the critical path).  Asking for more shared memory than a
   // gather CTA leaves free keeps them apart.
   if (wa.tmem_cols > 256) smem = std::max(smem, (size_t)ss_env_int("SSHSLIE_WGH_SMEM_KB", 160) * 1024);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (!attr_once.done()) {
     if (cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
         cudaSuccess) {
       ss_set_error("conv_wgrad_halo: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_once.set();
   }
   dim3 grid(wa.splits, wa.groups);
   int rc = SSHSLIE_OK;
@@ -1376,68 +1291,6 @@ int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const Um
   return ss_check_launch("conv_wgrad_halo_reduce");
 }
 
-size_t ss_wgjob_size() { return sizeof(WgJob); }
-int ss_umma_wgrad_halo_smem(const ConvGeom& g, int gN) {
-  WgHaloArgs wa;
-  if (!wgrad_halo_plan(g, gN, -1, &wa)) return 0;
-  return wa.stages * wa.stage_bytes + WGH_ONES_BYTES + 1024;
-}
-// fills one job descriptor (host copy, uploaded by the engine); returns 0 if the layer is not taken by the halo kernel
-int ss_wgjob_build(const ConvGeom& g, const UmmaMaps& maps, const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld,
-                   int gN, long long bias_off, float* partial, int geom_index, void* out) {
-  WgJob job;
-  memset(&job, 0, sizeof(job));
-  if (!wgrad_halo_plan(g, gN, bias_off, &job.wa)) {
-    ss_set_error("wgrad job: geometry not eligible for the halo kernel");
-    return SSHSLIE_ERR_ARG;
-  }
-  for (int i = 0; i < SS_MAX_SRC; ++i) job.halo[i] = maps.halo[i];
-  const int rc = ss_umma_build_gmap_halo(G, gB, gH, gW, ld, g, &job.gmap);
-  if (rc) return rc;
-  job.partial = partial;
-  job.geom = geom_index;
-  job.smem_bytes = job.wa.stages * job.wa.stage_bytes + WGH_ONES_BYTES + 1024;
-  memcpy(out, &job, sizeof(job));
-  return SSHSLIE_OK;
-}
-int ss_wgjob_smem(const void* job_host) { return reinterpret_cast<const WgJob*>(job_host)->smem_bytes; }
-int ss_launch_wgrad_group(const void* jobs_dev, const void* jobs_host, const int* ids, int n, const ConvGeom* geoms_dev,
-                          float* grads, cudaStream_t st) {
-  if (n < 1 || n > WG_GROUP_MAX) {
-    ss_set_error("wgrad group: %d jobs (1..%d supported)", n, WG_GROUP_MAX);
-    return SSHSLIE_ERR_ARG;
-  }
-  const WgJob* hj = reinterpret_cast<const WgJob*>(jobs_host);
-  WgGroupTable tbl;
-  memset(&tbl, 0, sizeof(tbl));
-  tbl.njobs = n;
-  int smem = 0;
-  for (int i = 0; i < n; ++i) {
-    const WgHaloArgs& wa = hj[ids[i]].wa;
-    tbl.job[i] = ids[i];
-    tbl.cta_start[i + 1] = tbl.cta_start[i] + wa.splits * wa.groups;
-    tbl.red_start[i + 1] = tbl.red_start[i] + wa.blocks_per_cta * wa.groups * (wa.N / 2);
-    smem = std::max(smem, hj[ids[i]].smem_bytes);
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_wgrad_halo_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
-        cudaSuccess) {
-      ss_set_error("wgrad group: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
-      return SSHSLIE_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  int rc = SSHSLIE_OK;
-  if (g_wgrad_part != 2) {
-    conv_wgrad_halo_group_kernel<<<tbl.cta_start[n], UM_THREADS, smem, st>>>(reinterpret_cast<const WgJob*>(jobs_dev), tbl);
-    rc = ss_check_launch("conv_wgrad_halo_group");
-    if (rc || g_wgrad_part == 1) return rc;
-  }
-  conv_wgrad_halo_reduce_group_kernel<<<tbl.red_start[n], dim3(128, 2), 0, st>>>(
-      geoms_dev, reinterpret_cast<const WgJob*>(jobs_dev), tbl, grads);
-  return ss_check_launch("conv_wgrad_halo_reduce_group");
-}
 
 // ---------------------------------------------------------------------------------------------
 // tcgen05.mma issue-rate probe (tools/umma_probe.py): a chain of n_mma bf16 MMAs (M=128, N, K=16) on operands already
@@ -1519,6 +1372,3 @@ extern "C" SSHSLIE_API int sshslie_umma_probe(int N, int n_mma, int n_acc, int c
   return ss_check_launch("umma_probe");
 }
 
-extern "C" SSHSLIE_API int sshslie_debug_read(long long* out16) {
-  return cudaMemcpyFromSymbol(out16, g_dbg, sizeof(long long) * 16) == cudaSuccess ? SSHSLIE_OK : SSHSLIE_ERR_CUDA;
-}

@@ -38,9 +38,9 @@ static void prof_note(const std::string& label, double flops, double bytes) {
   g_prof_flops += flops;
   g_prof_bytes += bytes;
 }
-static long long g_launch_count = 0;   // kernels of this library enqueued so far (bench.py's gpu_launches)
+static std::atomic<long long> g_launch_count{0};  // kernels of this library enqueued so far (bench.py's gpu_launches)
 void ss_count_launches(int n) { g_launch_count += n; }
-extern "C" SSHSLIE_API long long sshslie_launch_count(void) { return g_launch_count; }
+extern "C" SSHSLIE_API long long sshslie_launch_count(void) { return g_launch_count.load(); }
 int ss_check_launch(const char* what) {
   g_launch_count += 1;
   if (g_prof_on && g_prof_names.find(':') == std::string::npos) {
@@ -120,15 +120,7 @@ struct sshslie_engine {
   std::map<std::pair<int, const void*>, GMapBox> gmaps;   // wgrad G-tensor TMA descriptors
   bool train, force_simt;
   bool skip_wgrad = false;
-  // grouped halo weight gradients: jobs recorded while the plan is built, descriptors built at bind, uploaded once
-  struct WgJobRec { int gi; Tens G; int gN; int bias_layer; float* partial; };
-  std::vector<WgJobRec> wg_jobs;
-  std::vector<int> wg_pending;            // job ids waiting for the next flush (plan construction only)
-  std::vector<unsigned char> wg_jobs_host;
-  void* wg_jobs_dev = nullptr;
-  bool group_wgrad = false;               // SSHSLIE_WGRAD_GROUP=1: several layers per launch (measured: no gain)
   bool halo_on = true;
-  int group_size = 4;                     // pending jobs that trigger a grouped launch (SSHSLIE_WGRAD_GROUP_SIZE)
   bool wgrad_halo = true;               // SSHSLIE_WGRAD_HALO=0 keeps the per-tap weight-gradient kernel
   int64_t ws_bytes = 0;
   unsigned char* ws = nullptr;
@@ -556,59 +548,10 @@ static WAddr waddr_conv_dgrad(const sshslie_engine* e, int layer, int n_off = 0)
   (vec).push_back([=](cudaStream_t main_st) -> int { cudaStream_t st = e->fork(main_st); __VA_ARGS__ })
 #define PUSH_JOIN(vec) (vec).push_back([=](cudaStream_t st) -> int { return e->join(st); })
 
-#define WG_MAX_JOBS 64
-static int run_wgrad_group(sshslie_engine* e, const std::array<int, 12>& ids, int n, cudaStream_t st) {
-  if (e->skip_wgrad) return SSHSLIE_OK;
-  std::string lbl = "wgrad:";
-  double fl = 0;
-  for (int i = 0; i < n; ++i) {
-    const sshslie_engine::WgJobRec& j = e->wg_jobs[ids[i]];
-    const int l = e->geom_layer[j.gi];
-    lbl += (i ? "+" : "");
-    lbl += (l >= 0 && l < L_COUNT) ? kLayerNames[l] : "layer";
-    fl += geom_flops(e->geoms[j.gi]) * (double)j.gN / (double)e->geoms[j.gi].N;
-  }
-  lbl += n > 1 ? "[tcgen05-halo-grouped]" : "[tcgen05-halo]";
-  prof_note(lbl, fl, 0);
-  return ss_launch_wgrad_group(e->wg_jobs_dev, e->wg_jobs_host.data(), ids.data(), n, e->geoms_dev, e->grads, st);
-}
-// push one grouped launch for the pending jobs (side stream)
-static void flush_wgrads(sshslie_engine* e, std::vector<sshslie_engine::OpFn>& ops) {
-  while (!e->wg_pending.empty()) {
-    std::array<int, 12> ids;
-    int n = 0;
-    while (n < 12 && !e->wg_pending.empty()) { ids[n++] = e->wg_pending.front(); e->wg_pending.erase(e->wg_pending.begin()); }
-    PUSH_SIDE(ops, return run_wgrad_group(e, ids, n, st););
-  }
-}
-// a layer's weight gradient: recorded as a job of the next grouped launch when the halo kernel takes it, else launched
-// on its own (stride-2 layers, CUDA-core fallback)
+// a layer's weight gradient, forked onto a side stream
 static void queue_wgrad(sshslie_engine* e, std::vector<sshslie_engine::OpFn>& ops, int gi, const Tens& G, int gN,
                         int bias_layer) {
-  const ConvGeom& g = e->geoms[gi];
-  const bool eligible = e->group_wgrad && e->halo_on && e->wgrad_halo && !e->force_simt && g.halo_ok &&
-                        ss_umma_halo_supported(g) && ss_umma_wgrad_halo_supported(g, gN) &&
-                        (int)e->wg_jobs.size() < WG_MAX_JOBS;
-  if (!eligible) {
-    PUSH_SIDE(ops, return run_wgrad(e, gi, G, gN, 0, 0, 1, st, bias_layer););
-    return;
-  }
-  sshslie_engine::WgJobRec r;
-  r.gi = gi; r.G = G; r.gN = gN; r.bias_layer = bias_layer;
-  r.partial = e->falloc((int64_t)ss_umma_wgrad_halo_partial_floats(g, gN));
-  const int id = (int)e->wg_jobs.size();
-  e->wg_jobs.push_back(r);
-  // big-footprint jobs (the 9x9 layer: 65 KB per stage; 128-channel layers) go alone: a mixed grid would give every CTA
-  // their footprint
-  const bool big = ss_umma_wgrad_halo_smem(g, gN) > 110 * 1024;     // cannot share an SM with a second CTA anyway
-  if (big) {
-    flush_wgrads(e, ops);
-    e->wg_pending.push_back(id);
-    flush_wgrads(e, ops);
-    return;
-  }
-  e->wg_pending.push_back(id);
-  if ((int)e->wg_pending.size() >= e->group_size) flush_wgrads(e, ops);
+  PUSH_SIDE(ops, return run_wgrad(e, gi, G, gN, 0, 0, 1, st, bias_layer););
 }
 
 // forward of one DecompositionNet pass (model.py:49-70).  Returns the geom ids for reuse by the backward pass.
@@ -802,8 +745,6 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   e->ops_fwd.clear();
   e->ops_loss_bwd2_illum.clear();
   e->ops_bwd1.clear();
-  e->wg_jobs.clear();
-  e->wg_pending.clear();
   const int B = e->B, C = e->C, H = e->H, W = e->W;
   const int64_t n = (int64_t)B * H * W;
   const bool train = e->train;
@@ -812,7 +753,6 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   e->geoms_dev = (ConvGeom*)e->alloc(sizeof(ConvGeom) * 128);
   e->pack_start_dev = (int*)e->alloc(sizeof(int) * 130);
   e->mask_dev = e->falloc((int64_t)H * W);
-  e->wg_jobs_dev = e->alloc((int64_t)ss_wgjob_size() * WG_MAX_JOBS);
   if (train) {
     e->pix_rows = ss_pixel_losses_blocks(B, C, H, W);
     e->pix_partials = e->falloc((int64_t)e->pix_rows * 9);
@@ -988,7 +928,6 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     Tens dc8 = e->talloc(B, H, W, 128, true);
     PUSH(Lq, return ss_launch_head_bwd(dRe32, Re32, nullptr, 0, nullptr, nullptr, dc8.p, 128, B, C, H, W, st););
     plan_decomp_bwd(e, Lq, Sb, d2, G2, dc8, C, gr, true);
-    flush_wgrads(e, Lq);      // pass-2 weight gradients run beside the illumination net's backward chain
     // S = R*(Id+I)
     PUSH(Lq, return ss_launch_s_bwd(dS32, dSf32, gr.din.p, e->R32, e->I32, e->Id32, dR32, dI32, dId32, B, C, H, W, st););
 
@@ -1088,14 +1027,12 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
       Epi ep = epi_bf16(dRI, (C + 1 + 15) / 16 * 16);
       PUSH(Lq, return run_gather(e, gi, ep, -1, st););
     }
-    flush_wgrads(e, Lq);
     PUSH_JOIN(Lq);
 
     // ---- backward, pass 1 -------------------------------------------------------------------
     auto& B1 = e->ops_bwd1;
     PUSH(B1, return ss_launch_head_bwd(dR32, e->R32, dRI.p, 128, dI32, e->I32, dc8.p, 128, B, C, H, W, st););
     plan_decomp_bwd(e, B1, X, d1, G1, dc8, C + 1, gr, false);
-    flush_wgrads(e, B1);
     PUSH_JOIN(B1);
   }
 
@@ -1184,10 +1121,6 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
   {
     const char* we = getenv("SSHSLIE_WGRAD_HALO");
     e->wgrad_halo = !(we && we[0] == '0');
-    const char* gw = getenv("SSHSLIE_WGRAD_GROUP");
-    e->group_wgrad = (gw && gw[0] == '1');
-    const char* gs = getenv("SSHSLIE_WGRAD_GROUP_SIZE");
-    if (gs && atoi(gs) >= 1 && atoi(gs) <= 12) e->group_size = atoi(gs);
     const char* he0 = getenv("SSHSLIE_HALO");
     e->halo_on = !(he0 && he0[0] == '0');
     const char* pe = getenv("SSHSLIE_PIPE");
@@ -1257,23 +1190,6 @@ extern "C" int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t w
       const bool halo_on = !(he && he[0] == '0');  // halo-reuse kernels for every stride-1 layer; SSHSLIE_HALO=0 = per-tap
       e->geom_umma[i] = (halo_on && e->geoms[i].halo_ok && ss_umma_halo_supported(e->geoms[i])) ? 2 : 1;
     }
-  }
-  // grouped weight-gradient jobs: descriptors need the final tensor maps and pointers
-  e->wg_jobs_host.assign(e->wg_jobs.size() * ss_wgjob_size(), 0);
-  for (size_t j = 0; j < e->wg_jobs.size(); ++j) {
-    const sshslie_engine::WgJobRec& r = e->wg_jobs[j];
-    const Tens& G = r.G;
-    rc = ss_wgjob_build(e->geoms[r.gi], *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + r.gi * msz), G.p,
-                        (int64_t)G.H * G.W * G.ld, (int64_t)G.W * G.ld, (int64_t)G.ld, G.ld, r.gN,
-                        r.bias_layer >= 0 ? (long long)e->poff[2 * r.bias_layer + 1] : -1LL, r.partial, r.gi,
-                        e->wg_jobs_host.data() + j * ss_wgjob_size());
-    if (rc != SSHSLIE_OK) return rc;
-  }
-  if (!e->wg_jobs_host.empty() &&
-      cudaMemcpyAsync(e->wg_jobs_dev, e->wg_jobs_host.data(), e->wg_jobs_host.size(), cudaMemcpyHostToDevice, st) !=
-          cudaSuccess) {
-    ss_set_error("bind: job table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return SSHSLIE_ERR_CUDA;
   }
   for (auto& zr : e->zero_ranges)
     if (cudaMemsetAsync(e->ws + zr.first, 0, (size_t)zr.second, st) != cudaSuccess) {
@@ -1360,8 +1276,8 @@ extern "C" int sshslie_loss_and_grad(sshslie_engine* e, const float* x, const fl
 // single-layer entry point for kernel-level parity tests (tests/test_gpu_conv.py)
 // ---------------------------------------------------------------------------------------------
 static int pad64(int c) { return (c + 63) / 64 * 64; }
-static float g_conv2d_last_ms = 0.f;
-extern "C" SSHSLIE_API float sshslie_conv2d_last_ms(void) { return g_conv2d_last_ms; }
+static std::atomic<float> g_conv2d_last_ms{0.f};
+extern "C" SSHSLIE_API float sshslie_conv2d_last_ms(void) { return g_conv2d_last_ms.load(); }
 
 extern "C" int64_t sshslie_conv2d_scratch_bytes(int B, int Cin, int Cout, int H, int W, int k, int stride) {
   (void)k;

@@ -402,28 +402,28 @@ int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS
   if (reg_fft && H == F128_N && W == F128_N && ((uintptr_t)x & 15) == 0 && ((uintptr_t)S & 15) == 0 &&
       (!dS || ((uintptr_t)dS & 15) == 0)) {
     const size_t smem128 = (size_t)(F128_N * F128_PITCH + F128_N) * sizeof(float2);
-    static bool attr128 = false;
-    if (!attr128) {
+    static DeviceOnce attr128;
+    if (!attr128.done()) {
       if (cudaFuncSetAttribute(fourier_loss128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128) !=
           cudaSuccess) {
         ss_set_error("sshslie_fourier_loss: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
         return SSHSLIE_ERR_CUDA;
       }
-      attr128 = true;
+      attr128.set();
     }
     fourier_loss128_kernel<<<n_img, F128_THREADS, smem128, stream>>>(x, S, mask, dS, partial_out, grad_scale, accumulate);
     return ss_check_launch("fourier_loss128");
   }
   const size_t smem = (size_t)H * W * sizeof(float2) + 128 * sizeof(float2);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (!attr_once.done()) {
     if (cudaFuncSetAttribute(fourier_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
         cudaSuccess) {
       ss_set_error("sshslie_fourier_loss: cannot raise dynamic shared memory: %s",
                    cudaGetErrorString(cudaGetLastError()));
       return SSHSLIE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_once.set();
   }
   fourier_loss_kernel<<<n_img, FFT_THREADS, smem, stream>>>(x, S, mask, dS, partial_out, H, W, lgH, lgW, grad_scale,
                                                             accumulate);

@@ -1,10 +1,21 @@
 // Host-callable launchers of every kernel (internal header; the public ABI is include/sshslie_b200.h).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include "plan.h"
 #include "../../include/sshslie_b200.h"
 
 // conv_simt.cu
+
+// "already done on this device" flag for the cudaFuncSetAttribute calls of the launchers: the attribute is per device, so a
+// process that drives several GPUs sets it on each; two threads that race both set it (idempotent)
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool done() const { return (mask.load(std::memory_order_acquire) >> dev()) & 1ull; }
+  void set() { mask.fetch_or(1ull << dev(), std::memory_order_release); }
+};
+
 int ss_launch_conv_gather_simt(const ConvGeom* g_dev, const ConvGeom& g_host, const Epi& epi, cudaStream_t st);
 int ss_launch_conv_wgrad_simt(const ConvGeom* g_dev, const ConvGeom& g_host, const bf16* G, int64_t gB, int64_t gH,
                               int64_t gW, int gN, float* grads, cudaStream_t st);
@@ -31,14 +42,6 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g_host, con
                               int gN, long long bias_off, float* partial, float* grads, cudaStream_t st);
 size_t ss_umma_wgrad_partial_floats(const ConvGeom& g, int gN);
 size_t ss_umma_maps_size();
-// grouped halo weight gradients: job descriptors built on the host, uploaded once, launched several per grid
-size_t ss_wgjob_size();
-int ss_umma_wgrad_halo_smem(const ConvGeom& g, int gN);   // dynamic shared memory of the layer's halo wgrad CTA
-int ss_wgjob_build(const ConvGeom& g, const UmmaMaps& maps, const bf16* G, int64_t gB, int64_t gH, int64_t gW, int ld,
-                   int gN, long long bias_off, float* partial, int geom_index, void* out_host);
-int ss_wgjob_smem(const void* job_host);
-int ss_launch_wgrad_group(const void* jobs_dev, const void* jobs_host, const int* ids, int n, const ConvGeom* geoms_dev,
-                          float* grads, cudaStream_t st);
 void ss_set_wgrad_part(int part);   // profiling: 0 both kernels, 1 GEMM only, 2 split-K reduce only
 // halo-reuse weight gradient (stride-1 layers): G tiles are 16x8 like the halo tiles
 int ss_umma_wgrad_halo_supported(const ConvGeom& g, int gN);

@@ -443,14 +443,14 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
   p.k_sp = (float)(cfg.c_loss_spectral_cons / ((double)B * (C - 1) * H * W));
   if (pixel_tiled(C, H, W)) {
     const size_t smem = (size_t)2 * PT_C * PT_PLANE * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (!attr_once.done()) {
       if (cudaFuncSetAttribute(pixel_losses_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
           cudaSuccess) {
         ss_set_error("pixel_losses: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
         return SSHSLIE_ERR_CUDA;
       }
-      attr_set = true;
+      attr_once.set();
     }
     dim3 grid(W / PT_TW, H / PT_TH, B), block(PT_PIX, PL_CHUNKS);
     ss_launch_pdl(pixel_losses_tiled_kernel, dim3(grid), dim3(block), (size_t)(smem), st, p);

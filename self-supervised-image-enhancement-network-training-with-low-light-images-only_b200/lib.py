@@ -20,7 +20,7 @@ EXPORTS = [
     "sshslie_engine_destroy", "sshslie_engine_workspace_bytes", "sshslie_engine_bind", "sshslie_forward",
     "sshslie_loss_and_grad", "sshslie_adam_step", "sshslie_loss_scratch_bytes", "sshslie_fourier_loss", "sshslie_pixel_losses",
     "sshslie_conv2d_scratch_bytes", "sshslie_conv2d", "sshslie_profile_step", "sshslie_profile_row",
-    "sshslie_launch_count", "sshslie_umma_probe", "sshslie_debug_read", "sshslie_gather_patches", "sshslie_conv2d_last_ms", "sshslie_denorm_hwc", "sshslie_psnr_sam", "sshslie_ssim_sum",
+    "sshslie_launch_count", "sshslie_umma_probe", "sshslie_gather_patches", "sshslie_conv2d_last_ms", "sshslie_denorm_hwc", "sshslie_psnr_sam", "sshslie_ssim_sum",
     "sshslie_transformer_block_scratch_bytes", "sshslie_transformer_block",
 ]
 
