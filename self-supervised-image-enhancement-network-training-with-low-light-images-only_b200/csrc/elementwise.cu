@@ -436,13 +436,28 @@ int ss_launch_pool2(const bf16* du, const bf16* addp, const bf16* maskr, bf16* o
 
 // ---------------------------------------------------------------------------------------------
 // fixed-order reduction of per-block partials into the flat gradient buffer (deterministic replacement of fp32 atomics)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partials, int nrows, int ncols,
-                                                          const __grid_constant__ RedSegs segs) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ncols) return;
+// block = (32 columns, 32 row parts): part q adds rows q, q + 32, ... (independent loads), the 32 parts of a column are then
+// combined in a fixed order through shared memory.  (One thread per column walking all rows took 22 us on 512 rows.)
+__global__ void __launch_bounds__(1024) reduce_rows_kernel(const float* __restrict__ partials, int nrows, int ncols,
+                                                           const __grid_constant__ RedSegs segs) {
+  __shared__ float part[32][33];
+  const int j = blockIdx.x * 32 + threadIdx.x, q = threadIdx.y;
   float t = 0.f;
-  for (int r = 0; r < nrows; ++r) t += partials[(size_t)r * ncols + j];
+  if (j < ncols) {
+    int r = q;
+    for (; r + 96 < nrows; r += 128) {
+      const float a = partials[(size_t)r * ncols + j], b = partials[(size_t)(r + 32) * ncols + j];
+      const float c = partials[(size_t)(r + 64) * ncols + j], d = partials[(size_t)(r + 96) * ncols + j];
+      t += a; t += b; t += c; t += d;
+    }
+    for (; r < nrows; r += 32) t += partials[(size_t)r * ncols + j];
+  }
+  part[q][threadIdx.x] = t;
+  __syncthreads();
+  if (q != 0 || j >= ncols) return;
+  t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) t += part[i][threadIdx.x];
   int o = j;
   for (int s = 0; s < segs.n; ++s) {
     if (o < segs.len[s]) { segs.dst[s][o] += t; return; }
@@ -450,7 +465,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
   }
 }
 int ss_launch_reduce_rows(const float* partials, int nrows, int ncols, const RedSegs& segs, cudaStream_t st) {
-  reduce_rows_kernel<<<(ncols + 255) / 256, 256, 0, st>>>(partials, nrows, ncols, segs);
+  reduce_rows_kernel<<<(ncols + 31) / 32, dim3(32, 32), 0, st>>>(partials, nrows, ncols, segs);
   EW_CHECK("reduce_rows");
 }
 

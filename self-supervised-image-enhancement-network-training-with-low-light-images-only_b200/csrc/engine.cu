@@ -755,7 +755,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   e->mask_dev = e->falloc((int64_t)H * W);
   if (train) {
     e->pix_rows = ss_pixel_losses_blocks(B, C, H, W);
-    e->pix_partials = e->falloc((int64_t)e->pix_rows * 9);
+    e->pix_partials = e->falloc(ss_pixel_losses_scratch_floats(B, C, H, W));
     e->four_partials = e->falloc((int64_t)B * C);
     e->final_partials = e->falloc((int64_t)FINAL_WGRAD_MAX_BLOCKS * 577);
     e->attn_partials = e->falloc((int64_t)SS_ATTN_WGRAD_MAX_BLOCKS * SS_ATTN_WGRAD_COLS);

@@ -110,5 +110,6 @@ int ss_attention_backward_weights(const float* dt, float* grads, const int64_t* 
 int ss_pixel_losses(const float* x, const float* R, const float* I, const float* Id, const float* Re,
                     const sshslie_loss_cfg& cfg, int B, int C, int H, int W, float* partials, float* dR, float* dI,
                     float* dId, float* dS, float* dRe, cudaStream_t st);
+int64_t ss_pixel_losses_scratch_floats(int B, int C, int H, int W);   // partial rows + edge-weight maps
 int ss_pixel_losses_blocks(int B, int C, int H, int W);       // rows of 9 partial sums ss_pixel_losses writes
 int ss_reduce_partials(const float* partials, int nrows, int ncols, float* out, int accumulate, cudaStream_t st);

@@ -396,15 +396,277 @@ __global__ void __launch_bounds__(PT_PIX* PL_CHUNKS) pixel_losses_tiled_kernel(P
   (void)nthreads;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row-streaming variant (W % 128 == 0): no shared-memory staging.  A warp owns 128 consecutive pixels of one image row
+// (one float4 per lane: every global access is a full 512-byte row segment) and one eighth of the band axis; horizontal
+// neighbours come from the adjacent lanes by shuffle, the rows above and below from global memory (the second row of the
+// block / the L1 hold them).  Image borders are handled by CLAMPING the neighbour to the pixel itself: the difference is then
+// exactly 0, sgn(0) = 0, and every term of the absent edge vanishes without a branch.
+// The band-mean edge weights of L_I_smooth_low need all 64 bands before the main sweep can start, so they are produced by a
+// small kernel of their own (edge_weights_rows_kernel: one more read of R, 2 maps of B*H*W floats out).
+//   grid = (W / 128, ceil(H / RW_TH), B), block = (32, 8 band chunks, RW_TH rows)
+// ---------------------------------------------------------------------------------------------
+#define RW_TH 2
+SS_DEVINL float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+SS_DEVINL void f4_to(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+
+__global__ void __launch_bounds__(32 * PL_CHUNKS) edge_weights_rows_kernel(PixLossArgs p, float* __restrict__ wx,
+                                                                          float* __restrict__ wy) {
+  SS_PDL_ENTRY();
+  __shared__ float4 part[PL_CHUNKS][2][32];
+  const int W = p.W, H = p.H, C = p.C, HW = H * W;
+  const int lane = threadIdx.x, k = threadIdx.y;
+  const int w0 = blockIdx.x * 128 + lane * 4, h = blockIdx.y, b = blockIdx.z;
+  const int cpc = (C + PL_CHUNKS - 1) / PL_CHUNKS;
+  const int c_begin = k * cpc, c_end = min(C, c_begin + cpc);
+  const int dn = (h + 1 < H) ? W : 0;                       // clamped: the last row is its own lower neighbour
+  const bool edge_r = (lane == 31), has_next = (w0 + 4 < W);
+  const float* base = p.R + ((int64_t)b * C * H + h) * W + w0;
+  float mx[4] = {0.f, 0.f, 0.f, 0.f}, my[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int c = c_begin; c < c_end; ++c) {
+    const float* q = base + (int64_t)c * HW;
+    const float4 r0 = ldg4(q), rd = ldg4(q + dn);
+    float rn = __shfl_down_sync(0xffffffffu, r0.x, 1);
+    if (edge_r) rn = has_next ? __ldg(q + 4) : r0.w;
+    mx[0] += fabsf(r0.y - r0.x); mx[1] += fabsf(r0.z - r0.y); mx[2] += fabsf(r0.w - r0.z); mx[3] += fabsf(rn - r0.w);
+    my[0] += fabsf(rd.x - r0.x); my[1] += fabsf(rd.y - r0.y); my[2] += fabsf(rd.z - r0.z); my[3] += fabsf(rd.w - r0.w);
+  }
+  part[k][0][lane] = make_float4(mx[0], mx[1], mx[2], mx[3]);
+  part[k][1][lane] = make_float4(my[0], my[1], my[2], my[3]);
+  __syncthreads();
+  if (k >= 2) return;
+  float4 t = part[0][k][lane];
+#pragma unroll
+  for (int i = 1; i < PL_CHUNKS; ++i) {
+    const float4 u = part[i][k][lane];
+    t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+  }
+  const float sc = -p.a1 / (float)C;
+  t.x = __expf(sc * t.x); t.y = __expf(sc * t.y); t.z = __expf(sc * t.z); t.w = __expf(sc * t.w);
+  float* o = (k == 0 ? wx : wy) + ((int64_t)b * H + h) * W + w0;
+  *reinterpret_cast<float4*>(o) = t;
+}
+
+__global__ void __launch_bounds__(32 * PL_CHUNKS * RW_TH, 1)
+pixel_losses_rows_kernel(PixLossArgs p, const float* __restrict__ wx, const float* __restrict__ wy) {
+  SS_PDL_ENTRY();
+  __shared__ float4 gpart[RW_TH][PL_CHUNKS][2][32];
+  __shared__ float wred[PL_CHUNKS * RW_TH][9];
+  const int W = p.W, H = p.H, C = p.C, HW = H * W;
+  const int lane = threadIdx.x, k = threadIdx.y, rz = threadIdx.z;
+  const int w0 = blockIdx.x * 128 + lane * 4, b = blockIdx.z;
+  const int h_raw = blockIdx.y * RW_TH + rz;
+  const bool row_ok = h_raw < H;
+  const int h = row_ok ? h_raw : H - 1;                     // (an odd H leaves the block's second row idle: it recomputes the
+                                                            //  last row and its results are dropped)
+  const int cpc = (C + PL_CHUNKS - 1) / PL_CHUNKS;
+  const int c_begin = k * cpc, c_end = min(C, c_begin + cpc);
+  const int up = (h > 0) ? -W : 0, dn = (h + 1 < H) ? W : 0;
+  const bool first = (lane == 0), last = (lane == 31);
+  const bool has_prev = (w0 > 0), has_next = (w0 + 4 < W);
+  const int64_t pix = ((int64_t)b * H + h) * W + w0;
+
+  // ---- band-independent quantities of the thread's four pixels ----
+  float i0[4], gain[4], cL[4], cR[4], cU[4], cD[4], tL[4], tR[4], tU[4], tD[4];   // t* = forward differences of I_delta
+  float gI[4] = {0.f, 0.f, 0.f, 0.f}, gId[4] = {0.f, 0.f, 0.f, 0.f};
+  float s[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) s[i] = 0.f;
+  {
+    float ii[6], dd[6], iu[4], id_[4], du[4], dd_[4], wh[5], wd[4], wu[4];
+    f4_to(ldg4(p.I + pix), ii + 1); f4_to(ldg4(p.Id + pix), dd + 1);
+    f4_to(ldg4(p.I + pix + up), iu); f4_to(ldg4(p.I + pix + dn), id_);
+    f4_to(ldg4(p.Id + pix + up), du); f4_to(ldg4(p.Id + pix + dn), dd_);
+    f4_to(ldg4(wx + pix), wh + 1); f4_to(ldg4(wy + pix), wd); f4_to(ldg4(wy + pix + up), wu);
+    ii[0] = __shfl_up_sync(0xffffffffu, ii[4], 1); ii[5] = __shfl_down_sync(0xffffffffu, ii[1], 1);
+    dd[0] = __shfl_up_sync(0xffffffffu, dd[4], 1); dd[5] = __shfl_down_sync(0xffffffffu, dd[1], 1);
+    wh[0] = __shfl_up_sync(0xffffffffu, wh[4], 1);
+    if (first) {
+      ii[0] = has_prev ? __ldg(p.I + pix - 1) : ii[1];
+      dd[0] = has_prev ? __ldg(p.Id + pix - 1) : dd[1];
+      wh[0] = has_prev ? __ldg(wx + pix - 1) : 1.f;
+    }
+    if (last) {
+      ii[5] = has_next ? __ldg(p.I + pix + 4) : ii[4];
+      dd[5] = has_next ? __ldg(p.Id + pix + 4) : dd[4];
+    }
+    const float invC = 1.f / (float)C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = ii[j + 1], d0 = dd[j + 1];
+      const float iR = ii[j + 2] - v0, iL = v0 - ii[j], iD = id_[j] - v0, iU = v0 - iu[j];
+      const float wR = wh[j + 1], wL = wh[j], wD = wd[j], wU = wu[j];
+      i0[j] = v0; gain[j] = d0 + v0;
+      tR[j] = dd[j + 2] - d0; tL[j] = d0 - dd[j]; tD[j] = dd_[j] - d0; tU[j] = d0 - du[j];
+      cR[j] = p.k_ilx * wR * fabsf(iR) * p.a1 * invC; cL[j] = p.k_ilx * wL * fabsf(iL) * p.a1 * invC;
+      cD[j] = p.k_ily * wD * fabsf(iD) * p.a1 * invC; cU[j] = p.k_ily * wU * fabsf(iU) * p.a1 * invC;
+      if (k == 0) {   // once per pixel
+        s[1] += wR * fabsf(iR);
+        s[2] += wD * fabsf(iD);
+        gI[j] = p.k_ilx * (wL * sgnf(iL) - wR * sgnf(iR)) + p.k_ily * (wU * sgnf(iU) - wD * sgnf(iD));
+      }
+    }
+  }
+
+  // ---- one sweep over this thread's bands ----
+  const float* Rb = p.R + (int64_t)b * C * HW + (int64_t)h * W + w0;
+  const float* Eb = p.Re + (int64_t)b * C * HW + (int64_t)h * W + w0;
+  const float* Xb = p.x + (int64_t)b * C * HW + (int64_t)h * W + w0;
+  float sprev[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c_begin > 0 && c_begin < C) {
+    float t[4];
+    f4_to(ldg4(Rb + (int64_t)(c_begin - 1) * HW), t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sprev[j] = t[j] * gain[j];
+  }
+  float4 r_next = (c_begin < C) ? ldg4(Rb + (int64_t)c_begin * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    const int64_t off = (int64_t)c * HW;
+    float rr[6], qq[6], ru[4], rd[4], eu[4], ed[4], xx[4], rn[4];
+    const float4 r4 = r_next;
+    const float4 e4 = ldg4(Eb + off);
+    const float4 ru4 = ldg4(Rb + off + up), rd4 = ldg4(Rb + off + dn);
+    const float4 eu4 = ldg4(Eb + off + up), ed4 = ldg4(Eb + off + dn);
+    const float4 x4 = ldg4(Xb + off);
+    if (c + 1 < C) r_next = ldg4(Rb + off + HW);
+    f4_to(r4, rr + 1); f4_to(ru4, ru); f4_to(rd4, rd); f4_to(eu4, eu); f4_to(ed4, ed); f4_to(x4, xx); f4_to(r_next, rn);
+    qq[1] = r4.x - e4.x; qq[2] = r4.y - e4.y; qq[3] = r4.z - e4.z; qq[4] = r4.w - e4.w;
+    rr[0] = __shfl_up_sync(0xffffffffu, rr[4], 1); rr[5] = __shfl_down_sync(0xffffffffu, rr[1], 1);
+    qq[0] = __shfl_up_sync(0xffffffffu, qq[4], 1); qq[5] = __shfl_down_sync(0xffffffffu, qq[1], 1);
+    if (first) {
+      if (has_prev) { rr[0] = __ldg(Rb + off - 1); qq[0] = rr[0] - __ldg(Eb + off - 1); }
+      else { rr[0] = rr[1]; qq[0] = qq[1]; }
+    }
+    if (last) {
+      if (has_next) { rr[5] = __ldg(Rb + off + 4); qq[5] = rr[5] - __ldg(Eb + off + 4); }
+      else { rr[5] = rr[4]; qq[5] = qq[4]; }
+    }
+    // horizontal edges e = 0..4 between rr[e] and rr[e+1]: one exp each, used by both end pixels
+    float drh[5], dqh[5], exh[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      drh[e] = rr[e + 1] - rr[e];
+      dqh[e] = qq[e + 1] - qq[e];
+      exh[e] = __expf(-p.a2 * fabsf(drh[e]));
+    }
+    float oR[4], oE[4], oS[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float r0 = rr[j + 1], q0 = qq[j + 1];
+      float gR = 0.f;
+      const float u = r0 * i0[j] - xx[j];
+      s[0] += fabsf(u);
+      const float gu = p.k_rec * sgnf(u);
+      gR += gu * i0[j];
+      gI[j] += gu * r0;
+      s[3] += fabsf(q0);
+      float gq = p.k_rf * sgnf(q0);
+      {  // right edge (j+1), left edge (j)
+        const float exr = exh[j + 1], exl = exh[j];
+        s[4] += fabsf(dqh[j + 1]);
+        s[6] += fabsf(tR[j]) * exr;
+        gq -= p.k_rfx * sgnf(dqh[j + 1]);
+        gR += (cR[j] + p.k_idx * fabsf(tR[j]) * p.a2 * exr) * sgnf(drh[j + 1]);
+        gId[j] -= p.k_idx * sgnf(tR[j]) * exr;
+        gq += p.k_rfx * sgnf(dqh[j]);
+        gR -= (cL[j] + p.k_idx * fabsf(tL[j]) * p.a2 * exl) * sgnf(drh[j]);
+        gId[j] += p.k_idx * sgnf(tL[j]) * exl;
+      }
+      {  // lower edge
+        const float dr = rd[j] - r0;
+        const float dq = (rd[j] - ed[j]) - q0;
+        const float ex = __expf(-p.a2 * fabsf(dr));
+        s[5] += fabsf(dq);
+        s[7] += fabsf(tD[j]) * ex;
+        gq -= p.k_rfy * sgnf(dq);
+        gR += (cD[j] + p.k_idy * fabsf(tD[j]) * p.a2 * ex) * sgnf(dr);
+        gId[j] -= p.k_idy * sgnf(tD[j]) * ex;
+      }
+      {  // upper edge
+        const float dr = r0 - ru[j];
+        const float dq = q0 - (ru[j] - eu[j]);
+        const float ex = __expf(-p.a2 * fabsf(dr));
+        gq += p.k_rfy * sgnf(dq);
+        gR -= (cU[j] + p.k_idy * fabsf(tU[j]) * p.a2 * ex) * sgnf(dr);
+        gId[j] += p.k_idy * sgnf(tU[j]) * ex;
+      }
+      gR += gq;
+      // spectral smoothness on S = R*(Id+I):  dS_c = k (sgn(S_c - S_{c-1}) - sgn(S_{c+1} - S_c))
+      const float s0 = r0 * gain[j];
+      float gS = 0.f;
+      if (c > 0) gS += sgnf(s0 - sprev[j]);
+      if (c + 1 < C) {
+        const float sn = rn[j] * gain[j];
+        s[8] += fabsf(sn - s0);
+        gS -= sgnf(sn - s0);
+      }
+      sprev[j] = s0;
+      oR[j] = gR; oE[j] = -gq; oS[j] = p.k_sp * gS;
+    }
+    if (row_ok) {
+      const int64_t o = (int64_t)b * C * HW + (int64_t)h * W + w0 + off;
+      if (p.dR) *reinterpret_cast<float4*>(p.dR + o) = make_float4(oR[0], oR[1], oR[2], oR[3]);
+      if (p.dRe) *reinterpret_cast<float4*>(p.dRe + o) = make_float4(oE[0], oE[1], oE[2], oE[3]);
+      if (p.dS) *reinterpret_cast<float4*>(p.dS + o) = make_float4(oS[0], oS[1], oS[2], oS[3]);
+    }
+  }
+  // ---- dI, dI_delta: sum over the eight band chunks in a fixed order ----
+  gpart[rz][k][0][lane] = make_float4(gI[0], gI[1], gI[2], gI[3]);
+  gpart[rz][k][1][lane] = make_float4(gId[0], gId[1], gId[2], gId[3]);
+  if (!row_ok) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s[i] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float t = warp_sum(s[i]);
+    if (lane == 0) wred[rz * PL_CHUNKS + k][i] = t;
+  }
+  __syncthreads();
+  if (k < 2 && row_ok) {
+    float4 t = gpart[rz][0][k][lane];
+#pragma unroll
+    for (int i = 1; i < PL_CHUNKS; ++i) {
+      const float4 u = gpart[rz][i][k][lane];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    float* o = (k == 0) ? p.dI : p.dId;
+    if (o) *reinterpret_cast<float4*>(o + pix) = t;
+  }
+  const int tid = (rz * PL_CHUNKS + k) * 32 + lane;
+  if (tid < 9) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < PL_CHUNKS * RW_TH; ++wv) t += wred[wv][tid];
+    p.partials[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 9 + tid] = t;
+  }
+}
+
+static bool pixel_rows(int C, int H, int W) {
+  static const bool rows_ok = !(getenv("SSHSLIE_LOSS_ROWS") && getenv("SSHSLIE_LOSS_ROWS")[0] == '0');
+  (void)H;
+  return rows_ok && C >= 2 && (W % 128) == 0;
+}
 static bool pixel_tiled(int C, int H, int W) {
   static const bool tiled_ok = !(getenv("SSHSLIE_LOSS_TILED") && getenv("SSHSLIE_LOSS_TILED")[0] == '0');
   return tiled_ok && C == PT_C && (W % PT_TW) == 0 && (H % PT_TH) == 0;
 }
 // rows of 9 partial sums the kernel writes for this shape (= its grid size)
 int ss_pixel_losses_blocks(int B, int C, int H, int W) {
+  if (pixel_rows(C, H, W)) return (W / 128) * ((H + RW_TH - 1) / RW_TH) * B;
   if (pixel_tiled(C, H, W)) return (W / PT_TW) * (H / PT_TH) * B;
   const int wx = W < PL_WX ? W : PL_WX;
   return ((W + wx - 1) / wx) * H * B;
+}
+
+// floats of scratch ss_pixel_losses needs: the rows of partial sums, then (row-streaming kernel) the two edge-weight maps
+int64_t ss_pixel_losses_scratch_floats(int B, int C, int H, int W) {
+  int64_t n = (int64_t)ss_pixel_losses_blocks(B, C, H, W) * 9;
+  n = (n + 3) & ~(int64_t)3;                                 // the maps are accessed as float4
+  if (pixel_rows(C, H, W)) n += (int64_t)2 * B * H * W;
+  return n;
 }
 
 // out[i] (+)= sum over rows of partials[row][i]: one warp per column, lanes stride the rows, fixed shuffle tree
@@ -441,6 +703,17 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
   p.k_idx = (float)(cfg.c_loss_i_smooth_delta / (nx1 * C));
   p.k_idy = (float)(cfg.c_loss_i_smooth_delta / (ny1 * C));
   p.k_sp = (float)(cfg.c_loss_spectral_cons / ((double)B * (C - 1) * H * W));
+  if (pixel_rows(C, H, W)) {
+    const int64_t rows9 = ((int64_t)ss_pixel_losses_blocks(B, C, H, W) * 9 + 3) & ~(int64_t)3;
+    float* wx = partials + rows9;
+    float* wy = wx + (int64_t)B * H * W;
+    ss_launch_pdl(edge_weights_rows_kernel, dim3(W / 128, H, B), dim3(32, PL_CHUNKS), (size_t)0, st, p, wx, wy);
+    int rc = ss_check_launch("edge_weights_rows");
+    if (rc) return rc;
+    ss_launch_pdl(pixel_losses_rows_kernel, dim3(W / 128, (H + RW_TH - 1) / RW_TH, B), dim3(32, PL_CHUNKS, RW_TH), (size_t)0,
+                  st, p, (const float*)wx, (const float*)wy);
+    return ss_check_launch("pixel_losses_rows");
+  }
   if (pixel_tiled(C, H, W)) {
     const size_t smem = (size_t)2 * PT_C * PT_PLANE * sizeof(float);
     static DeviceOnce attr_once;
@@ -463,9 +736,9 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
 }
 
 extern "C" int64_t sshslie_loss_scratch_bytes(int B, int C, int H, int W) {
-  const int64_t rows = ss_pixel_losses_blocks(B, C, H, W);
+  const int64_t pix = ss_pixel_losses_scratch_floats(B, C, H, W);
   const int64_t planes = (int64_t)B * C;                      // the Fourier kernels write one partial per (b, band) plane
-  return (rows * 9 > planes ? rows * 9 : planes) * (int64_t)sizeof(float);
+  return (pix > planes ? pix : planes) * (int64_t)sizeof(float);
 }
 
 extern "C" int sshslie_pixel_losses(const float* x, const float* R, const float* I, const float* Idelta,
