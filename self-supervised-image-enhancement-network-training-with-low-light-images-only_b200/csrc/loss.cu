@@ -406,7 +406,12 @@ __global__ void __launch_bounds__(PT_PIX* PL_CHUNKS) pixel_losses_tiled_kernel(P
 // small kernel of their own (edge_weights_rows_kernel: one more read of R, 2 maps of B*H*W floats out).
 //   grid = (W / 128, ceil(H / RW_TH), B), block = (32, 8 band chunks, RW_TH rows)
 // ---------------------------------------------------------------------------------------------
-#define RW_TH 2
+#define RW_TH 1
+// k * sgn(v) with sgn(0) = 0 (torch.sign): the sign bit of v is XORed into k
+SS_DEVINL float ksgn(float k, float v) {
+  const float t = __int_as_float(__float_as_int(k) ^ (__float_as_int(v) & (int)0x80000000));
+  return (v != 0.f) ? t : 0.f;
+}
 SS_DEVINL float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 SS_DEVINL void f4_to(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
 
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(32 * PL_CHUNKS) edge_weights_rows_kernel(PixLo
   *reinterpret_cast<float4*>(o) = t;
 }
 
-__global__ void __launch_bounds__(32 * PL_CHUNKS * RW_TH, 1)
+__global__ void __launch_bounds__(32 * PL_CHUNKS * RW_TH, 2 / RW_TH)
 pixel_losses_rows_kernel(PixLossArgs p, const float* __restrict__ wx, const float* __restrict__ wy) {
   SS_PDL_ENTRY();
   __shared__ float4 gpart[RW_TH][PL_CHUNKS][2][32];
@@ -468,7 +473,9 @@ pixel_losses_rows_kernel(PixLossArgs p, const float* __restrict__ wx, const floa
   const int64_t pix = ((int64_t)b * H + h) * W + w0;
 
   // ---- band-independent quantities of the thread's four pixels ----
-  float i0[4], gain[4], cL[4], cR[4], cU[4], cD[4], tL[4], tR[4], tU[4], tD[4];   // t* = forward differences of I_delta
+  // horizontal edges e = 0..4 of the thread (edge e joins pixels e-1 and e; 0 and 4 reach into the neighbouring lanes):
+  //   ch = d L_I_smooth_low / d|dR_c|, Kh = k_idx |d I_delta| a2, gh = k_idx sgn(d I_delta), ah = |d I_delta|
+  float i0[4], gain[4], ch[5], Kh[5], gh[5], ah[5], cU[4], cD[4], tU[4], tD[4];   // t* = forward differences of I_delta
   float gI[4] = {0.f, 0.f, 0.f, 0.f}, gId[4] = {0.f, 0.f, 0.f, 0.f};
   float s[9];
 #pragma unroll
@@ -492,19 +499,28 @@ pixel_losses_rows_kernel(PixLossArgs p, const float* __restrict__ wx, const floa
       dd[5] = has_next ? __ldg(p.Id + pix + 4) : dd[4];
     }
     const float invC = 1.f / (float)C;
+    float sgi[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const float ih = ii[e + 1] - ii[e], th = dd[e + 1] - dd[e];
+      ch[e] = p.k_ilx * wh[e] * fabsf(ih) * p.a1 * invC;
+      Kh[e] = p.k_idx * fabsf(th) * p.a2;
+      gh[e] = ksgn(p.k_idx, th);
+      ah[e] = fabsf(th);
+      sgi[e] = wh[e] * sgnf(ih);
+      if (k == 0 && e > 0) s[1] += wh[e] * fabsf(ih);          // edge e is the right edge of pixel e-1
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float v0 = ii[j + 1], d0 = dd[j + 1];
-      const float iR = ii[j + 2] - v0, iL = v0 - ii[j], iD = id_[j] - v0, iU = v0 - iu[j];
-      const float wR = wh[j + 1], wL = wh[j], wD = wd[j], wU = wu[j];
+      const float iD = id_[j] - v0, iU = v0 - iu[j];
+      const float wD = wd[j], wU = wu[j];
       i0[j] = v0; gain[j] = d0 + v0;
-      tR[j] = dd[j + 2] - d0; tL[j] = d0 - dd[j]; tD[j] = dd_[j] - d0; tU[j] = d0 - du[j];
-      cR[j] = p.k_ilx * wR * fabsf(iR) * p.a1 * invC; cL[j] = p.k_ilx * wL * fabsf(iL) * p.a1 * invC;
+      tD[j] = dd_[j] - d0; tU[j] = d0 - du[j];
       cD[j] = p.k_ily * wD * fabsf(iD) * p.a1 * invC; cU[j] = p.k_ily * wU * fabsf(iU) * p.a1 * invC;
       if (k == 0) {   // once per pixel
-        s[1] += wR * fabsf(iR);
         s[2] += wD * fabsf(iD);
-        gI[j] = p.k_ilx * (wL * sgnf(iL) - wR * sgnf(iR)) + p.k_ily * (wU * sgnf(iU) - wD * sgnf(iD));
+        gI[j] = p.k_ilx * (sgi[j] - sgi[j + 1]) + p.k_ily * (wU * sgnf(iU) - wD * sgnf(iD));
       }
     }
   }
@@ -543,67 +559,62 @@ pixel_losses_rows_kernel(PixLossArgs p, const float* __restrict__ wx, const floa
       if (has_next) { rr[5] = __ldg(Rb + off + 4); qq[5] = rr[5] - __ldg(Eb + off + 4); }
       else { rr[5] = rr[4]; qq[5] = qq[4]; }
     }
-    // horizontal edges e = 0..4 between rr[e] and rr[e+1]: one exp each, used by both end pixels
-    float drh[5], dqh[5], exh[5];
+    // horizontal edges e = 0..4 between rr[e] and rr[e+1]: evaluated once, applied with opposite signs to both end pixels
+    float Eh[5], Gh[5], Dh[5];
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
-      drh[e] = rr[e + 1] - rr[e];
-      dqh[e] = qq[e + 1] - qq[e];
-      exh[e] = __expf(-p.a2 * fabsf(drh[e]));
+      const float dr = rr[e + 1] - rr[e], dq = qq[e + 1] - qq[e];
+      const float ex = __expf(-p.a2 * fabsf(dr));
+      Eh[e] = ksgn(ch[e] + Kh[e] * ex, dr);
+      Gh[e] = ksgn(p.k_rfx, dq);
+      Dh[e] = gh[e] * ex;
+      if (e > 0) {
+        s[4] += fabsf(dq);
+        s[6] += ah[e] * ex;
+      }
     }
     float oR[4], oE[4], oS[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float r0 = rr[j + 1], q0 = qq[j + 1];
-      float gR = 0.f;
       const float u = r0 * i0[j] - xx[j];
       s[0] += fabsf(u);
-      const float gu = p.k_rec * sgnf(u);
-      gR += gu * i0[j];
+      const float gu = ksgn(p.k_rec, u);
+      float gR = gu * i0[j] + (Eh[j + 1] - Eh[j]);
       gI[j] += gu * r0;
       s[3] += fabsf(q0);
-      float gq = p.k_rf * sgnf(q0);
-      {  // right edge (j+1), left edge (j)
-        const float exr = exh[j + 1], exl = exh[j];
-        s[4] += fabsf(dqh[j + 1]);
-        s[6] += fabsf(tR[j]) * exr;
-        gq -= p.k_rfx * sgnf(dqh[j + 1]);
-        gR += (cR[j] + p.k_idx * fabsf(tR[j]) * p.a2 * exr) * sgnf(drh[j + 1]);
-        gId[j] -= p.k_idx * sgnf(tR[j]) * exr;
-        gq += p.k_rfx * sgnf(dqh[j]);
-        gR -= (cL[j] + p.k_idx * fabsf(tL[j]) * p.a2 * exl) * sgnf(drh[j]);
-        gId[j] += p.k_idx * sgnf(tL[j]) * exl;
-      }
+      float gq = ksgn(p.k_rf, q0) + (Gh[j] - Gh[j + 1]);
+      gId[j] += Dh[j] - Dh[j + 1];
       {  // lower edge
         const float dr = rd[j] - r0;
         const float dq = (rd[j] - ed[j]) - q0;
         const float ex = __expf(-p.a2 * fabsf(dr));
         s[5] += fabsf(dq);
         s[7] += fabsf(tD[j]) * ex;
-        gq -= p.k_rfy * sgnf(dq);
-        gR += (cD[j] + p.k_idy * fabsf(tD[j]) * p.a2 * ex) * sgnf(dr);
-        gId[j] -= p.k_idy * sgnf(tD[j]) * ex;
+        gq -= ksgn(p.k_rfy, dq);
+        gR += ksgn(cD[j] + p.k_idy * fabsf(tD[j]) * p.a2 * ex, dr);
+        gId[j] -= ksgn(p.k_idy, tD[j]) * ex;
       }
       {  // upper edge
         const float dr = r0 - ru[j];
         const float dq = q0 - (ru[j] - eu[j]);
         const float ex = __expf(-p.a2 * fabsf(dr));
-        gq += p.k_rfy * sgnf(dq);
-        gR -= (cU[j] + p.k_idy * fabsf(tU[j]) * p.a2 * ex) * sgnf(dr);
-        gId[j] += p.k_idy * sgnf(tU[j]) * ex;
+        gq += ksgn(p.k_rfy, dq);
+        gR -= ksgn(cU[j] + p.k_idy * fabsf(tU[j]) * p.a2 * ex, dr);
+        gId[j] += ksgn(p.k_idy, tU[j]) * ex;
       }
       gR += gq;
       // spectral smoothness on S = R*(Id+I):  dS_c = k (sgn(S_c - S_{c-1}) - sgn(S_{c+1} - S_c))
       const float s0 = r0 * gain[j];
       float gS = 0.f;
-      if (c > 0) gS += sgnf(s0 - sprev[j]);
+      if (c > 0) gS = ksgn(p.k_sp, s0 - sprev[j]);
       if (c + 1 < C) {
         const float sn = rn[j] * gain[j];
         s[8] += fabsf(sn - s0);
-        gS -= sgnf(sn - s0);
+        gS -= ksgn(p.k_sp, sn - s0);
       }
       sprev[j] = s0;
-      oR[j] = gR; oE[j] = -gq; oS[j] = p.k_sp * gS;
+      oR[j] = gR; oE[j] = -gq; oS[j] = gS;
     }
     if (row_ok) {
       const int64_t o = (int64_t)b * C * HW + (int64_t)h * W + w0 + off;

@@ -170,7 +170,7 @@ def _loss_inputs(B, C, H, W, seed=0):
     return x, R, I, Id, Re
 
 
-@pytest.mark.parametrize("shape", [(1, 64, 16, 24), (2, 64, 32, 32), (2, 64, 128, 128), (1, 6, 5, 256), (2, 20, 7, 128)])
+@pytest.mark.parametrize("shape", [(1, 64, 16, 24), (2, 64, 32, 32), (2, 64, 128, 128), (1, 6, 5, 256), (2, 20, 7, 128), (1, 5, 9, 70)])
 def test_pixel_losses(shape):
     """fp32 kernel vs oracle autograd on identical inputs: sums rel 2e-5; gradients 1e-5 of their max + exact zeros."""
     from gpu_util import cfg_struct, stream
