@@ -419,7 +419,7 @@ conv_gather_pipe_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
         const uint32_t ab = (uint32_t)(2 * g + (m & 1)), aph = (uint32_t)((m >> 1) & 1);
         const int b = t.b;
         const int oh = t.thi * HALO_TH + (row >> 3), ow = t.twi * HALO_TW + (row & 7);
-        const bool ok = oh < pa.OH;
+        const bool ok = oh < pa.OH && ow < pa.OW;      // partial tiles: zero-filled loads, skipped / clipped stores
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + ab * (uint32_t)Npad;
         if (pa.staged) {
           // staging buffer sb of this lane, use u: the TMA stores that last read it have finished reading
@@ -540,7 +540,7 @@ static int encode_out(const bf16* base, int64_t sB, int64_t sH, int64_t sW, int 
 static int pipe_plan(const ConvGeom& g, const Epi& epi, PipePlan* out) {
   PipeArgs pa;
   memset(&pa, 0, sizeof(pa));
-  if (!g.halo_ok || !ss_umma_supported(g) || (g.OW % HALO_TW) || g.Npad > 256) return 0;
+  if (!g.halo_ok || !ss_umma_supported(g) || g.Npad > 256) return 0;
   int pad = 0;
   for (int i = 0; i < g.nslabs; ++i) {
     const Slab& sl = g.slab[i];
@@ -557,7 +557,7 @@ static int pipe_plan(const ConvGeom& g, const Epi& epi, PipePlan* out) {
   pa.pad = pad;
   const int rows = (HALO_TH + 2 * pad) * (HALO_TW + 2 * pad);
   pa.halo_bytes = (rows * 128 + 1023) / 1024 * 1024;
-  pa.tiles_w = g.OW / HALO_TW;
+  pa.tiles_w = (g.OW + HALO_TW - 1) / HALO_TW;
   pa.tiles_h = (g.OH + HALO_TH - 1) / HALO_TH;
   pa.n_tiles = g.B * pa.tiles_h * pa.tiles_w;
   pa.nslabs = g.nslabs; pa.Npad = g.Npad; pa.N = g.N; pa.OH = g.OH; pa.OW = g.OW;

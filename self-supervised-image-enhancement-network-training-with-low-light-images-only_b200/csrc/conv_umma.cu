@@ -219,7 +219,7 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
   const uint32_t ring_base = dyn_base + (uint32_t)(T * nh * halo_bytes);
   const uint32_t stage_bytes = (uint32_t)G * b_bytes;
   const int pitch = HALO_TW + 2 * pad;
-  const int tiles_w = ha.OW / HALO_TW, tiles_h = (ha.OH + HALO_TH - 1) / HALO_TH;
+  const int tiles_w = (ha.OW + HALO_TW - 1) / HALO_TW, tiles_h = (ha.OH + HALO_TH - 1) / HALO_TH;
   const int t_first = blockIdx.x * T;            // the launcher guarantees n_tiles % T == 0
   const int n_iter = (nslabs + G - 1) / G;
 
@@ -346,7 +346,7 @@ conv_gather_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_cons
       const int thi = ti % tiles_h;
       const int b = ti / tiles_h;
       const int oh = thi * HALO_TH + (row >> 3), ow = twi * HALO_TW + (row & 7);
-      const bool ok = oh < ha.OH;
+      const bool ok = oh < ha.OH && ow < ha.OW;      // partial tiles: loads were zero-filled, stores are skipped
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Npad);
       int n0 = 0;
       for (; n0 + 32 <= Npad; n0 += 32) {
@@ -410,7 +410,6 @@ int ss_tma_encode_4d(CUtensorMap* out, int fp32, void* base, const uint64_t* dim
 int ss_umma_supported(const ConvGeom& g) {
   if (g.Npad < 16 || g.Npad > 256 || (g.Npad % 16)) return 0;
   if (g.tw < 8 || g.tw * g.th != 128) return 0;
-  if (g.OW % g.tw) return 0;                       // partial tiles along W are not handled (rows along H are)
   for (int s = 0; s < g.nsrc; ++s) {
     const SrcView& v = g.src[s];
     if (((uintptr_t)v.base & 15) || (v.sW % 8) || (v.sH % 8) || (v.sB % 8)) return 0;
@@ -426,7 +425,6 @@ int ss_env_int(const char* name, int dflt) {
 static int halo_args(const ConvGeom& g, HaloArgs* out) {
   HaloArgs ha;
   memset(&ha, 0, sizeof(ha));
-  if (g.OW % HALO_TW) return 0;
   int pad = 0;
   for (int i = 0; i < g.nslabs; ++i) {
     const Slab& sl = g.slab[i];
@@ -443,7 +441,7 @@ static int halo_args(const ConvGeom& g, HaloArgs* out) {
   ha.pad = pad;
   const int rows = (HALO_TH + 2 * pad) * (HALO_TW + 2 * pad);
   ha.halo_bytes = (rows * 128 + 1023) / 1024 * 1024;
-  ha.n_tiles = g.B * ((g.OH + HALO_TH - 1) / HALO_TH) * (g.OW / HALO_TW);
+  ha.n_tiles = g.B * ((g.OH + HALO_TH - 1) / HALO_TH) * ((g.OW + HALO_TW - 1) / HALO_TW);
   const int b_bytes = g.Npad * 128;
   // slabs per ring stage: <= 32 KB of weights (16*T MMAs per barrier round at Npad = 64), balanced over the rounds, and
   // small enough that halo + two stages stay under half an SM's shared memory (two co-resident CTAs when T = 1)
@@ -1004,7 +1002,7 @@ SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const 
   const int t_begin = bx * wa.tiles_per_cta;
   const int t_end = min(wa.n_tiles, t_begin + wa.tiles_per_cta);
   const int ntiles = t_end - t_begin;           // >= 1 by construction of the grid
-  const int tiles_w = wa.OW / HALO_TW, tiles_h = (wa.OH + HALO_TH - 1) / HALO_TH;
+  const int tiles_w = (wa.OW + HALO_TW - 1) / HALO_TW, tiles_h = (wa.OH + HALO_TH - 1) / HALO_TH;
 
   if (warp == 0) {
     if (lane == 0) {

@@ -13,47 +13,46 @@
 // ---------------------------------------------------------------------------------------------
 // x (B,C,H,W) fp32  ->  out (B,H,W,ldo) bf16        [decomposition_net input, model.py:51-52]
 // ---------------------------------------------------------------------------------------------
+// blocks tile ONE image (grid.z = b): 32 pixels x 32 channels through a padded shared tile; any H*W (tail pixels guarded)
 __global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int C, int HW, int ldo) {
   SS_PDL_ENTRY();
   __shared__ float tile[32][33];
-  const int64_t p0 = (int64_t)blockIdx.x * 32;          // linear pixel over B*HW
-  const int b = (int)(p0 / HW);
-  const int hw0 = (int)(p0 - (int64_t)b * HW);
+  const int b = blockIdx.z;
+  const int hw0 = blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i;
-    tile[i][threadIdx.x] = (c < C) ? x[((int64_t)b * C + c) * HW + hw0 + threadIdx.x] : 0.f;
+    const int c = c0 + i, hw = hw0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && hw < HW) ? x[((int64_t)b * C + c) * HW + hw] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {            // i = pixel, threadIdx.x = channel
     const int c = c0 + threadIdx.x;
-    if (c < C) out[(p0 + i) * ldo + c] = f2bf(tile[threadIdx.x][i]);
+    if (c < C && hw0 + i < HW) out[((int64_t)b * HW + hw0 + i) * ldo + c] = f2bf(tile[threadIdx.x][i]);
   }
 }
 int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st) {
-  dim3 grid((unsigned)((int64_t)B * H * W / 32), (C + 31) / 32);
+  dim3 grid((unsigned)((H * W + 31) / 32), (C + 31) / 32, B);
   ss_launch_pdl(nchw32_to_nhwc16_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), st, x, out, C, H * W, ldo);
   EW_CHECK("nchw32_to_nhwc16");
 }
 
 __global__ void nhwc16_to_nchw32_kernel(const bf16* __restrict__ in, float* __restrict__ y, int C, int HW, int ldi) {
   __shared__ float tile[32][33];
-  const int64_t p0 = (int64_t)blockIdx.x * 32;
-  const int b = (int)(p0 / HW);
-  const int hw0 = (int)(p0 - (int64_t)b * HW);
+  const int b = blockIdx.z;
+  const int hw0 = blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {            // i = pixel, x = channel
     const int c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (c < C) ? bf2f(in[(p0 + i) * ldi + c]) : 0.f;
+    tile[i][threadIdx.x] = (c < C && hw0 + i < HW) ? bf2f(in[((int64_t)b * HW + hw0 + i) * ldi + c]) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {            // i = channel, x = pixel
-    const int c = c0 + i;
-    if (c < C) y[((int64_t)b * C + c) * HW + hw0 + threadIdx.x] = tile[threadIdx.x][i];
+    const int c = c0 + i, hw = hw0 + threadIdx.x;
+    if (c < C && hw < HW) y[((int64_t)b * C + c) * HW + hw] = tile[threadIdx.x][i];
   }
 }
 int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, int W, int ldi, cudaStream_t st) {
-  dim3 grid((unsigned)((int64_t)B * H * W / 32), (C + 31) / 32);
+  dim3 grid((unsigned)((H * W + 31) / 32), (C + 31) / 32, B);
   nhwc16_to_nchw32_kernel<<<grid, dim3(32, 8), 0, st>>>(in, y, C, H * W, ldi);
   EW_CHECK("nhwc16_to_nchw32");
 }
@@ -62,6 +61,17 @@ int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, in
 // out[b, y, x, :] = r[b, y/2, x/2, :] (+ a[b, y/2, x/2, :])      nearest x2 of (relu-out + skip), 64 channels
 // [F.interpolate(mode='nearest') of deconv_k + conv_k, model.py:156-165]
 // ---------------------------------------------------------------------------------------------
+SS_DEVINL uint4 add8(const uint4& p, const uint4& q) {
+  float f[8], g[8];
+  unpack8(p, f);
+  unpack8(q, g);
+  uint4 v;
+  v.x = pack2(f[0] + g[0], f[1] + g[1]);
+  v.y = pack2(f[2] + g[2], f[3] + g[3]);
+  v.z = pack2(f[4] + g[4], f[5] + g[5]);
+  v.w = pack2(f[6] + g[6], f[7] + g[7]);
+  return v;
+}
 __global__ void upsample2_add_kernel(const bf16* __restrict__ r, const bf16* __restrict__ a, bf16* __restrict__ out,
                                      int h, int w, int64_t total /* B*h*w*8 vectors of the SOURCE */) {
   SS_PDL_ENTRY();
@@ -90,31 +100,48 @@ __global__ void upsample2_add_kernel(const bf16* __restrict__ r, const bf16* __r
   o[(int64_t)W2 * 8] = v;
   o[(int64_t)W2 * 8 + 8] = v;
 }
+// F.interpolate(size=(ho, wo), mode='nearest') for any sizes: src = min(floor(dst * (float)in / out), in - 1), the index
+// ATen computes (UpSampleKernel.cpp nearest_idx; equals dst >> 1 for out == 2 in).  One thread per DESTINATION vector.
+SS_DEVINL int nearest_src(int d, float scale, int in) { return min((int)floorf((float)d * scale), in - 1); }
+__global__ void upsample_nearest_add_kernel(const uint4* __restrict__ r, const uint4* __restrict__ a, uint4* __restrict__ out,
+                                            int h, int w, int ho, int wo, float sh, float sw, int64_t total) {
+  SS_PDL_ENTRY();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i & 7);
+  const int64_t pix = i >> 3;
+  const int x = (int)(pix % wo);
+  const int64_t t = pix / wo;
+  const int y = (int)(t % ho);
+  const int64_t b = t / ho;
+  const int64_t s = ((b * h + nearest_src(y, sh, h)) * w + nearest_src(x, sw, w)) * 8 + q;
+  out[i] = a ? add8(r[s], a[s]) : r[s];
+}
+// (h, w) -> (ho, wo); the exact-doubling case keeps the one-read-four-writes kernel
+int ss_launch_upsample_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, int ho, int wo, cudaStream_t st) {
+  if (ho == 2 * h && wo == 2 * w) {
+    const int64_t total = (int64_t)B * h * w * 8;
+    ss_launch_pdl(upsample2_add_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, r, a, out, h, w, total);
+    EW_CHECK("upsample2_add");
+  }
+  const int64_t total = (int64_t)B * ho * wo * 8;
+  ss_launch_pdl(upsample_nearest_add_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st,
+                (const uint4*)r, (const uint4*)a, (uint4*)out, h, w, ho, wo, (float)h / (float)ho, (float)w / (float)wo, total);
+  EW_CHECK("upsample_nearest_add");
+}
 int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, cudaStream_t st) {
-  const int64_t total = (int64_t)B * h * w * 8;
-  ss_launch_pdl(upsample2_add_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, r, a, out, h, w, total);
-  EW_CHECK("upsample2_add");
+  return ss_launch_upsample_add(r, a, out, B, h, w, 2 * h, 2 * w, st);
 }
 
 // ---------------------------------------------------------------------------------------------
 // fg[b,y,x,:] = [ (r1+a2)[y/4,x/4] | (r2+a1)[y/2,x/2] | hi(r3+a0)[y,x] | lo(r3+a0)[y,x] ]   256 channels  [model.py:168-172]
 // ---------------------------------------------------------------------------------------------
-SS_DEVINL uint4 add8(const uint4& p, const uint4& q) {
-  float f[8], g[8];
-  unpack8(p, f);
-  unpack8(q, g);
-  uint4 v;
-  v.x = pack2(f[0] + g[0], f[1] + g[1]);
-  v.y = pack2(f[2] + g[2], f[3] + g[3]);
-  v.z = pack2(f[4] + g[4], f[5] + g[5]);
-  v.w = pack2(f[6] + g[6], f[7] + g[7]);
-  return v;
-}
 __global__ void fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __restrict__ a2,
                                    const uint4* __restrict__ r2, const uint4* __restrict__ a1,
                                    const uint4* __restrict__ r3, const uint4* __restrict__ r3l,
                                    const uint4* __restrict__ a0, const uint4* __restrict__ a0l, uint4* __restrict__ fg,
-                                   int H, int W, int64_t total /* B*H*W*24 */) {
+                                   int H, int W, int h2, int w2, int h1, int w1, float sh2, float sw2, float sh1,
+                                   float sw1, int64_t total /* B*H*W*24 */) {
   SS_PDL_ENTRY();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -125,10 +152,10 @@ __global__ void fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __
   const int y = (int)(t % H);
   const int64_t b = t / H;
   if (q < 8) {
-    const int64_t s = ((b * (H / 4) + y / 4) * (W / 4) + x / 4) * 8 + q;
+    const int64_t s = ((b * h2 + nearest_src(y, sh2, h2)) * w2 + nearest_src(x, sw2, w2)) * 8 + q;
     fg[pix * 32 + q] = add8(r1[s], a2[s]);
   } else if (q < 16) {
-    const int64_t s = ((b * (H / 2) + y / 2) * (W / 2) + x / 2) * 8 + (q - 8);
+    const int64_t s = ((b * h1 + nearest_src(y, sh1, h1)) * w1 + nearest_src(x, sw1, w1)) * 8 + (q - 8);
     fg[pix * 32 + q] = add8(r2[s], a1[s]);
   } else {
     // full-resolution block d3 = deconv3 + conv0 in ~16-bit mantissa: hi -> channels [128,192), residual -> [192,256)
@@ -155,12 +182,13 @@ __global__ void fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __
   }
 }
 int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
-                          const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W,
-                          cudaStream_t st) {
+                          const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W, int h2, int w2,
+                          int h1, int w1, cudaStream_t st) {
   const int64_t total = (int64_t)B * H * W * 24;
   ss_launch_pdl(fuse_concat_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, 
       (const uint4*)r1, (const uint4*)a2, (const uint4*)r2, (const uint4*)a1, (const uint4*)r3, (const uint4*)r3l,
-      (const uint4*)a0, (const uint4*)a0l, (uint4*)fg, H, W, total);
+      (const uint4*)a0, (const uint4*)a0l, (uint4*)fg, H, W, h2, w2, h1, w1, (float)h2 / (float)H, (float)w2 / (float)W,
+      (float)h1 / (float)H, (float)w1 / (float)W, total);
   EW_CHECK("fuse_concat");
 }
 
@@ -171,14 +199,15 @@ __global__ void make_s_kernel(const float* __restrict__ R, const float* __restri
                               float* __restrict__ S32, bf16* __restrict__ Sb, int C, int HW) {
   SS_PDL_ENTRY();
   __shared__ float tile[32][33];
-  const int64_t p0 = (int64_t)blockIdx.x * 32;
-  const int b = (int)(p0 / HW);
-  const int hw0 = (int)(p0 - (int64_t)b * HW);
+  const int b = blockIdx.z;
+  const int hw0 = blockIdx.x * 32;
+  const int64_t p0 = (int64_t)b * HW + hw0;
   const int c0 = blockIdx.y * 32;
-  const float id = Id[p0 + threadIdx.x], il = I[p0 + threadIdx.x];
+  const bool in = hw0 + (int)threadIdx.x < HW;
+  const float id = in ? Id[p0 + threadIdx.x] : 0.f, il = in ? I[p0 + threadIdx.x] : 0.f;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i;
-    if (c < C) {
+    if (c < C && in) {
       const int64_t a = ((int64_t)b * C + c) * HW + hw0 + threadIdx.x;
       const float r = R[a];
       const float s = r * id + r * il;
@@ -190,13 +219,13 @@ __global__ void make_s_kernel(const float* __restrict__ R, const float* __restri
   if (Sb) {
     for (int i = threadIdx.y; i < 32; i += 8) {
       const int c = c0 + threadIdx.x;
-      if (c < C) Sb[(p0 + i) * C + c] = f2bf(tile[threadIdx.x][i]);
+      if (c < C && hw0 + i < HW) Sb[(p0 + i) * C + c] = f2bf(tile[threadIdx.x][i]);
     }
   }
 }
 int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
                      cudaStream_t st) {
-  dim3 grid((unsigned)((int64_t)B * H * W / 32), (C + 31) / 32);
+  dim3 grid((unsigned)((H * W + 31) / 32), (C + 31) / 32, B);
   ss_launch_pdl(make_s_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), st, R, I, Id, S32, Sb, C, H * W);
   EW_CHECK("make_s");
 }

@@ -748,6 +748,8 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   const int B = e->B, C = e->C, H = e->H, W = e->W;
   const int64_t n = (int64_t)B * H * W;
   const bool train = e->train;
+  // the illumination net's pyramid: a 3x3 stride-2 pad-1 conv maps n -> ceil(n / 2) (model.py:127-129); H, W are even
+  const int h1 = (H + 1) / 2, w1 = (W + 1) / 2, h2 = (h1 + 1) / 2, w2 = (w1 + 1) / 2, h3 = (h2 + 1) / 2, w3 = (w2 + 1) / 2;
 
   // device copies of the plan
   e->geoms_dev = (ConvGeom*)e->alloc(sizeof(ConvGeom) * 128);
@@ -776,13 +778,13 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     return d;
   };
   DecompBufs d1 = decomp_bufs();
-  Tens a0 = e->talloc(B, H, W, 64), a1 = e->talloc(B, H / 2, W / 2, 64), a2 = e->talloc(B, H / 4, W / 4, 64),
-       a3 = e->talloc(B, H / 8, W / 8, 64), tt = e->talloc(B, H / 8, W / 8, 64);
+  Tens a0 = e->talloc(B, H, W, 64), a1 = e->talloc(B, h1, w1, 64), a2 = e->talloc(B, h2, w2, 64),
+       a3 = e->talloc(B, h3, w3, 64), tt = e->talloc(B, h3, w3, 64);
   Tens a0l = e->talloc(B, H, W, 64), r3l = e->talloc(B, H, W, 64), ffl = e->talloc(B, H, W, 64);   // bf16 residuals
-  Tens u1 = e->talloc(B, H / 4, W / 4, 64), r1 = e->talloc(B, H / 4, W / 4, 64), u2 = e->talloc(B, H / 2, W / 2, 64),
-       r2 = e->talloc(B, H / 2, W / 2, 64), u3 = e->talloc(B, H, W, 64), r3 = e->talloc(B, H, W, 64);
+  Tens u1 = e->talloc(B, h2, w2, 64), r1 = e->talloc(B, h2, w2, 64), u2 = e->talloc(B, h1, w1, 64),
+       r2 = e->talloc(B, h1, w1, 64), u3 = e->talloc(B, H, W, 64), r3 = e->talloc(B, H, W, 64);
   Tens fg = e->talloc(B, H, W, 256), ff = e->talloc(B, H, W, 64);
-  const int L = (H / 8) * (W / 8);
+  const int L = h3 * w3;
   const int64_t T64 = (int64_t)B * L * 64;
   AttnBuffers ab;
   memset(&ab, 0, sizeof(ab));
@@ -828,46 +830,46 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   }
   {
     WAddr wa = waddr_conv_fwd(e, L_I_CONV1);
-    g_i1 = e->add_geom(geom_conv(B, H / 2, W / 2, {{a0, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
+    g_i1 = e->add_geom(geom_conv(B, h1, w1, {{a0, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
     Epi ep = epi_bf16(a1, 64); ep.relu = 1;
     PUSH(F, return run_gather(e, g_i1, ep, L_I_CONV1, st););
   }
   {
     WAddr wa = waddr_conv_fwd(e, L_I_CONV2);
-    g_i2 = e->add_geom(geom_conv(B, H / 4, W / 4, {{a1, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
+    g_i2 = e->add_geom(geom_conv(B, h2, w2, {{a1, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
     Epi ep = epi_bf16(a2, 64); ep.relu = 1;
     PUSH(F, return run_gather(e, g_i2, ep, L_I_CONV2, st););
   }
   {
     WAddr wa = waddr_conv_fwd(e, L_I_CONV3);
-    g_i3 = e->add_geom(geom_conv(B, H / 8, W / 8, {{a2, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
+    g_i3 = e->add_geom(geom_conv(B, h3, w3, {{a2, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
     Epi ep = epi_bf16(a3, 64); ep.relu = 1;
     PUSH(F, return run_gather(e, g_i3, ep, L_I_CONV3, st););
   }
   const int64_t* apoff = e->poff + 2 * L_Q;
   PUSH(F, return ss_attention_forward(a3.p, tt.p, e->params, apoff, ab, B, L, st););
-  PUSH(F, return ss_launch_upsample2_add(tt.p, nullptr, u1.p, B, H / 8, W / 8, st););
+  PUSH(F, return ss_launch_upsample_add(tt.p, nullptr, u1.p, B, h3, w3, h2, w2, st););
   {
     WAddr wa = waddr_conv_fwd(e, L_I_DECONV1);
-    g_d1 = e->add_geom(geom_conv(B, H / 4, W / 4, {{u1, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
+    g_d1 = e->add_geom(geom_conv(B, h2, w2, {{u1, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
     Epi ep = epi_bf16(r1, 64); ep.relu = 1;
     PUSH(F, return run_gather(e, g_d1, ep, L_I_DECONV1, st););
   }
-  PUSH(F, return ss_launch_upsample2_add(r1.p, a2.p, u2.p, B, H / 4, W / 4, st););
+  PUSH(F, return ss_launch_upsample_add(r1.p, a2.p, u2.p, B, h2, w2, h1, w1, st););
   {
     WAddr wa = waddr_conv_fwd(e, L_I_DECONV2);
-    g_d2 = e->add_geom(geom_conv(B, H / 2, W / 2, {{u2, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
+    g_d2 = e->add_geom(geom_conv(B, h1, w1, {{u2, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
     Epi ep = epi_bf16(r2, 64); ep.relu = 1;
     PUSH(F, return run_gather(e, g_d2, ep, L_I_DECONV2, st););
   }
-  PUSH(F, return ss_launch_upsample2_add(r2.p, a1.p, u3.p, B, H / 2, W / 2, st););
+  PUSH(F, return ss_launch_upsample_add(r2.p, a1.p, u3.p, B, h1, w1, H, W, st););
   {
     WAddr wa = waddr_conv_fwd(e, L_I_DECONV3);
     g_d3 = e->add_geom(geom_conv(B, H, W, {{u3, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
     Epi ep = epi_bf16(r3, 64); ep.relu = 1; ep.out_lo = r3l.p;
     PUSH(F, return run_gather(e, g_d3, ep, L_I_DECONV3, st););
   }
-  PUSH(F, return ss_launch_fuse_concat(r1.p, a2.p, r2.p, a1.p, r3.p, r3l.p, a0.p, a0l.p, fg.p, B, H, W, st););
+  PUSH(F, return ss_launch_fuse_concat(r1.p, a2.p, r2.p, a1.p, r3.p, r3l.p, a0.p, a0l.p, fg.p, B, H, W, h2, w2, h1, w1, st););
   {
     WAddr wa = waddr_conv_fwd(e, L_I_FUSION);
     g_fus = e->add_geom(geom_conv(B, H, W, {{fg, 0, 192, 0}, {fg, 192, 64, 128, 1}}, 1, 1, 0, +1, 64, wa));
@@ -906,9 +908,11 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     // The Fourier term needs only x and S: it runs on a side stream BESIDE the second decomposition pass, writes its
     // gradient into a plane of its own (dSf32, summed in s_bwd) and is joined before the loss values are finalised.
     float* dSf32 = e->falloc(n * C);
+    const int64_t fwork_n = ss_fourier_work_floats(B * C, H, W);     // patches other than power-of-two <= 128: DFT path
+    float* fwork = fwork_n ? e->falloc(fwork_n) : nullptr;
     PUSH_SIDE(Lq, prof_note("loss:fourier_fft+grad", 0, 12.0 * 1048576.0 * B);
                   return ss_fourier_loss(e->x, e->S32, e->mask_dev, dSf32, e->four_partials, B * C, H, W,
-                                         (float)(e->cfg.c_loss_fourier / ((double)B * C * H * W)), 0, st););
+                                         (float)(e->cfg.c_loss_fourier / ((double)B * C * H * W)), 0, fwork, st););
     DecompGeoms G2 = plan_decomp_fwd(e, Lq, Sb, d2, head2);          // model.py:546
 
     // algorithmic HBM bytes: 24.25 MiB per patch for the 5-term loss + gradients, 12 MiB for the Fourier term
@@ -1101,16 +1105,19 @@ static void make_mask(std::vector<float>& m, int H, int W) {
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channels, int height, int width, int flags) {
-  if (!out || batch < 1 || channels != 64 || height < 16 || width < 16 || (height % 8) || (width % 8)) {
-    ss_set_error("sshslie_engine_create: need batch>=1, channels==64, H,W multiples of 8 and >=16 (got B=%d C=%d %dx%d)",
+  // DecompositionNet halves and re-doubles the image (stride-2 conv, then a transposed conv with output_padding 1,
+  // model.py:37-43), so the reference itself needs even H and W; nothing else is required of an inference shape
+  if (!out || batch < 1 || channels != 64 || height < 16 || width < 16 || (height % 2) || (width % 2)) {
+    ss_set_error("sshslie_engine_create: need batch>=1, channels==64, even H,W >= 16 (got B=%d C=%d %dx%d)",
                  batch, channels, height, width);
     return SSHSLIE_ERR_ARG;
   }
   if ((flags & SSHSLIE_FLAG_TRAIN)) {
-    bool pow2 = (height & (height - 1)) == 0 && (width & (width - 1)) == 0;
-    if (!pow2 || height > 128 || width > 128) {
-      ss_set_error("sshslie_engine_create: training needs power-of-two H,W <= 128 for the shared-memory FFT loss "
-                   "(config patch_size is 128); got %dx%d", height, width);
+    // the backward kernels of the illumination net (2x2 pooling of upsample gradients, concat split) assume exact
+    // halving at every level; the Fourier term takes any size (shared-memory FFT for powers of two <= 128, DFT otherwise)
+    if ((height % 8) || (width % 8) || height > 1024 || width > 1024) {
+      ss_set_error("sshslie_engine_create: training patches must be multiples of 8, at most 1024 a side (got %dx%d)",
+                   height, width);
       return SSHSLIE_ERR_ARG;
     }
   }

@@ -382,6 +382,148 @@ fourier_loss128_kernel(const float* __restrict__ x, const float* __restrict__ s,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Any other plane size (patches of 96, 256, ... - the reference's patch_size is a free config value, config/*.yml:12):
+// the same loss through plain DFTs, O(N) per output, with the complex plane in a global workspace.  Four line passes
+// (rows, columns, spectrum, columns^-1, rows^-1) replace the shared-memory transform; the spectrum arithmetic is the same.
+// A block takes 32 lines into shared memory (odd pitch: lanes run over LINES, conflict-free), each warp then produces
+// DFT_KB outputs per sweep with a warp-uniform (broadcast) twiddle.  A correctness-first path: ~2 ms at B=2 x 256 x 256.
+// ---------------------------------------------------------------------------------------------
+#define DFT_LINES 32
+#define DFT_WARPS 8
+#define DFT_KB 4
+// MODE 0: complex in (zin) -> complex out (zout, may alias zin: a block owns its lines)
+// MODE 1: real pair (x, s) in -> complex out          MODE 2: complex in -> real out: dS (+)= scale * Re
+// element (line, n) lives at (line / lpp) * plane + (line % lpp) * ls + n * es
+template <bool INV, int MODE>
+__global__ void __launch_bounds__(32 * DFT_WARPS) dft_lines_kernel(const float2* __restrict__ zin, const float* __restrict__ xr,
+                                                                   const float* __restrict__ sr, float2* __restrict__ zout,
+                                                                   float* __restrict__ dS, int n_lines, int N, int lpp,
+                                                                   int64_t plane, int ls, int es, float scale,
+                                                                   int accumulate) {
+  extern __shared__ __align__(16) unsigned char dft_smem[];
+  float2* tile = reinterpret_cast<float2*>(dft_smem);          // [DFT_LINES][pitch]
+  const int pitch = N | 1;
+  float2* tw = tile + DFT_LINES * pitch;                       // (cos, sin)(2 pi n / N)
+  const int tid = threadIdx.x, lane = tid & 31, wj = tid >> 5;
+  const int line0 = blockIdx.x * DFT_LINES;
+  for (int n = tid; n < N; n += 32 * DFT_WARPS) {
+    float sn, cs;
+    sincospif(2.f * (float)n / (float)N, &sn, &cs);
+    tw[n] = make_float2(cs, sn);
+  }
+  const bool lines_fast = (ls == 1);                           // adjacent lines are adjacent in memory (column pass)
+  for (int i = tid; i < DFT_LINES * N; i += 32 * DFT_WARPS) {
+    const int l = lines_fast ? (i & (DFT_LINES - 1)) : (i / N);
+    const int n = lines_fast ? (i / DFT_LINES) : (i - l * N);
+    const int line = line0 + l;
+    float2 v = make_float2(0.f, 0.f);
+    if (line < n_lines) {
+      const int64_t a = (int64_t)(line / lpp) * plane + (int64_t)(line % lpp) * ls + (int64_t)n * es;
+      v = (MODE == 1) ? make_float2(__ldg(xr + a), __ldg(sr + a)) : zin[a];
+    }
+    tile[l * pitch + n] = v;
+  }
+  __syncthreads();
+  const int line = line0 + lane;
+  const int64_t base = (int64_t)(line / lpp) * plane + (int64_t)(line % lpp) * ls;
+  const float2* row = tile + lane * pitch;
+  for (int kb = wj * DFT_KB; kb < N; kb += DFT_WARPS * DFT_KB) {
+    float2 acc[DFT_KB];
+    int idx[DFT_KB];
+#pragma unroll
+    for (int q = 0; q < DFT_KB; ++q) { acc[q] = make_float2(0.f, 0.f); idx[q] = 0; }
+    for (int n = 0; n < N; ++n) {
+      const float2 v = row[n];
+#pragma unroll
+      for (int q = 0; q < DFT_KB; ++q) {
+        const float2 w = tw[idx[q]];                           // warp-uniform index: one broadcast read
+        const float wy = INV ? w.y : -w.y;                     // forward: e^{-i t}, inverse: e^{+i t}
+        acc[q].x += v.x * w.x - v.y * wy;
+        acc[q].y += v.x * wy + v.y * w.x;
+        idx[q] += kb + q;
+        if (idx[q] >= N) idx[q] -= N;
+      }
+    }
+    if (line < n_lines) {
+#pragma unroll
+      for (int q = 0; q < DFT_KB; ++q) {
+        if (kb + q >= N) continue;
+        const int64_t a = base + (int64_t)(kb + q) * es;
+        if (MODE == 2) dS[a] = accumulate ? dS[a] + scale * acc[q].x : scale * acc[q].x;
+        else zout[a] = acc[q];
+      }
+    }
+  }
+}
+
+// spectrum pass of the DFT path, one block per plane, natural order (same arithmetic as the shared-memory kernels)
+__global__ void __launch_bounds__(1024) dft_spectrum_kernel(float2* __restrict__ z, const float* __restrict__ mask,
+                                                            float* __restrict__ partial_out, int H, int W) {
+  __shared__ float red[32];
+  float2* zp = z + (int64_t)blockIdx.x * H * W;
+  float lsum = 0.f;
+  for (int p = threadIdx.x; p < H * W; p += 1024) {
+    const int ky = p / W, kx = p - ky * W;
+    const int nky = ky ? H - ky : 0, nkx = kx ? W - kx : 0;
+    const int pn = nky * W + nkx;
+    if (pn < p) continue;                        // the pair is owned by its smaller index
+    const float2 a = zp[p], c = zp[pn];
+    const float2 X = make_float2(0.5f * (a.x + c.x), 0.5f * (a.y - c.y));
+    const float2 S = make_float2(0.5f * (a.y + c.y), -0.5f * (a.x - c.x));
+    const float ax = sqrtf(X.x * X.x + X.y * X.y);
+    const float as = sqrtf(S.x * S.x + S.y * S.y);
+    const float mk = mask[p], mn = mask[pn];
+    const float diff = ax - as;
+    const float ad = fabsf(diff);
+    lsum += (pn == p) ? mk * ad : (mk + mn) * ad;
+    const float g = (as > 0.f) ? -sgnf(diff) / as : 0.f;
+    zp[p] = make_float2(mk * g * S.x, mk * g * S.y);
+    if (pn != p) zp[pn] = make_float2(mn * g * S.x, -mn * g * S.y);
+  }
+  const float t = block_sum(lsum, red);
+  if (threadIdx.x == 0) partial_out[blockIdx.x] = t;
+}
+
+static bool fft_in_smem(int H, int W) {
+  return H >= 8 && W >= 8 && H <= 128 && W <= 128 && (H & (H - 1)) == 0 && (W & (W - 1)) == 0;
+}
+// floats of global workspace ss_fourier_loss needs for this plane size (0: the transform fits shared memory)
+int64_t ss_fourier_work_floats(int n_img, int H, int W) {
+  return fft_in_smem(H, W) ? 0 : (int64_t)2 * n_img * H * W;
+}
+#define DFT_MAX_N 1024
+template <bool INV, int MODE>
+static int dft_pass(const float2* zin, const float* xr, const float* sr, float2* zout, float* dS, int n_lines, int N, int lpp,
+                    int64_t plane, int ls, int es, float scale, int accumulate, cudaStream_t st) {
+  const size_t smem = ((size_t)DFT_LINES * (N | 1) + N) * sizeof(float2);
+  static DeviceOnce once;
+  if (!once.done()) {
+    if (cudaFuncSetAttribute(dft_lines_kernel<INV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) !=
+        cudaSuccess) {
+      ss_set_error("sshslie_fourier_loss: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      return SSHSLIE_ERR_CUDA;
+    }
+    once.set();
+  }
+  dft_lines_kernel<INV, MODE><<<(n_lines + DFT_LINES - 1) / DFT_LINES, 32 * DFT_WARPS, smem, st>>>(
+      zin, xr, sr, zout, dS, n_lines, N, lpp, plane, ls, es, scale, accumulate);
+  return ss_check_launch("dft_lines");
+}
+static int fourier_loss_dft(const float* x, const float* S, const float* mask, float* dS, float* partial_out, float2* z,
+                            int n_img, int H, int W, float grad_scale, int accumulate, cudaStream_t st) {
+  const int64_t plane = (int64_t)H * W;
+  int rc = dft_pass<false, 1>(nullptr, x, S, z, nullptr, n_img * H, W, H, plane, W, 1, 0.f, 0, st);         // rows
+  if (!rc) rc = dft_pass<false, 0>(z, nullptr, nullptr, z, nullptr, n_img * W, H, W, plane, 1, W, 0.f, 0, st);   // columns
+  if (rc) return rc;
+  dft_spectrum_kernel<<<n_img, 1024, 0, st>>>(z, mask, partial_out, H, W);
+  rc = ss_check_launch("dft_spectrum");
+  if (rc || !dS) return rc;
+  rc = dft_pass<true, 0>(z, nullptr, nullptr, z, nullptr, n_img * W, H, W, plane, 1, W, 0.f, 0, st);
+  if (!rc) rc = dft_pass<true, 2>(z, nullptr, nullptr, nullptr, dS, n_img * H, W, H, plane, W, 1, grad_scale, accumulate, st);
+  return rc;
+}
+
 static int ilog2_exact(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -392,12 +534,20 @@ static int ilog2_exact(int v) {
 // that it can run beside the second decomposition pass instead of after the pixel-space terms)
 // partial_out[n_img]: the masked-magnitude L1 sum of every plane (the caller adds them up in a fixed order)
 int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* partial_out, int n_img, int H,
-                    int W, float grad_scale, int accumulate, cudaStream_t stream) {
-  const int lgH = ilog2_exact(H), lgW = ilog2_exact(W);
-  if (!x || !S || !mask || !partial_out || n_img < 1 || lgH < 3 || lgW < 3 || H > 128 || W > 128) {
-    ss_set_error("sshslie_fourier_loss: H and W must be powers of two in [8,128] (got %dx%d)", H, W);
+                    int W, float grad_scale, int accumulate, float* work, cudaStream_t stream) {
+  if (!x || !S || !mask || !partial_out || n_img < 1 || H < 2 || W < 2 || H > DFT_MAX_N || W > DFT_MAX_N) {
+    ss_set_error("sshslie_fourier_loss: bad argument (planes of 2..%d pixels a side; got %dx%d)", DFT_MAX_N, H, W);
     return SSHSLIE_ERR_ARG;
   }
+  if (!fft_in_smem(H, W)) {
+    if (!work) {
+      ss_set_error("sshslie_fourier_loss: %dx%d planes need ss_fourier_work_floats of workspace", H, W);
+      return SSHSLIE_ERR_WORKSPACE;
+    }
+    return fourier_loss_dft(x, S, mask, dS, partial_out, reinterpret_cast<float2*>(work), n_img, H, W, grad_scale,
+                            accumulate, stream);
+  }
+  const int lgH = ilog2_exact(H), lgW = ilog2_exact(W);
   static const bool reg_fft = !(getenv("SSHSLIE_FFT128") && getenv("SSHSLIE_FFT128")[0] == '0');
   if (reg_fft && H == F128_N && W == F128_N && ((uintptr_t)x & 15) == 0 && ((uintptr_t)S & 15) == 0 &&
       (!dS || ((uintptr_t)dS & 15) == 0)) {
@@ -432,11 +582,15 @@ int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS
 extern "C" int sshslie_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out,
                                     int n_img, int H, int W, float grad_scale, void* scratch, int64_t scratch_bytes,
                                     void* stream) {
-  if (!sum_out || !scratch || scratch_bytes < (int64_t)n_img * (int64_t)sizeof(float)) {
-    ss_set_error("sshslie_fourier_loss: need sum_out and n_img floats of scratch");
+  // scratch: n_img partial sums (rounded up to 4 floats), then the complex planes of the DFT path when the size needs it
+  const int64_t head = ((int64_t)n_img + 3) / 4 * 4;
+  const int64_t need = (head + ss_fourier_work_floats(n_img, H, W)) * (int64_t)sizeof(float);
+  if (!sum_out || !scratch || scratch_bytes < need) {
+    ss_set_error("sshslie_fourier_loss: need sum_out and %lld bytes of scratch (sshslie_loss_scratch_bytes)", (long long)need);
     return SSHSLIE_ERR_WORKSPACE;
   }
-  const int rc = ss_fourier_loss(x, S, mask, dS, (float*)scratch, n_img, H, W, grad_scale, 1, (cudaStream_t)stream);
+  const int rc = ss_fourier_loss(x, S, mask, dS, (float*)scratch, n_img, H, W, grad_scale, 1, (float*)scratch + head,
+                                 (cudaStream_t)stream);
   if (rc) return rc;
   return ss_reduce_partials((const float*)scratch, n_img, 1, sum_out, 1, (cudaStream_t)stream);
 }

@@ -61,15 +61,18 @@ int ss_launch_conv_gather_pipe(const ConvGeom& g, const UmmaMaps& maps, const Ep
 int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st);
 int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, int W, int ldi, cudaStream_t st);
 int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, cudaStream_t st);
+// nearest resize (h, w) -> (ho, wo) of r (+ a), ATen index semantics
+int ss_launch_upsample_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, int ho, int wo, cudaStream_t st);
 int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
-                          const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W,
-                          cudaStream_t st);
+                          const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W, int h2, int w2,
+                          int h1, int w1, cudaStream_t st);
 int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
                      cudaStream_t st);
 int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, const float* R, const float* I,
                     const float* Id, float* dR32, float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st);
 int ss_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* partial_out, int n_img, int H,
-                    int W, float grad_scale, int accumulate, cudaStream_t stream);
+                    int W, float grad_scale, int accumulate, float* work, cudaStream_t stream);
+int64_t ss_fourier_work_floats(int n_img, int H, int W);   // workspace of the DFT path (0 for power-of-two planes <= 128)
 int ss_launch_head_bwd(const float* dR32, const float* R32, const bf16* dRI, int ld_dri, const float* dI32,
                        const float* I32, bf16* dc8, int ld_out, int B, int C, int H, int W, cudaStream_t st);
 int ss_launch_concat_bwd(const bf16* dfg, const bf16* r3, bf16* dr3, bf16* p2, bf16* p1, int B, int H, int W,

@@ -748,8 +748,10 @@ int ss_pixel_losses(const float* x, const float* R, const float* I, const float*
 
 extern "C" int64_t sshslie_loss_scratch_bytes(int B, int C, int H, int W) {
   const int64_t pix = ss_pixel_losses_scratch_floats(B, C, H, W);
-  const int64_t planes = (int64_t)B * C;                      // the Fourier kernels write one partial per (b, band) plane
-  return (pix > planes ? pix : planes) * (int64_t)sizeof(float);
+  // the Fourier kernels write one partial per (b, band) plane and, for sizes outside the shared-memory FFT, transform in a
+  // global workspace behind them
+  const int64_t four = ((int64_t)B * C + 3) / 4 * 4 + ss_fourier_work_floats(B * C, H, W);
+  return (pix > four ? pix : four) * (int64_t)sizeof(float);
 }
 
 extern "C" int sshslie_pixel_losses(const float* x, const float* R, const float* I, const float* Idelta,

@@ -230,7 +230,7 @@ def test_pixel_losses(shape):
         assert bad.float().mean().item() < 1e-4, (name, bad.float().mean().item(), tol)
 
 
-@pytest.mark.parametrize("shape", [(3, 32, 32), (4, 64, 128), (6, 128, 128)])
+@pytest.mark.parametrize("shape", [(3, 32, 32), (4, 64, 128), (6, 128, 128), (3, 96, 96), (2, 256, 256), (5, 24, 40)])
 def test_fourier_loss(shape):
     """Shared-memory FFT loss + gradient vs torch.fft autograd: value rel 2e-5, gradient 2e-4 of its max."""
     from gpu_util import stream
@@ -247,9 +247,10 @@ def test_fourier_loss(shape):
     dS = torch.zeros_like(sd)
     acc = torch.zeros(1, device="cuda")
     lib = S.lib.load()
-    scratch = torch.empty(4 * n, dtype=torch.uint8, device="cuda")
+    nscr = lib.sshslie_loss_scratch_bytes(1, n, H, W)        # partial sums + (sizes outside the shared-memory FFT) DFT planes
+    scratch = torch.empty(nscr, dtype=torch.uint8, device="cuda")
     S.lib.check(lib.sshslie_fourier_loss(S.lib.ptr(xd), S.lib.ptr(sd), S.lib.ptr(mask), S.lib.ptr(dS), S.lib.ptr(acc),
-                                         n, H, W, 1.0 / (n * H * W), S.lib.ptr(scratch), 4 * n, stream()), "fourier_loss")
+                                         n, H, W, 1.0 / (n * H * W), S.lib.ptr(scratch), nscr, stream()), "fourier_loss")
     torch.cuda.synchronize()
     np.testing.assert_allclose(float(acc) / (n * H * W), float(loss), rtol=2e-5)
     torch.testing.assert_close(dS.cpu(), gs, rtol=1e-3, atol=2e-4 * float(gs.abs().max()))

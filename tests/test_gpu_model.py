@@ -250,6 +250,36 @@ def test_forward_rectangular_and_ragged_tokens(shape):
     assert (S.cpu() - Sr).abs().max() <= 5e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 34, 18), (1, 130, 126), (1, 500, 500)])
+def test_forward_any_even_size(shape):
+    """Any even H, W: the pyramid levels are ceil(n/2) (model.py:127-129), so 130x126 runs at
+    65x63 / 33x32 / 17x16 and every F.interpolate(size=skip.shape, mode='nearest') (model.py:156-169) has a non-integer
+    ratio; tiles are partial along both axes.  500x500 (L = 63 x 63 = 3969 tokens) takes the tensor-core attention."""
+    from oracle import sshslie_oracle as O
+    B, H, W = shape
+    m = _model(O.JYU_COEF)
+    x = _rect_input(B, H, W, 5)
+    with torch.no_grad():
+        R, I, Id, S = m.forward(x.cuda())
+    torch.cuda.synchronize()
+    assert R.shape == (B, 64, H, W) and I.shape == (B, 1, H, W) and Id.shape == (B, 1, H, W)
+    Rr, Ir, Idr, Sr = O.forward(O.init_params(41), x)
+    assert (R.cpu() - Rr).abs().max() <= 5e-3
+    assert (I.cpu() - Ir).abs().max() <= 5e-3
+    assert (Id.cpu() - Idr).abs().max() <= 4e-3
+    assert (S.cpu() - Sr).abs().max() <= 5e-3
+
+
+def test_odd_size_is_refused():
+    """The reference itself cannot run an odd image (deconv output 2*ceil(H/2) != H, torch.cat fails, model.py:55-58)."""
+    from oracle import sshslie_oracle as O
+    import sshslie_b200 as S
+    m = _model(O.JYU_COEF)
+    with pytest.raises(S.lib.SshslieError):
+        with torch.no_grad():
+            m.forward(torch.rand(1, 64, 33, 32, device="cuda"))
+
+
 def test_loss_and_grads_rectangular_odd_batch():
     """Training step on a non-square power-of-two patch with an odd batch (B=3, 64x128): losses and gradients vs the oracle."""
     from oracle import sshslie_oracle as O
@@ -265,6 +295,31 @@ def test_loss_and_grads_rectangular_odd_batch():
     g = torch.cat([p.grad.detach().flatten().cpu() for p in m.parameters()])
     r = torch.cat([v.flatten() for v in ref_g.values()])
     assert _cos(g, r) >= 0.995
+
+
+@pytest.mark.parametrize("shape", [(2, 96, 96), (1, 256, 256), (1, 72, 120)])
+def test_train_step_other_patch_sizes(shape):
+    """patch_size is a free config value (config/*.yml:12): 96 and 72x120 are not powers of two and 256 does not fit the
+    shared-memory FFT, so the Fourier term runs through the DFT path; 256 also puts the transformer block at 1024 tokens
+    (tensor-core attention forward, its large-L backward).  Losses and the full gradient vs the oracle."""
+    from oracle import sshslie_oracle as O
+    B, H, W = shape
+    coef = O.JYU_COEF
+    m = _model(coef)
+    x = _rect_input(B, H, W, 11)
+    m.optimizer.zero_grad()
+    loss, losses = m.compute_loss(x.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref, ref_g, _ = O.loss_and_grads(O.init_params(41), x, coef)
+    for k in O.LOSS_KEYS:
+        np.testing.assert_allclose(losses[k], ref[k], rtol=LOSS_RTOL.get(k, 2e-2), atol=1e-5, err_msg=k)
+    g = torch.cat([p.grad.detach().flatten().cpu() for p in m.parameters()])
+    r = torch.cat([v.flatten() for v in ref_g.values()])
+    assert _cos(g, r) >= 0.995
+    m.optimizer.step()                                   # and the step itself runs
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("case", ["cv_b1_128", "jyu_b2_32_trained", "cv_b1_64_trained"])
