@@ -65,8 +65,10 @@ SSHSLIE_API const char* sshslie_last_error(void);
  * at offsets[i] and has sizes[i] floats.  Returns the total float count (1,141,922 for channels=64). */
 SSHSLIE_API int64_t sshslie_param_table(int channels, int64_t* offsets, int64_t* sizes);
 
-/* Engine = host-side launch plan for one (batch, channels, height, width).  height and width must be
- * multiples of 8 (the reference itself needs them even, model.py:59; the /8 pyramid adds the rest). */
+/* Engine = host-side launch plan for one (batch, channels, height, width).  channels == 64; height and width even and
+ * >= 16 (the reference itself needs them even: stride-2 conv + ConvTranspose2d(output_padding=1), model.py:37-43; the
+ * illumination pyramid is ceil(n/2) per level with ATen's nearest indices, model.py:127-129, 156-169).  With
+ * SSHSLIE_FLAG_TRAIN height and width must be multiples of 8 (any: patch_size is a free config value). */
 SSHSLIE_API int sshslie_engine_create(sshslie_engine** out, int batch, int channels, int height, int width, int flags);
 SSHSLIE_API void sshslie_engine_destroy(sshslie_engine* e);
 SSHSLIE_API int64_t sshslie_engine_workspace_bytes(const sshslie_engine* e);
@@ -136,8 +138,9 @@ SSHSLIE_API int sshslie_ssim_sum(const float* pred_hwc, const float* target_hwc,
 SSHSLIE_API int64_t sshslie_loss_scratch_bytes(int B, int C, int H, int W);
 
 /* fourier_spectrum_loss (model.py:456-473) forward + d/dS.  x,S,dS: (n_img,H,W) fp32 planes, H and W
- * powers of two in [8,128]; mask (H,W) fp32; adds sum_k mask*| |X|-|S| | to *sum_out (not zeroed);
- * dS += grad_scale * d(sum)/dS when dS != NULL.  scratch: >= n_img floats. */
+ * in [2,1024] (powers of two up to 128: FFT with the plane in shared memory; anything else: DFT line passes over a
+ * complex plane in the scratch); mask (H,W) fp32; adds sum_k mask*| |X|-|S| | to *sum_out (not zeroed);
+ * dS += grad_scale * d(sum)/dS when dS != NULL.  scratch: >= sshslie_loss_scratch_bytes(1, n_img, H, W). */
 SSHSLIE_API int sshslie_fourier_loss(const float* x, const float* S, const float* mask, float* dS, float* sum_out,
                          int n_img, int H, int W, float grad_scale, void* scratch, int64_t scratch_bytes, void* stream);
 

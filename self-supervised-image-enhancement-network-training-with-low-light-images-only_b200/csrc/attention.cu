@@ -752,6 +752,8 @@ static int attn_attrs() {
   return 0;
 }
 
+int ss_attn_tc_min_l() { return ss_env_int("SSHSLIE_ATTN_TC_MIN_L", SS_ATTN_TC_MIN_L); }
+
 // parameter order inside the flat buffer: poff[0..9] = q.w q.b k.w k.b v.w v.b ff1.w ff1.b ff2.w ff2.b
 int ss_attention_forward(const bf16* a3, bf16* t_out, const float* P, const int64_t* poff, AttnBuffers bf, int B, int L,
                          cudaStream_t st) {
@@ -761,7 +763,7 @@ int ss_attention_forward(const bf16* a3, bf16* t_out, const float* P, const int6
   ss_launch_pdl(attn_qkv4_kernel, dim3((T + AF_QB - 1) / AF_QB), dim3(192), (size_t)(kSmemQkv4), st, a3, P, poff[0], poff[1], poff[2], poff[3], poff[4],
                                                                    poff[5], bf.x, bf.q, bf.k, bf.v, T);
   static const bool tc_ok = !(getenv("SSHSLIE_ATTN_TC") && getenv("SSHSLIE_ATTN_TC")[0] == '0');
-  if (tc_ok && bf.qp && bf.kvp && L >= SS_ATTN_TC_MIN_L) {
+  if (tc_ok && bf.qp && bf.kvp && L >= ss_attn_tc_min_l()) {
     // large token grids (full-image inference): softmax(Q K^T) V on the tensor cores, then the FFN
     int rc = ss_check_launch("attention_qkv");
     if (!rc) rc = ss_attention_core_tc(bf.q, bf.k, bf.v, bf.qp, bf.kvp, bf.o, bf.lse, B, L, st);

@@ -158,6 +158,7 @@ struct sshslie_engine {
   std::vector<int> pipe_valid;
   std::vector<char> pipe_use;            // 0 = undecided, 1 = pipelined kernel, 2 = halo kernel
   bool pipe_on = true;
+  int pipe_min_tiles_head = 1024;        // same threshold for the sigmoid head (its staged fp32 stores are the gain)
   int pipe_min_tiles = 1024;             // below this the halo kernel (2-3 small co-resident CTAs per SM) has the lower latency
   int pipe_max_slabs = 36;               // the 9x9 layer (81 streamed slabs) is 8 % faster on the halo kernel
   ConvGeom* geoms_dev = nullptr;
@@ -428,8 +429,9 @@ static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaSt
       e->pipe_blob.resize(e->geoms.size() * ss_pipe_plan_size(), 0);
     }
     if (e->pipe_use[gi] == 0) {
-      const int n_tiles = g.B * ((g.OH + 15) / 16) * (g.OW / 8);
-      e->pipe_use[gi] = (n_tiles >= e->pipe_min_tiles && g.nslabs <= e->pipe_max_slabs && ss_umma_pipe_supported(g, epi)) ? 1 : 2;
+      const int n_tiles = g.B * ((g.OH + 15) / 16) * ((g.OW + 7) / 8);
+      const int min_tiles = (epi.mode == EPI_HEAD) ? e->pipe_min_tiles_head : e->pipe_min_tiles;
+      e->pipe_use[gi] = (n_tiles >= min_tiles && g.nslabs <= e->pipe_max_slabs && ss_umma_pipe_supported(g, epi)) ? 1 : 2;
     }
   }
   prof_note(geom_label(e, gi, e->geom_role[gi] ? "dgrad" : "fwd"), geom_flops(g), 0);
@@ -790,7 +792,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   memset(&ab, 0, sizeof(ab));
   ab.x = e->falloc(T64); ab.q = e->falloc(T64); ab.k = e->falloc(T64); ab.v = e->falloc(T64); ab.o = e->falloc(T64);
   ab.lse = e->falloc((int64_t)B * 4 * L); ab.h = e->falloc(T64); ab.t32 = e->falloc(T64);
-  if (L >= SS_ATTN_TC_MIN_L) {       // per-head bf16 operands of the tensor-core attention core
+  if (L >= ss_attn_tc_min_l()) {       // per-head bf16 operands of the tensor-core attention core
     ab.qp = (bf16*)e->alloc(T64 * 4 * (int64_t)sizeof(bf16));
     ab.kvp = (bf16*)e->alloc(T64 * 4 * (int64_t)sizeof(bf16));
   }
@@ -1134,6 +1136,8 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
     e->pipe_on = !(pe && pe[0] == '0');
     const char* pm = getenv("SSHSLIE_PIPE_MIN_TILES");
     if (pm && pm[0]) e->pipe_min_tiles = atoi(pm);
+    const char* pmh = getenv("SSHSLIE_PIPE_MIN_TILES_HEAD");
+    if (pmh && pmh[0]) e->pipe_min_tiles_head = atoi(pmh);
     const char* px = getenv("SSHSLIE_PIPE_MAX_SLABS");
     if (px && px[0]) e->pipe_max_slabs = atoi(px);
     const char* sk = getenv("SSHSLIE_SKIP_WGRAD");
@@ -1315,7 +1319,7 @@ extern "C" int sshslie_conv2d(int kind, int impl, int transposed, float* x, floa
   sshslie_engine* e = &E;
   e->B = B; e->C = 64; e->H = H; e->W = W; e->flags = 0; e->train = false; e->force_simt = (impl == 0);
   e->pipe_on = (impl == 3);               // impl 3 = the persistent pipelined gather kernel (stride-1 layers)
-  e->pipe_min_tiles = 0; e->pipe_max_slabs = SS_MAX_SLABS;
+  e->pipe_min_tiles = 0; e->pipe_min_tiles_head = 0; e->pipe_max_slabs = SS_MAX_SLABS;
   e->base = (unsigned char*)scratch; e->cursor = 0;
   memset(e->poff, 0, sizeof(e->poff));
   e->shapes[0] = {transposed ? Cin : Cout, transposed ? Cout : Cin, k, transposed != 0};
@@ -1524,7 +1528,7 @@ extern "C" int sshslie_transformer_block(int with_backward, const float* x, cons
   ab.dq = e->falloc(T64); ab.dk = e->falloc(T64); ab.dv = e->falloc(T64); ab.d_o = e->falloc(T64);
   ab.dh = e->falloc(T64); ab.dx = e->falloc(T64); ab.Dv = e->falloc((int64_t)B * 4 * L);
   float* dt32 = e->falloc(T64);
-  if (L >= SS_ATTN_TC_MIN_L) {
+  if (L >= ss_attn_tc_min_l()) {
     ab.qp = (bf16*)e->alloc(T64 * 4 * 2);
     ab.kvp = (bf16*)e->alloc(T64 * 4 * 2);
   }

@@ -97,6 +97,8 @@ struct AttnBuffers {
   bf16 *qp, *kvp;                                            // per-head bf16 hi+lo operands of the tensor-core core (L >= SS_ATTN_TC_MIN_L)
 };
 #define SS_ATTN_TC_MIN_L 1024
+int ss_env_int(const char* name, int dflt);
+int ss_attn_tc_min_l();      // SS_ATTN_TC_MIN_L unless SSHSLIE_ATTN_TC_MIN_L overrides it (tuning)
 // attention_tc.cu: tcgen05 attention core (q, k, v fp32 [B*L][64] -> o fp32 [B*L][64], lse [B][4][L])
 int ss_attention_core_tc(const float* q, const float* k, const float* v, bf16* qp, bf16* kvp, float* o, float* lse, int B,
                          int L, cudaStream_t st);

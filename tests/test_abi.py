@@ -58,10 +58,15 @@ def test_engine_plan_is_host_only():
     infer_bytes = lib.sshslie_engine_workspace_bytes(h)
     lib.sshslie_engine_destroy(h)
     assert 50e6 < train_bytes < 2e9 and 100e6 < infer_bytes < 8e9
+    # any even size plans for inference, any multiple of 8 for training (256: the Fourier term's DFT planes are in the workspace)
+    for args in [(1, 64, 130, 126, 0), (1, 64, 500, 500, 0), (1, 64, 256, 256, S.lib.FLAG_TRAIN), (2, 64, 96, 72, S.lib.FLAG_TRAIN)]:
+        assert lib.sshslie_engine_create(ctypes.byref(h), *args) == 0, args
+        assert lib.sshslie_engine_workspace_bytes(h) > 0
+        lib.sshslie_engine_destroy(h)
 
 
-@pytest.mark.parametrize("args", [(2, 32, 128, 128, 0), (2, 64, 130, 128, 0), (0, 64, 128, 128, 0),
-                                  (1, 64, 256, 256, S.lib.FLAG_TRAIN)])
+@pytest.mark.parametrize("args", [(2, 32, 128, 128, 0), (2, 64, 131, 128, 0), (0, 64, 128, 128, 0), (1, 64, 14, 16, 0),
+                                  (1, 64, 132, 128, S.lib.FLAG_TRAIN), (1, 64, 2048, 128, S.lib.FLAG_TRAIN)])
 def test_engine_rejects_unsupported_shapes(args):
     lib = S.lib.load()
     h = ctypes.c_void_p()
