@@ -7,12 +7,55 @@
 
 #define EW_CHECK(name) return ss_check_launch(name)
 
+#define C64_PITCH 33
+SS_DEVINL void tile_to_vec8(const float (*tile)[C64_PITCH], int i, int q, float* f) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = tile[8 * q + k][i];
+}
+SS_DEVINL uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack2(f[0], f[1]); v.y = pack2(f[2], f[3]); v.z = pack2(f[4], f[5]); v.w = pack2(f[6], f[7]);
+  return v;
+}
+
+
 // A 32-pixel x 32-channel transposing tile.  blockDim = (32, 8).  HW is a multiple of 32 (H, W multiples of 8),
 // so the 32 consecutive pixels of a tile never straddle two images.
 
 // ---------------------------------------------------------------------------------------------
 // x (B,C,H,W) fp32  ->  out (B,H,W,ldo) bf16        [decomposition_net input, model.py:51-52]
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// 64-channel fast paths (every tensor of this network): a block moves 32 pixels x ALL 64 channels through one padded tile.
+//   plane side (NCHW fp32): thread (x = pixel, y) touches channels y, y + 8, ... : eight independent 128-byte row segments per
+//                           warp and array, all loads issued before the first use
+//   pixel side (NHWC bf16): thread t owns pixel t / 8 and the 8 channels [8 (t % 8), +8): ONE 16-byte access, 128 contiguous
+//                           bytes per pixel; tile[c][i] with pitch 33 is conflict-free for both access patterns
+// (the generic kernels below them walk the channels in chunks of 32 with two barriers per chunk and 2-byte bf16 accesses:
+//  55-60 % of the time of each went into that.)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw32_to_nhwc16_c64_kernel(const float* __restrict__ x, bf16* __restrict__ out,
+                                                                   int HW, int ldo) {
+  SS_PDL_ENTRY();
+  __shared__ float tile[64][C64_PITCH];
+  const int b = blockIdx.y, hw0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool in = hw0 + tx < HW;
+  const float* xp = x + (int64_t)b * 64 * HW + hw0 + tx;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = in ? __ldg(xp + (int64_t)(ty + 8 * j) * HW) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tile[ty + 8 * j][tx] = v[j];
+  __syncthreads();
+  const int t = ty * 32 + tx, i = t >> 3, q = t & 7;
+  if (hw0 + i < HW) {
+    float f[8];
+    tile_to_vec8(tile, i, q, f);
+    *reinterpret_cast<uint4*>(out + ((int64_t)b * HW + hw0 + i) * ldo + 8 * q) = pack8(f);
+  }
+}
+
 // blocks tile ONE image (grid.z = b): 32 pixels x 32 channels through a padded shared tile; any H*W (tail pixels guarded)
 __global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int C, int HW, int ldo) {
   SS_PDL_ENTRY();
@@ -31,6 +74,10 @@ __global__ void nchw32_to_nhwc16_kernel(const float* __restrict__ x, bf16* __res
   }
 }
 int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st) {
+  if (C == 64 && (ldo % 8) == 0 && ((uintptr_t)out & 15) == 0) {
+    ss_launch_pdl(nchw32_to_nhwc16_c64_kernel, dim3((unsigned)((H * W + 31) / 32), B), dim3(32, 8), (size_t)0, st, x, out, H * W, ldo);
+    EW_CHECK("nchw32_to_nhwc16_c64");
+  }
   dim3 grid((unsigned)((H * W + 31) / 32), (C + 31) / 32, B);
   ss_launch_pdl(nchw32_to_nhwc16_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), st, x, out, C, H * W, ldo);
   EW_CHECK("nchw32_to_nhwc16");
@@ -136,55 +183,54 @@ int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int 
 // ---------------------------------------------------------------------------------------------
 // fg[b,y,x,:] = [ (r1+a2)[y/4,x/4] | (r2+a1)[y/2,x/2] | hi(r3+a0)[y,x] | lo(r3+a0)[y,x] ]   256 channels  [model.py:168-172]
 // ---------------------------------------------------------------------------------------------
-__global__ void fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __restrict__ a2,
-                                   const uint4* __restrict__ r2, const uint4* __restrict__ a1,
-                                   const uint4* __restrict__ r3, const uint4* __restrict__ r3l,
-                                   const uint4* __restrict__ a0, const uint4* __restrict__ a0l, uint4* __restrict__ fg,
-                                   int H, int W, int h2, int w2, int h1, int w1, float sh2, float sw2, float sh1,
-                                   float sw1, int64_t total /* B*H*W*24 */) {
+// one thread = one (pixel, 8-channel vector) of ALL four 64-channel groups: eight independent 16-byte loads in flight, four
+// 16-byte stores; the eight threads of a pixel write 128 contiguous bytes per group (no divergence inside a warp)
+__global__ void __launch_bounds__(256) fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __restrict__ a2,
+                                                          const uint4* __restrict__ r2, const uint4* __restrict__ a1,
+                                                          const uint4* __restrict__ r3, const uint4* __restrict__ r3l,
+                                                          const uint4* __restrict__ a0, const uint4* __restrict__ a0l,
+                                                          uint4* __restrict__ fg, int H, int W, int h2, int w2, int h1, int w1,
+                                                          float sh2, float sw2, float sh1, float sw1,
+                                                          int64_t total /* B*H*W*8 */) {
   SS_PDL_ENTRY();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int q = (int)(i % 24);
-  const int64_t pix = i / 24;
+  const int q = (int)(i & 7);
+  const int64_t pix = i >> 3;
   const int x = (int)(pix % W);
   const int64_t t = pix / W;
   const int y = (int)(t % H);
   const int64_t b = t / H;
-  if (q < 8) {
-    const int64_t s = ((b * h2 + nearest_src(y, sh2, h2)) * w2 + nearest_src(x, sw2, w2)) * 8 + q;
-    fg[pix * 32 + q] = add8(r1[s], a2[s]);
-  } else if (q < 16) {
-    const int64_t s = ((b * h1 + nearest_src(y, sh1, h1)) * w1 + nearest_src(x, sw1, w1)) * 8 + (q - 8);
-    fg[pix * 32 + q] = add8(r2[s], a1[s]);
-  } else {
-    // full-resolution block d3 = deconv3 + conv0 in ~16-bit mantissa: hi -> channels [128,192), residual -> [192,256)
-    const int64_t s = pix * 8 + (q - 16);
-    float f[8], g[8], hsum[8];
-    unpack8(r3[s], f);
-    unpack8(a0[s], g);
+  const int64_t s1 = ((b * h2 + nearest_src(y, sh2, h2)) * w2 + nearest_src(x, sw2, w2)) * 8 + q;
+  const int64_t s2 = ((b * h1 + nearest_src(y, sh1, h1)) * w1 + nearest_src(x, sw1, w1)) * 8 + q;
+  const uint4 v_r1 = __ldg(r1 + s1), v_a2 = __ldg(a2 + s1), v_r2 = __ldg(r2 + s2), v_a1 = __ldg(a1 + s2);
+  const uint4 v_r3 = __ldg(r3 + i), v_a0 = __ldg(a0 + i);
+  uint4 v_r3l = make_uint4(0u, 0u, 0u, 0u), v_a0l = v_r3l;
+  if (r3l) { v_r3l = __ldg(r3l + i); v_a0l = __ldg(a0l + i); }
+  uint4* o = fg + pix * 32 + q;
+  o[0] = add8(v_r1, v_a2);
+  o[8] = add8(v_r2, v_a1);
+  // full-resolution block d3 = deconv3 + conv0 in ~16-bit mantissa: hi -> channels [128,192), residual -> [192,256)
+  float f[8], g[8], hsum[8], r[8];
+  unpack8(v_r3, f);
+  unpack8(v_a0, g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) hsum[j] = f[j] + g[j];
-    if (r3l) {
-      unpack8(r3l[s], f);
-      unpack8(a0l[s], g);
+  for (int j = 0; j < 8; ++j) hsum[j] = f[j] + g[j];
+  if (r3l) {
+    unpack8(v_r3l, f);
+    unpack8(v_a0l, g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) hsum[j] += f[j] + g[j];
-    }
-    uint4 hi, lo;
-    float r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = hsum[j] - bf2f(f2bf(hsum[j]));
-    hi.x = pack2(hsum[0], hsum[1]); hi.y = pack2(hsum[2], hsum[3]); hi.z = pack2(hsum[4], hsum[5]); hi.w = pack2(hsum[6], hsum[7]);
-    lo.x = pack2(r[0], r[1]); lo.y = pack2(r[2], r[3]); lo.z = pack2(r[4], r[5]); lo.w = pack2(r[6], r[7]);
-    fg[pix * 32 + q] = hi;
-    fg[pix * 32 + q + 8] = lo;
+    for (int j = 0; j < 8; ++j) hsum[j] += f[j] + g[j];
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = hsum[j] - bf2f(f2bf(hsum[j]));
+  o[16] = pack8(hsum);
+  o[24] = pack8(r);
 }
 int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
                           const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W, int h2, int w2,
                           int h1, int w1, cudaStream_t st) {
-  const int64_t total = (int64_t)B * H * W * 24;
+  const int64_t total = (int64_t)B * H * W * 8;
   ss_launch_pdl(fuse_concat_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, 
       (const uint4*)r1, (const uint4*)a2, (const uint4*)r2, (const uint4*)a1, (const uint4*)r3, (const uint4*)r3l,
       (const uint4*)a0, (const uint4*)a0l, (uint4*)fg, H, W, h2, w2, h1, w1, (float)h2 / (float)H, (float)w2 / (float)W,
@@ -195,6 +241,35 @@ int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const 
 // ---------------------------------------------------------------------------------------------
 // S = R*I_delta + R*I_low  (model.py:233) -> S32 (B,C,H,W) fp32 and Sb (B,H,W,C) bf16 (2nd decomposition input)
 // ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) make_s_c64_kernel(const float* __restrict__ R, const float* __restrict__ I,
+                                                         const float* __restrict__ Id, float* __restrict__ S32,
+                                                         bf16* __restrict__ Sb, int HW) {
+  SS_PDL_ENTRY();
+  __shared__ float tile[64][C64_PITCH];
+  const int b = blockIdx.y, hw0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool in = hw0 + tx < HW;
+  const int64_t p = (int64_t)b * HW + hw0 + tx;
+  const int64_t a0 = (int64_t)b * 64 * HW + hw0 + tx;
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = in ? __ldg(R + a0 + (int64_t)(ty + 8 * j) * HW) : 0.f;
+  const float id = in ? __ldg(Id + p) : 0.f, il = in ? __ldg(I + p) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float sv = r[j] * id + r[j] * il;
+    if (in) S32[a0 + (int64_t)(ty + 8 * j) * HW] = sv;
+    tile[ty + 8 * j][tx] = sv;
+  }
+  if (!Sb) return;
+  __syncthreads();
+  const int t = ty * 32 + tx, i = t >> 3, q = t & 7;
+  if (hw0 + i < HW) {
+    float f[8];
+    tile_to_vec8(tile, i, q, f);
+    *reinterpret_cast<uint4*>(Sb + ((int64_t)b * HW + hw0 + i) * 64 + 8 * q) = pack8(f);
+  }
+}
 __global__ void make_s_kernel(const float* __restrict__ R, const float* __restrict__ I, const float* __restrict__ Id,
                               float* __restrict__ S32, bf16* __restrict__ Sb, int C, int HW) {
   SS_PDL_ENTRY();
@@ -225,6 +300,10 @@ __global__ void make_s_kernel(const float* __restrict__ R, const float* __restri
 }
 int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
                      cudaStream_t st) {
+  if (C == 64 && ((uintptr_t)Sb & 15) == 0) {
+    ss_launch_pdl(make_s_c64_kernel, dim3((unsigned)((H * W + 31) / 32), B), dim3(32, 8), (size_t)0, st, R, I, Id, S32, Sb, H * W);
+    EW_CHECK("make_s_c64");
+  }
   dim3 grid((unsigned)((H * W + 31) / 32), (C + 31) / 32, B);
   ss_launch_pdl(make_s_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), st, R, I, Id, S32, Sb, C, H * W);
   EW_CHECK("make_s");
@@ -234,6 +313,54 @@ int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32
 // backward of S = R*(Id + I):  dS = dS32 (loss terms) + dSb (second decomposition pass, bf16 NHWC)
 //   dR32 += dS*(Id+I) ;  t = sum_c dS*R ;  dId32 += t ;  dI32 += t        (block = 32 pixels x all channels)
 // ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) s_bwd_c64_kernel(const float* __restrict__ dS32, const float* __restrict__ dSf32,
+                                                        const bf16* __restrict__ dSb, const float* __restrict__ R,
+                                                        const float* __restrict__ I, const float* __restrict__ Id,
+                                                        float* __restrict__ dR32, float* __restrict__ dI32,
+                                                        float* __restrict__ dId32, int HW) {
+  SS_PDL_ENTRY();
+  __shared__ float tile[64][C64_PITCH];
+  __shared__ float part[8][32];
+  const int b = blockIdx.y, hw0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int t_ = ty * 32 + tx, i = t_ >> 3, q = t_ & 7;
+  const int64_t p = (int64_t)b * HW + hw0 + tx;
+  const int64_t a0 = (int64_t)b * 64 * HW + hw0 + tx;
+  // every load of the thread first: the bf16 gradient of the second decomposition pass (pixel side), then the planes
+  const uint4 dv = *reinterpret_cast<const uint4*>(dSb + ((int64_t)b * HW + hw0 + i) * 64 + 8 * q);
+  float ds[8], rr[8], dr[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int64_t a = a0 + (int64_t)(ty + 8 * j) * HW;
+    ds[j] = __ldg(dS32 + a) + (dSf32 ? __ldg(dSf32 + a) : 0.f);
+    rr[j] = __ldg(R + a);
+    dr[j] = dR32[a];
+  }
+  const float gain = __ldg(Id + p) + __ldg(I + p);
+  {
+    float f[8];
+    unpack8(dv, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[8 * q + k][i] = f[k];
+  }
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float d = ds[j] + tile[ty + 8 * j][tx];
+    dR32[a0 + (int64_t)(ty + 8 * j) * HW] = dr[j] + d * gain;
+    t = fmaf(d, rr[j], t);
+  }
+  part[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0) {
+    float sm = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm += part[k][tx];
+    dId32[p] += sm;
+    dI32[p] += sm;
+  }
+}
 __global__ void s_bwd_kernel(const float* __restrict__ dS32, const float* __restrict__ dSf32,
                              const bf16* __restrict__ dSb, const float* __restrict__ R,
                              const float* __restrict__ I, const float* __restrict__ Id, float* __restrict__ dR32,
@@ -275,6 +402,11 @@ __global__ void s_bwd_kernel(const float* __restrict__ dS32, const float* __rest
 }
 int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, const float* R, const float* I,
                     const float* Id, float* dR32, float* dI32, float* dId32, int B, int C, int H, int W, cudaStream_t st) {
+  if (C == 64 && (H * W) % 32 == 0 && ((uintptr_t)dSb & 15) == 0) {
+    ss_launch_pdl(s_bwd_c64_kernel, dim3((unsigned)(H * W / 32), B), dim3(32, 8), (size_t)0, st, dS32, dSf32, dSb, R, I, Id, dR32,
+                  dI32, dId32, H * W);
+    EW_CHECK("s_bwd_c64");
+  }
   ss_launch_pdl(s_bwd_kernel, dim3((unsigned)((int64_t)B * H * W / 32)), dim3(dim3(32, 8)), (size_t)(0), st, dS32, dSf32, dSb, R, I, Id, dR32, dI32,
                                                                            dId32, C, H * W);
   EW_CHECK("s_bwd");
@@ -286,6 +418,50 @@ int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, cons
 //   dc8[pix, C] = (dI32[pix] + dRI[pix, C]) * I(1-I)          (only when dI32 != NULL; else no column C)
 //   columns above are left untouched (zeroed once at bind time)
 // ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_bwd_c64_kernel(const float* __restrict__ dR32, const float* __restrict__ R32,
+                                                           const bf16* __restrict__ dRI, int ld_dri,
+                                                           const float* __restrict__ dI32, const float* __restrict__ I32,
+                                                           bf16* __restrict__ dc8, int ld_out, int HW) {
+  SS_PDL_ENTRY();
+  __shared__ float tg[64][C64_PITCH];   // raw gradient
+  __shared__ float tr[64][C64_PITCH];   // sigmoid'(.) = R(1-R)
+  const int b = blockIdx.y, hw0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int t = ty * 32 + tx, i = t >> 3, q = t & 7;
+  const int64_t a0 = (int64_t)b * 64 * HW + hw0 + tx;
+  const int64_t pi = (int64_t)b * HW + hw0 + i;
+  uint4 dv = make_uint4(0u, 0u, 0u, 0u);
+  if (dRI) dv = *reinterpret_cast<const uint4*>(dRI + pi * ld_dri + 8 * q);
+  float g[8], r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int64_t a = a0 + (int64_t)(ty + 8 * j) * HW;
+    g[j] = __ldg(dR32 + a);
+    r[j] = __ldg(R32 + a);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    tg[ty + 8 * j][tx] = g[j];
+    tr[ty + 8 * j][tx] = r[j] * (1.f - r[j]);
+  }
+  __syncthreads();
+  {
+    float f[8], d[8], o[8];
+    unpack8(dv, f);
+    tile_to_vec8(tg, i, q, o);
+    tile_to_vec8(tr, i, q, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (o[k] + f[k]) * d[k];
+    *reinterpret_cast<uint4*>(dc8 + pi * ld_out + 8 * q) = pack8(o);
+  }
+  if (dI32 && ty == 0) {
+    const int64_t p = (int64_t)b * HW + hw0 + tx;
+    float gi = dI32[p];
+    if (dRI) gi += bf2f(dRI[p * ld_dri + 64]);
+    const float il = I32[p];
+    dc8[p * ld_out + 64] = f2bf(gi * il * (1.f - il));
+  }
+}
 __global__ void head_bwd_kernel(const float* __restrict__ dR32, const float* __restrict__ R32,
                                 const bf16* __restrict__ dRI, int ld_dri, const float* __restrict__ dI32,
                                 const float* __restrict__ I32, bf16* __restrict__ dc8, int ld_out, int C, int HW) {
@@ -329,6 +505,12 @@ __global__ void head_bwd_kernel(const float* __restrict__ dR32, const float* __r
 }
 int ss_launch_head_bwd(const float* dR32, const float* R32, const bf16* dRI, int ld_dri, const float* dI32,
                        const float* I32, bf16* dc8, int ld_out, int B, int C, int H, int W, cudaStream_t st) {
+  if (C == 64 && (H * W) % 32 == 0 && (ld_out % 8) == 0 && ((uintptr_t)dc8 & 15) == 0 &&
+      (!dRI || ((ld_dri % 8) == 0 && ((uintptr_t)dRI & 15) == 0))) {
+    ss_launch_pdl(head_bwd_c64_kernel, dim3((unsigned)(H * W / 32), B), dim3(32, 8), (size_t)0, st, dR32, R32, dRI, ld_dri, dI32,
+                  I32, dc8, ld_out, H * W);
+    EW_CHECK("head_bwd_c64");
+  }
   ss_launch_pdl(head_bwd_kernel, dim3((unsigned)((int64_t)B * H * W / 32)), dim3(dim3(32, 8)), (size_t)(0), st, dR32, R32, dRI, ld_dri, dI32, I32, dc8,
                                                                               ld_out, C, H * W);
   EW_CHECK("head_bwd");
