@@ -1181,7 +1181,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_halo_reduce_kernel(const ConvG
 
 static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHaloArgs* out) {
   HaloArgs ha;
-  if (!g.halo_ok || !ss_umma_supported(g) || g.N > 128 || !halo_args(g, &ha)) return 0;
+  if (g.halo_ok != 1 || !ss_umma_supported(g) || g.N > 128 || !halo_args(g, &ha)) return 0;   // 2 = gather kernels only
   WgHaloArgs wa;
   memset(&wa, 0, sizeof(wa));
   wa.nh = ha.nh;

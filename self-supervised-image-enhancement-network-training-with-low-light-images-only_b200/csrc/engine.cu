@@ -158,6 +158,7 @@ struct sshslie_engine {
   std::vector<int> pipe_valid;
   std::vector<char> pipe_use;            // 0 = undecided, 1 = pipelined kernel, 2 = halo kernel
   bool pipe_on = true;
+  int s2_min_tiles = 512;                // stride-2 / transposed layers: halo-reuse kernels from this many tiles (per class)
   int pipe_min_tiles_head = 1024;        // same threshold for the sigmoid head (its staged fp32 stores are the gain)
   int pipe_min_tiles = 1024;             // below this the halo kernel (2-3 small co-resident CTAs per SM) has the lower latency
   int pipe_max_slabs = 36;               // the 9x9 layer (81 streamed slabs) is 8 % faster on the halo kernel
@@ -236,6 +237,10 @@ struct sshslie_engine {
   }
 };
 
+static bool s2_halo_enabled() {
+  const char* v = getenv("SSHSLIE_S2_HALO");
+  return !(v && v[0] == '0');
+}
 static ConvGeom geom_init(int B, int OH, int OW, int N, const WAddr& wa) {
   ConvGeom g;
   memset(&g, 0, sizeof(g));
@@ -287,7 +292,9 @@ static ConvGeom geom_conv(int B, int OH, int OW, const std::vector<SrcSpec>& src
           geom_add_slabs(g, (int)s, sign * kh + (sign > 0 ? -pad : pad), sign * kw + (sign > 0 ? -pad : pad), srcs[s],
                          kh, kw, wa);
   } else {
-    // stride 2 forward-type read: in = 2*out + k_idx - pad  ->  parity views of the single source
+    // stride 2 forward-type read: in = 2*out + k_idx - pad  ->  parity views of the single source.  Inside a view the taps
+    // are a stride-1 stencil again (offsets -1 / 0), so the halo-reuse gather kernels apply with one window per view.
+    g.halo_ok = s2_halo_enabled() ? 2 : 0;
     const SrcSpec& s = srcs[0];
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) g.src[g.nsrc++] = view_parity(s.t, ph, pw);
@@ -304,6 +311,7 @@ static ConvGeom geom_conv(int B, int OH, int OW, const std::vector<SrcSpec>& src
 static ConvGeom geom_tconv_class(int B, int OHc, int OWc, const SrcSpec& s, int k, int pad, int qh, int qw, int N,
                                  const WAddr& wa) {
   ConvGeom g = geom_init(B, OHc, OWc, N, wa);
+  g.halo_ok = s2_halo_enabled() ? 2 : 0;      // offsets 0 / +1 of a full view: a stride-1 stencil
   g.src[g.nsrc++] = view_full(s.t);
   for (int kh = 0; kh < k; ++kh) {
     if ((qh + pad - kh) & 1) continue;
@@ -457,6 +465,16 @@ static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaSt
       e->pipe_use[gi] = (n_tiles >= min_tiles && g.nslabs <= e->pipe_max_slabs && ss_umma_pipe_supported(g, epi)) ? 1 : 2;
     }
   }
+  // stride-2 / transposed geoms below the tile threshold stay on the per-tap kernel (fewer, smaller windows per launch)
+  const bool s2_small = g.halo_ok == 2 && g.B * ((g.OH + 15) / 16) * ((g.OW + 7) / 8) < e->s2_min_tiles;
+  if (e->geom_umma[gi] == 2 && s2_small) {
+    prof_note(std::string(e->geom_role[gi] ? "dgrad:" : "fwd:") +
+                  (e->geom_layer[gi] >= 0 && e->geom_layer[gi] < L_COUNT ? kLayerNames[e->geom_layer[gi]] : "layer") + "[tcgen05]",
+              geom_flops(g), 0);
+    return ss_launch_conv_gather_umma(e->geoms_dev + gi, g,
+                                      *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
+                                      epi, st);
+  }
   prof_note(geom_label(e, gi, e->geom_role[gi] ? "dgrad" : "fwd"), geom_flops(g), 0);
   if (e->geom_umma[gi] == 2 && e->pipe_on && e->pipe_use[gi] == 1)
     return ss_launch_conv_gather_pipe(g, *reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi * ss_umma_maps_size()),
@@ -473,9 +491,16 @@ static int run_gather(sshslie_engine* e, int gi, Epi epi, int bias_layer, cudaSt
 }
 // four parity classes (consecutive geoms gi0..gi0+3, same tile grid, same Npad) in one launch when all are on tcgen05
 static int run_gather4(sshslie_engine* e, int gi0, const Epi* epis, int bias_layer, cudaStream_t st) {
-  bool merged = true;
-  for (int q = 0; q < 4; ++q)
-    merged = merged && e->geom_umma[gi0 + q] == 1 && e->geoms[gi0 + q].Npad == e->geoms[gi0].Npad;
+  // one per-tap launch over the four classes (blockIdx.y = class) for small problems; above s2_min_tiles per class each
+  // class goes through the halo-reuse kernels on its own (4 launches, each at 3-5x the per-tap kernel's rate)
+  const ConvGeom& g0 = e->geoms[gi0];
+  const int class_tiles = g0.B * ((g0.OH + 15) / 16) * ((g0.OW + 7) / 8);
+  bool merged = true, halo4 = class_tiles >= e->s2_min_tiles;
+  for (int q = 0; q < 4; ++q) {
+    merged = merged && e->geom_umma[gi0 + q] >= 1 && e->geoms[gi0 + q].Npad == e->geoms[gi0].Npad;
+    halo4 = halo4 && e->geom_umma[gi0 + q] == 2;
+  }
+  merged = merged && !halo4;
   if (!merged) {
     for (int q = 0; q < 4; ++q) {
       const int rc = run_gather(e, gi0 + q, epis[q], bias_layer, st);
@@ -487,7 +512,9 @@ static int run_gather4(sshslie_engine* e, int gi0, const Epi* epis, int bias_lay
   if (bias_layer >= 0) epi.bias = e->params + e->poff[2 * bias_layer + 1];
   double fl = 0;
   for (int q = 0; q < 4; ++q) fl += geom_flops(e->geoms[gi0 + q]);
-  prof_note(geom_label(e, gi0, e->geom_role[gi0] ? "dgrad" : "fwd") + "x4", fl, 0);
+  prof_note(std::string(e->geom_role[gi0] ? "dgrad:" : "fwd:") +
+                (e->geom_layer[gi0] >= 0 && e->geom_layer[gi0] < L_COUNT ? kLayerNames[e->geom_layer[gi0]] : "layer") +
+                "[tcgen05]x4", fl, 0);
   return ss_launch_conv_gather_umma4(e->geoms_dev + gi0, &e->geoms[gi0],
                                      reinterpret_cast<const UmmaMaps*>(e->maps_blob.data() + gi0 * ss_umma_maps_size()),
                                      epi, st);
@@ -1159,6 +1186,8 @@ extern "C" int sshslie_engine_create(sshslie_engine** out, int batch, int channe
     e->pipe_on = !(pe && pe[0] == '0');
     const char* pm = getenv("SSHSLIE_PIPE_MIN_TILES");
     if (pm && pm[0]) e->pipe_min_tiles = atoi(pm);
+    const char* s2m = getenv("SSHSLIE_S2_MIN_TILES");
+    if (s2m && s2m[0]) e->s2_min_tiles = atoi(s2m);
     const char* pmh = getenv("SSHSLIE_PIPE_MIN_TILES_HEAD");
     if (pmh && pmh[0]) e->pipe_min_tiles_head = atoi(pmh);
     const char* px = getenv("SSHSLIE_PIPE_MAX_SLABS");

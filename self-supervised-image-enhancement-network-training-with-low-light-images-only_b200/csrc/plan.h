@@ -50,7 +50,8 @@ struct ConvGeom {
   bf16* wp;
   // tcgen05 tiling: the 128 GEMM rows of a tile are a (th x tw) block of the OHxOW grid, tw*th == 128
   int tw, th;
-  int halo_ok;                // stride-1 full views: the halo-reuse kernel may take this geom
+  int halo_ok;                // 1: stride-1 full views, the halo-reuse kernels (gather and weight gradient) may take this geom;
+                              // 2: stride-2 parity views / transposed parity classes, the halo GATHER kernels may
 };
 
 // Epilogue applied to 16 consecutive columns of one GEMM row (one output pixel).

@@ -502,6 +502,9 @@ def test_model_parity_with_pipelined_kernels(staged, monkeypatch):
     monkeypatch.setenv("SSHSLIE_PIPE_MIN_TILES", "0")
     monkeypatch.setenv("SSHSLIE_PIPE_MAX_SLABS", "81")
     monkeypatch.setenv("SSHSLIE_PIPE_STAGED", staged)
+    # stride-2 convs (parity views) and transposed convs / strided data gradients (one launch per output parity class) also
+    # move to the halo-reuse kernels from 512 tiles per class: force that too
+    monkeypatch.setenv("SSHSLIE_S2_MIN_TILES", "0")
     m = _model(O.JYU_COEF)
     x = O.synthetic_patches(2, 64, 128, seed=41)
     with torch.no_grad():
