@@ -36,17 +36,22 @@ def main():
         name, path = arg.split("=", 1)
         raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
-        hdr, units, vals = rows[0], rows[1], rows[2]
-        lines.append(f"== {name}   ({os.path.basename(path)})")
-        lines.append(f"{'Kernel Name':74s} {vals[hdr.index('Kernel Name')][:110]}")
-        tot = 0.0
-        for w in WANT:
-            if w in hdr:
-                i = hdr.index(w)
-                lines.append(f"{w:74s} {vals[i]} {units[i]}")
-                if w.startswith("dram__bytes"):
-                    tot += to_bytes(vals[i], units[i])
-        traffic[name] = int(tot)
+        hdr, units = rows[0], rows[1]
+        kernels = rows[2:]
+        for vals in kernels:
+            kname = vals[hdr.index('Kernel Name')]
+            short = kname.split('(')[0].split('<')[0].replace('void ', '')
+            key = name if len(kernels) == 1 else f"{name}:{short}"
+            lines.append(f"== {key}   ({os.path.basename(path)})")
+            lines.append(f"{'Kernel Name':74s} {kname[:110]}")
+            tot = 0.0
+            for w in WANT:
+                if w in hdr:
+                    i = hdr.index(w)
+                    lines.append(f"{w:74s} {vals[i]} {units[i]}")
+                    if w.startswith("dram__bytes"):
+                        tot += to_bytes(vals[i], units[i])
+            traffic[key] = int(tot)
     open(os.path.join(out_dir, f"{prefix}_ncu_full_summary.txt"), "w").write("\n".join(lines) + "\n")
     json.dump(traffic, open(os.path.join(out_dir, f"{prefix}_traffic.json"), "w"), indent=1)
     # launch list
