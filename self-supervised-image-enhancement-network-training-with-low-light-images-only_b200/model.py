@@ -249,16 +249,30 @@ def _fast_backward(own, total):
 
 
 class LazyLosses(dict):
-    """dict[str, float] whose values are read back from the device (one sync) on first access."""
+    """dict[str, float] whose values are read back from the device on first access.
+
+    Given a CUDA tensor, construction enqueues an asynchronous copy of the seven floats into pinned host memory and records
+    an event; the first access waits for THAT event only - not for work enqueued afterwards - so a loop that logs the losses
+    of step i after launching step i+1 never stalls the device (the reference's `.item()` calls, model.py:566-574, stall
+    it once per step)."""
 
     def __init__(self, dev_tensor, term_scale=1.0):
         super().__init__()
         self._dev = dev_tensor
+        self._event = None
+        if dev_tensor.is_cuda:
+            host = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
+            host.copy_(dev_tensor.detach(), non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record()
+            self._dev = host
         self._ready = False
         self._term_scale = term_scale          # data parallel: the six term values arrive as sums over the ranks
 
     def _sync(self):
         if not self._ready:
+            if self._event is not None:
+                self._event.synchronize()
             vals = self._dev.detach().cpu().tolist()
             for i, (k, v) in enumerate(zip(LOSS_KEYS, vals)):
                 dict.__setitem__(self, k, v if i == 0 else v * self._term_scale)
@@ -620,7 +634,7 @@ class LowLightEnhance(nn.Module):
             total.backward = _fast_backward(self, total)       # instance attribute shadows Tensor.backward
         else:
             total = self._losses_dev[0].clone()
-        return total, LazyLosses(self._losses_dev[:7].clone(), 1.0 / self._dp_world if dp else 1.0)
+        return total, LazyLosses(self._losses_dev[:7], 1.0 / self._dp_world if dp else 1.0)
 
     def profile_step(self, input_low, train=True):
         """One eager training step (train=False: forward only) with device timing per launch group: list of

@@ -477,6 +477,28 @@ def test_forward_returns_fresh_tensors():
     assert Ra.data_ptr() != Rb.data_ptr() and torch.equal(Ra, keep) and not torch.equal(Ra, Rb)
 
 
+def test_losses_read_late_keep_their_step():
+    """The loss dict is filled from an async copy made right behind its own step: reading it after LATER steps were launched
+    returns that step's values (what bench.py's e2e loop relies on)."""
+    from oracle import sshslie_oracle as O
+    xs = [O.synthetic_patches(2, 64, 32, seed=50 + i).cuda() for i in range(3)]
+    m = _model(O.JYU_COEF, graph=True)
+    eager = []
+    for x in xs:                                    # read immediately
+        m.optimizer.zero_grad()
+        _, l = m.compute_loss(x)
+        eager.append(l.copy())
+    late = []
+    for x in xs:                                    # launch all three, read afterwards
+        m.optimizer.zero_grad()
+        _, l = m.compute_loss(x)
+        late.append(l)
+    torch.cuda.synchronize()
+    for a, b in zip(eager, late):
+        assert a == b.copy()
+    assert eager[0]["total_loss"] != eager[1]["total_loss"]
+
+
 def test_step_is_bit_repeatable():
     """The reference runs with cudnn.deterministic=True (main.py:165): two runs of the same step give bit-identical
     losses and gradients (no floating-point atomics anywhere on the training path)."""

@@ -38,10 +38,16 @@ def main():
         rows = list(csv.reader(raw.splitlines()))
         hdr, units = rows[0], rows[1]
         kernels = rows[2:]
-        for vals in kernels:
+        names = name.split("|")                       # "a|b=file": successive kernels of the report are named a, b
+        for ki, vals in enumerate(kernels):
             kname = vals[hdr.index('Kernel Name')]
             short = kname.split('(')[0].split('<')[0].replace('void ', '')
-            key = name if len(kernels) == 1 else f"{name}:{short}"
+            if len(names) > 1:
+                key = names[ki] if ki < len(names) else f"{names[-1]}:{short}"
+            else:
+                key = name if len(kernels) == 1 else f"{name}:{short}"
+            if key in traffic:
+                continue
             lines.append(f"== {key}   ({os.path.basename(path)})")
             lines.append(f"{'Kernel Name':74s} {kname[:110]}")
             tot = 0.0
