@@ -977,6 +977,8 @@ struct WgHaloArgs {
   uint32_t pair_lo[WGH_MAX_PAIRS];   // (window offset of slab a) >> 4  |  ((offset of slab b - offset of slab a) >> 4) << 16
   uint8_t pair_a[WGH_MAX_PAIRS];     // slab indices of the two M halves (pair_b = 255: none)
   uint8_t pair_b[WGH_MAX_PAIRS];
+  uint8_t ord[2 * WGH_MAX_PAIRS];    // per group (entries [2 p_begin, 2 p_end)): its slots 2 * (pair - p_begin) + half, sorted
+                                     // by weight offset (the reduce kernel writes the gradient in memory order)
 };
 
 // body shared by the single-layer kernel (arguments in the constant bank) and the grouped kernel (arguments of the CTA's
@@ -1136,47 +1138,56 @@ conv_wgrad_halo_kernel(const __grid_constant__ UmmaMaps maps, const __grid_const
 }
 
 // second stage for the halo kernel: same partial layout as conv_wgrad_reduce_kernel, slab mapping through the pair table.
-// One thread per output element (accumulator row, column): it adds the `splits` partials of its element in a fixed order,
-// eight independent loads in flight at a time (the previous version - 1024-thread blocks that met in shared memory - ran
-// at 1.7 TB/s on partials that sit in L2: 22 us for the 9x9 layer at the training batch).
-// block = (128 rows, 2 columns), blockIdx = (accumulator block, group, column pair)
-SS_DEVINL void wgrad_halo_reduce_body(const ConvGeom* __restrict__ gp, const float* __restrict__ partial,
-                                      const WgHaloArgs& wa, float* __restrict__ grads, const int blk, const int group,
-                                      const int n) {
-  const int row = threadIdx.x;
+// One block per (output column n, pair group), one thread per (accumulator block, row): it adds the `splits` partials of
+// its element in a fixed order (eight independent loads in flight) and parks the sum in shared memory; the block then
+// adds its sums to the weight-gradient tensor IN MEMORY ORDER - for one (n, input channel) the taps of a group are
+// adjacent words (the host sorts the group's slabs by weight offset), so a warp updates runs of consecutive words.
+// (Writing straight from the accumulator layout - consecutive threads = consecutive input channels, K*K words apart -
+//  made every thread's read-modify-write its own 32-byte sector: 19 of the 9x9 layer's 22 us.)
+#define WGR_PITCH 65
+__global__ void __launch_bounds__(1024) conv_wgrad_halo_reduce_kernel(const ConvGeom* __restrict__ gp,
+                                                                      const float* __restrict__ partial,
+                                                                      const __grid_constant__ WgHaloArgs wa,
+                                                                      float* __restrict__ grads) {
+  __shared__ float out[16 * WGR_PITCH];            // [slot t = 2 * block + M half][64 channels], pitch 65: conflict-free
+  const int n = blockIdx.x, group = blockIdx.y;
   const int p_begin = group * wa.pairs_per_group;
   const int p_end = min(wa.npairs, p_begin + wa.pairs_per_group);
   const int np = p_end - p_begin;
-  const bool is_bias = (blk == np) && (group == 0) && (wa.bias_off >= 0);
-  if (blk > np || (blk == np && !is_bias) || n >= wa.N) return;
-  const size_t cta_stride = (size_t)wa.groups * wa.blocks_per_cta * wa.N * 128;
-  const float* p = partial + ((size_t)group * wa.blocks_per_cta + blk) * (size_t)wa.N * 128 + (size_t)n * 128 + row;
-  float tot = 0.f;
-  int sp = 0;
-  for (; sp + 8 <= wa.splits; sp += 8) {
-    float v[8];
+  const int blk = threadIdx.x >> 7, row = threadIdx.x & 127;
+  const bool is_bias = (blk == np) && (group == 0) && (wa.bias_off >= 0) && row == 0;
+  if (blk < np || is_bias) {
+    const size_t cta_stride = (size_t)wa.groups * wa.blocks_per_cta * wa.N * 128;
+    const float* p = partial + ((size_t)group * wa.blocks_per_cta + blk) * (size_t)wa.N * 128 + (size_t)n * 128 + row;
+    float tot = 0.f;
+    int sp = 0;
+    for (; sp + 8 <= wa.splits; sp += 8) {
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(sp + u) * cta_stride);
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(sp + u) * cta_stride);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) tot += v[u];                     // fixed order -> deterministic
+      for (int u = 0; u < 8; ++u) tot += v[u];                     // fixed order -> deterministic
+    }
+    for (; sp < wa.splits; ++sp) tot += __ldg(p + (size_t)sp * cta_stride);
+    if (is_bias) {
+      if (n < wa.gN) grads[wa.bias_off + n] += tot;
+    } else {
+      out[(2 * blk + (row >> 6)) * WGR_PITCH + (row & 63)] = tot;
+    }
   }
-  for (; sp < wa.splits; ++sp) tot += __ldg(p + (size_t)sp * cta_stride);
-  if (is_bias) {
-    if (row == 0 && n < wa.gN) grads[wa.bias_off + n] += tot;
-    return;
+  __syncthreads();
+  if (n >= gp->N || n >= wa.gN) return;
+  const int nslots = 2 * np;
+  for (int i = threadIdx.x; i < nslots * 64; i += 1024) {
+    const int j = i / nslots, q = i - j * nslots;
+    const int t = wa.ord[2 * p_begin + q];                          // slot of the q-th lowest weight offset of the group
+    const int pr = p_begin + (t >> 1);
+    const int sidx = (t & 1) ? (int)wa.pair_b[pr] : (int)wa.pair_a[pr];
+    if (sidx == 255) continue;
+    const Slab sl = gp->slab[sidx];
+    if (j >= sl.wcn) continue;
+    grads[gp->w_off + sl.woff + (int64_t)j * gp->w_sC + (int64_t)n * gp->w_sN] += out[t * WGR_PITCH + j];
   }
-  const int s = (row >> 6) ? (int)wa.pair_b[p_begin + blk] : (int)wa.pair_a[p_begin + blk];
-  const int j = row & 63;
-  if (s == 255) return;
-  const Slab sl = gp->slab[s];
-  if (j >= sl.wcn) return;
-  if (n < gp->N && n < wa.gN) grads[gp->w_off + sl.woff + (int64_t)j * gp->w_sC + (int64_t)n * gp->w_sN] += tot;
-}
-__global__ void __launch_bounds__(256) conv_wgrad_halo_reduce_kernel(const ConvGeom* __restrict__ gp,
-                                                                     const float* __restrict__ partial,
-                                                                     const __grid_constant__ WgHaloArgs wa,
-                                                                     float* __restrict__ grads) {
-  wgrad_halo_reduce_body(gp, partial, wa, grads, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z * 2 + (int)threadIdx.y);
 }
 
 static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHaloArgs* out) {
@@ -1217,6 +1228,19 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   wa.pairs_per_group = (wa.npairs + wa.groups - 1) / wa.groups;
   wa.groups = (wa.npairs + wa.pairs_per_group - 1) / wa.pairs_per_group;
   wa.blocks_per_cta = wa.pairs_per_group + 1;
+  // per group: its accumulator slots (2 * pair + M half) in the order of their weight offsets
+  for (int gidx = 0; gidx < wa.groups; ++gidx) {
+    const int p_begin = gidx * wa.pairs_per_group, p_end = std::min(wa.npairs, p_begin + wa.pairs_per_group);
+    const int nslots = 2 * (p_end - p_begin);
+    std::pair<long long, int> key[2 * WGH_MAX_PAIRS];
+    for (int t = 0; t < nslots; ++t) {
+      const int pr = p_begin + (t >> 1);
+      const int sidx = (t & 1) ? (int)wa.pair_b[pr] : (int)wa.pair_a[pr];
+      key[t] = std::make_pair(sidx == 255 ? (1LL << 60) : (long long)g.slab[sidx].woff, t);
+    }
+    std::sort(key, key + nslots);
+    for (int t = 0; t < nslots; ++t) wa.ord[2 * p_begin + t] = (uint8_t)key[t].second;
+  }
   wa.n_tiles = ha.n_tiles;
   // split the pixel axis: every CTA should own >= 4 pixel tiles (the split-K partials cost 32 KB x blocks per CTA)
   const int min_tiles = std::max(1, ss_env_int("SSHSLIE_WGH_MIN_TILES", 8));
@@ -1284,8 +1308,7 @@ int ss_launch_conv_wgrad_halo(const ConvGeom* g_dev, const ConvGeom& g, const Um
     rc = ss_check_launch("conv_wgrad_halo");
     if (rc || g_wgrad_part == 1) return rc;
   }
-  dim3 rgrid(wa.blocks_per_cta, wa.groups, wa.N / 2);
-  conv_wgrad_halo_reduce_kernel<<<rgrid, dim3(128, 2), 0, st>>>(g_dev, partial, wa, grads);
+  conv_wgrad_halo_reduce_kernel<<<dim3(wa.N, wa.groups), 1024, 0, st>>>(g_dev, partial, wa, grads);
   return ss_check_launch("conv_wgrad_halo_reduce");
 }
 
