@@ -30,7 +30,8 @@ DEFAULTS = dict(
     eval_every_epoch=200, plot_every_epoch=200, c_loss_reconstruction=10., c_loss_r_fidelity=1.,
     c_loss_i_smooth_low=1., c_loss_i_smooth_delta=20., c_loss_fourier=0.2, c_loss_spectral_cons=1.,
     alpha_i_smooth_low=1., alpha_i_smooth_delta=10., save_reflectance=False, save_illumination=False,
-    save_i_delta=False, model_name='no_name_model', pretrained_model='', freeze_decom_epochs=0)
+    save_i_delta=False, model_name='no_name_model', pretrained_model='', freeze_decom_epochs=0,
+    test_model_dir='')      # phase=test only: checkpoint directory to load ('' = the newest Decomposition_* of this model)
 
 
 def parse_args(argv=None):
@@ -49,8 +50,15 @@ def parse_args(argv=None):
     args.model_ckpt_dir = './checkpoint/' + args.model_name
     args.eval_result_dir = './results/eval_results_' + args.full_model_name
     args.test_result_dir = './results/test_results_' + args.full_model_name
-    # the reference reads 'decomposition_<ts>' but writes 'Decomposition_<ts>' (SURVEY A.1); use the written name
-    args.test_model_dir = os.path.join(args.model_ckpt_dir, 'Decomposition_' + args.timestamp)
+    # the reference reads 'decomposition_<ts>' but writes 'Decomposition_<ts>' (SURVEY A.1); use the written name.
+    # A standalone `--phase test` run has a fresh timestamp, so that directory cannot exist: take --test_model_dir, else
+    # the newest Decomposition_* directory of this model.
+    if not args.test_model_dir:
+        args.test_model_dir = os.path.join(args.model_ckpt_dir, 'Decomposition_' + args.timestamp)
+        if args.phase == 'test':
+            found = sorted(glob(os.path.join(args.model_ckpt_dir, 'Decomposition_*')), key=os.path.getmtime)
+            if found:
+                args.test_model_dir = found[-1]
     return args
 
 
@@ -92,7 +100,9 @@ def main(args):
     torch.manual_seed(args.seed_value)
     if not (args.use_gpu and torch.cuda.is_available()):
         raise SystemExit("sshslie_b200 needs a CUDA device (use_gpu=1 on a B200); the hot path has no CPU implementation")
-    device = torch.device('cuda')
+    idx = int(str(args.gpu_idx).split(',')[0] or 0)               # the reference sets CUDA_VISIBLE_DEVICES from gpu_idx
+    device = torch.device(f'cuda:{idx}' if idx < torch.cuda.device_count() else 'cuda:0')
+    torch.cuda.set_device(device)
     model = build_model(args, device)
     if args.pretrained_model and os.path.exists(args.pretrained_model):
         ckpt = torch.load(args.pretrained_model, map_location=device)
