@@ -81,6 +81,11 @@ SSHSLIE_API int sshslie_engine_bind(sshslie_engine* e, void* workspace, int64_t 
 SSHSLIE_API int sshslie_forward(sshslie_engine* e, const float* x, const float* params,
                     float* R, float* I, float* I_delta, float* S, void* stream);
 
+/* IllumAdjustmentNet.forward(I, R) on its own (model.py:143-175): I (B,1,H,W), R (B,C,H,W) fp32 in, I_delta (B,1,H,W) fp32
+ * out; the engine may be an inference or a training engine of that shape. */
+SSHSLIE_API int sshslie_illum_forward(sshslie_engine* e, const float* I, const float* R, const float* params, float* I_delta,
+                          void* stream);
+
 /* LowLightEnhance.compute_loss + loss.backward() (model.py:544-575, 315): writes the seven loss values
  * (order of SSHSLIE_NUM_LOSSES) to losses[7], d(total_loss)/d(params) to grads (flat, overwritten),
  * and the four forward outputs when the pointers are non-null.  phase_mask selects sub-ranges of the

@@ -239,6 +239,43 @@ int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// cat[R, I] (model.py:146) in the layout the illumination net reads: RI (B,H,W,192) bf16 =
+//   [ bf16(R) (64) | bf16(I), 63 zero lanes (never written) | bf16(R - bf16(R)) (64) ]      (hi + lo pair)
+// normally written by the sigmoid head's epilogue; this kernel builds it from caller-provided fp32 planes
+// (IllumAdjustmentNet.forward on its own).  64 bands.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_ri_kernel(const float* __restrict__ R, const float* __restrict__ I,
+                                                      bf16* __restrict__ RI, int HW) {
+  __shared__ float tile[64][C64_PITCH];
+  const int b = blockIdx.y, hw0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool in = hw0 + tx < HW;
+  const float* rp = R + (int64_t)b * 64 * HW + hw0 + tx;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = in ? __ldg(rp + (int64_t)(ty + 8 * j) * HW) : 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tile[ty + 8 * j][tx] = v[j];
+  __syncthreads();
+  const int t = ty * 32 + tx, i = t >> 3, q = t & 7;
+  if (hw0 + i < HW) {
+    float f[8], lo[8];
+    tile_to_vec8(tile, i, q, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) lo[k] = f[k] - bf2f(f2bf(f[k]));
+    bf16* o = RI + ((int64_t)b * HW + hw0 + i) * 192;
+    *reinterpret_cast<uint4*>(o + 8 * q) = pack8(f);
+    *reinterpret_cast<uint4*>(o + 128 + 8 * q) = pack8(lo);
+    if (q == 0) o[64] = f2bf(__ldg(I + (int64_t)b * HW + hw0 + i));
+  }
+}
+int ss_launch_pack_ri(const float* R, const float* I, bf16* RI, int B, int C, int H, int W, cudaStream_t st) {
+  if (C != 64) { ss_set_error("pack_ri: 64 bands only"); return SSHSLIE_ERR_ARG; }
+  pack_ri_kernel<<<dim3((unsigned)((H * W + 31) / 32), B), dim3(32, 8), 0, st>>>(R, I, RI, H * W);
+  EW_CHECK("pack_ri");
+}
+
+// ---------------------------------------------------------------------------------------------
 // S = R*I_delta + R*I_low  (model.py:233) -> S32 (B,C,H,W) fp32 and Sb (B,H,W,C) bf16 (2nd decomposition input)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) make_s_c64_kernel(const float* __restrict__ R, const float* __restrict__ I,

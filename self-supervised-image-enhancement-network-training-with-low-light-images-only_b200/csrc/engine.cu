@@ -158,6 +158,8 @@ struct sshslie_engine {
   std::vector<int> pipe_valid;
   std::vector<char> pipe_use;            // 0 = undecided, 1 = pipelined kernel, 2 = halo kernel
   bool pipe_on = true;
+  int fwd_pack_begin = -1, fwd_illum_begin = -1, fwd_illum_end = -1;   // op ranges of ops_fwd (sshslie_illum_forward)
+  bf16* RI_ptr = nullptr;
   int s2_min_tiles = 512;                // stride-2 / transposed layers: halo-reuse kernels from this many tiles (per class)
   int pipe_min_tiles_head = 1024;        // same threshold for the sigmoid head (its staged fp32 stores are the gain)
   int pipe_min_tiles = 1024;             // below this the halo kernel (2-3 small co-resident CTAs per SM) has the lower latency
@@ -859,6 +861,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
             return cudaMemsetAsync(e->grads, 0, e->nparams * sizeof(float), st) == cudaSuccess ? 0 : SSHSLIE_ERR_CUDA;);
   }
   PUSH(F, return ss_launch_nchw32_to_nhwc16(e->x, X.p, B, C, H, W, 64, st););
+  e->fwd_pack_begin = (int)F.size();
   // fp32 master weights -> packed bf16: the first two layers' weights (conv0, 9x9) on the caller's stream, everything
   // else on a side stream, joined after the 9x9 layer (pack_split = first pack block of the third geom)
   PUSH(F, return ss_launch_pack_weights(e->geoms_dev, e->pack_start_dev, (int)e->geoms.size(), e->pack_blocks,
@@ -873,6 +876,8 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   DecompGeoms G1 = plan_decomp_fwd(e, F, X, d1, head1, true);
 
   // IllumAdjustmentNet (model.py:143-175)
+  e->fwd_illum_begin = (int)F.size();
+  e->RI_ptr = RI.p;
   int g_i0, g_i1, g_i2, g_i3, g_d1, g_d2, g_d3, g_fus, g_fin;
   {
     WAddr wa = waddr_conv_fwd(e, L_I_CONV0);
@@ -936,6 +941,7 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     ep.mode = EPI_PLANE32; ep.plane32 = e->Id32; ep.H = H; ep.W = W;
     PUSH(F, return run_gather(e, g_fin, ep, L_I_FINAL, st););
   }
+  e->fwd_illum_end = (int)F.size();
   Tens Sb;
   if (train) Sb = e->talloc(B, H, W, 64);
   {
@@ -1312,6 +1318,25 @@ extern "C" int sshslie_forward(sshslie_engine* e, const float* x, const float* p
   int rc = run_ops(e->ops_fwd, st);
   if (!rc && e->train) rc = e->join(st);
   return rc;
+}
+
+// IllumAdjustmentNet.forward(I, R) on its own (model.py:143-175): packs cat[R, I] the way the sigmoid head leaves it for the
+// illumination net (bf16 hi | I | bf16 residual), then runs the illumination part of the forward plan.
+extern "C" int sshslie_illum_forward(sshslie_engine* e, const float* I, const float* R, const float* params, float* I_delta,
+                                     void* stream) {
+  if (!e || !I || !R || !params || !I_delta) { ss_set_error("sshslie_illum_forward: null argument"); return SSHSLIE_ERR_ARG; }
+  if (!e->bound) { ss_set_error("sshslie_illum_forward: engine not bound to a workspace"); return SSHSLIE_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  e->params = params;
+  const bool saved_side = e->use_side;
+  e->use_side = false;                       // everything on the caller's stream: the weight packing has no 9x9 layer to hide behind
+  int rc = SSHSLIE_OK;
+  for (int i = e->fwd_pack_begin; i < e->fwd_pack_begin + 2 && !rc; ++i) rc = e->ops_fwd[i](st);
+  if (!rc) rc = ss_launch_pack_ri(R, I, e->RI_ptr, e->B, e->C, e->H, e->W, st);
+  for (int i = e->fwd_illum_begin; i < e->fwd_illum_end && !rc; ++i) rc = e->ops_fwd[i](st);
+  e->use_side = saved_side;
+  if (rc) return rc;
+  return copy_out(I_delta, e->Id32, (int64_t)e->B * e->H * e->W, st);
 }
 
 extern "C" int sshslie_loss_and_grad(sshslie_engine* e, const float* x, const float* params,

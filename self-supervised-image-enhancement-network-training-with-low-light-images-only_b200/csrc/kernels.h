@@ -66,6 +66,7 @@ int ss_launch_upsample_add(const bf16* r, const bf16* a, bf16* out, int B, int h
 int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
                           const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W, int h2, int w2,
                           int h1, int w1, cudaStream_t st);
+int ss_launch_pack_ri(const float* R, const float* I, bf16* RI, int B, int C, int H, int W, cudaStream_t st);
 int ss_launch_make_s(const float* R, const float* I, const float* Id, float* S32, bf16* Sb, int B, int C, int H, int W,
                      cudaStream_t st);
 int ss_launch_s_bwd(const float* dS32, const float* dSf32, const bf16* dSb, const float* R, const float* I,

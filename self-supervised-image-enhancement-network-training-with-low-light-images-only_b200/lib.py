@@ -18,7 +18,7 @@ FLAG_FORCE_SIMT = 2
 EXPORTS = [
     "sshslie_version", "sshslie_last_error", "sshslie_param_table", "sshslie_engine_create",
     "sshslie_engine_destroy", "sshslie_engine_workspace_bytes", "sshslie_engine_bind", "sshslie_forward",
-    "sshslie_loss_and_grad", "sshslie_adam_step", "sshslie_loss_scratch_bytes", "sshslie_fourier_loss", "sshslie_pixel_losses",
+    "sshslie_loss_and_grad", "sshslie_illum_forward", "sshslie_adam_step", "sshslie_loss_scratch_bytes", "sshslie_fourier_loss", "sshslie_pixel_losses",
     "sshslie_conv2d_scratch_bytes", "sshslie_conv2d", "sshslie_profile_step", "sshslie_profile_row",
     "sshslie_launch_count", "sshslie_umma_probe", "sshslie_gather_patches", "sshslie_conv2d_last_ms", "sshslie_denorm_hwc", "sshslie_psnr_sam", "sshslie_ssim_sum",
     "sshslie_transformer_block_scratch_bytes", "sshslie_transformer_block",
@@ -59,6 +59,7 @@ def load():
     lib.sshslie_engine_workspace_bytes.restype = i64
     lib.sshslie_engine_bind.argtypes = [vp, vp, i64, vp]
     lib.sshslie_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.sshslie_illum_forward.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.sshslie_loss_and_grad.argtypes = [vp, vp, vp, ctypes.POINTER(LossCfg), vp, vp, vp, vp, vp, vp, i32, vp]
     lib.sshslie_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]
     lib.sshslie_loss_scratch_bytes.restype = i64

@@ -90,10 +90,14 @@ class IllumAdjustmentNet(nn.Module):
         self.deconv3 = conv(channel, channel, kernel_size, activation=True)
         self.feature_fusion = conv(channel * 3, channel, 1, activation=False)
         self.final_conv = nn.Conv2d(channel, 1, 3, stride=1, padding=1)
+        self._owner = None
 
     def forward(self, I, R):
-        raise L.SshslieError("IllumAdjustmentNet alone is not an entry point of the CUDA path; "
-                             "call LowLightEnhance.forward (model.py:229-234)")
+        """model.py:143-175: I (B,1,H,W), R (B,C,H,W) -> I_delta (B,1,H,W), through the owner's engine of that shape."""
+        owner = getattr(self, "_owner", None)
+        if owner is None:
+            raise L.SshslieError("IllumAdjustmentNet must be owned by a LowLightEnhance to run")
+        return owner[0].illum_forward(I, R)
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -440,6 +444,7 @@ class LowLightEnhance(nn.Module):
         self.decomposition_net = DecompositionNet(in_channels=input_channels)
         self.illum_adjust_net = IllumAdjustmentNet(in_channels=input_channels)
         self.decomposition_net._owner = [self]
+        self.illum_adjust_net._owner = [self]       # (a list: the owner must not become a sub-module of its own child)
 
         self._plist = list(self.parameters())
         total, offs, sizes = L.param_table(input_channels)
@@ -593,6 +598,22 @@ class LowLightEnhance(nn.Module):
         L.check(lib.sshslie_forward(eng.handle, L.ptr(eng.x), L.ptr(self._flat), L.ptr(R), L.ptr(I),
                                     L.ptr(Id), L.ptr(S), stream), "sshslie_forward")
         return R, I, Id, S
+
+    def illum_forward(self, I, R):
+        """`self.illum_adjust_net(I, R)` (model.py:232): the illumination net alone on caller-provided I and R."""
+        self._ensure_flat()
+        if not (I.is_cuda and R.is_cuda):
+            raise L.SshslieError("sshslie_b200 runs on CUDA tensors only (no CPU implementation of the hot path)")
+        if I.dim() != 4 or R.dim() != 4 or I.shape[1] != 1 or I.shape[0] != R.shape[0] or I.shape[2:] != R.shape[2:]:
+            raise L.SshslieError(f"illum_adjust_net: expected I (B,1,H,W) and R (B,C,H,W), got {tuple(I.shape)} {tuple(R.shape)}")
+        eng = self._engine(R, train=False)
+        lib = L.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self._flat.device).cuda_stream)
+        Ic, Rc = I.float().contiguous(), R.float().contiguous()
+        Id = torch.empty_like(Ic)
+        L.check(lib.sshslie_illum_forward(eng.handle, L.ptr(Ic), L.ptr(Rc), L.ptr(self._flat), L.ptr(Id), stream),
+                "sshslie_illum_forward")
+        return Id
 
     def _launch_loss_and_grad(self, eng, phase_mask=3):
         lib = L.load()

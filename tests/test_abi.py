@@ -79,7 +79,7 @@ def test_cpu_tensors_fail_loudly():
     with pytest.raises(S.lib.SshslieError):
         m.compute_loss(torch.rand(1, 64, 32, 32))
     with pytest.raises(S.lib.SshslieError):
-        m.illum_adjust_net(torch.rand(1, 1, 8, 8), torch.rand(1, 64, 8, 8))
+        m.illum_adjust_net(torch.rand(1, 1, 16, 16), torch.rand(1, 64, 16, 16))
 
 
 def test_bench_reference_arm_prints_contract_line():

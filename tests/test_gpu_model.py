@@ -270,6 +270,29 @@ def test_forward_any_even_size(shape):
     assert (S.cpu() - Sr).abs().max() <= 5e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64), (1, 40, 56)])
+def test_sub_networks_are_callable(shape):
+    """`decomposition_net(x) -> (R, L)` and `illum_adjust_net(I, R) -> I_delta` on their own (model.py:49-70, 143-175), the
+    second on caller-provided inputs that did NOT come from the decomposition net."""
+    from oracle import sshslie_oracle as O
+    B, H, W = shape
+    m = _model(O.JYU_COEF)
+    p = O.init_params(41)
+    x = _rect_input(B, H, W, 21)
+    with torch.no_grad():
+        R, I = m.decomposition_net(x.cuda())
+    Rr, Ir = O.decomposition_net(p, x)
+    assert (R.cpu() - Rr).abs().max() <= 5e-3 and (I.cpu() - Ir).abs().max() <= 5e-3
+    g = torch.Generator().manual_seed(5)
+    Rin = torch.rand(B, 64, H, W, generator=g)
+    Iin = torch.rand(B, 1, H, W, generator=g)
+    with torch.no_grad():
+        Id = m.illum_adjust_net(Iin.cuda(), Rin.cuda())
+    Idr = O.illum_adjust_net(p, Iin, Rin)
+    assert Id.shape == (B, 1, H, W)
+    assert (Id.cpu() - Idr).abs().max() <= 4e-3 * max(1.0, float(Idr.abs().max()))
+
+
 def test_odd_size_is_refused():
     """The reference itself cannot run an odd image (deconv output 2*ceil(H/2) != H, torch.cat fails, model.py:55-58)."""
     from oracle import sshslie_oracle as O
