@@ -176,9 +176,6 @@ int ss_launch_upsample_add(const bf16* r, const bf16* a, bf16* out, int B, int h
                 (const uint4*)r, (const uint4*)a, (uint4*)out, h, w, ho, wo, (float)h / (float)ho, (float)w / (float)wo, total);
   EW_CHECK("upsample_nearest_add");
 }
-int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, cudaStream_t st) {
-  return ss_launch_upsample_add(r, a, out, B, h, w, 2 * h, 2 * w, st);
-}
 
 // ---------------------------------------------------------------------------------------------
 // fg[b,y,x,:] = [ (r1+a2)[y/4,x/4] | (r2+a1)[y/2,x/2] | hi(r3+a0)[y,x] | lo(r3+a0)[y,x] ]   256 channels  [model.py:168-172]

@@ -60,7 +60,6 @@ int ss_launch_conv_gather_pipe(const ConvGeom& g, const UmmaMaps& maps, const Ep
 // elementwise.cu
 int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, int W, int ldo, cudaStream_t st);
 int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, int W, int ldi, cudaStream_t st);
-int ss_launch_upsample2_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, cudaStream_t st);
 // nearest resize (h, w) -> (ho, wo) of r (+ a), ATen index semantics
 int ss_launch_upsample_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, int ho, int wo, cudaStream_t st);
 int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
