@@ -1258,7 +1258,6 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   int stages = (int)((216 * 1024 - WGH_ONES_BYTES) / wa.stage_bytes);
   stages = std::min(3, stages);
   if (2 * wa.stage_bytes + WGH_ONES_BYTES <= 108 * 1024) stages = 2;
-  stages = std::min(4, std::max(1, ss_env_int("SSHSLIE_WGH_STAGES", stages)));
   if (stages < 2 || stages * wa.stage_bytes + WGH_ONES_BYTES > 216 * 1024) return 0;
   wa.stages = stages;
   *out = wa;
