@@ -981,8 +981,7 @@ struct WgHaloArgs {
                                      // by weight offset (the reduce kernel writes the gradient in memory order)
 };
 
-// body shared by the single-layer kernel (arguments in the constant bank) and the grouped kernel (arguments of the CTA's
-// job staged in shared memory, tensor maps in global memory): bx = pixel split, by = pair group
+// body of the kernel (arguments in the constant bank): bx = pixel split, by = pair group
 SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const CUtensorMap* __restrict__ gmap_p,
                                const WgHaloArgs& wa, float* __restrict__ partial, const int bx, const int by) {
   extern __shared__ unsigned char smem_dyn[];
@@ -1053,12 +1052,12 @@ SS_DEVINL void wgrad_halo_body(const CUtensorMap* __restrict__ halo_maps, const 
       }
     }
   } else if (warp == 1 || warp == WGH_ISSUERS) {
-    // Measured on B200 (tools/wgrad_breadcrumbs.py): this loop runs at ~50 clk per M128 N64 K16 MMA, the shared-memory
+    // Measured on B200 (cycle breadcrumbs, round 1): this loop runs at ~50 clk per M128 N64 K16 MMA, the shared-memory
     // operand-read limit of SS-mode MMAs at N = 64 (tools/umma_probe.py: 48 clk, same for K- and MN-major operands).
     // Neither issuing from two warps (WGH_ISSUERS = 2) nor interleaving accumulators changed that.
     const int issuer = (warp == 1) ? 0 : 1;
-    // (in the grouped kernel `wa` lives in shared memory: every loop-invariant word goes through a shuffle once, so that
-    // ptxas can keep descriptors in uniform registers instead of wrapping each UTCHMMA in an R2UR waterfall)
+    // (every loop-invariant word goes through a shuffle once, so that ptxas can keep descriptors in uniform registers
+    // instead of wrapping each UTCHMMA in an R2UR waterfall)
     const uint32_t idesc = uniform32(make_idesc(128, wa.N, 1, 1));
     const uint32_t tm = uniform32(tmem_base);
     // A: two 64-channel atoms (the two taps), LBO per pair; K groups of 8 pixels = tile rows, SBO = pitch * 128 B
