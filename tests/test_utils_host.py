@@ -77,3 +77,20 @@ def test_load_hsi_matches_reference(tmp_path, norm, kw):
     np.testing.assert_array_equal(ours, ref)
     for mode in range(8):
         np.testing.assert_array_equal(U.data_augmentation(x, mode), R.data_augmentation(x, mode))
+
+
+def test_nearest_index_formula_is_atens():
+    """The index the CUDA resize kernels use (elementwise.cu nearest_src: min(floor(dst * (float)in / out), in - 1)) is what
+    F.interpolate(mode='nearest') does for every pyramid size an even image can produce (model.py:156-169)."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    for n in list(range(16, 140, 2)) + [500, 510, 1022]:
+        h1 = (n + 1) // 2
+        h2 = (h1 + 1) // 2
+        h3 = (h2 + 1) // 2
+        for src, dst in ((h3, h2), (h2, h1), (h1, n), (h2, n)):
+            ref = F.interpolate(torch.arange(src, dtype=torch.float32).view(1, 1, 1, src), size=(1, dst), mode="nearest")
+            scale = np.float32(src) / np.float32(dst)
+            mine = np.minimum(np.floor(np.arange(dst, dtype=np.float32) * scale).astype(np.int64), src - 1)
+            assert np.array_equal(ref.view(-1).numpy().astype(np.int64), mine), (src, dst)
