@@ -162,7 +162,9 @@ def transformer_block(p: Params, x, prefix="illum_adjust_net.attn.", heads=4, he
 def illum_adjust_net(p: Params, I, R, prefix="illum_adjust_net.", q=_ident):
     """model.py:143-175."""
     a0 = q(_conv(p, prefix + "conv0.0", q(torch.cat([R, I], 1), "RI")), "a0")
-    a1 = q(_conv(p, prefix + "conv1.0", a0, stride=2, relu=True), "a1")
+    a1_raw = _conv(p, prefix + "conv1.0", a0, stride=2, relu=True)
+    a1 = q(a1_raw, "a1")                 # as conv2 reads it
+    a1s = q(a1_raw, "a1_skip")           # as the skip connections read it (identical unless q distinguishes the two)
     a2 = q(_conv(p, prefix + "conv2.0", a1, stride=2, relu=True), "a2")
     a3 = q(_conv(p, prefix + "conv3.0", a2, stride=2, relu=True), "a3")
     t = q(transformer_block(p, a3, prefix + "attn."), "t")
@@ -170,7 +172,7 @@ def illum_adjust_net(p: Params, I, R, prefix="illum_adjust_net.", q=_ident):
     r1 = q(_conv(p, prefix + "deconv1.0", up(t, a2), relu=True), "r1")
     d1 = q(r1 + a2, "d1")
     r2 = q(_conv(p, prefix + "deconv2.0", up(d1, a1), relu=True), "r2")
-    d2 = q(r2 + a1, "d2")
+    d2 = q(r2 + a1s, "d2")
     r3 = q(_conv(p, prefix + "deconv3.0", up(d2, a0), relu=True), "r3")
     d3 = q(r3 + a0, "d3")
     fg = torch.cat([up(d1, d3), up(d2, d3), d3], 1)
@@ -218,7 +220,9 @@ class _RoundBf16Pair(torch.autograd.Function):
         return g.to(torch.bfloat16).to(torch.float32)
 
 
-HI_LO_TENSORS = ("RI", "a0", "r3", "d3", "ff")      # full-resolution tensors feeding final_conv
+# tensors the CUDA path keeps as bf16 pairs: the full-resolution tensors feeding final_conv, and the
+# half-resolution skip d2 = deconv2 + conv1 (conv1's output keeps its residual for the skip connections only)
+HI_LO_TENSORS = ("RI", "a0", "r3", "d3", "ff", "a1_skip", "d2")
 
 
 def cuda_storage(t, name=None):

@@ -52,8 +52,8 @@
 
 struct PipeArgs {
   int nh;                      // distinct (source, channel-slab) halo windows per tile
-  int src[SS_MAX_SRC];
-  int c0[SS_MAX_SRC];
+  int src[SS_MAX_WIN];
+  int c0[SS_MAX_WIN];
   int pad, halo_bytes, tmem_cols, n_tiles;
   int nhb;                     // halo buffers (2..4)
   int lanes;                   // 1 or 2 issuer + epilogue lanes (2 needs 4 accumulators: 4 * Npad <= 512 TMEM columns)
@@ -179,13 +179,15 @@ SS_DEVINL void epi_head16_staged(const Epi& e, int c, bool ok, int b, int oh, in
     }
   }
   const int64_t pix = ((int64_t)b * e.H + oh) * e.W + ow;
+  float i_lo = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int n = c + i;
     const float s = sigmoidf_(v[i]);
     if (n < e.C) stg32[n * 128 + row] = s;
     else if (n == e.C && e.I32 && ok) e.I32[pix] = s;
-    v[i] = (n <= e.C) ? s : 0.f;
+    v[i] = (n <= e.C) ? s : ((n == e.C + 1 && e.ri_lo_off > 0) ? i_lo : 0.f);     // lane C + 1: I's bf16 residual
+    if (n == e.C) i_lo = s - bf2f(f2bf(s));
   }
   if (e.RI && ok) {
     bf16* p = e.RI + pix * e.ri_c + c;
@@ -549,7 +551,7 @@ static int pipe_plan(const ConvGeom& g, const Epi& epi, PipePlan* out) {
     for (int j = 0; j < pa.nh; ++j)
       if (pa.src[j] == sl.src && pa.c0[j] == sl.c0) h = j;
     if (h < 0) {
-      if (pa.nh == SS_MAX_SRC) return 0;
+      if (pa.nh == SS_MAX_WIN) return 0;
       pa.src[pa.nh] = sl.src; pa.c0[pa.nh] = sl.c0; ++pa.nh;
     }
   }

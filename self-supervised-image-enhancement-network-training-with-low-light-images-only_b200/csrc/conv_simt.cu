@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ConvGeom* __res
   const int s = k >> 6, c = k & 63;
   const Slab sl = g->slab[s];
   float w = 0.f;
-  if (n < g->N && c < sl.wcn) w = __ldg(params + g->w_off + (int64_t)n * g->w_sN + sl.woff + (int64_t)c * g->w_sC);
+  const int cw = (g->dup_c >= 0 && sl.c0 + c == g->dup_c) ? c - 1 : c;      // a residual lane reads its hi lane's weight
+  if (n < g->N && cw >= 0 && cw < sl.wcn) w = __ldg(params + g->w_off + (int64_t)n * g->w_sN + sl.woff + (int64_t)cw * g->w_sC);
   g->wp[((size_t)s * g->Npad + n) * SS_SLAB + c] = f2bf(w);   // slab-major: one slab = Npad x 64 contiguous bf16
 }
 

@@ -183,8 +183,8 @@ conv_gather_umma4_kernel(const __grid_constant__ ConvGeom4 g4, const __grid_cons
 
 struct HaloArgs {
   int nh;                  // distinct (source, channel-slab) halo windows per tile
-  int src[SS_MAX_SRC];
-  int c0[SS_MAX_SRC];
+  int src[SS_MAX_WIN];
+  int c0[SS_MAX_WIN];
   int pad;                 // p = max |dh|,|dw|
   int T;                   // pixel tiles per CTA (template parameter of the kernel)
   int halo_bytes;          // one window, rounded up to 1024
@@ -433,7 +433,7 @@ static int halo_args(const ConvGeom& g, HaloArgs* out) {
     for (int j = 0; j < ha.nh; ++j)
       if (ha.src[j] == sl.src && ha.c0[j] == sl.c0) h = j;
     if (h < 0) {
-      if (ha.nh == SS_MAX_SRC) return 0;
+      if (ha.nh == SS_MAX_WIN) return 0;
       ha.src[ha.nh] = sl.src; ha.c0[ha.nh] = sl.c0; ++ha.nh;
     }
   }
@@ -965,8 +965,8 @@ int ss_launch_conv_wgrad_umma(const ConvGeom* g_dev, const ConvGeom& g, const Um
 #define WGH_MAX_GROUP_PAIRS 7          // 512 TMEM columns / N = 64, minus the bias block
 struct WgHaloArgs {
   int nh;
-  int src[SS_MAX_SRC];
-  int c0[SS_MAX_SRC];
+  int src[SS_MAX_WIN];
+  int c0[SS_MAX_WIN];
   int pad, halo_bytes;
   int N, gN, g_atoms;          // UMMA N (64 / 128), valid gradient channels, 64-channel atoms of G per tile
   int tmem_cols;
@@ -1195,7 +1195,7 @@ static int wgrad_halo_plan(const ConvGeom& g, int gN, long long bias_off, WgHalo
   WgHaloArgs wa;
   memset(&wa, 0, sizeof(wa));
   wa.nh = ha.nh;
-  for (int i = 0; i < SS_MAX_SRC; ++i) { wa.src[i] = ha.src[i]; wa.c0[i] = ha.c0[i]; }
+  for (int i = 0; i < SS_MAX_WIN; ++i) { wa.src[i] = ha.src[i]; wa.c0[i] = ha.c0[i]; }
   wa.pad = ha.pad; wa.halo_bytes = ha.halo_bytes;
   wa.gN = gN; wa.bias_off = bias_off;
   wa.N = (gN > 64) ? 128 : 64;

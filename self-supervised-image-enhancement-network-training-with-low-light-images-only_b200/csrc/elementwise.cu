@@ -164,6 +164,42 @@ __global__ void upsample_nearest_add_kernel(const uint4* __restrict__ r, const u
   const int64_t s = ((b * h + nearest_src(y, sh, h)) * w + nearest_src(x, sw, w)) * 8 + q;
   out[i] = a ? add8(r[s], a[s]) : r[s];
 }
+// the same resize of (r + a + a_lo), stored as a bf16 pair: hi = bf16(v), lo = bf16(v - hi)   [up(deconv2 + conv1), model.py:161-164]
+__global__ void upsample_nearest_add_pair_kernel(const uint4* __restrict__ r, const uint4* __restrict__ a,
+                                                 const uint4* __restrict__ al, uint4* __restrict__ out,
+                                                 uint4* __restrict__ out_lo, int h, int w, int ho, int wo, float sh,
+                                                 float sw, int64_t total) {
+  SS_PDL_ENTRY();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int q = (int)(i & 7);
+  const int64_t pix = i >> 3;
+  const int x = (int)(pix % wo);
+  const int64_t t = pix / wo;
+  const int y = (int)(t % ho);
+  const int64_t b = t / ho;
+  const int64_t s = ((b * h + nearest_src(y, sh, h)) * w + nearest_src(x, sw, w)) * 8 + q;
+  float f[8], g[8], l[8], lo[8];
+  unpack8(__ldg(r + s), f);
+  unpack8(__ldg(a + s), g);
+  unpack8(__ldg(al + s), l);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    f[j] = f[j] + g[j] + l[j];
+    lo[j] = f[j] - bf2f(f2bf(f[j]));
+  }
+  out[i] = pack8(f);
+  out_lo[i] = pack8(lo);
+}
+int ss_launch_upsample_add_pair(const bf16* r, const bf16* a, const bf16* a_lo, bf16* out, bf16* out_lo, int B, int h, int w,
+                                int ho, int wo, cudaStream_t st) {
+  const int64_t total = (int64_t)B * ho * wo * 8;
+  ss_launch_pdl(upsample_nearest_add_pair_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st,
+                (const uint4*)r, (const uint4*)a, (const uint4*)a_lo, (uint4*)out, (uint4*)out_lo, h, w, ho, wo,
+                (float)h / (float)ho, (float)w / (float)wo, total);
+  EW_CHECK("upsample_nearest_add_pair");
+}
+
 // (h, w) -> (ho, wo); the exact-doubling case keeps the one-read-four-writes kernel
 int ss_launch_upsample_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, int ho, int wo, cudaStream_t st) {
   if (ho == 2 * h && wo == 2 * w) {
@@ -178,12 +214,13 @@ int ss_launch_upsample_add(const bf16* r, const bf16* a, bf16* out, int B, int h
 }
 
 // ---------------------------------------------------------------------------------------------
-// fg[b,y,x,:] = [ (r1+a2)[y/4,x/4] | (r2+a1)[y/2,x/2] | hi(r3+a0)[y,x] | lo(r3+a0)[y,x] ]   256 channels  [model.py:168-172]
+// fg[b,y,x,:] = [ (r1+a2)[y/4,x/4] | hi(r2+a1)[y/2,x/2] | hi(r3+a0)[y,x] | lo(r3+a0)[y,x] | lo(r2+a1)[y/2,x/2] ]   320 channels  [model.py:168-172]
 // ---------------------------------------------------------------------------------------------
 // one thread = one (pixel, 8-channel vector) of ALL four 64-channel groups: eight independent 16-byte loads in flight, four
 // 16-byte stores; the eight threads of a pixel write 128 contiguous bytes per group (no divergence inside a warp)
 __global__ void __launch_bounds__(256) fuse_concat_kernel(const uint4* __restrict__ r1, const uint4* __restrict__ a2,
                                                           const uint4* __restrict__ r2, const uint4* __restrict__ a1,
+                                                          const uint4* __restrict__ a1l,
                                                           const uint4* __restrict__ r3, const uint4* __restrict__ r3l,
                                                           const uint4* __restrict__ a0, const uint4* __restrict__ a0l,
                                                           uint4* __restrict__ fg, int H, int W, int h2, int w2, int h1, int w1,
@@ -201,12 +238,25 @@ __global__ void __launch_bounds__(256) fuse_concat_kernel(const uint4* __restric
   const int64_t s1 = ((b * h2 + nearest_src(y, sh2, h2)) * w2 + nearest_src(x, sw2, w2)) * 8 + q;
   const int64_t s2 = ((b * h1 + nearest_src(y, sh1, h1)) * w1 + nearest_src(x, sw1, w1)) * 8 + q;
   const uint4 v_r1 = __ldg(r1 + s1), v_a2 = __ldg(a2 + s1), v_r2 = __ldg(r2 + s2), v_a1 = __ldg(a1 + s2);
+  const uint4 v_a1l = __ldg(a1l + s2);
   const uint4 v_r3 = __ldg(r3 + i), v_a0 = __ldg(a0 + i);
   uint4 v_r3l = make_uint4(0u, 0u, 0u, 0u), v_a0l = v_r3l;
   if (r3l) { v_r3l = __ldg(r3l + i); v_a0l = __ldg(a0l + i); }
-  uint4* o = fg + pix * 32 + q;
+  uint4* o = fg + pix * 40 + q;             // 320 channels: [d1 | d2 hi | d3 hi | d3 lo | d2 lo]
   o[0] = add8(v_r1, v_a2);
-  o[8] = add8(v_r2, v_a1);
+  {  // d2 = deconv2 + conv1 (with conv1's residual) as a bf16 pair
+    float f2[8], g2[8], l2[8], lo2[8];
+    unpack8(v_r2, f2);
+    unpack8(v_a1, g2);
+    unpack8(v_a1l, l2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f2[j] = f2[j] + g2[j] + l2[j];
+      lo2[j] = f2[j] - bf2f(f2bf(f2[j]));
+    }
+    o[8] = pack8(f2);
+    o[32] = pack8(lo2);
+  }
   // full-resolution block d3 = deconv3 + conv0 in ~16-bit mantissa: hi -> channels [128,192), residual -> [192,256)
   float f[8], g[8], hsum[8], r[8];
   unpack8(v_r3, f);
@@ -224,12 +274,12 @@ __global__ void __launch_bounds__(256) fuse_concat_kernel(const uint4* __restric
   o[16] = pack8(hsum);
   o[24] = pack8(r);
 }
-int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
+int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* a1l, const bf16* r3,
                           const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W, int h2, int w2,
                           int h1, int w1, cudaStream_t st) {
   const int64_t total = (int64_t)B * H * W * 8;
   ss_launch_pdl(fuse_concat_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), st, 
-      (const uint4*)r1, (const uint4*)a2, (const uint4*)r2, (const uint4*)a1, (const uint4*)r3, (const uint4*)r3l,
+      (const uint4*)r1, (const uint4*)a2, (const uint4*)r2, (const uint4*)a1, (const uint4*)a1l, (const uint4*)r3, (const uint4*)r3l,
       (const uint4*)a0, (const uint4*)a0l, (uint4*)fg, H, W, h2, w2, h1, w1, (float)h2 / (float)H, (float)w2 / (float)W,
       (float)h1 / (float)H, (float)w1 / (float)W, total);
   EW_CHECK("fuse_concat");
@@ -237,7 +287,7 @@ int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const 
 
 // ---------------------------------------------------------------------------------------------
 // cat[R, I] (model.py:146) in the layout the illumination net reads: RI (B,H,W,192) bf16 =
-//   [ bf16(R) (64) | bf16(I), 63 zero lanes (never written) | bf16(R - bf16(R)) (64) ]      (hi + lo pair)
+//   [ bf16(R) (64) | bf16(I), bf16(I - bf16(I)), 62 zero lanes (never written) | bf16(R - bf16(R)) (64) ]   (hi + lo pairs)
 // normally written by the sigmoid head's epilogue; this kernel builds it from caller-provided fp32 planes
 // (IllumAdjustmentNet.forward on its own).  64 bands.
 // ---------------------------------------------------------------------------------------------
@@ -263,7 +313,11 @@ __global__ void __launch_bounds__(256) pack_ri_kernel(const float* __restrict__ 
     bf16* o = RI + ((int64_t)b * HW + hw0 + i) * 192;
     *reinterpret_cast<uint4*>(o + 8 * q) = pack8(f);
     *reinterpret_cast<uint4*>(o + 128 + 8 * q) = pack8(lo);
-    if (q == 0) o[64] = f2bf(__ldg(I + (int64_t)b * HW + hw0 + i));
+    if (q == 0) {
+      const float iv = __ldg(I + (int64_t)b * HW + hw0 + i);
+      o[64] = f2bf(iv);
+      o[65] = f2bf(iv - bf2f(f2bf(iv)));
+    }
   }
 }
 int ss_launch_pack_ri(const float* R, const float* I, bf16* RI, int B, int C, int H, int W, cudaStream_t st) {

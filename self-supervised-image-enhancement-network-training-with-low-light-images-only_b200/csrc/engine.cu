@@ -247,6 +247,7 @@ static ConvGeom geom_init(int B, int OH, int OW, int N, const WAddr& wa) {
   ConvGeom g;
   memset(&g, 0, sizeof(g));
   g.B = B; g.OH = OH; g.OW = OW;
+  g.dup_c = -1;
   g.N = N; g.Npad = (N + 15) / 16 * 16;
   g.w_off = wa.w_off; g.w_sN = wa.sN; g.w_sC = wa.sC;
   // tcgen05 tile: th x tw output pixels = 128 GEMM rows
@@ -297,14 +298,16 @@ static ConvGeom geom_conv(int B, int OH, int OW, const std::vector<SrcSpec>& src
     // stride 2 forward-type read: in = 2*out + k_idx - pad  ->  parity views of the single source.  Inside a view the taps
     // are a stride-1 stencil again (offsets -1 / 0), so the halo-reuse gather kernels apply with one window per view.
     g.halo_ok = s2_halo_enabled() ? 2 : 0;
-    const SrcSpec& s = srcs[0];
-    for (int ph = 0; ph < 2; ++ph)
-      for (int pw = 0; pw < 2; ++pw) g.src[g.nsrc++] = view_parity(s.t, ph, pw);
+    // (a bf16 pair = two sources = 2 x 4 views, the residual one flagged `lo`)
+    for (size_t si = 0; si < srcs.size(); ++si)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) g.src[g.nsrc++] = view_parity(srcs[si].t, ph, pw);
     for (int kh = 0; kh < k; ++kh)
       for (int kw = 0; kw < k; ++kw) {
         const int eh = kh - pad, ew = kw - pad;
         const int ph = ((eh % 2) + 2) % 2, pw = ((ew % 2) + 2) % 2;
-        geom_add_slabs(g, ph * 2 + pw, (eh - ph) / 2, (ew - pw) / 2, s, kh, kw, wa);
+        for (size_t si = 0; si < srcs.size(); ++si)
+          geom_add_slabs(g, (int)si * 4 + ph * 2 + pw, (eh - ph) / 2, (ew - pw) / 2, srcs[si], kh, kw, wa);
       }
   }
   return g;
@@ -835,9 +838,13 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   Tens a0 = e->talloc(B, H, W, 64), a1 = e->talloc(B, h1, w1, 64), a2 = e->talloc(B, h2, w2, 64),
        a3 = e->talloc(B, h3, w3, 64), tt = e->talloc(B, h3, w3, 64);
   Tens a0l = e->talloc(B, H, W, 64), r3l = e->talloc(B, H, W, 64), ffl = e->talloc(B, H, W, 64);   // bf16 residuals
+  // the half-resolution skip d2 = deconv2 + conv1 (model.py:161) feeds deconv3 and the concat at full resolution: its
+  // rounding noise reaches I_delta directly, so conv1's output keeps its residual for the skip (a1l) and the up-sampled
+  // sum is stored as a bf16 pair (u3 | u3l) - DESIGN.md 4
+  Tens a1l = e->talloc(B, h1, w1, 64), u3l = e->talloc(B, H, W, 64);
   Tens u1 = e->talloc(B, h2, w2, 64), r1 = e->talloc(B, h2, w2, 64), u2 = e->talloc(B, h1, w1, 64),
        r2 = e->talloc(B, h1, w1, 64), u3 = e->talloc(B, H, W, 64), r3 = e->talloc(B, H, W, 64);
-  Tens fg = e->talloc(B, H, W, 256), ff = e->talloc(B, H, W, 64);
+  Tens fg = e->talloc(B, H, W, 320), ff = e->talloc(B, H, W, 64);
   const int L = h3 * w3;
   const int64_t T64 = (int64_t)B * L * 64;
   AttnBuffers ab;
@@ -881,14 +888,16 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
   int g_i0, g_i1, g_i2, g_i3, g_d1, g_d2, g_d3, g_fus, g_fin;
   {
     WAddr wa = waddr_conv_fwd(e, L_I_CONV0);
-    g_i0 = e->add_geom(geom_conv(B, H, W, {{RI, 0, C + 1, 0}, {RI, 128, C, 0, 1}}, 3, 1, 1, +1, 64, wa));
+    ConvGeom gi0 = geom_conv(B, H, W, {{RI, 0, C + 1, 0}, {RI, 128, C, 0, 1}}, 3, 1, 1, +1, 64, wa);
+    gi0.dup_c = C + 1;                    // lane C + 1 of cat[R, I] holds I's bf16 residual (written by the sigmoid head)
+    g_i0 = e->add_geom(gi0);
     Epi ep = epi_bf16(a0, 64); ep.out_lo = a0l.p;
     PUSH(F, return run_gather(e, g_i0, ep, L_I_CONV0, st););
   }
   {
     WAddr wa = waddr_conv_fwd(e, L_I_CONV1);
-    g_i1 = e->add_geom(geom_conv(B, h1, w1, {{a0, 0, 64, 0}}, 3, 2, 1, +1, 64, wa));
-    Epi ep = epi_bf16(a1, 64); ep.relu = 1;
+    g_i1 = e->add_geom(geom_conv(B, h1, w1, {{a0, 0, 64, 0}, {a0l, 0, 64, 0, 1}}, 3, 2, 1, +1, 64, wa));
+    Epi ep = epi_bf16(a1, 64); ep.relu = 1; ep.out_lo = a1l.p;
     PUSH(F, return run_gather(e, g_i1, ep, L_I_CONV1, st););
   }
   {
@@ -919,17 +928,17 @@ static int build_plan(sshslie_engine* e, unsigned char* base) {
     Epi ep = epi_bf16(r2, 64); ep.relu = 1;
     PUSH(F, return run_gather(e, g_d2, ep, L_I_DECONV2, st););
   }
-  PUSH(F, return ss_launch_upsample_add(r2.p, a1.p, u3.p, B, h1, w1, H, W, st););
+  PUSH(F, return ss_launch_upsample_add_pair(r2.p, a1.p, a1l.p, u3.p, u3l.p, B, h1, w1, H, W, st););
   {
     WAddr wa = waddr_conv_fwd(e, L_I_DECONV3);
-    g_d3 = e->add_geom(geom_conv(B, H, W, {{u3, 0, 64, 0}}, 3, 1, 1, +1, 64, wa));
+    g_d3 = e->add_geom(geom_conv(B, H, W, {{u3, 0, 64, 0}, {u3l, 0, 64, 0, 1}}, 3, 1, 1, +1, 64, wa));
     Epi ep = epi_bf16(r3, 64); ep.relu = 1; ep.out_lo = r3l.p;
     PUSH(F, return run_gather(e, g_d3, ep, L_I_DECONV3, st););
   }
-  PUSH(F, return ss_launch_fuse_concat(r1.p, a2.p, r2.p, a1.p, r3.p, r3l.p, a0.p, a0l.p, fg.p, B, H, W, h2, w2, h1, w1, st););
+  PUSH(F, return ss_launch_fuse_concat(r1.p, a2.p, r2.p, a1.p, a1l.p, r3.p, r3l.p, a0.p, a0l.p, fg.p, B, H, W, h2, w2, h1, w1, st););
   {
     WAddr wa = waddr_conv_fwd(e, L_I_FUSION);
-    g_fus = e->add_geom(geom_conv(B, H, W, {{fg, 0, 192, 0}, {fg, 192, 64, 128, 1}}, 1, 1, 0, +1, 64, wa));
+    g_fus = e->add_geom(geom_conv(B, H, W, {{fg, 0, 192, 0}, {fg, 192, 64, 128, 1}, {fg, 256, 64, 64, 1}}, 1, 1, 0, +1, 64, wa));
     Epi ep = epi_bf16(ff, 64); ep.out_lo = ffl.p;
     PUSH(F, return run_gather(e, g_fus, ep, L_I_FUSION, st););
   }

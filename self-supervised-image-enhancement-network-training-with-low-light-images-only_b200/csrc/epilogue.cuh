@@ -73,6 +73,7 @@ SS_DEVINL void epi_apply16(const Epi& e, int b, int oh, int ow, int n0, int N, f
     }
   } else if (e.mode == EPI_HEAD) {
     const int64_t pix = ((int64_t)b * e.H + oh) * e.W + ow;
+    float i_lo = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int n = n0 + i;
@@ -82,7 +83,9 @@ SS_DEVINL void epi_apply16(const Epi& e, int b, int oh, int ow, int n0, int N, f
       } else if (n == e.C && e.I32) {
         e.I32[pix] = s;
       }
-      v[i] = (n <= e.C) ? s : 0.f;
+      // lane C + 1 of cat[R, I]: I's bf16 residual (static register indices only: the lane follows I's in the same chunk)
+      v[i] = (n <= e.C) ? s : ((n == e.C + 1 && e.ri_lo_off > 0) ? i_lo : 0.f);
+      if (n == e.C) i_lo = s - bf2f(f2bf(s));
     }
     if (e.RI) {
       bf16* p = e.RI + pix * e.ri_c + n0;

@@ -62,7 +62,9 @@ int ss_launch_nchw32_to_nhwc16(const float* x, bf16* out, int B, int C, int H, i
 int ss_launch_nhwc16_to_nchw32(const bf16* in, float* y, int B, int C, int H, int W, int ldi, cudaStream_t st);
 // nearest resize (h, w) -> (ho, wo) of r (+ a), ATen index semantics
 int ss_launch_upsample_add(const bf16* r, const bf16* a, bf16* out, int B, int h, int w, int ho, int wo, cudaStream_t st);
-int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* r3,
+int ss_launch_upsample_add_pair(const bf16* r, const bf16* a, const bf16* a_lo, bf16* out, bf16* out_lo, int B, int h, int w,
+                                int ho, int wo, cudaStream_t st);
+int ss_launch_fuse_concat(const bf16* r1, const bf16* a2, const bf16* r2, const bf16* a1, const bf16* a1l, const bf16* r3,
                           const bf16* r3l, const bf16* a0, const bf16* a0l, bf16* fg, int B, int H, int W, int h2, int w2,
                           int h1, int w1, cudaStream_t st);
 int ss_launch_pack_ri(const float* R, const float* I, bf16* RI, int B, int C, int H, int W, cudaStream_t st);

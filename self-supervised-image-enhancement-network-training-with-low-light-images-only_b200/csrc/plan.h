@@ -17,7 +17,8 @@
 
 typedef __nv_bfloat16 bf16;
 
-#define SS_MAX_SRC 4
+#define SS_MAX_SRC 8            // views of one geom: a stride-2 conv over a bf16 pair reads 2 x 4 parity views
+#define SS_MAX_WIN 6           // distinct (source, 64-channel slab) halo windows of one tile (the fusion conv reads 5)
 #define SS_MAX_SLABS 81       // 9x9 taps x one 64-channel slab
 #define SS_SLAB 64            // K-slab width in channels (= 128 bytes of bf16 = one SWIZZLE_128B row)
 
@@ -50,6 +51,8 @@ struct ConvGeom {
   bf16* wp;
   // tcgen05 tiling: the 128 GEMM rows of a tile are a (th x tw) block of the OHxOW grid, tw*th == 128
   int tw, th;
+  int dup_c;                  // >= 0: input channel dup_c (source channel index) is the bf16 residual of channel dup_c - 1 and
+                              // shares its weight (the packer copies it; the weight gradient ignores the lane); -1: none
   int halo_ok;                // 1: stride-1 full views, the halo-reuse kernels (gather and weight gradient) may take this geom;
                               // 2: stride-2 parity views / transposed parity classes, the halo GATHER kernels may
 };

@@ -16,7 +16,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-LOSS_RTOL = {"L_I_smooth_delta": 0.05}
+LOSS_RTOL = {"L_I_smooth_delta": 0.02}      # measured 0.55 % at B=2 x 128 x 128 (JYU weights): the term is weighted x2000
 
 
 def _coefs():
@@ -61,7 +61,9 @@ def test_forward_matches_oracle(shape, impl):
 def test_loss_and_grads_match_oracle(case, impl):
     """Two oracles (both oracle/sshslie_oracle.py, fp32 arithmetic):
       fp32    : the reference semantics.  Loss terms per LOSS_RTOL; full 1.14M-gradient cosine >= 0.995; every
-                tensor carrying >= 1 % of the gradient norm has cosine >= 0.96 and norm within 15 %.
+                tensor carrying >= 1 % of the gradient norm has cosine >= 0.96 and norm within 15 %; at the full patch
+                size every tensor carrying >= 1e-4 of the norm has its norm within 10 % (measured: 0.969 .. 1.024 - the
+                decomposition bottleneck was 0.82 before the half-resolution skip, conv1's input and I got bf16 pairs).
       storage : the same computation with activations/gradients rounded to bf16 at the tensors the CUDA path
                 stores in bf16 (q=bf16_storage).  This isolates implementation error from storage noise:
                 loss terms within 2e-3, full cosine >= 0.9995, tensors with >= 0.5 % of the norm cosine >= 0.95
@@ -82,8 +84,8 @@ def test_loss_and_grads_match_oracle(case, impl):
     l16, g16, _ = O.loss_and_grads(p, x, coef, q=O.cuda_storage)
     for k in O.LOSS_KEYS:
         np.testing.assert_allclose(losses[k], l32[k], rtol=LOSS_RTOL.get(k, 2e-2), atol=1e-5, err_msg=k)
-        # the storage emulation is exact for plain-bf16 tensors; the hi+lo tensors differ in detail (I has no lo part,
-        # conv1 of the illumination net reads only the hi half), which only L_I_smooth_delta can see
+        # the storage emulation follows the CUDA path tensor by tensor (oracle.HI_LO_TENSORS); L_I_smooth_delta, a mean of
+        # |forward differences| of ~1e-3, is the one term that sees the remaining accumulation-order differences
         np.testing.assert_allclose(losses[k], l16[k], rtol=2e-2 if k == "L_I_smooth_delta" else 2e-3, atol=1e-6,
                                    err_msg=k + " (storage-precision oracle)")
     np.testing.assert_allclose(float(loss.detach()), l32["total_loss"], rtol=2e-2)
@@ -100,6 +102,8 @@ def test_loss_and_grads_match_oracle(case, impl):
         if share >= 0.01:
             assert _cos(G[k], g32[k]) >= 0.96, (k, _cos(G[k], g32[k]))
             np.testing.assert_allclose(float(G[k].norm()), float(g32[k].norm()), rtol=0.15, err_msg=k)
+        if size >= 128 and impl == "tcgen05" and share >= 1e-4:
+            np.testing.assert_allclose(float(G[k].norm()), float(g32[k].norm()), rtol=0.10, err_msg=k)
         if share >= 0.005:
             assert _cos(G[k], g16[k]) >= 0.95, (k, _cos(G[k], g16[k]))
         else:
